@@ -1,0 +1,246 @@
+/*
+ * pqlb200.h - C ABI of libpqlb200.so: the B200 (sm_100a) learner hot path of Parallel Q-Learning.
+ *
+ * Every entry point takes plain device pointers and sizes, enqueues work on the given
+ * cudaStream_t (passed as void*), never allocates, never synchronises and never keeps a
+ * pointer after returning.  Return value: 0 = ok, <0 = argument error
+ * (PQLB_E_*), >0 = cudaError_t of the failed launch.  Each function names the reference
+ * code it replaces (paths relative to the reference checkout).
+ *
+ * Layouts
+ * -------
+ * Transition record (ring and n-step window), fp32 words, `rec_ld` words per record
+ * (a multiple of 8 words = 32 B so that a record covers whole DRAM sectors):
+ *     [0, O)                     obs
+ *     [obs_pad, obs_pad+O)       next_obs          obs_pad = round_up(O, 4)
+ *     [2*obs_pad, 2*obs_pad+A)   action
+ *     [2*obs_pad + act_pad]      reward            act_pad = round_up(A, 4)
+ *     [2*obs_pad + act_pad + 1]  done   (ring: 0.0f / 1.0f == the reference's bool column;
+ *                                        n-step window: the raw float the actor supplied)
+ * Critic input row ("x"): torch.cat((state, action)) order - [0,O) normalised obs, [O,O+A)
+ * action - with x_ld = round_up(O+A, 4) words per row; padding words are zero.
+ * Parameter arena: one flat fp32 buffer per network set; every nn.Linear weight is stored
+ * [out, round_up(in,4)] row-major (padding columns zero), then its bias; each tensor starts
+ * at a 32-word aligned offset.
+ */
+#ifndef PQLB200_H
+#define PQLB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PQLB_OK 0
+#define PQLB_E_ARG (-1)      /* null pointer / non-positive size / bad enum           */
+#define PQLB_E_SHAPE (-2)    /* sizes inconsistent with each other (torch: shape error) */
+#define PQLB_E_ALIGN (-3)    /* pointer or leading dimension not aligned as required   */
+#define PQLB_E_DRIVER (-4)   /* cuTensorMapEncodeTiled unavailable / failed            */
+#define PQLB_E_UNSUPPORTED (-5)
+
+typedef void* pqlb_stream_t; /* cudaStream_t */
+
+int pqlb_version(void);
+const char* pqlb_error_string(int code);
+/* Number of CUDA kernels this library has launched so far in this process. */
+uint64_t pqlb_launch_count(void);
+/* Geometry helpers (pure host arithmetic). */
+int pqlb_obs_pad(int obs_dim);
+int pqlb_record_ld(int obs_dim, int act_dim);
+int pqlb_x_ld(int obs_dim, int act_dim);
+
+/* ---- K1: ring scatter-insert -------------------------------------------------------------
+ * Replaces ReplayBuffer.add_to_buffer, pql/replay/simple_replay.py:40-83 (the ten slice
+ * copies and the dones.bool() cast).  Row i of the n input rows goes to slot
+ * (next_p + i) when it fits, and the LAST (next_p+n-capacity) rows go to slots [0, ...) when
+ * the insert wraps (strict p > capacity).  Pointer bookkeeping stays on the host.
+ * Inputs are [n,O] [n,A] [n] [n,O] [n] fp32, contiguous.  Requires n <= capacity + (capacity-next_p). */
+int pqlb_ring_insert(float* ring, int64_t capacity, int obs_dim, int act_dim,
+                     const float* obs, const float* action, const float* reward,
+                     const float* next_obs, const float* done,
+                     int64_t n, int64_t next_p, pqlb_stream_t stream);
+
+/* Observation-only ring of the P-learner, pql/algo/pql_p_learner.py:66-83.  ring is [capacity, O]. */
+int pqlb_obsring_insert(float* ring, int64_t capacity, int obs_dim, const float* obs,
+                        int64_t n, int64_t next_p, pqlb_stream_t stream);
+
+/* ---- K1': n-step window push ---------------------------------------------------------------
+ * Replaces NStepReplay.add_to_buffer + fifo_shift + compute_nstep_return,
+ * pql/replay/nstep_replay.py:29-92.  Inputs [E,T,*] fp32 contiguous (env-major), window is
+ * [E, nstep, rec_ld] records addressed circularly by global step index, `count` = number of
+ * steps pushed before this call.  Emits (T - max(0, nstep-1-count)) * E rows, time-major
+ * (row = w*E + e).  T == 1 is one launch; T > 1 is an emit launch followed by a window-store
+ * launch (stream order keeps emitted rows independent of the new window).  gammas: nstep fp32
+ * on the host. */
+int pqlb_nstep_push(float* window, int num_envs, int nstep, int obs_dim, int act_dim,
+                    const float* obs, const float* action, const float* reward,
+                    const float* next_obs, const float* done, int T, int64_t count,
+                    const float* gammas_host,
+                    float* out_obs, float* out_action, float* out_reward, float* out_next_obs,
+                    float* out_done, pqlb_stream_t stream);
+
+/* ---- K2: uniform random-index gather ---------------------------------------------------------
+ * Replaces the five buf[indices] gathers + .float() of ReplayBuffer.sample_batch,
+ * pql/replay/simple_replay.py:98-104 (indices come from the caller: torch.randint keeps the
+ * reference's Philox stream).  Outputs [B,O] [B,A] [B] [B,O] [B] fp32. */
+int pqlb_sample_gather(const float* ring, int64_t capacity, int obs_dim, int act_dim,
+                       const int64_t* idx, int64_t batch,
+                       float* out_obs, float* out_action, float* out_reward,
+                       float* out_next_obs, float* out_done, pqlb_stream_t stream);
+
+/* Fused gather for the V-learner: sample_batch + normalize (pql/utils/common.py:139-145) +
+ * torch.cat((state, action)) (pql/models/mlp.py:198), values rounded to TF32 (RN) because they
+ * are tensor-core operands.  x_cur = [norm(obs) | action | 0], x_tgt[:, :O] = norm(next_obs)
+ * (its action columns are written later by the actor head).  mean/var may be NULL (obs_norm off). */
+int pqlb_sample_critic_batch(const float* ring, int64_t capacity, int obs_dim, int act_dim,
+                             const int64_t* idx, int64_t batch,
+                             const float* mean, const float* var, float eps,
+                             float* x_cur, float* x_tgt, int x_ld,
+                             float* reward, float* done, pqlb_stream_t stream);
+
+/* Fused gather for the P-learner: memory[indices] + normalize, pql/algo/pql_p_learner.py:49-52.
+ * Writes x[:, :O] (TF32-rounded) and zeroes the padding columns [O+A, x_ld). */
+int pqlb_sample_obs_batch(const float* obsring, int64_t capacity, int obs_dim,
+                          const int64_t* idx, int64_t batch,
+                          const float* mean, const float* var, float eps,
+                          float* x, int x_ld, int act_dim, pqlb_stream_t stream);
+
+/* ---- K3: dense layers on tcgen05 (kind::tf32, fp32 accumulate in TMEM) ---------------------- */
+enum pqlb_epilogue {
+  PQLB_EPI_STORE = 0,          /* out = acc                     (split-K partial, no rounding)  */
+  PQLB_EPI_BIAS = 1,           /* out = acc + bias                                             */
+  PQLB_EPI_BIAS_ELU = 2,       /* out = rn_tf32(elu(acc + bias))            mlp.py:15-24       */
+  PQLB_EPI_BIAS_ELU_HEAD = 3,  /* + q[row] = sum_n elu(..)*head_w[n] + head_b   (scalar Q head) */
+  PQLB_EPI_BIAS_TANH = 4,      /* out = rn_tf32(tanh(acc + bias)), out2 = fp32  mlp.py:177-179  */
+  PQLB_EPI_BIAS_TANH_NOISE = 5,/* out = rn_tf32(clamp(tanh(.)+clamp(noise,+-nb),+-1)) noise.py:19-27 */
+  PQLB_EPI_BIAS_SOFTMAX = 6,   /* out = softmax(acc + bias) over n_valid columns  mlp.py:263    */
+  PQLB_EPI_MUL_ELUGRAD = 7,    /* out = rn_tf32(acc * (h > 0 ? 1 : h + 1)), h = aux             */
+  PQLB_EPI_MUL_TANHGRAD = 8    /* out = rn_tf32(acc * (1 - a*a)), a = aux                       */
+};
+enum pqlb_major { PQLB_K_MAJOR = 0, PQLB_MN_MAJOR = 1 };
+
+#define PQLB_MAX_GROUPS 4
+
+/* One member of a grouped GEMM  D[M,N] = epi(A . B)  (all groups share the shape).
+ * K-major operand: memory [rows][K] (row stride ld words).  MN-major operand: memory [K][rows].
+ * a2/b2 (optional) continue the contraction with a second operand pair (K2 more columns). */
+typedef struct {
+  const float* a; int64_t lda;
+  const float* b; int64_t ldb;
+  const float* a2; int64_t lda2;
+  const float* b2; int64_t ldb2;
+  const float* bias;          /* [N] or NULL                       */
+  const float* aux;  int64_t ldaux;   /* epilogue input [M, ldaux]  */
+  const float* head_w;        /* [N] for BIAS_ELU_HEAD             */
+  const float* head_b;        /* [1]                               */
+  float* q;                   /* [M] for BIAS_ELU_HEAD             */
+  float* out;  int64_t ldo;   /* [M, ldo] or NULL (HEAD may skip)  */
+  float* out2; int64_t ldo2;  /* second output (BIAS_TANH) or NULL */
+  int64_t split_stride;       /* EPI_STORE: words between split-K partials */
+} pqlb_gemm_group;
+
+typedef struct {
+  int M, N, K, K2;            /* logical sizes; contraction K (+K2)            */
+  int a_major, b_major;       /* enum pqlb_major                               */
+  int epilogue;               /* enum pqlb_epilogue                            */
+  int tile_n;                 /* 16, 32, 64, 128 or 256                        */
+  int splits;                 /* split-K factor (EPI_STORE only), else 1       */
+  int n_groups;               /* 1..PQLB_MAX_GROUPS                            */
+  int col_lo, col_hi;         /* only output columns [col_lo,col_hi) are stored, at out[row*ldo + n-col_lo];
+                                 col_hi == 0 means [0, N).  aux/bias are indexed with the absolute n. */
+  float noise_bound;          /* BIAS_TANH_NOISE                               */
+  pqlb_gemm_group g[PQLB_MAX_GROUPS];
+} pqlb_gemm_desc;
+
+/* Replaces the nn.Linear / nn.ELU / tanh / softmax launches of pql/models/mlp.py:15-24,
+ * 177-179, 197-199, 261-263 and their autograd backward (cuBLAS sgemm + ATen elementwise). */
+int pqlb_gemm_tf32(const pqlb_gemm_desc* desc, pqlb_stream_t stream);
+
+/* dst = rn_tf32(src) elementwise (tensor-core operand copies of weights). */
+int pqlb_round_tf32(const float* src, float* dst, int64_t n, pqlb_stream_t stream);
+
+/* ---- twin-Q TD target, loss and head gradient -------------------------------------------------
+ * Replaces pql/algo/pql_v_learner.py:104-108 (torch.min, TD target, 2x mse_loss) and the
+ * backward of the scalar head: y = r + (1-d)*gamma_n*min(tq1,tq2); loss = mean((q1-y)^2) +
+ * mean((q2-y)^2); dq_i = 2(q_i-y)/B; dz3_i = rn_tf32(dq_i * w4_i * elu'(h3_i)).
+ * Per-block partials (block = 128 rows): loss_part[nblk], and gw4/gb4 partials written to
+ * ws_i[blk*129 + {0..127, 128}] for the deterministic reduction in pqlb_grad_reduce. */
+int pqlb_doubleq_td_loss(const float* q1, const float* q2, const float* tq1, const float* tq2,
+                         const float* reward, const float* done, float gamma_n, int64_t batch,
+                         const float* h3_1, const float* h3_2, const float* w4_1, const float* w4_2,
+                         float* dz3_1, float* dz3_2, float* y_out,
+                         float* ws_head1, float* ws_head2, float* loss_part, pqlb_stream_t stream);
+
+/* DPG actor loss, pql/algo/pql_p_learner.py:55-57: loss = -mean(min(q1,q2));
+ * dq_i = -(1/B) on the smaller head (split 1/2 on ties, torch.minimum backward);
+ * dz3_i = rn_tf32(dq_i * w4_i * elu'(h3_i)). */
+int pqlb_dpg_loss(const float* q1, const float* q2, int64_t batch,
+                  const float* h3_1, const float* h3_2, const float* w4_1, const float* w4_2,
+                  float* dz3_1, float* dz3_2, float* loss_part, pqlb_stream_t stream);
+
+/* C51: projection of both target distributions + elementwise min (pql/utils/distl_util.py:4-20,
+ * pql/algo/pql_v_learner.py:83-102), BCE loss against both current distributions and the
+ * gradient w.r.t. the logits through softmax.  p1,p2,tp1,tp2 are [B, ld] probabilities; dlogit1,2
+ * are rounded to TF32.  Accumulation order inside a row equals the reference CPU order. */
+int pqlb_c51_td_loss(const float* p1, const float* p2, const float* tp1, const float* tp2, int ld,
+                     const float* reward, const float* done, const float* z_atoms, float gamma_n,
+                     float v_min, float v_max, int num_atoms, int64_t batch,
+                     float* target_out, float* dlogit1, float* dlogit2, int ld_d,
+                     float* loss_part, pqlb_stream_t stream);
+
+/* C51 actor loss, pql/algo/pql_p_learner.py:55-57 through DistributionalDoubleQ.get_q_min
+ * (pql/models/mlp.py:255-259): q_i = sum_j p_i[j] z[j], loss = -mean(min(q1,q2)); the gradient
+ * goes through the softmax: dlogit_i[j] = dq_i p_i[j] (z[j] - q_i), rounded to TF32.
+ * dlogit1/2 may both be NULL (inference: only q_min_out / loss_part are written). */
+int pqlb_c51_dpg_loss(const float* p1, const float* p2, int ld, const float* z_atoms,
+                      int num_atoms, int64_t batch, float* dlogit1, float* dlogit2, int ld_d,
+                      float* q_min_out, float* loss_part, pqlb_stream_t stream);
+
+/* Column sums of dz (bias gradients), deterministic two-stage: part[blk*N + n] over 128-row blocks. */
+int pqlb_colsum_partial(const float* dz, int64_t ld, int64_t rows, int n_cols, float* part,
+                        pqlb_stream_t stream);
+
+/* The same reduction for up to PQLB_MAX_COLSUM matrices (all bias gradients of one update) in
+ * one launch. */
+#define PQLB_MAX_COLSUM 8
+typedef struct {
+  int n; int64_t rows;
+  const float* dz[PQLB_MAX_COLSUM]; int64_t ld[PQLB_MAX_COLSUM]; int n_cols[PQLB_MAX_COLSUM];
+  float* part[PQLB_MAX_COLSUM];
+} pqlb_colsum_desc;
+int pqlb_colsum_partial_multi(const pqlb_colsum_desc* desc, pqlb_stream_t stream);
+
+/* x[r] = rn_tf32([a[r,:na] | b[r,:nb] | 0]) with row stride x_ld: torch.cat((state, action), 1)
+ * of pql/models/mlp.py:198,262 plus operand rounding (module-level forward; b may be NULL). */
+int pqlb_pack_x(const float* a, int64_t lda, int na, const float* b, int64_t ldb, int nb,
+                float* x, int x_ld, int64_t rows, pqlb_stream_t stream);
+
+/* ---- K4: gradient reduction, clip, AdamW, Polyak ---------------------------------------------
+ * seg table (device, int64 x 5 per segment): {arena_off, count, ws_off, ws_stride, n_part}.
+ * pqlb_grad_reduce: grad[arena_off+i] = sum_{s<n_part} ws[ws_off + s*ws_stride + i] (fixed order)
+ * and sumsq_part[seg] = sum of squares of the segment (fixed order). */
+int pqlb_grad_reduce(const int64_t* seg_table, int n_seg, const float* ws, float* grad,
+                     float* sumsq_part, pqlb_stream_t stream);
+/* sum of squares only (after a gradient all-reduce). */
+int pqlb_grad_sumsq(const int64_t* seg_table, int n_seg, const float* grad, float* sumsq_part,
+                    pqlb_stream_t stream);
+/* Replaces clip_grad_norm_ + AdamW.step + soft_update (pql/algo/pql_v_learner.py:124-133, :112;
+ * pql/utils/torch_util.py:9-12; torch/optim/adam.py order):
+ * coef = min(1, max_norm/(sqrt(sum sumsq_part)+1e-6)) (max_norm < 0: no clipping);
+ * p,m,v updated in place; target <- p*tau + target*(1-tau) when target != NULL;
+ * p_tf32 / target_tf32 = rn_tf32 copies (NULL to skip).  `step` is 1-based.
+ * grad_scale multiplies the gradient first (1/world for data parallel). */
+int pqlb_adamw_polyak(float* param, const float* grad, float* m, float* v, float* target,
+                      float* param_tf32, float* target_tf32, int64_t n,
+                      const float* sumsq_part, int n_part, float grad_scale, float max_norm,
+                      float lr, float beta1, float beta2, float eps, float weight_decay,
+                      int64_t step, float tau, float* grad_norm_out, pqlb_stream_t stream);
+
+/* Final deterministic sum of per-block loss partials: out[0] = scale * sum(part[0..n)). */
+int pqlb_sum_partials(const float* part, int n, float scale, float* out, pqlb_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PQLB200_H */

@@ -1,0 +1,124 @@
+"""Prepared launches of the C-ABI kernels (include/pqlb200.h).
+
+A learner builds its whole update once as a list of prepared calls over preallocated buffers
+(all device pointers fixed), then ``learn()`` just replays the list - on torch's current
+stream, so the same list can be captured into a CUDA graph.  Nothing here computes anything
+on the host or in PyTorch: every object is an argument pack for one ``extern "C"`` entry point.
+"""
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._lib import (EPI_BIAS, EPI_BIAS_ELU, EPI_BIAS_ELU_HEAD, EPI_BIAS_SOFTMAX, EPI_BIAS_TANH,  # noqa: F401
+                   EPI_BIAS_TANH_NOISE, EPI_MUL_ELUGRAD, EPI_MUL_TANHGRAD, EPI_STORE, K_MAJOR,
+                   MN_MAJOR)
+
+
+def addr(t, off=0):
+    """Device address of element ``off`` (fp32 words) of tensor ``t`` (None -> 0)."""
+    if t is None:
+        return 0
+    if isinstance(t, int):
+        return t + 4 * off
+    return t.data_ptr() + t.element_size() * off
+
+
+def _p(a):
+    return C.c_void_p(a if a else None)
+
+
+class Call:
+    """One prepared C-ABI call: ``Call(name, *args)`` -> ``call()`` launches on the current stream."""
+
+    def __init__(self, name, *args, keep=()):
+        self.name, self.args, self._keep = name, args, keep
+
+    def __call__(self):
+        _lib.call(self.name, *self.args)
+
+
+class Gemm(Call):
+    """Grouped ``D[M,N] = epilogue(A . B)`` on tcgen05 (pqlb_gemm_tf32).
+
+    ``groups``: list of dicts with keys a, lda, b, ldb, [a2, lda2, b2, ldb2], bias, aux, ldaux,
+    head_w, head_b, q, out, ldo, out2, ldo2, split_stride; pointer values are device addresses
+    (``addr(tensor, word_offset)``)."""
+
+    PTRS = ("a", "b", "a2", "b2", "bias", "aux", "head_w", "head_b", "q", "out", "out2")
+    INTS = ("lda", "ldb", "lda2", "ldb2", "ldaux", "ldo", "ldo2", "split_stride")
+
+    def __init__(self, M, N, K, groups, *, epilogue, tile_n, a_major=K_MAJOR, b_major=K_MAJOR,
+                 splits=1, K2=0, col_lo=0, col_hi=0, noise_bound=0.0, keep=()):
+        d = _lib.GemmDesc()
+        d.M, d.N, d.K, d.K2 = int(M), int(N), int(K), int(K2)
+        d.a_major, d.b_major, d.epilogue, d.tile_n = a_major, b_major, epilogue, int(tile_n)
+        d.splits, d.n_groups = int(splits), len(groups)
+        d.col_lo, d.col_hi, d.noise_bound = int(col_lo), int(col_hi), float(noise_bound)
+        if not 1 <= len(groups) <= _lib.MAX_GROUPS:
+            raise ValueError("1..%d groups per launch" % _lib.MAX_GROUPS)
+        for i, g in enumerate(groups):
+            unknown = set(g) - set(self.PTRS) - set(self.INTS)
+            if unknown:
+                raise KeyError(f"unknown gemm group fields {sorted(unknown)}")
+            for k in self.PTRS:
+                setattr(d.g[i], k, g.get(k, 0) or None)
+            for k in self.INTS:
+                setattr(d.g[i], k, int(g.get(k, 0)))
+        self.desc = d
+        super().__init__("pqlb_gemm_tf32", C.byref(d), keep=keep)
+
+
+def pick_tile_n(N):
+    for t in (16, 32, 64, 128, 256):
+        if N <= t:
+            return t
+    return 256
+
+
+def wgrad_tiling(M, N, K, n_groups, target_ctas=148):
+    """Tile width and split-K factor of a weight-gradient GEMM (contraction over the batch):
+    the smallest split count that still fills the SMs, with kb_total % splits == 0."""
+    kb = (K + 31) // 32
+    best = None
+    for tile_n in (256, 128, 64):
+        if tile_n > 64 and N <= tile_n // 2:
+            continue
+        tiles = ((M + 127) // 128) * ((N + tile_n - 1) // tile_n) * n_groups
+        for splits in (1, 2, 4, 8, 16, 32, 64):
+            if kb % splits:
+                continue
+            ctas = tiles * splits
+            if ctas >= target_ctas * 0.8 or splits == 64 or kb // splits <= 2:
+                cand = (splits, -tile_n)
+                if best is None or cand < best[0]:
+                    best = (cand, tile_n, splits)
+                break
+    if best is None:
+        return pick_tile_n(min(N, 256)), 1
+    return best[1], best[2]
+
+
+class Workspace:
+    """Bump allocator over one fp32 device buffer (so a learner's scratch is one allocation
+    and every sub-buffer address is fixed for the lifetime of the prepared plan)."""
+
+    def __init__(self, device):
+        self.device = device
+        self._specs = []
+        self._total = 0
+        self.buf = None
+
+    def reserve(self, name, n_words, align=32):
+        off = (self._total + align - 1) // align * align
+        self._specs.append((name, off, int(n_words)))
+        self._total = off + int(n_words)
+        return off
+
+    def commit(self):
+        self.buf = torch.zeros(max(self._total, 1), dtype=torch.float32, device=self.device)
+        self.views = {name: self.buf[off:off + n] for name, off, n in self._specs}
+        return self
+
+    def __getitem__(self, name):
+        return self.views[name]

@@ -1,0 +1,418 @@
+// K3 building block: grouped GEMM  D[M,N] = epilogue(A . B)  on the 5th-gen tensor cores.
+//
+//   * operands fp32 in HBM/L2, already RN-rounded to TF32 by their producers; tiles are staged
+//     into shared memory by TMA (cp.async.bulk.tensor, 128-byte swizzle) through a
+//     full/empty mbarrier ring;
+//   * one elected thread issues tcgen05.mma.cta_group::1.kind::tf32 (M=128, N=tile_n, K=8) with
+//     shared-memory descriptors; the fp32 accumulator lives in TMEM;
+//   * four epilogue warps read the accumulator back with tcgen05.ld (32 lanes x 32 columns per
+//     warp) and apply the fused epilogue (bias / ELU / tanh+noise / softmax / ELU' / tanh' /
+//     scalar Q head / split-K partial store).
+//
+// Both operands may be K-major (memory [rows][K], forward + the A side of dgrad) or MN-major
+// (memory [K][rows], the weight side of dgrad and both sides of wgrad), so no transposed copy
+// of activations or weights is ever materialised.
+//
+// Replaces: nn.Linear / nn.ELU / tanh / softmax forward and autograd backward launches of
+// pql/models/mlp.py:15-24,177-179,197-199,261-263 (cuBLAS fp32 sgemm + ATen elementwise).
+#include <cuda.h>
+#include <cudaTypedefs.h>
+
+#include "common.cuh"
+
+namespace pqlb {
+
+constexpr int kGemmThreads = 192;       // warp 0: TMA, warp 1: TMEM alloc + MMA, warps 2-5: epilogue
+constexpr int kTileM = 128;
+constexpr int kTileK = 32;              // fp32 words per k-block = one 128-byte swizzle row
+constexpr int kATileBytes = kTileM * 128;
+constexpr int kMaxStages = 8;
+constexpr int kSmemBudget = 200 * 1024;
+
+struct alignas(64) GroupDev {
+  CUtensorMap tmA, tmB, tmA2, tmB2;
+  const float* bias; const float* aux; const float* head_w; const float* head_b;
+  float* q; float* out; float* out2;
+  long long ldaux, ldo, ldo2, split_stride;
+};
+
+struct alignas(64) GemmDev {
+  GroupDev g[PQLB_MAX_GROUPS];
+  int M, N, K, K2;
+  int a_mn, b_mn, epi, tile_n;
+  int splits, kb1, kb_total, kb_per_split;
+  int stages, stage_bytes, b_tile_bytes, tmem_cols;
+  int col_lo, col_hi;
+  float noise_bound;
+  unsigned idesc;
+};
+
+// ------------------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  return ok != 0;
+}
+// Bounded wait: a protocol bug must surface as a launch failure, never as a hung GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 4000000000LL) __trap();
+  }
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+      ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// Shared-memory matrix descriptor (sm_100 format, cute/arch/mma_sm100_desc.hpp):
+// start>>4 [0,14), LBO>>4 [16,30), SBO>>4 [32,46), version=1 [46,48), layout type [61,64):
+// SWIZZLE_128B = 2 (K-major tiles), SWIZZLE_128B_BASE32B = 1 (the only layout the tensor core
+// accepts for MN-major 32-bit operands: 32-byte chunks swizzled inside 128-byte rows, 4-row atoms).
+constexpr uint32_t kLayoutSw128 = 2, kLayoutSw128Base32 = 1;
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout) {
+  uint64_t d = 0;
+  d |= (uint64_t)((addr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)layout << 61;
+  return d;
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// ------------------------------------------------------------------------------ the kernel
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_tf32_kernel(const __grid_constant__ GemmDev P) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t full_bar[kMaxStages];
+  __shared__ __align__(8) uint64_t empty_bar[kMaxStages];
+  __shared__ __align__(8) uint64_t accum_bar;
+  __shared__ uint32_t tmem_slot;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int grp = blockIdx.z / P.splits;
+  const int split = blockIdx.z - grp * P.splits;
+  const GroupDev& G = P.g[grp];
+  const int m0 = blockIdx.x * kTileM;
+  const int n0 = blockIdx.y * P.tile_n;
+  const int kb_begin = split * P.kb_per_split;
+  const int kb_end = min(kb_begin + P.kb_per_split, P.kb_total);
+
+  const uint32_t tiles = (smem_u32(smem_raw) + 1023u) & ~1023u;   // SWIZZLE_128B wants 1024-B alignment
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < P.stages; ++s) { mbar_init(smem_u32(&full_bar[s]), 1); mbar_init(smem_u32(&empty_bar[s]), 1); }
+    mbar_init(smem_u32(&accum_bar), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"((uint32_t)P.tmem_cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_d = tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      const uint32_t tx_bytes = kATileBytes + P.b_tile_bytes;
+      int stage = 0; uint32_t phase = 0;
+      for (int kb = kb_begin; kb < kb_end; ++kb) {
+        mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1u);
+        const uint32_t bar = smem_u32(&full_bar[stage]);
+        mbar_expect_tx(bar, tx_bytes);
+        const bool second = kb >= P.kb1;
+        const int k0 = (second ? kb - P.kb1 : kb) * kTileK;
+        const CUtensorMap* mapA = second ? &G.tmA2 : &G.tmA;
+        const CUtensorMap* mapB = second ? &G.tmB2 : &G.tmB;
+        const uint32_t sa = tiles + stage * P.stage_bytes;
+        const uint32_t sb = sa + kATileBytes;
+        if (!P.a_mn) tma_load_2d(sa, mapA, k0, m0, bar);
+        else for (int cb = 0; cb < kTileM / 32; ++cb) tma_load_2d(sa + cb * 4096, mapA, m0 + cb * 32, k0, bar);
+        if (!P.b_mn) tma_load_2d(sb, mapB, k0, n0, bar);
+        else for (int cb = 0; cb < (P.tile_n + 31) / 32; ++cb) tma_load_2d(sb + cb * 4096, mapB, n0 + cb * 32, k0, bar);
+        if (++stage == P.stages) { stage = 0; phase ^= 1u; }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0; uint32_t accumulate = 0;
+      for (int kb = kb_begin; kb < kb_end; ++kb) {
+        mbar_wait(smem_u32(&full_bar[stage]), phase);
+        tcgen05_fence_after();
+        const bool second = kb >= P.kb1;
+        const int kseg = second ? P.K2 : P.K;
+        const int krem = kseg - (second ? kb - P.kb1 : kb) * kTileK;
+        const int ksteps = krem >= kTileK ? 4 : (krem + 7) / 8;
+        const uint32_t sa = tiles + stage * P.stage_bytes;
+        const uint32_t sb = sa + kATileBytes;
+        // K-major: 8-row groups 1024 B apart (SBO), k-step = 32 B inside the swizzle row.
+        // MN-major: 32-element column blocks 4096 B apart (LBO), 4-k-row swizzle atoms 512 B
+        // apart (SBO); one MMA (K = 8) consumes two atoms = 1024 B per k-step.
+        const uint64_t adesc = P.a_mn ? make_smem_desc(sa, 4096, 512, kLayoutSw128Base32) : make_smem_desc(sa, 16, 1024, kLayoutSw128);
+        const uint64_t bdesc = P.b_mn ? make_smem_desc(sb, 4096, 512, kLayoutSw128Base32) : make_smem_desc(sb, 16, 1024, kLayoutSw128);
+        const uint32_t a_step = P.a_mn ? (1024u >> 4) : (32u >> 4);
+        const uint32_t b_step = P.b_mn ? (1024u >> 4) : (32u >> 4);
+        for (int k = 0; k < ksteps; ++k) {
+          umma_tf32(tmem_d, adesc + (uint64_t)(a_step * k), bdesc + (uint64_t)(b_step * k), P.idesc, accumulate);
+          accumulate = 1;
+        }
+        umma_commit(smem_u32(&empty_bar[stage]));          // frees the smem slot when the MMAs retire
+        if (++stage == P.stages) { stage = 0; phase ^= 1u; }
+      }
+      umma_commit(smem_u32(&accum_bar));                    // accumulator complete
+    }
+  } else {
+    // ===================== epilogue (warps 2..5) =====================
+    const int quarter = warp & 3;                           // TMEM lanes [32q, 32q+32) belong to warp%4 == q
+    const int row = m0 + quarter * 32 + lane;
+    const bool row_ok = row < P.M;
+    mbar_wait(smem_u32(&accum_bar), 0);
+    tcgen05_fence_after();
+    const uint32_t taddr = tmem_d + ((uint32_t)(quarter * 32) << 16);
+    const int col_lo = P.col_lo, col_hi = P.col_hi;
+    const int epi = P.epi;
+
+    if (epi == PQLB_EPI_BIAS_SOFTMAX) {
+      // all N (<= 64) logits of a row live in this thread: softmax in registers
+      float v[64];
+      tmem_ld32(taddr, v);
+      if (P.tile_n > 32) tmem_ld32(taddr + 32, v + 32);
+      float mx = -INFINITY;
+#pragma unroll
+      for (int j = 0; j < 64; ++j) if (j < P.N) { v[j] += G.bias[j]; mx = fmaxf(mx, v[j]); }
+      float sum = 0.f;
+#pragma unroll
+      for (int j = 0; j < 64; ++j) if (j < P.N) { v[j] = expf(v[j] - mx); sum += v[j]; }
+      if (row_ok) {
+#pragma unroll
+        for (int j = 0; j < 64; ++j) if (j < P.N) G.out[(long long)row * G.ldo + j] = v[j] / sum;
+      }
+    } else {
+      float qacc = 0.f;
+      const int chunk = P.tile_n >= 32 ? 32 : 16;
+      for (int c0 = 0; c0 < P.tile_n; c0 += chunk) {
+        float v[32];
+        if (chunk == 32) tmem_ld32(taddr + c0, v); else tmem_ld16(taddr + c0, v);
+        const int nb = n0 + c0;
+        if (!row_ok) continue;
+        float* orow = nullptr;
+        if (G.out) orow = G.out + (long long)row * G.ldo + (epi == PQLB_EPI_STORE ? (long long)split * G.split_stride : 0ll);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          if (j >= chunk) break;
+          const int n = nb + j;
+          if (n >= P.N) break;
+          float x = v[j];
+          switch (epi) {
+            case PQLB_EPI_STORE: break;
+            case PQLB_EPI_BIAS: x += G.bias[n]; break;
+            case PQLB_EPI_BIAS_ELU: x = rn_tf32(elu1(x + G.bias[n])); break;
+            case PQLB_EPI_BIAS_ELU_HEAD: { const float h = elu1(x + G.bias[n]); qacc = fmaf(h, G.head_w[n], qacc); x = rn_tf32(h); } break;
+            case PQLB_EPI_BIAS_TANH: { const float a = tanhf(x + G.bias[n]); if (G.out2) G.out2[(long long)row * G.ldo2 + n] = a; x = rn_tf32(a); } break;
+            case PQLB_EPI_BIAS_TANH_NOISE: {
+              const float a = tanhf(x + G.bias[n]);
+              const float z = fminf(fmaxf(G.aux[(long long)row * G.ldaux + n], -P.noise_bound), P.noise_bound);
+              x = rn_tf32(fminf(fmaxf(a + z, -1.f), 1.f));
+            } break;
+            case PQLB_EPI_MUL_ELUGRAD: { const float h = G.aux[(long long)row * G.ldaux + n]; x = rn_tf32(x * (h > 0.f ? 1.f : h + 1.f)); } break;
+            case PQLB_EPI_MUL_TANHGRAD: { const float a = G.aux[(long long)row * G.ldaux + n]; x = rn_tf32(x * (1.f - a * a)); } break;
+            default: break;
+          }
+          v[j] = x;
+        }
+        if (orow) {
+          // vector path when the 32-column chunk is fully inside [col_lo, col_hi) and 16-B aligned
+          const int lo = max(nb, col_lo), hi = min(min(nb + chunk, P.N), col_hi);
+          float* dst = orow + (nb - col_lo);
+          if (lo == nb && hi == nb + chunk && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              if (j >= chunk) break;
+              *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              if (j >= chunk) break;
+              const int n = nb + j;
+              if (n >= lo && n < hi) dst[j] = v[j];
+            }
+          }
+        }
+      }
+      if (epi == PQLB_EPI_BIAS_ELU_HEAD && row_ok) G.q[row] = qacc + G.head_b[0];
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"((uint32_t)P.tmem_cols) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------ host side
+static PFN_cuTensorMapEncodeTiled get_encode_fn() {
+  static PFN_cuTensorMapEncodeTiled fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled>(p);
+  }
+  return fn;
+}
+
+// 2-D fp32 tensor map with 128-byte swizzle; dim0 is the contiguous dimension.
+static int make_map(CUtensorMap* map, const float* base, uint64_t dim0, uint64_t dim1, int64_t ld_words,
+                    uint32_t box0, uint32_t box1, CUtensorMapSwizzle swizzle) {
+  PFN_cuTensorMapEncodeTiled enc = get_encode_fn();
+  if (!enc) return PQLB_E_DRIVER;
+  if (!aligned16(base) || (ld_words % 4) != 0 || ld_words < (int64_t)dim0) return PQLB_E_ALIGN;
+  cuuint64_t gdim[2] = {dim0, dim1};
+  cuuint64_t gstr[1] = {(cuuint64_t)ld_words * 4};
+  cuuint32_t box[2] = {box0, box1};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), gdim, gstr, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? PQLB_OK : PQLB_E_DRIVER;
+}
+
+static int make_operand_map(CUtensorMap* map, const float* base, int64_t ld, int major, int rows, int k,
+                            int tile_rows) {
+  if (major == PQLB_K_MAJOR)   // memory [rows][k]
+    return make_map(map, base, (uint64_t)k, (uint64_t)rows, ld, kTileK, (uint32_t)tile_rows, CU_TENSOR_MAP_SWIZZLE_128B);
+  // memory [k][rows]: boxes of 32 rows(MN) x 32 k, 32-byte swizzle atoms (see make_smem_desc)
+  return make_map(map, base, (uint64_t)rows, (uint64_t)k, ld, 32, kTileK, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+}
+
+}  // namespace pqlb
+
+using namespace pqlb;
+
+extern "C" int pqlb_gemm_tf32(const pqlb_gemm_desc* d, pqlb_stream_t stream) {
+  PQLB_CHECK_ARG(d != nullptr);
+  PQLB_CHECK_ARG(d->M > 0 && d->N > 0 && d->K > 0 && d->K2 >= 0);
+  PQLB_CHECK_ARG(d->n_groups >= 1 && d->n_groups <= PQLB_MAX_GROUPS && d->splits >= 1);
+  PQLB_CHECK_ARG(d->epilogue >= PQLB_EPI_STORE && d->epilogue <= PQLB_EPI_MUL_TANHGRAD);
+  const int tn = d->tile_n;
+  PQLB_CHECK_ARG(tn == 16 || tn == 32 || tn == 64 || tn == 128 || tn == 256);
+  PQLB_CHECK_ARG(d->splits == 1 || d->epilogue == PQLB_EPI_STORE);
+  if (d->epilogue == PQLB_EPI_BIAS_ELU_HEAD) PQLB_CHECK_SHAPE(d->N <= tn);
+  if (d->epilogue == PQLB_EPI_BIAS_SOFTMAX) PQLB_CHECK_SHAPE(d->N <= tn && tn <= 64 && tn >= 32);
+
+  static GemmDev P;   // host staging copy (single-threaded callers, SURVEY §8b threading)
+  P.M = d->M; P.N = d->N; P.K = d->K; P.K2 = d->K2;
+  P.a_mn = d->a_major == PQLB_MN_MAJOR; P.b_mn = d->b_major == PQLB_MN_MAJOR;
+  P.epi = d->epilogue; P.tile_n = tn; P.splits = d->splits;
+  P.kb1 = (d->K + kTileK - 1) / kTileK;
+  P.kb_total = P.kb1 + (d->K2 + kTileK - 1) / kTileK;
+  PQLB_CHECK_SHAPE(P.kb_total % d->splits == 0);
+  P.kb_per_split = P.kb_total / d->splits;
+  P.b_tile_bytes = P.b_mn ? ((tn + 31) / 32) * 4096 : tn * 128;
+  P.stage_bytes = kATileBytes + ((P.b_tile_bytes + 1023) / 1024) * 1024;
+  int stages = kSmemBudget / P.stage_bytes;
+  if (stages > kMaxStages) stages = kMaxStages;
+  if (stages > P.kb_per_split) stages = P.kb_per_split < 2 ? 2 : P.kb_per_split;
+  if (stages < 2) stages = 2;
+  P.stages = stages;
+  P.tmem_cols = tn < 32 ? 32 : tn;
+  P.col_lo = d->col_lo; P.col_hi = d->col_hi > 0 ? d->col_hi : d->N;
+  PQLB_CHECK_SHAPE(P.col_lo >= 0 && P.col_lo < P.col_hi && P.col_hi <= d->N);
+  P.noise_bound = d->noise_bound;
+  // instruction descriptor (cute::UMMA::InstrDescriptor): c=F32 [4,6), a/b=TF32 [7,10)/[10,13),
+  // a_major [15], b_major [16], N>>3 [17,23), M>>4 [24,29)
+  P.idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((unsigned)P.a_mn << 15) | ((unsigned)P.b_mn << 16) |
+            ((unsigned)(tn >> 3) << 17) | ((unsigned)(kTileM >> 4) << 24);
+
+  for (int i = 0; i < d->n_groups; ++i) {
+    const pqlb_gemm_group& s = d->g[i];
+    GroupDev& G = P.g[i];
+    PQLB_CHECK_ARG(s.a && s.b);
+    int rc;
+    if ((rc = make_operand_map(&G.tmA, s.a, s.lda, d->a_major, d->M, d->K, kTileM)) != PQLB_OK) return rc;
+    if ((rc = make_operand_map(&G.tmB, s.b, s.ldb, d->b_major, d->N, d->K, tn)) != PQLB_OK) return rc;
+    if (d->K2 > 0) {
+      PQLB_CHECK_ARG(s.a2 && s.b2);
+      if ((rc = make_operand_map(&G.tmA2, s.a2, s.lda2, d->a_major, d->M, d->K2, kTileM)) != PQLB_OK) return rc;
+      if ((rc = make_operand_map(&G.tmB2, s.b2, s.ldb2, d->b_major, d->N, d->K2, tn)) != PQLB_OK) return rc;
+    } else { G.tmA2 = G.tmA; G.tmB2 = G.tmB; }
+    const int e = d->epilogue;
+    if (e != PQLB_EPI_STORE && e != PQLB_EPI_MUL_ELUGRAD && e != PQLB_EPI_MUL_TANHGRAD) PQLB_CHECK_ARG(s.bias);
+    if (e == PQLB_EPI_MUL_ELUGRAD || e == PQLB_EPI_MUL_TANHGRAD || e == PQLB_EPI_BIAS_TANH_NOISE) PQLB_CHECK_ARG(s.aux);
+    if (e == PQLB_EPI_BIAS_ELU_HEAD) PQLB_CHECK_ARG(s.head_w && s.head_b && s.q); else PQLB_CHECK_ARG(s.out);
+    G.bias = s.bias; G.aux = s.aux; G.head_w = s.head_w; G.head_b = s.head_b; G.q = s.q;
+    G.out = s.out; G.out2 = s.out2; G.ldaux = s.ldaux; G.ldo = s.ldo; G.ldo2 = s.ldo2;
+    G.split_stride = s.split_stride;
+  }
+
+  const int smem_bytes = P.stages * P.stage_bytes + 1024;
+  static bool smem_attr_set = false;      // static (barriers) + dynamic must stay <= 227 KB
+  if (!smem_attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget + 2048);
+    if (e != cudaSuccess) return (int)e;
+    smem_attr_set = true;
+  }
+  dim3 grid((unsigned)((d->M + kTileM - 1) / kTileM), (unsigned)((d->N + tn - 1) / tn), (unsigned)(d->n_groups * d->splits));
+  gemm_tf32_kernel<<<grid, kGemmThreads, smem_bytes, (cudaStream_t)stream>>>(P);
+  PQLB_LAUNCH_RET();
+}

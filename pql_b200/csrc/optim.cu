@@ -1,0 +1,268 @@
+// K4: deterministic gradient reduction, global-norm clip, AdamW and Polyak in one pass over a
+// flat fp32 parameter arena (HBM/L2-bound elementwise work).  Reference behaviour:
+// pql/algo/pql_v_learner.py:124-133 (zero_grad/backward/clip_grad_norm_/AdamW.step),
+// pql/utils/torch_util.py:9-12 (soft_update); arithmetic order: torch/optim/adam.py and
+// torch/nn/utils/clip_grad.py as summarised in SURVEY.md App. E.
+#include <math.h>
+
+#include "common.cuh"
+
+namespace pqlb {
+
+constexpr int kOptThreads = 256;
+constexpr int kSegElems = 1024;   // elements per reduce segment (4 per thread)
+
+// Fixed-shape block reduction: xor-shuffle tree inside each warp, then warp 0 adds the eight
+// warp sums in index order.  Same launch shape => same association => bit-reproducible.
+__device__ __forceinline__ float block_sum_256(float v, float* smem8) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  const int w = threadIdx.x >> 5;
+  if ((threadIdx.x & 31) == 0) smem8[w] = v;
+  __syncthreads();
+  float tot = 0.f;
+#pragma unroll
+  for (int i = 0; i < kOptThreads / 32; ++i) tot += smem8[i];
+  __syncthreads();
+  return tot;
+}
+
+__global__ void __launch_bounds__(kOptThreads)
+grad_reduce_kernel(const int64_t* __restrict__ seg, const float* __restrict__ ws,
+                   float* __restrict__ grad, float* __restrict__ sumsq_part, bool reduce) {
+  __shared__ float red[8];
+  const int64_t* s = seg + (int64_t)blockIdx.x * 5;
+  const int64_t arena_off = s[0], count = s[1], ws_off = s[2], ws_stride = s[3], n_part = s[4];
+  float sq = 0.f;
+  for (int i = threadIdx.x; i < count; i += kOptThreads) {
+    float g;
+    if (reduce && n_part > 0) {
+      g = 0.f;
+      const float* p = ws + ws_off + i;
+      for (int64_t k = 0; k < n_part; ++k) g += p[k * ws_stride];
+      grad[arena_off + i] = g;
+    } else {
+      g = grad[arena_off + i];
+    }
+    sq += g * g;
+  }
+  const float tot = block_sum_256(sq, red);
+  if (threadIdx.x == 0) sumsq_part[blockIdx.x] = tot;
+}
+
+struct AdamScalars {
+  float grad_scale, max_norm, decay, one_minus_b1, b2, one_minus_b2, step_size, bc2_sqrt, eps;
+  float tau, one_minus_tau;
+};
+
+__global__ void __launch_bounds__(kOptThreads)
+adamw_polyak_kernel(float* __restrict__ param, const float* __restrict__ grad, float* __restrict__ m,
+                    float* __restrict__ v, float* __restrict__ target, float* __restrict__ p_tf32,
+                    float* __restrict__ t_tf32, int64_t n, const float* __restrict__ sumsq_part,
+                    int n_part, AdamScalars a, float* __restrict__ grad_norm_out) {
+  __shared__ float red[8];
+  // global L2 norm of the (scaled) gradient from the per-segment partials, fixed order
+  float part = 0.f;
+  for (int i = threadIdx.x; i < n_part; i += kOptThreads) part += sumsq_part[i];
+  const float total = block_sum_256(part, red);
+  const float norm = sqrtf(total) * a.grad_scale;
+  float coef = 1.f;
+  if (a.max_norm >= 0.f) coef = fminf(a.max_norm / (norm + 1e-6f), 1.f);   // clip_grad.py
+  if (blockIdx.x == 0 && threadIdx.x == 0 && grad_norm_out) grad_norm_out[0] = norm;
+  const float gmul = a.grad_scale * coef;
+
+  const int64_t i4 = ((int64_t)blockIdx.x * kOptThreads + threadIdx.x) * 4;
+  if (i4 >= n) return;
+  const int cnt = (n - i4) >= 4 ? 4 : (int)(n - i4);
+  float p[4], g[4], mm[4], vv[4], tt[4];
+  if (cnt == 4) {
+    *reinterpret_cast<float4*>(p) = *reinterpret_cast<const float4*>(param + i4);
+    *reinterpret_cast<float4*>(g) = *reinterpret_cast<const float4*>(grad + i4);
+    *reinterpret_cast<float4*>(mm) = *reinterpret_cast<const float4*>(m + i4);
+    *reinterpret_cast<float4*>(vv) = *reinterpret_cast<const float4*>(v + i4);
+    if (target) *reinterpret_cast<float4*>(tt) = *reinterpret_cast<const float4*>(target + i4);
+  } else {
+    for (int k = 0; k < cnt; ++k) { p[k] = param[i4 + k]; g[k] = grad[i4 + k]; mm[k] = m[i4 + k]; vv[k] = v[i4 + k]; if (target) tt[k] = target[i4 + k]; }
+  }
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    if (k >= cnt) break;
+    const float gk = g[k] * gmul;
+    p[k] = p[k] * a.decay;                                          // param.mul_(1 - lr*wd)
+    mm[k] = mm[k] + a.one_minus_b1 * (gk - mm[k]);                  // exp_avg.lerp_(grad, 1-b1)
+    vv[k] = vv[k] * a.b2 + a.one_minus_b2 * gk * gk;                // mul_(b2).addcmul_(g,g,1-b2)
+    const float denom = sqrtf(vv[k]) / a.bc2_sqrt + a.eps;
+    p[k] = p[k] - a.step_size * (mm[k] / denom);                    // addcdiv_(m, denom, -step_size)
+    if (target) tt[k] = p[k] * a.tau + tt[k] * a.one_minus_tau;     // soft_update
+  }
+  if (cnt == 4) {
+    *reinterpret_cast<float4*>(param + i4) = *reinterpret_cast<float4*>(p);
+    *reinterpret_cast<float4*>(m + i4) = *reinterpret_cast<float4*>(mm);
+    *reinterpret_cast<float4*>(v + i4) = *reinterpret_cast<float4*>(vv);
+    if (target) *reinterpret_cast<float4*>(target + i4) = *reinterpret_cast<float4*>(tt);
+    if (p_tf32) *reinterpret_cast<float4*>(p_tf32 + i4) = make_float4(rn_tf32(p[0]), rn_tf32(p[1]), rn_tf32(p[2]), rn_tf32(p[3]));
+    if (target && t_tf32) *reinterpret_cast<float4*>(t_tf32 + i4) = make_float4(rn_tf32(tt[0]), rn_tf32(tt[1]), rn_tf32(tt[2]), rn_tf32(tt[3]));
+  } else {
+    for (int k = 0; k < cnt; ++k) {
+      param[i4 + k] = p[k]; m[i4 + k] = mm[k]; v[i4 + k] = vv[k];
+      if (target) target[i4 + k] = tt[k];
+      if (p_tf32) p_tf32[i4 + k] = rn_tf32(p[k]);
+      if (target && t_tf32) t_tf32[i4 + k] = rn_tf32(tt[k]);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kOptThreads)
+round_tf32_kernel(const float* __restrict__ src, float* __restrict__ dst, int64_t n) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) dst[i] = rn_tf32(src[i]);
+}
+
+// part[blk*n_cols + c] = sum over the 128 rows of block blk of dz[row, c].  A block covers
+// 128 rows x 32 columns: warp w sums rows [16w, 16w+16) in ascending order, then the eight warp
+// sums are added in warp order (fixed association => deterministic).
+__global__ void __launch_bounds__(kOptThreads)
+colsum_partial_kernel(const float* __restrict__ dz, int64_t ld, int64_t rows, int n_cols,
+                      float* __restrict__ part) {
+  __shared__ float red[8][32];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int c = blockIdx.y * 32 + lane;
+  const int64_t r0 = (int64_t)blockIdx.x * 128 + w * 16;
+  float acc = 0.f;
+  if (c < n_cols) {
+#pragma unroll
+    for (int r = 0; r < 16; ++r) {
+      const int64_t row = r0 + r;
+      acc += row < rows ? dz[row * ld + c] : 0.f;
+    }
+  }
+  red[w][lane] = acc;
+  __syncthreads();
+  if (w == 0 && c < n_cols) {
+    float tot = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) tot += red[i][lane];
+    part[(int64_t)blockIdx.x * n_cols + c] = tot;
+  }
+}
+
+struct ColsumMulti { const float* dz[PQLB_MAX_COLSUM]; float* part[PQLB_MAX_COLSUM]; long long ld[PQLB_MAX_COLSUM]; int n_cols[PQLB_MAX_COLSUM]; };
+
+// Same reduction as colsum_partial_kernel for up to PQLB_MAX_COLSUM matrices in one launch
+// (blockIdx.z selects the matrix): all bias gradients of one update.
+__global__ void __launch_bounds__(kOptThreads)
+colsum_multi_kernel(ColsumMulti d, int64_t rows) {
+  __shared__ float red[8][32];
+  const int e = blockIdx.z;
+  const int n_cols = d.n_cols[e];
+  if ((int)blockIdx.y * 32 >= n_cols) return;
+  const float* __restrict__ dz = d.dz[e];
+  const long long ld = d.ld[e];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int c = blockIdx.y * 32 + lane;
+  const int64_t r0 = (int64_t)blockIdx.x * 128 + w * 16;
+  float acc = 0.f;
+  if (c < n_cols) {
+#pragma unroll
+    for (int r = 0; r < 16; ++r) {
+      const int64_t row = r0 + r;
+      acc += row < rows ? dz[row * ld + c] : 0.f;
+    }
+  }
+  red[w][lane] = acc;
+  __syncthreads();
+  if (w == 0 && c < n_cols) {
+    float tot = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) tot += red[i][lane];
+    d.part[e][(int64_t)blockIdx.x * n_cols + c] = tot;
+  }
+}
+
+__global__ void __launch_bounds__(kOptThreads)
+sum_partials_kernel(const float* __restrict__ part, int n, float scale, float* __restrict__ out) {
+  __shared__ float red[8];
+  float acc = 0.f;
+  for (int i = threadIdx.x; i < n; i += kOptThreads) acc += part[i];
+  const float tot = block_sum_256(acc, red);
+  if (threadIdx.x == 0) out[0] = tot * scale;
+}
+
+}  // namespace pqlb
+
+using namespace pqlb;
+
+extern "C" int pqlb_grad_reduce(const int64_t* seg_table, int n_seg, const float* ws, float* grad,
+                                float* sumsq_part, pqlb_stream_t stream) {
+  PQLB_CHECK_ARG(seg_table && n_seg > 0 && ws && grad && sumsq_part);
+  grad_reduce_kernel<<<n_seg, kOptThreads, 0, (cudaStream_t)stream>>>(seg_table, ws, grad, sumsq_part, true);
+  PQLB_LAUNCH_RET();
+}
+
+extern "C" int pqlb_grad_sumsq(const int64_t* seg_table, int n_seg, const float* grad,
+                               float* sumsq_part, pqlb_stream_t stream) {
+  PQLB_CHECK_ARG(seg_table && n_seg > 0 && grad && sumsq_part);
+  grad_reduce_kernel<<<n_seg, kOptThreads, 0, (cudaStream_t)stream>>>(seg_table, nullptr, const_cast<float*>(grad), sumsq_part, false);
+  PQLB_LAUNCH_RET();
+}
+
+extern "C" int pqlb_adamw_polyak(float* param, const float* grad, float* m, float* v, float* target,
+                                 float* param_tf32, float* target_tf32, int64_t n,
+                                 const float* sumsq_part, int n_part, float grad_scale,
+                                 float max_norm, float lr, float beta1, float beta2, float eps,
+                                 float weight_decay, int64_t step, float tau, float* grad_norm_out,
+                                 pqlb_stream_t stream) {
+  PQLB_CHECK_ARG(param && grad && m && v && n > 0 && sumsq_part && n_part > 0 && step >= 1);
+  PQLB_CHECK_ALIGN(aligned16(param) && aligned16(grad) && aligned16(m) && aligned16(v));
+  PQLB_CHECK_ALIGN((!target || aligned16(target)) && (!param_tf32 || aligned16(param_tf32)) &&
+                   (!target_tf32 || aligned16(target_tf32)));
+  // scalar corrections in double like torch's python-side arithmetic (adam.py)
+  const double b1 = beta1, b2 = beta2, dlr = lr;
+  const double bc1 = 1.0 - pow(b1, (double)step);
+  const double bc2 = 1.0 - pow(b2, (double)step);
+  AdamScalars a;
+  a.grad_scale = grad_scale; a.max_norm = max_norm;
+  a.decay = (float)(1.0 - dlr * (double)weight_decay);
+  a.one_minus_b1 = (float)(1.0 - b1); a.b2 = beta2; a.one_minus_b2 = (float)(1.0 - b2);
+  a.step_size = (float)(dlr / bc1); a.bc2_sqrt = (float)sqrt(bc2); a.eps = eps;
+  a.tau = tau; a.one_minus_tau = (float)(1.0 - (double)tau);
+  const int64_t blocks = (n + kOptThreads * 4 - 1) / (kOptThreads * 4);
+  adamw_polyak_kernel<<<(unsigned)blocks, kOptThreads, 0, (cudaStream_t)stream>>>(
+      param, grad, m, v, target, param_tf32, target_tf32, n, sumsq_part, n_part, a, grad_norm_out);
+  PQLB_LAUNCH_RET();
+}
+
+extern "C" int pqlb_round_tf32(const float* src, float* dst, int64_t n, pqlb_stream_t stream) {
+  PQLB_CHECK_ARG(src && dst && n > 0);
+  round_tf32_kernel<<<grid_for(n, kOptThreads, 4), kOptThreads, 0, (cudaStream_t)stream>>>(src, dst, n);
+  PQLB_LAUNCH_RET();
+}
+
+extern "C" int pqlb_colsum_partial(const float* dz, int64_t ld, int64_t rows, int n_cols, float* part,
+                                   pqlb_stream_t stream) {
+  PQLB_CHECK_ARG(dz && rows > 0 && n_cols > 0 && part && ld >= n_cols);
+  dim3 grid((unsigned)((rows + 127) / 128), (unsigned)((n_cols + 31) / 32));
+  colsum_partial_kernel<<<grid, kOptThreads, 0, (cudaStream_t)stream>>>(dz, ld, rows, n_cols, part);
+  PQLB_LAUNCH_RET();
+}
+
+extern "C" int pqlb_sum_partials(const float* part, int n, float scale, float* out, pqlb_stream_t stream) {
+  PQLB_CHECK_ARG(part && n > 0 && out);
+  sum_partials_kernel<<<1, kOptThreads, 0, (cudaStream_t)stream>>>(part, n, scale, out);
+  PQLB_LAUNCH_RET();
+}
+
+extern "C" int pqlb_colsum_partial_multi(const pqlb_colsum_desc* d, pqlb_stream_t stream) {
+  PQLB_CHECK_ARG(d && d->n >= 1 && d->n <= PQLB_MAX_COLSUM && d->rows > 0);
+  ColsumMulti m; int max_cols = 0;
+  for (int i = 0; i < PQLB_MAX_COLSUM; ++i) {
+    const bool on = i < d->n;
+    if (on) PQLB_CHECK_ARG(d->dz[i] && d->part[i] && d->n_cols[i] > 0 && d->ld[i] >= d->n_cols[i]);
+    m.dz[i] = on ? d->dz[i] : nullptr; m.part[i] = on ? d->part[i] : nullptr;
+    m.ld[i] = on ? d->ld[i] : 0; m.n_cols[i] = on ? d->n_cols[i] : 0;
+    if (on && d->n_cols[i] > max_cols) max_cols = d->n_cols[i];
+  }
+  dim3 grid((unsigned)((d->rows + 127) / 128), (unsigned)((max_cols + 31) / 32), (unsigned)d->n);
+  colsum_multi_kernel<<<grid, kOptThreads, 0, (cudaStream_t)stream>>>(m, d->rows);
+  PQLB_LAUNCH_RET();
+}

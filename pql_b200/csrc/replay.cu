@@ -1,0 +1,433 @@
+// K1 / K1' / K2: replay ring insert, n-step window push, uniform-index gather (HBM-bound
+// byte movers).  Reference behaviour: pql/replay/simple_replay.py:40-104,
+// pql/replay/nstep_replay.py:29-92, pql/algo/pql_p_learner.py:66-83.
+//
+// Work decomposition: every kernel flattens its copy into "items" of VEC consecutive fp32
+// words of one field of one row, so that consecutive lanes touch consecutive addresses on both
+// the read and the write side, and each thread keeps UNROLL independent loads in flight.
+#include "common.cuh"
+
+namespace pqlb {
+
+constexpr int kThreads = 256;
+constexpr int kUnroll = 4;
+
+template <int VEC> struct VecT;
+template <> struct VecT<4> { using type = float4; };
+template <> struct VecT<1> { using type = float; };
+
+struct FieldMap {          // per-row item decomposition (in VEC units)
+  int ov, av, per_row;     // obs items, action items, items per row = 2*ov + av
+};
+template <int VEC> __host__ __device__ inline FieldMap field_map(const RecGeom& g) {
+  FieldMap f; f.ov = g.O / VEC; f.av = g.A / VEC; f.per_row = 2 * f.ov + f.av; return f;
+}
+
+// -------------------------------------------------------------------------------- K1 insert
+template <int VEC>
+__global__ void __launch_bounds__(kThreads)
+ring_insert_kernel(float* __restrict__ ring, RecGeom g,
+                   const float* __restrict__ obs, const float* __restrict__ act,
+                   const float* __restrict__ rew, const float* __restrict__ nobs,
+                   const float* __restrict__ done, int64_t n, int64_t next_p, int64_t head,
+                   int64_t tail) {
+  using V = typename VecT<VEC>::type;
+  const FieldMap f = field_map<VEC>(g);
+  const int64_t total = n * f.per_row;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+
+  auto slot_of = [&](int64_t row) -> int64_t {
+    if (row < head) { int64_t s = next_p + row; return s < tail ? -1 : s; }   // superseded by the wrapped tail
+    return row - head;
+  };
+
+  for (int64_t base = tid; base < total; base += stride * kUnroll) {
+    V val[kUnroll]; float* dst[kUnroll];
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) {
+      const int64_t item = base + (int64_t)u * stride;
+      dst[u] = nullptr;
+      if (item < total) {
+        const int64_t row = item / f.per_row;
+        const int sub = (int)(item - row * f.per_row);
+        const int64_t s = slot_of(row);
+        const float* src; int off;
+        if (sub < f.ov)            { src = obs  + row * g.O + sub * VEC;               off = g.off_obs  + sub * VEC; }
+        else if (sub < 2 * f.ov)   { src = nobs + row * g.O + (sub - f.ov) * VEC;      off = g.off_next + (sub - f.ov) * VEC; }
+        else                       { src = act  + row * g.A + (sub - 2 * f.ov) * VEC;  off = g.off_act  + (sub - 2 * f.ov) * VEC; }
+        val[u] = *reinterpret_cast<const V*>(src);
+        if (s >= 0) dst[u] = ring + s * g.rec_ld + off;
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u)
+      if (dst[u]) *reinterpret_cast<V*>(dst[u]) = val[u];
+  }
+  // reward + done: one float2 per row; done is stored as the reference's bool column (x != 0)
+  for (int64_t row = tid; row < n; row += stride) {
+    const int64_t s = slot_of(row);
+    if (s >= 0) {
+      float2 rd = make_float2(rew[row], done[row] != 0.f ? 1.f : 0.f);
+      *reinterpret_cast<float2*>(ring + s * g.rec_ld + g.off_rew) = rd;
+    }
+  }
+}
+
+template <int VEC>
+__global__ void __launch_bounds__(kThreads)
+obsring_insert_kernel(float* __restrict__ ring, int O, const float* __restrict__ obs, int64_t n,
+                      int64_t next_p, int64_t head, int64_t tail) {
+  using V = typename VecT<VEC>::type;
+  const int ov = O / VEC;
+  const int64_t total = n * ov;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t base = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; base < total; base += stride * kUnroll) {
+    V val[kUnroll]; float* dst[kUnroll];
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) {
+      const int64_t item = base + (int64_t)u * stride;
+      dst[u] = nullptr;
+      if (item < total) {
+        const int64_t row = item / ov;
+        const int sub = (int)(item - row * ov);
+        int64_t s;
+        if (row < head) { s = next_p + row; if (s < tail) s = -1; } else s = row - head;
+        val[u] = *reinterpret_cast<const V*>(obs + row * O + sub * VEC);
+        if (s >= 0) dst[u] = ring + s * O + sub * VEC;
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u)
+      if (dst[u]) *reinterpret_cast<V*>(dst[u]) = val[u];
+  }
+}
+
+// -------------------------------------------------------------------------------- K1' n-step
+struct Gammas { float g[32]; };
+
+// One warp per (t, e).  Window entries are addressed by global step index g (slot g % nstep);
+// entries with g >= count0 are read from this call's input block instead, so every emitted
+// row depends only on the window as it was BEFORE the call.  mode bit 0 = emit rows, bit 1 =
+// store the last nstep steps of the block into the window.  T == 1 does both in one launch (a
+// warp reads slots (c-n+1..c-1) % n and then overwrites slot c % n of its own env); for T > 1
+// the host issues the emit launch and then the store launch, so no emitted row can observe a
+// slot that another warp has already overwritten.
+__global__ void __launch_bounds__(kThreads)
+nstep_push_kernel(float* __restrict__ window, int E, int n, RecGeom g,
+                  const float* __restrict__ obs, const float* __restrict__ act,
+                  const float* __restrict__ rew, const float* __restrict__ nobs,
+                  const float* __restrict__ done, int T, int64_t count0, Gammas gam, int t0, int mode,
+                  float* __restrict__ o_obs, float* __restrict__ o_act, float* __restrict__ o_rew,
+                  float* __restrict__ o_nobs, float* __restrict__ o_done) {
+  const int lane = threadIdx.x & 31;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const int64_t total = (int64_t)T * E;
+  for (int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < total; w += nwarps) {
+    const int t = (int)(w / E);
+    const int e = (int)(w - (int64_t)t * E);
+    const int64_t c = count0 + t;
+    if ((mode & 1) && t >= t0) {
+      float r = 0.f, d = 0.f;
+      if (lane < n) {
+        const int64_t gj = c - n + 1 + lane;
+        if (gj >= count0) { const int64_t i = (int64_t)e * T + (gj - count0); r = rew[i]; d = done[i]; }
+        else { const float* rec = window + ((int64_t)e * n + (gj % n)) * g.rec_ld; r = rec[g.off_rew]; d = rec[g.off_done]; }
+      }
+      // k* = first maximum of done over the window (torch argmax), any = some entry non-zero
+      float dmax = __shfl_sync(0xffffffffu, d, 0); int kstar = 0; bool any = dmax != 0.f; float dlast = dmax;
+      for (int j = 1; j < n; ++j) {
+        const float dj = __shfl_sync(0xffffffffu, d, j);
+        if (dj > dmax) { dmax = dj; kstar = j; }
+        any |= (dj != 0.f); dlast = dj;
+      }
+      // sum_k (r_k * gamma_k) * mask_k, left to right, every product/sum rounded (no FMA)
+      float acc = 0.f;
+      for (int j = 0; j < n; ++j) {
+        const float rj = __shfl_sync(0xffffffffu, r, j);
+        const float m = (!any || j <= kstar) ? 1.f : 0.f;
+        const float term = __fmul_rn(__fmul_rn(rj, gam.g[j]), m);
+        acc = (j == 0) ? term : __fadd_rn(acc, term);
+      }
+      const int64_t row = (int64_t)(t - t0) * E + e;
+      auto src_of = [&](int j, const float* in_field, int dim, int rec_off) -> const float* {
+        const int64_t gj = c - n + 1 + j;
+        if (gj >= count0) return in_field + ((int64_t)e * T + (gj - count0)) * dim;
+        return window + ((int64_t)e * n + (gj % n)) * g.rec_ld + rec_off;
+      };
+      const float* s_obs = src_of(0, obs, g.O, g.off_obs);
+      const float* s_act = src_of(0, act, g.A, g.off_act);
+      const float* s_nxt = src_of(any ? kstar : n - 1, nobs, g.O, g.off_next);
+      for (int k = lane; k < g.O; k += 32) { o_obs[row * g.O + k] = s_obs[k]; o_nobs[row * g.O + k] = s_nxt[k]; }
+      for (int k = lane; k < g.A; k += 32) o_act[row * g.A + k] = s_act[k];
+      if (lane == 0) { o_rew[row] = acc; o_done[row] = any ? 1.f : dlast; }
+    }
+    if ((mode & 2) && t >= T - n) {   // the last n steps of the block become the stored window
+      float* rec = window + ((int64_t)e * n + (c % n)) * g.rec_ld;
+      const int64_t i = (int64_t)e * T + t;
+      for (int k = lane; k < g.O; k += 32) { rec[g.off_obs + k] = obs[i * g.O + k]; rec[g.off_next + k] = nobs[i * g.O + k]; }
+      for (int k = lane; k < g.A; k += 32) rec[g.off_act + k] = act[i * g.A + k];
+      if (lane == 0) { rec[g.off_rew] = rew[i]; rec[g.off_done] = done[i]; }
+    }
+  }
+}
+
+// -------------------------------------------------------------------------------- K2 gather
+template <int VEC>
+__global__ void __launch_bounds__(kThreads)
+sample_gather_kernel(const float* __restrict__ ring, RecGeom g, const int64_t* __restrict__ idx,
+                     int64_t B, float* __restrict__ o_obs, float* __restrict__ o_act,
+                     float* __restrict__ o_rew, float* __restrict__ o_nobs, float* __restrict__ o_done) {
+  using V = typename VecT<VEC>::type;
+  const FieldMap f = field_map<VEC>(g);
+  const int64_t total = B * f.per_row;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  for (int64_t base = tid; base < total; base += stride * kUnroll) {
+    V val[kUnroll]; float* dst[kUnroll];
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) {
+      const int64_t item = base + (int64_t)u * stride;
+      dst[u] = nullptr;
+      if (item < total) {
+        const int64_t b = item / f.per_row;
+        const int sub = (int)(item - b * f.per_row);
+        const float* rec = ring + __ldg(idx + b) * g.rec_ld;
+        if (sub < f.ov)          { val[u] = *reinterpret_cast<const V*>(rec + g.off_obs + sub * VEC);             dst[u] = o_obs + b * g.O + sub * VEC; }
+        else if (sub < 2 * f.ov) { val[u] = *reinterpret_cast<const V*>(rec + g.off_next + (sub - f.ov) * VEC);   dst[u] = o_nobs + b * g.O + (sub - f.ov) * VEC; }
+        else                     { val[u] = *reinterpret_cast<const V*>(rec + g.off_act + (sub - 2 * f.ov) * VEC); dst[u] = o_act + b * g.A + (sub - 2 * f.ov) * VEC; }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u)
+      if (dst[u]) *reinterpret_cast<V*>(dst[u]) = val[u];
+  }
+  for (int64_t b = tid; b < B; b += stride) {
+    const float2 rd = *reinterpret_cast<const float2*>(ring + __ldg(idx + b) * g.rec_ld + g.off_rew);
+    o_rew[b] = rd.x; o_done[b] = rd.y;      // bool column -> .float() is 0.0 / 1.0 already
+  }
+}
+
+__device__ __forceinline__ float norm_clamp(float x, float m, float v, float eps) {
+  // common.py:139-145: clamp((x - mean) / sqrt(var + eps), -5, 5)
+  float y = __fdiv_rn(__fsub_rn(x, m), __fsqrt_rn(__fadd_rn(v, eps)));
+  return fminf(fmaxf(y, -5.f), 5.f);
+}
+
+// Fused V-learner batch: x_cur = [norm(obs)|action|0], x_tgt = [norm(next_obs)| (actor head) |0];
+// TF32-rounded because both are tensor-core operands.
+__global__ void __launch_bounds__(kThreads)
+sample_critic_batch_kernel(const float* __restrict__ ring, RecGeom g, const int64_t* __restrict__ idx,
+                           int64_t B, const float* __restrict__ mean, const float* __restrict__ var,
+                           float eps, float* __restrict__ x_cur, float* __restrict__ x_tgt, int x_ld,
+                           float* __restrict__ o_rew, float* __restrict__ o_done) {
+  const int per_row = g.O + x_ld;          // next_obs columns, then one full x_cur row
+  const int64_t total = B * per_row;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  for (int64_t item = tid; item < total; item += stride) {
+    const int64_t b = item / per_row;
+    const int sub = (int)(item - b * per_row);
+    const float* rec = ring + __ldg(idx + b) * g.rec_ld;
+    if (sub < g.O) {
+      float v = rec[g.off_next + sub];
+      if (mean) v = norm_clamp(v, mean[sub], var[sub], eps);
+      x_tgt[b * x_ld + sub] = rn_tf32(v);
+    } else {
+      const int k = sub - g.O;             // column of x_cur
+      float v = 0.f;
+      if (k < g.O) { v = rec[g.off_obs + k]; if (mean) v = norm_clamp(v, mean[k], var[k], eps); }
+      else if (k < g.O + g.A) v = rec[g.off_act + (k - g.O)];
+      else x_tgt[b * x_ld + k] = 0.f;      // zero padding of the target input row
+      x_cur[b * x_ld + k] = rn_tf32(v);
+    }
+  }
+  for (int64_t b = tid; b < B; b += stride) {
+    const float2 rd = *reinterpret_cast<const float2*>(ring + __ldg(idx + b) * g.rec_ld + g.off_rew);
+    o_rew[b] = rd.x; o_done[b] = rd.y;
+  }
+}
+
+__global__ void __launch_bounds__(kThreads)
+sample_obs_batch_kernel(const float* __restrict__ obsring, int O, const int64_t* __restrict__ idx,
+                        int64_t B, const float* __restrict__ mean, const float* __restrict__ var,
+                        float eps, float* __restrict__ x, int x_ld, int A) {
+  const int64_t total = B * x_ld;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t item = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; item < total; item += stride) {
+    const int64_t b = item / x_ld;
+    const int k = (int)(item - b * x_ld);
+    if (k < O) {
+      float v = obsring[__ldg(idx + b) * O + k];
+      if (mean) v = norm_clamp(v, mean[k], var[k], eps);
+      x[b * x_ld + k] = rn_tf32(v);
+    } else if (k >= O + A) {
+      x[b * x_ld + k] = 0.f;               // action columns [O, O+A) belong to the actor head
+    }
+  }
+}
+
+// x[row] = rn_tf32([a[row, :na] | b[row, :nb] | 0...]) : torch.cat((state, action)) of
+// mlp.py:198 plus the operand rounding/padding the tensor-core layers expect.
+__global__ void __launch_bounds__(kThreads)
+pack_x_kernel(const float* __restrict__ a, int64_t lda, int na, const float* __restrict__ b,
+              int64_t ldb, int nb, float* __restrict__ x, int x_ld, int64_t rows) {
+  const int64_t total = rows * x_ld;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t item = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; item < total; item += stride) {
+    const int64_t r = item / x_ld;
+    const int k = (int)(item - r * x_ld);
+    float v = 0.f;
+    if (k < na) v = a[r * lda + k];
+    else if (k < na + nb) v = b[r * ldb + (k - na)];
+    x[item] = rn_tf32(v);
+  }
+}
+
+static inline void split_insert(int64_t n, int64_t next_p, int64_t capacity, int64_t* head, int64_t* tail) {
+  const int64_t p = next_p + n;
+  if (p > capacity) { *head = capacity - next_p; *tail = p - capacity; }
+  else { *head = n; *tail = 0; }
+}
+
+}  // namespace pqlb
+
+using namespace pqlb;
+
+extern "C" int pqlb_obs_pad(int obs_dim) { return round_up(obs_dim, 4); }
+extern "C" int pqlb_record_ld(int obs_dim, int act_dim) { return rec_geom(obs_dim, act_dim).rec_ld; }
+extern "C" int pqlb_x_ld(int obs_dim, int act_dim) { return round_up(obs_dim + act_dim, 4); }
+
+extern "C" int pqlb_ring_insert(float* ring, int64_t capacity, int obs_dim, int act_dim,
+                                const float* obs, const float* action, const float* reward,
+                                const float* next_obs, const float* done, int64_t n,
+                                int64_t next_p, pqlb_stream_t stream) {
+  PQLB_CHECK_ARG(ring && capacity > 0 && obs_dim > 0 && act_dim > 0 && n >= 0);
+  PQLB_CHECK_ARG(next_p >= 0 && next_p <= capacity);
+  if (n == 0) return PQLB_OK;
+  PQLB_CHECK_ARG(obs && action && reward && next_obs && done);
+  int64_t head, tail; split_insert(n, next_p, capacity, &head, &tail);
+  PQLB_CHECK_SHAPE(tail <= capacity);      // reference: slice-assign shape mismatch
+  PQLB_CHECK_ALIGN(aligned16(ring));
+  const RecGeom g = rec_geom(obs_dim, act_dim);
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool vec4 = obs_dim % 4 == 0 && act_dim % 4 == 0 && aligned16(obs) && aligned16(action) && aligned16(next_obs);
+  if (vec4) {
+    const int64_t items = n * field_map<4>(g).per_row;
+    ring_insert_kernel<4><<<grid_for(items, kThreads, kUnroll), kThreads, 0, st>>>(
+        ring, g, obs, action, reward, next_obs, done, n, next_p, head, tail);
+  } else {
+    const int64_t items = n * field_map<1>(g).per_row;
+    ring_insert_kernel<1><<<grid_for(items, kThreads, kUnroll), kThreads, 0, st>>>(
+        ring, g, obs, action, reward, next_obs, done, n, next_p, head, tail);
+  }
+  PQLB_LAUNCH_RET();
+}
+
+extern "C" int pqlb_obsring_insert(float* ring, int64_t capacity, int obs_dim, const float* obs,
+                                   int64_t n, int64_t next_p, pqlb_stream_t stream) {
+  PQLB_CHECK_ARG(ring && capacity > 0 && obs_dim > 0 && n >= 0 && next_p >= 0 && next_p <= capacity);
+  if (n == 0) return PQLB_OK;
+  PQLB_CHECK_ARG(obs);
+  int64_t head, tail; split_insert(n, next_p, capacity, &head, &tail);
+  PQLB_CHECK_SHAPE(tail <= capacity);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (obs_dim % 4 == 0 && aligned16(obs) && aligned16(ring)) {
+    obsring_insert_kernel<4><<<grid_for(n * (obs_dim / 4), kThreads, kUnroll), kThreads, 0, st>>>(
+        ring, obs_dim, obs, n, next_p, head, tail);
+  } else {
+    obsring_insert_kernel<1><<<grid_for(n * obs_dim, kThreads, kUnroll), kThreads, 0, st>>>(
+        ring, obs_dim, obs, n, next_p, head, tail);
+  }
+  PQLB_LAUNCH_RET();
+}
+
+extern "C" int pqlb_nstep_push(float* window, int num_envs, int nstep, int obs_dim, int act_dim,
+                               const float* obs, const float* action, const float* reward,
+                               const float* next_obs, const float* done, int T, int64_t count,
+                               const float* gammas_host, float* out_obs, float* out_action,
+                               float* out_reward, float* out_next_obs, float* out_done,
+                               pqlb_stream_t stream) {
+  PQLB_CHECK_ARG(window && num_envs > 0 && nstep >= 2 && nstep <= 32 && obs_dim > 0 && act_dim > 0);
+  PQLB_CHECK_ARG(obs && action && reward && next_obs && done && gammas_host && T > 0 && count >= 0);
+  int64_t t0_64 = (int64_t)nstep - 1 - count; if (t0_64 < 0) t0_64 = 0;
+  const int t0 = (int)(t0_64 > T ? T : t0_64);
+  if (t0 < T) PQLB_CHECK_ARG(out_obs && out_action && out_reward && out_next_obs && out_done);
+  Gammas gam; for (int i = 0; i < 32; ++i) gam.g[i] = i < nstep ? gammas_host[i] : 0.f;
+  const RecGeom g = rec_geom(obs_dim, act_dim);
+  const int64_t warps = (int64_t)T * num_envs;
+  int blocks = (int)((warps * 32 + kThreads - 1) / kThreads);
+  if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
+  if (T == 1) {
+    nstep_push_kernel<<<blocks, kThreads, 0, (cudaStream_t)stream>>>(
+        window, num_envs, nstep, g, obs, action, reward, next_obs, done, T, count, gam, t0, 3,
+        out_obs, out_action, out_reward, out_next_obs, out_done);
+  } else {
+    if (t0 < T) {
+      nstep_push_kernel<<<blocks, kThreads, 0, (cudaStream_t)stream>>>(
+          window, num_envs, nstep, g, obs, action, reward, next_obs, done, T, count, gam, t0, 1,
+          out_obs, out_action, out_reward, out_next_obs, out_done);
+      PQLB_COUNT_LAUNCH(1);
+    }
+    nstep_push_kernel<<<blocks, kThreads, 0, (cudaStream_t)stream>>>(
+        window, num_envs, nstep, g, obs, action, reward, next_obs, done, T, count, gam, t0, 2,
+        out_obs, out_action, out_reward, out_next_obs, out_done);
+  }
+  PQLB_LAUNCH_RET();
+}
+
+extern "C" int pqlb_sample_gather(const float* ring, int64_t capacity, int obs_dim, int act_dim,
+                                  const int64_t* idx, int64_t batch, float* out_obs,
+                                  float* out_action, float* out_reward, float* out_next_obs,
+                                  float* out_done, pqlb_stream_t stream) {
+  PQLB_CHECK_ARG(ring && capacity > 0 && obs_dim > 0 && act_dim > 0 && batch >= 0);
+  if (batch == 0) return PQLB_OK;
+  PQLB_CHECK_ARG(idx && out_obs && out_action && out_reward && out_next_obs && out_done);
+  const RecGeom g = rec_geom(obs_dim, act_dim);
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool vec4 = obs_dim % 4 == 0 && act_dim % 4 == 0 && aligned16(ring) && aligned16(out_obs) &&
+                    aligned16(out_action) && aligned16(out_next_obs);
+  if (vec4) {
+    sample_gather_kernel<4><<<grid_for(batch * field_map<4>(g).per_row, kThreads, kUnroll), kThreads, 0, st>>>(
+        ring, g, idx, batch, out_obs, out_action, out_reward, out_next_obs, out_done);
+  } else {
+    sample_gather_kernel<1><<<grid_for(batch * field_map<1>(g).per_row, kThreads, kUnroll), kThreads, 0, st>>>(
+        ring, g, idx, batch, out_obs, out_action, out_reward, out_next_obs, out_done);
+  }
+  PQLB_LAUNCH_RET();
+}
+
+extern "C" int pqlb_sample_critic_batch(const float* ring, int64_t capacity, int obs_dim, int act_dim,
+                                        const int64_t* idx, int64_t batch, const float* mean,
+                                        const float* var, float eps, float* x_cur, float* x_tgt,
+                                        int x_ld, float* reward, float* done, pqlb_stream_t stream) {
+  PQLB_CHECK_ARG(ring && capacity > 0 && obs_dim > 0 && act_dim > 0 && batch > 0 && idx);
+  PQLB_CHECK_ARG(x_cur && x_tgt && reward && done && ((mean == nullptr) == (var == nullptr)));
+  const RecGeom g = rec_geom(obs_dim, act_dim);
+  PQLB_CHECK_SHAPE(x_ld >= obs_dim + act_dim && x_ld % 4 == 0);
+  const int per_row = obs_dim + x_ld;
+  sample_critic_batch_kernel<<<grid_for(batch * per_row, kThreads, 2), kThreads, 0, (cudaStream_t)stream>>>(
+      ring, g, idx, batch, mean, var, eps, x_cur, x_tgt, x_ld, reward, done);
+  PQLB_LAUNCH_RET();
+}
+
+extern "C" int pqlb_sample_obs_batch(const float* obsring, int64_t capacity, int obs_dim,
+                                     const int64_t* idx, int64_t batch, const float* mean,
+                                     const float* var, float eps, float* x, int x_ld,
+                                     int act_dim, pqlb_stream_t stream) {
+  PQLB_CHECK_ARG(obsring && capacity > 0 && obs_dim > 0 && batch > 0 && idx && x && act_dim >= 0);
+  PQLB_CHECK_ARG((mean == nullptr) == (var == nullptr));
+  PQLB_CHECK_SHAPE(x_ld >= obs_dim + act_dim);
+  sample_obs_batch_kernel<<<grid_for(batch * x_ld, kThreads, 2), kThreads, 0, (cudaStream_t)stream>>>(
+      obsring, obs_dim, idx, batch, mean, var, eps, x, x_ld, act_dim);
+  PQLB_LAUNCH_RET();
+}
+
+extern "C" int pqlb_pack_x(const float* a, int64_t lda, int na, const float* b, int64_t ldb, int nb,
+                           float* x, int x_ld, int64_t rows, pqlb_stream_t stream) {
+  PQLB_CHECK_ARG(a && na > 0 && nb >= 0 && (nb == 0 || b) && x && rows > 0);
+  PQLB_CHECK_SHAPE(x_ld >= na + nb && lda >= na && (nb == 0 || ldb >= nb));
+  pack_x_kernel<<<grid_for(rows * x_ld, kThreads, 2), kThreads, 0, (cudaStream_t)stream>>>(
+      a, lda, na, b, ldb, nb, x, x_ld, rows);
+  PQLB_LAUNCH_RET();
+}

@@ -1,0 +1,174 @@
+"""GPU tier: the tcgen05 TF32 grouped GEMM (pqlb_gemm_tf32) against an fp64 matmul of the
+same TF32-rounded operands.  With pre-rounded operands every product is exact and only the
+fp32 accumulation order differs, so the tolerance is 2e-5 of the output's largest magnitude."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda:0"
+
+
+def rn_tf32(x):
+    """cvt.rna.tf32.f32: round to nearest (ties away) to a 10-bit mantissa."""
+    i = x.contiguous().view(torch.int32)
+    return ((i + 0x1000) & ~0x1FFF).view(torch.float32)
+
+
+def mk(shape, g, scale=1.0):
+    return rn_tf32(torch.randn(*shape, generator=g, device=DEV) * scale)
+
+
+def elu(x):
+    return torch.where(x > 0, x, torch.expm1(x))
+
+
+def check(out, ref, tol=2e-5, what=""):
+    scale = ref.abs().max().item() + 1e-30
+    err = (out.double() - ref.double()).abs().max().item() / scale
+    assert err <= tol, f"{what}: max err {err:.3e} of max |ref|"
+
+
+@pytest.fixture(scope="module")
+def K():
+    from pql_b200 import _kernels
+    return _kernels
+
+
+@pytest.mark.parametrize("M,N,Kdim,tile_n", [(128, 128, 32, 128), (300, 512, 104, 256), (256, 256, 512, 128),
+                                             (1000, 128, 256, 64), (130, 512, 231, 256), (128, 16, 128, 16),
+                                             (128, 48, 64, 64)])
+def test_forward_bias_elu(K, M, N, Kdim, tile_n):
+    g = torch.Generator(device=DEV).manual_seed(M + N + Kdim)
+    ld = (Kdim + 3) // 4 * 4
+    a = torch.zeros(M, ld, device=DEV); a[:, :Kdim] = mk((M, Kdim), g)
+    w = torch.zeros(N, ld, device=DEV); w[:, :Kdim] = mk((N, Kdim), g, 0.1)
+    bias = torch.randn(N, generator=g, device=DEV)
+    out = torch.full((M, N), 7.0, device=DEV)
+    K.Gemm(M, N, Kdim, [dict(a=K.addr(a), lda=ld, b=K.addr(w), ldb=ld, bias=K.addr(bias), out=K.addr(out), ldo=N)],
+           epilogue=K.EPI_BIAS_ELU, tile_n=tile_n)()
+    ref = rn_tf32(elu((a[:, :Kdim].double() @ w[:, :Kdim].double().t()).float() + bias))
+    torch.cuda.synchronize()
+    check(out, ref, 1e-3, "bias_elu")          # outputs are TF32-rounded: half-ulp = 2^-11 relative
+    out2 = torch.zeros(M, N, device=DEV)
+    K.Gemm(M, N, Kdim, [dict(a=K.addr(a), lda=ld, b=K.addr(w), ldb=ld, bias=K.addr(bias), out=K.addr(out2), ldo=N)],
+           epilogue=K.EPI_BIAS, tile_n=tile_n)()
+    check(out2, a[:, :Kdim].double() @ w[:, :Kdim].double().t() + bias.double(), 2e-5, "bias")
+
+
+def test_grouped_head_epilogue(K):
+    """Four groups in one launch, scalar Q head fused into the layer-3 epilogue."""
+    M, N, Kd = 384, 128, 256
+    g = torch.Generator(device=DEV).manual_seed(5)
+    groups, refs, keep = [], [], []
+    for i in range(4):
+        a, w = mk((M, Kd), g), mk((N, Kd), g, 0.1)
+        bias, hw, hb = torch.randn(N, generator=g, device=DEV), torch.randn(N, generator=g, device=DEV), torch.randn(1, generator=g, device=DEV)
+        q = torch.zeros(M, device=DEV)
+        out = torch.zeros(M, N, device=DEV) if i % 2 == 0 else None
+        groups.append(dict(a=K.addr(a), lda=Kd, b=K.addr(w), ldb=Kd, bias=K.addr(bias), head_w=K.addr(hw),
+                           head_b=K.addr(hb), q=K.addr(q), out=K.addr(out), ldo=N))
+        h = elu((a.double() @ w.double().t()).float() + bias)
+        refs.append((h, h.double() @ hw.double() + hb.double(), q, out))
+        keep += [a, w, bias, hw, hb]
+    K.Gemm(M, N, Kd, groups, epilogue=K.EPI_BIAS_ELU_HEAD, tile_n=128)()
+    torch.cuda.synchronize()
+    for h, qref, q, out in refs:
+        check(q, qref, 2e-5, "head q")
+        if out is not None:
+            check(out, rn_tf32(h), 1e-3, "head h3")
+
+
+def test_dgrad_mn_major_b_with_elugrad(K):
+    """dz_prev = (dz . W) * elu'(h): A K-major, B = W[out,in] read as [K][N] (MN-major)."""
+    M, n_out, n_in = 260, 128, 256
+    g = torch.Generator(device=DEV).manual_seed(6)
+    dz, w = mk((M, n_out), g), mk((n_out, n_in), g, 0.1)
+    h = rn_tf32(elu(torch.randn(M, n_in, generator=g, device=DEV)))
+    out = torch.zeros(M, n_in, device=DEV)
+    K.Gemm(M, n_in, n_out, [dict(a=K.addr(dz), lda=n_out, b=K.addr(w), ldb=n_in, aux=K.addr(h), ldaux=n_in,
+                                  out=K.addr(out), ldo=n_in)],
+           epilogue=K.EPI_MUL_ELUGRAD, tile_n=256, b_major=K.MN_MAJOR)()
+    ref = (dz.double() @ w.double()).float() * torch.where(h > 0, torch.ones_like(h), h + 1)
+    check(out, rn_tf32(ref), 1e-3, "dgrad")
+
+
+def test_dgrad_two_operand_pairs_and_column_window(K):
+    """P-learner layer-1 dgrad: sum over both critics (a2/b2 continuation), only the action
+    columns [O, O+A) stored, tanh' epilogue."""
+    M, O, A, H = 200, 211, 20, 512
+    ldw = 232
+    g = torch.Generator(device=DEV).manual_seed(7)
+    dz1, dz2 = mk((M, H), g), mk((M, H), g)
+    w1 = torch.zeros(H, ldw, device=DEV); w1[:, :O + A] = mk((H, O + A), g, 0.1)
+    w2 = torch.zeros(H, ldw, device=DEV); w2[:, :O + A] = mk((H, O + A), g, 0.1)
+    act = torch.tanh(torch.randn(M, A, generator=g, device=DEV))
+    out = torch.zeros(M, A, device=DEV)
+    K.Gemm(M, O + A, H, [dict(a=K.addr(dz1), lda=H, b=K.addr(w1), ldb=ldw, a2=K.addr(dz2), lda2=H, b2=K.addr(w2),
+                              ldb2=ldw, aux=K.addr(act, -O), ldaux=A, out=K.addr(out), ldo=A)],
+           epilogue=K.EPI_MUL_TANHGRAD, tile_n=256, b_major=K.MN_MAJOR, K2=H, col_lo=O, col_hi=O + A)()
+    ref = ((dz1.double() @ w1.double() + dz2.double() @ w2.double())[:, O:O + A]).float() * (1 - act * act)
+    check(out, rn_tf32(ref), 1e-3, "dgrad2")
+
+
+@pytest.mark.parametrize("n_out,n_in,B,tile_n,splits", [(512, 104, 1024, 64, 4), (128, 256, 2048, 64, 16),
+                                                        (256, 512, 512, 128, 2), (16, 128, 512, 128, 1),
+                                                        (51, 128, 256, 128, 2), (512, 231, 384, 128, 4)])
+def test_wgrad_mn_mn_split_k(K, n_out, n_in, B, tile_n, splits):
+    """dW[out,in] = dz^T . h with both operands MN-major and the contraction over the batch."""
+    g = torch.Generator(device=DEV).manual_seed(n_out + n_in)
+    ldz = (n_out + 3) // 4 * 4 if n_out != 51 else 64
+    ldh = (n_in + 3) // 4 * 4
+    dz = torch.zeros(B, ldz, device=DEV); dz[:, :n_out] = mk((B, n_out), g)
+    h = torch.zeros(B, ldh, device=DEV); h[:, :n_in] = mk((B, n_in), g)
+    stride = n_out * ldh
+    part = torch.zeros(splits, n_out, ldh, device=DEV)
+    K.Gemm(n_out, n_in, B, [dict(a=K.addr(dz), lda=ldz, b=K.addr(h), ldb=ldh, out=K.addr(part), ldo=ldh,
+                                  split_stride=stride)],
+           epilogue=K.EPI_STORE, tile_n=tile_n, a_major=K.MN_MAJOR, b_major=K.MN_MAJOR, splits=splits)()
+    ref = dz[:, :n_out].double().t() @ h[:, :n_in].double()
+    check(part.sum(0)[:, :n_in], ref, 2e-5, "wgrad")
+    assert torch.count_nonzero(part[:, :, n_in:]) == 0
+
+
+def test_actor_head_tanh_and_noise(K):
+    M, Kd, A, O, x_ld = 300, 128, 16, 88, 104
+    g = torch.Generator(device=DEV).manual_seed(9)
+    h, w = mk((M, Kd), g), mk((A, Kd), g, 0.3)
+    bias = torch.randn(A, generator=g, device=DEV) * 0.1
+    noise = torch.randn(M, A, generator=g, device=DEV) * 0.8
+    x = torch.zeros(M, x_ld, device=DEV)
+    K.Gemm(M, A, Kd, [dict(a=K.addr(h), lda=Kd, b=K.addr(w), ldb=Kd, bias=K.addr(bias), aux=K.addr(noise), ldaux=A,
+                           out=K.addr(x, O), ldo=x_ld)],
+           epilogue=K.EPI_BIAS_TANH_NOISE, tile_n=16, noise_bound=0.2)()
+    a = torch.tanh((h.double() @ w.double().t()).float() + bias)
+    ref = torch.clamp(a + torch.clamp(noise, -0.2, 0.2), -1, 1)
+    check(x[:, O:O + A], rn_tf32(ref), 1e-3, "tanh_noise")
+    assert torch.count_nonzero(x[:, :O]) == 0
+    act = torch.zeros(M, A, device=DEV)
+    K.Gemm(M, A, Kd, [dict(a=K.addr(h), lda=Kd, b=K.addr(w), ldb=Kd, bias=K.addr(bias), out=K.addr(x, O), ldo=x_ld,
+                           out2=K.addr(act), ldo2=A)], epilogue=K.EPI_BIAS_TANH, tile_n=16)()
+    check(act, a, 2e-5, "tanh fp32 copy")
+    check(x[:, O:O + A], rn_tf32(a), 1e-3, "tanh")
+
+
+def test_softmax_head(K):
+    M, Kd, N = 260, 128, 51
+    g = torch.Generator(device=DEV).manual_seed(10)
+    h, w = mk((M, Kd), g), mk((N, Kd), g, 0.3)
+    bias = torch.randn(N, generator=g, device=DEV) * 0.1
+    p = torch.zeros(M, 64, device=DEV)
+    K.Gemm(M, N, Kd, [dict(a=K.addr(h), lda=Kd, b=K.addr(w), ldb=Kd, bias=K.addr(bias), out=K.addr(p), ldo=64)],
+           epilogue=K.EPI_BIAS_SOFTMAX, tile_n=64)()
+    ref = torch.softmax((h.double() @ w.double().t()).float() + bias, dim=1)
+    check(p[:, :N], ref, 2e-5, "softmax")
+    assert torch.count_nonzero(p[:, N:]) == 0
+
+
+def test_round_tf32(K):
+    from pql_b200 import _lib
+    x = torch.randn(100003, device=DEV)
+    y = torch.empty_like(x)
+    _lib.call("pqlb_round_tf32", _lib.ptr(x), _lib.ptr(y), x.numel())
+    assert torch.equal(y, rn_tf32(x))
