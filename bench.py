@@ -1,0 +1,356 @@
+#!/usr/bin/env python
+"""Benchmark of the PQL learner hot path (BASELINE.json: critic updates/s at batch 8192 + replay GB/s).
+
+One STEP is one env step's worth of learner work at the reference's default ratios
+(pql_algo.yaml:17-18): n-step push + ring insert of 4096 env transitions, obs-ring insert,
+8 critic updates (PQLVLearner.learn, batch 8192) and 4 actor updates (PQLPLearner.learn),
+on synthetic AllegroHand-shaped transitions (obs 88, act 16), 1M-slot replay (800 MB > L2).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+N > 1 is launched under torchrun (one rank per GPU, NCCL): every rank owns its envs and replay
+shard, critic / actor gradients are all-reduced before clip + AdamW (weak scaling).
+``--impl reference`` times the CPU restatement of the reference path (oracle/, torch fp32 on
+all host threads) on a bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+O, A, E, B, CAP, NSTEP = 88, 16, 4096, 8192, 1_000_000, 3
+V_PER_STEP, P_PER_STEP = 8, 4
+FLOP_V = 3_684_352          # GEMM FLOPs per sample of one critic update
+FLOP_P = 2_913_280          # ... of one actor update
+BYTES_INSERT = 1549         # algorithmic bytes per inserted transition
+BYTES_SAMPLE = 1557         # ... per sampled transition
+N_BLOCKS = 16
+
+
+def synth_block(rs, T=1):
+    """One [E, T, *] block like PQLActor.explore_env produces (SURVEY 8d synthetic inputs)."""
+    obs = rs.standard_normal((E, T, O)).astype(np.float32)
+    nxt = rs.standard_normal((E, T, O)).astype(np.float32)
+    act = rs.uniform(-1, 1, (E, T, A)).astype(np.float32)
+    rew = (rs.standard_normal((E, T, 1)) * 0.01).astype(np.float32)
+    done = (rs.uniform(0, 1, (E, T, 1)) < 0.01).astype(np.float32)
+    return obs, act, rew, nxt, done
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc is not None:
+            time.sleep(0.15)
+            self.proc.terminate()
+            self.th.join(timeout=2)
+
+    def summary(self):
+        sm = [float(r[0]) for r in self.rows if len(r) >= 8 and r[0].replace(".", "").isdigit()]
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in self.rows if len(r) >= 8 for n, v in zip(names, r[4:8]) if v.lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(self.rows[0][1]), "reasons": reasons,
+                "power_w_max": max(float(r[2]) for r in self.rows if len(r) >= 8), "samples": len(sm)}
+
+
+def cpu_reference_rate(seconds_budget=20.0, threads=None):
+    """The reference's CPU torch path (oracle restatement, every host thread) on a bounded sample:
+    a few full-size updates (batch 8192, AllegroHand shape) at the 8 V : 4 P : 1 insert ratio."""
+    from oracle import learner as L
+    from oracle import replay as R
+    if threads:
+        torch.set_num_threads(threads)
+    g = torch.Generator().manual_seed(0)
+    q1, q2 = L.init_mlp(O + A, 1, g), L.init_mlp(O + A, 1, g)
+    actor = L.init_mlp(O, A, g)
+    v, p = L.VLearnerOracle(q1, q2), L.PLearnerOracle(actor)
+    rs = np.random.RandomState(0)
+    cap = 100_000
+    ring = R.RingOracle(cap, O, A)
+    ns = R.NStepOracle(O, A, E, NSTEP, 0.99)
+    ring.insert(*ns.push(*synth_block(rs, 8)))
+    norm = (torch.zeros(O), torch.ones(O), 1e-4)
+    blocks = [synth_block(rs) for _ in range(4)]
+    t_ins = t_v = t_p = 0.0
+    n_steps = 0
+    t_start = time.perf_counter()
+    while True:
+        t0 = time.perf_counter()
+        ring.insert(*ns.push(*blocks[n_steps % 4]))
+        t1 = time.perf_counter()
+        for _ in range(V_PER_STEP):
+            idx = rs.randint(0, ring.cur_capacity, size=B)
+            batch = tuple(torch.from_numpy(x) for x in ring.gather(idx))
+            v.learn(batch, torch.randn(B, A) * 0.8, actor, norm)
+        t2 = time.perf_counter()
+        for _ in range(P_PER_STEP):
+            idx = rs.randint(0, ring.cur_capacity, size=B)
+            p.learn(torch.from_numpy(ring.buf_obs[idx]), q1, q2, norm)
+        t3 = time.perf_counter()
+        t_ins += t1 - t0; t_v += t2 - t1; t_p += t3 - t2
+        n_steps += 1
+        if time.perf_counter() - t_start > seconds_budget or n_steps >= 50:
+            break
+    total = t_ins + t_v + t_p
+    return dict(value=V_PER_STEP * n_steps / total, unit="critic updates/s", cores=torch.get_num_threads(), kind="port",
+                sample=f"{n_steps} steps of (1 insert of {E} rows + {V_PER_STEP} critic + {P_PER_STEP} actor updates, batch {B}) "
+                       f"through oracle/ (torch-CPU fp32 restatement of the reference path, 100k-slot ring)",
+                ms_per_step=1e3 * total / n_steps, ms_per_critic_update=1e3 * t_v / (n_steps * V_PER_STEP),
+                ms_per_actor_update=1e3 * t_p / (n_steps * P_PER_STEP), ms_per_insert=1e3 * t_ins / n_steps)
+
+
+def config_dict(n_gpus):
+    return {"workload": "configs[1]: DoubleQ V-learner + P-learner, AllegroHand shape (obs 88, act 16), batch 8192, "
+                        "1M-slot replay, n-step 3, 4096-env synthetic insert stream, Polyak target update",
+            "step": f"1 n-step push + ring insert of {E} transitions, {V_PER_STEP} critic updates, {P_PER_STEP} actor updates",
+            "critic_updates_per_step": V_PER_STEP, "actor_updates_per_step": P_PER_STEP, "batch_per_gpu": B,
+            "num_envs_per_gpu": E, "replay_slots_per_gpu": CAP, "parallelism": f"dp{n_gpus}",
+            "cache": "replay ring 800 MB per GPU > 126 MB L2 (random gathers miss L2); weights/activations are the "
+                     "step's own working set and are not flushed"}
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    r = cpu_reference_rate(seconds_budget=max(5.0, min(120.0, 4.0 * (args.steps + args.warmup))))
+    line = {"metric": "critic updates/s (batch 8192)", "value": r["value"], "unit": "critic updates/s", "impl": "reference",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"],
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": config_dict(args.gpus), "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": r["value"], "unit": "critic updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    if args.warmup < 3:
+        args.warmup = 3
+    import __graft_entry__ as entry
+    if rank == 0 and not os.path.exists(entry.LIB):
+        entry.build()
+    torch.cuda.set_device(local)
+    dev = torch.device(f"cuda:{local}")
+    import torch.distributed as dist
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+        dist.barrier()
+    from pql_b200 import _kernels as K
+    from pql_b200 import _lib
+    from pql_b200.algo import PQLPLearner, PQLVLearner
+    from pql_b200.replay import NStepReplay
+    from pql_b200.utils import default_pql_cfg
+
+    torch.manual_seed(42 + rank)
+    cfg = default_pql_cfg(batch_size=B, memory_size=CAP, num_envs=E, v_learner_gpu=local, p_learner_gpu=local)
+    cfg.data_parallel = world > 1
+    cfg.use_cuda_graph = not args.no_graph
+    v = PQLVLearner(O, A, cfg)
+    p = PQLPLearner(O, A, cfg)
+    if world > 1:      # identical initial weights on every rank
+        dist.broadcast(v.critic.arena.flat, 0)
+        dist.broadcast(p.actor.arena.flat, 0)
+    ns = NStepReplay(O, A, num_envs=E, nstep=NSTEP, device=dev, gamma=0.99)
+    rs = np.random.RandomState(42 + rank)
+    host_blocks = [tuple(torch.from_numpy(x).pin_memory() for x in synth_block(rs)) for _ in range(N_BLOCKS)]
+    dev_blocks = [tuple(x.to(dev) for x in blk) for blk in host_blocks]
+    h2d_bytes = sum(x.numel() * 4 for x in host_blocks[0])
+    all_obs = torch.cat([b[0].reshape(-1, O) for b in host_blocks])
+    norm = (all_obs.mean(0).to(dev), all_obs.var(0).to(dev), 1e-4)      # RunningMeanStd.get_states stand-in
+
+    # warm-up block of 32 steps (train_pql.py:58) then fill the ring so that sampling spans all 800 MB
+    warm = tuple(torch.from_numpy(x).to(dev) for x in synth_block(rs, 32))
+    traj = ns.add_to_buffer(*warm)
+    critic, _, _ = v.start()
+    actor, _, _ = p.start()
+    v.update(actor, traj, norm, 0)
+    p.update(critic, traj[0], norm, 0)
+    i = 0
+    while not v.memory.if_full:
+        traj = ns.add_to_buffer(*dev_blocks[i % N_BLOCKS]); i += 1
+        v.memory.add_to_buffer(traj)
+    state = {"actor": actor, "critic": critic, "d2h": 0}
+
+    def super_step(k, host_inputs):
+        blk = host_blocks[k % N_BLOCKS] if host_inputs else dev_blocks[k % N_BLOCKS]
+        if host_inputs:
+            blk = tuple(x.to(dev, non_blocking=True) for x in blk)
+        tr = ns.add_to_buffer(*blk)
+        state["critic"], vloss, _ = v.update(state["actor"], tr, norm, 0)     # returns the loss mean: D2H
+        state["actor"], ploss, _ = p.update(state["critic"], tr[0], norm, 0)
+        for j in range(V_PER_STEP):
+            v.learn()
+            if (j + 1) % (V_PER_STEP // P_PER_STEP) == 0:
+                p.learn()
+        return vloss, ploss
+
+    def timed(n, host_inputs, base):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record()
+        for k in range(n):
+            losses = super_step(base + k, host_inputs)
+        e1.record()
+        torch.cuda.synchronize(dev)
+        wall = time.perf_counter() - t0
+        if world > 1:
+            dist.barrier()
+        ms = max(e0.elapsed_time(e1), 0.0)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = t.item()
+        return ms, wall, losses
+
+    timed(args.warmup, False, 0)
+    launches0 = _lib.launch_count()
+    with ClockSampler(local) as clk:
+        ms, wall, losses = timed(args.steps, False, args.warmup)
+    launches = _lib.launch_count() - launches0
+    clocks = clk.summary()
+    timed(2, True, 0)
+    ms_e2e, wall_e2e, _ = timed(args.steps, True, args.warmup)
+
+    # ---- per-kernel device time over the same super-step (CUDA events around every launch)
+    K.PROFILE = {}
+    prev_graph = getattr(v, "_graph_off", None)
+    v.disable_graph(); p.disable_graph()
+    prof_steps = 3
+    for k in range(prof_steps):
+        super_step(k, False)
+    torch.cuda.synchronize(dev)
+    per_kernel = {name: sum(a.elapsed_time(b) for a, b in evs) / prof_steps for name, evs in K.PROFILE.items()}
+    n_gemm = len(K.PROFILE.get("pqlb_gemm_tf32", [])) // prof_steps
+    K.PROFILE = None
+    v.enable_graph(); p.enable_graph()
+
+    # ---- replay kernels alone (HBM roofline): single calls and L2-exceeding calls
+    def ev_time(fn, n):
+        fn(); torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record(); torch.cuda.synchronize(dev)
+        return e0.elapsed_time(e1) / n
+    rows1 = tuple(x.reshape(E, -1) for x in dev_blocks[0])
+    big_n = 30 * E
+    gen = torch.Generator(device=dev).manual_seed(1)
+    rows_big = (torch.randn(big_n, O, device=dev, generator=gen), torch.rand(big_n, A, device=dev, generator=gen),
+                torch.randn(big_n, 1, device=dev, generator=gen), torch.randn(big_n, O, device=dev, generator=gen),
+                torch.zeros(big_n, 1, device=dev))
+    mem = v.memory
+    idx1 = torch.randint(CAP, (B,), device=dev)
+    idx8 = torch.randint(CAP, (8 * B,), device=dev)
+    out1 = mem.gather(idx1); out8 = mem.gather(idx8)
+
+    def raw_insert(rows):
+        n = rows[0].shape[0]
+        _lib.call("pqlb_ring_insert", _lib.ptr(mem.ring), CAP, O, A, *(_lib.ptr(x) for x in rows), n, 12345)
+
+    def raw_gather(idx, out):
+        _lib.call("pqlb_sample_gather", _lib.ptr(mem.ring), CAP, O, A, _lib.ptr(idx), idx.numel(), *(_lib.ptr(x) for x in out))
+    replay = {}
+    for name, fn, units, per in (("insert_4096", lambda: raw_insert(rows1), E, BYTES_INSERT),
+                                 ("insert_122880", lambda: raw_insert(rows_big), big_n, BYTES_INSERT),
+                                 ("sample_8192", lambda: raw_gather(idx1, out1), B, BYTES_SAMPLE),
+                                 ("sample_65536", lambda: raw_gather(idx8, out8), 8 * B, BYTES_SAMPLE)):
+        t_ms = ev_time(fn, 200 if units <= 8 * B else 50)
+        replay[name] = {"us": round(t_ms * 1e3, 2), "gbs": round(units * per / (t_ms * 1e-3) / 1e9, 1)}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except OSError:
+        pass
+    hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    tf32_peak = peaks.get("bf16_tflops_sustained", 1400.0) / 2.0
+    peak_src = "measured (MEASURED_PEAKS.json)" if peaks else "fallback (B200_PROFILING.md)"
+    gemm_ms = per_kernel.get("pqlb_gemm_tf32", float("nan"))
+    flops_step = B * (V_PER_STEP * FLOP_V + P_PER_STEP * FLOP_P)
+    achieved = flops_step / (gemm_ms * 1e-3) / 1e12
+    value = world * V_PER_STEP * args.steps / (ms * 1e-3)
+    e2e = world * V_PER_STEP * args.steps / (ms_e2e * 1e-3)
+    line = {"metric": "critic updates/s (batch 8192)", "value": value, "unit": "critic updates/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "tf32 (fp32 accumulate)", "data": "synthetic",
+            "config": config_dict(world), "clocks": clocks,
+            "e2e": {"value": e2e, "unit": "critic updates/s", "h2d_bytes_per_step": h2d_bytes,
+                    "d2h_bytes_per_step": 2 * 5 * 4, "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": launches,
+            "roofline": {"kernel": "gemm_tf32_kernel (tcgen05 kind::tf32; all dense-layer launches of one step)",
+                         "bound": "tensor", "achieved": achieved, "peak": tf32_peak, "unit": "TFLOP/s",
+                         "frac": achieved / tf32_peak, "traffic": None, "launches_per_step": n_gemm,
+                         "ms_per_step_in_kernel": gemm_ms,
+                         "peak_source": f"{peak_src}: tf32 dense = 1/2 of the sustained cuBLAS bf16 figure"},
+            "kernel_ms_per_step": {k: round(x, 4) for k, x in sorted(per_kernel.items(), key=lambda kv: -kv[1])},
+            "replay": {"kernels": replay, "hbm_peak_gbs": hbm_peak, "peak_source": peak_src,
+                       "insert_frac_of_hbm": replay["insert_122880"]["gbs"] / hbm_peak,
+                       "sample_frac_of_hbm": replay["sample_65536"]["gbs"] / hbm_peak,
+                       "bytes_per_unit": {"insert": BYTES_INSERT, "sample": BYTES_SAMPLE}},
+            "host_wall_ms_per_step": 1e3 * wall / args.steps,
+            "losses": {"critic": float(losses[0]), "actor": float(losses[1])}}
+    if not args.no_cpu_baseline and world == 1:
+        r = cpu_reference_rate(seconds_budget=15.0)
+        line["cpu_baseline"] = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

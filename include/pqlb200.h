@@ -43,6 +43,9 @@ typedef void* pqlb_stream_t; /* cudaStream_t */
 
 int pqlb_version(void);
 const char* pqlb_error_string(int code);
+/* One-time per-device setup (shared-memory opt-in, driver entry points).  Implicit in the first
+ * pqlb_gemm_tf32 call; call it explicitly before capturing a CUDA graph. */
+int pqlb_init(void);
 /* Number of CUDA kernels this library has launched so far in this process. */
 uint64_t pqlb_launch_count(void);
 /* Geometry helpers (pure host arithmetic). */
@@ -229,16 +232,23 @@ int pqlb_grad_sumsq(const int64_t* seg_table, int n_seg, const float* grad, floa
  * pql/utils/torch_util.py:9-12; torch/optim/adam.py order):
  * coef = min(1, max_norm/(sqrt(sum sumsq_part)+1e-6)) (max_norm < 0: no clipping);
  * p,m,v updated in place; target <- p*tau + target*(1-tau) when target != NULL;
- * p_tf32 / target_tf32 = rn_tf32 copies (NULL to skip).  `step` is 1-based.
+ * p_tf32 / target_tf32 = rn_tf32 copies (NULL to skip).  The 1-based AdamW step count is `step`,
+ * or step_dev[0] + 1 when step_dev != NULL (a device-resident count of completed updates, advanced
+ * by pqlb_sum_partials, so that a whole update can be replayed from a CUDA graph).
  * grad_scale multiplies the gradient first (1/world for data parallel). */
 int pqlb_adamw_polyak(float* param, const float* grad, float* m, float* v, float* target,
                       float* param_tf32, float* target_tf32, int64_t n,
                       const float* sumsq_part, int n_part, float grad_scale, float max_norm,
                       float lr, float beta1, float beta2, float eps, float weight_decay,
-                      int64_t step, float tau, float* grad_norm_out, pqlb_stream_t stream);
+                      int64_t step, const int64_t* step_dev, float tau, float* grad_norm_out,
+                      pqlb_stream_t stream);
 
-/* Final deterministic sum of per-block loss partials: out[0] = scale * sum(part[0..n)). */
-int pqlb_sum_partials(const float* part, int n, float scale, float* out, pqlb_stream_t stream);
+/* Final deterministic sum of per-block loss partials: out[0] = scale * sum(part[0..n)).  When
+ * counter != NULL: ring[counter[0] % ring_len] = out[0] (the loss window of the reference's
+ * Tracker(5), pql/utils/common.py:103-126, kept on the device instead of loss.item()), then
+ * ++counter[0]. */
+int pqlb_sum_partials(const float* part, int n, float scale, float* out, int64_t* counter,
+                      float* ring, int ring_len, pqlb_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -28,6 +28,9 @@ def _p(a):
     return C.c_void_p(a if a else None)
 
 
+PROFILE = None      # bench.py sets this to {} to collect (start, end) CUDA events per entry point
+
+
 class Call:
     """One prepared C-ABI call: ``Call(name, *args)`` -> ``call()`` launches on the current stream."""
 
@@ -35,7 +38,14 @@ class Call:
         self.name, self.args, self._keep = name, args, keep
 
     def __call__(self):
+        if PROFILE is None:
+            _lib.call(self.name, *self.args)
+            return
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
         _lib.call(self.name, *self.args)
+        e1.record()
+        PROFILE.setdefault(self.name, []).append((e0, e1))
 
 
 class Gemm(Call):

@@ -50,6 +50,7 @@ _PROTOS = {
     "pqlb_version": (_int, []),
     "pqlb_error_string": (C.c_char_p, [_int]),
     "pqlb_launch_count": (C.c_uint64, []),
+    "pqlb_init": (_int, []),
     "pqlb_obs_pad": (_int, [_int]),
     "pqlb_record_ld": (_int, [_int, _int]),
     "pqlb_x_ld": (_int, [_int, _int]),
@@ -75,8 +76,8 @@ _PROTOS = {
     "pqlb_grad_reduce": (_int, [_f, _int, _f, _f, _f, _st]),
     "pqlb_grad_sumsq": (_int, [_f, _int, _f, _f, _st]),
     "pqlb_adamw_polyak": (_int, [_f, _f, _f, _f, _f, _f, _f, _i64, _f, _int, _flt, _flt, _flt, _flt,
-                                 _flt, _flt, _flt, _i64, _flt, _f, _st]),
-    "pqlb_sum_partials": (_int, [_f, _int, _flt, _f, _st]),
+                                 _flt, _flt, _flt, _i64, _f, _flt, _f, _st]),
+    "pqlb_sum_partials": (_int, [_f, _int, _flt, _f, _f, _f, _int, _st]),
 }
 
 _lib = None

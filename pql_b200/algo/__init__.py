@@ -1,0 +1,2 @@
+from .pql_p_learner import PQLPLearner  # noqa: F401
+from .pql_v_learner import PQLVLearner  # noqa: F401

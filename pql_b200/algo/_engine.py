@@ -1,0 +1,487 @@
+"""Prepared kernel plans of the two PQL updates.
+
+``CriticUpdate`` is one ``PQLVLearner.learn()`` (pql/algo/pql_v_learner.py:73-115) and
+``ActorUpdate`` one ``PQLPLearner.learn()`` (pql/algo/pql_p_learner.py:47-64), each expressed as
+a fixed list of C-ABI launches over preallocated buffers: gather+normalise, tcgen05 forward
+layers with fused ELU / tanh / softmax / scalar-head epilogues, the loss kernel, dgrad and
+split-K wgrad GEMMs, one deterministic gradient reduction, and the fused clip + AdamW (+ Polyak)
+step.  No PyTorch op computes anything here; torch only owns the memory and the RNG draws the
+learners pass in.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from .. import _kernels as K
+from .. import _lib
+from ..models.mlp import HIDDEN, NetAddrs, NetLayout, _ru, fwd_tile, trunk_calls
+
+H1, H2, H3 = HIDDEN
+SEG = 1024
+
+
+class _Optim:
+    """Flat AdamW state + split-K / partial-sum workspace bookkeeping for one parameter arena."""
+
+    def __init__(self, layout, device):
+        self.layout = layout
+        n = layout.total
+        self.grad = torch.zeros(n, device=device)
+        self.m = torch.zeros(n, device=device)
+        self.v = torch.zeros(n, device=device)
+        self.count = torch.zeros(1, dtype=torch.int64, device=device)   # completed updates (device-resident)
+        self._segs = []            # rows of the segment table
+
+    @property
+    def step(self):
+        """Completed AdamW steps (host read = synchronisation; tests and checkpoints only)."""
+        return int(self.count.item())
+
+    @step.setter
+    def step(self, t):
+        self.count.fill_(int(t))
+
+    def add_source(self, arena_off, count, ws_off, ws_stride, n_part):
+        """grad[arena_off + i] = sum_{s < n_part} ws[ws_off + s * ws_stride + i], i < count."""
+        for o in range(0, count, SEG):
+            self._segs.append([arena_off + o, min(SEG, count - o), ws_off + o, ws_stride, n_part])
+
+    def finish(self, device):
+        self.seg_table = torch.tensor(self._segs, dtype=torch.int64, device=device)
+        self.n_seg = len(self._segs)
+        self.sumsq = torch.zeros(self.n_seg, device=device)
+
+
+def _colsum_call(B, entries, keep):
+    d = _lib.ColsumDesc()
+    d.n, d.rows = len(entries), B
+    for i, (dz, ld, n_cols, part) in enumerate(entries):
+        d.dz[i], d.ld[i], d.n_cols[i], d.part[i] = dz, ld, n_cols, part
+    return K.Call("pqlb_colsum_partial_multi", C.byref(d), keep=(d, keep))
+
+
+class _UpdateBase:
+    def __init__(self, obs_dim, action_dim, batch, device, distl, num_atoms, v_min, v_max, loss_ring=None):
+        self.O, self.A, self.B = int(obs_dim), int(action_dim), int(batch)
+        self.device = torch.device(device)
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.load().pqlb_init(), "pqlb_init")
+        self.loss_ring = loss_ring if loss_ring is not None else torch.zeros(5, device=self.device)
+        self.graphs = None
+        self._bufs = []
+        self.distl = bool(distl)
+        self.N = int(num_atoms) if distl else 1
+        self.v_min, self.v_max = float(v_min), float(v_max)
+        self.x_ld = _ru(self.O + self.A, 4)
+        self.a_ld = _ru(self.A, 4)
+        self.nblk = (self.B + 127) // 128
+        self.Lc = NetLayout(self.O + self.A, self.N, 2)
+        self.La = NetLayout(self.O, self.A, 1)
+        self.pd = 64 if distl else 0           # row stride of the probability / dlogit buffers
+        self.calls = []
+        self.z = torch.linspace(v_min, v_max, self.N, device=self.device) if distl else None
+
+    def _buf(self, *shape):
+        """Zero-initialised fp32 device buffer that lives as long as the plan: the prepared
+        launches hold raw addresses, so every buffer must stay referenced (a freed block would be
+        handed back to the driver by the empty_cache() that precedes a CUDA-graph capture)."""
+        t = torch.zeros(*shape, dtype=torch.float32, device=self.device)
+        self._bufs.append(t)
+        return t
+
+    def _ws_init(self, wgrads, n_nets, bias_cols, extra=0):
+        """One workspace for every split-K / per-block partial sum of the update, sized up front
+        so that all addresses are fixed while the launch list is being prepared."""
+        total = extra + 64
+        for n_out, n_in, ldw in wgrads:
+            _, splits = K.wgrad_tiling(n_out, n_in, self.B, n_nets)
+            total += n_nets * _ru(splits * n_out * ldw, 32)
+        total += sum(_ru(self.nblk * c, 32) for c in bias_cols)
+        self.ws = self._buf(total)
+        self._ws_used = 0
+
+    def _ws_alloc(self, n):
+        off = self._ws_used
+        self._ws_used = _ru(off + n, 32)
+        assert self._ws_used <= self.ws.numel(), "workspace under-sized"
+        return off
+
+    # ---- pieces shared by both updates -----------------------------------------------------
+    def _critic_backward(self, nets, dz3, dz2, dz1, h1, h2):
+        """dgrad through layers 3 and 2 of both critics (weights read as [K][N], no transposes)."""
+        B = self.B
+        g3 = [dict(a=K.addr(dz3[i]), lda=H3, b=nets[i].W[2], ldb=H2, aux=K.addr(h2[i]), ldaux=H2,
+                   out=K.addr(dz2[i]), ldo=H2) for i in range(2)]
+        g2 = [dict(a=K.addr(dz2[i]), lda=H2, b=nets[i].W[1], ldb=H1, aux=K.addr(h1[i]), ldaux=H1,
+                   out=K.addr(dz1[i]), ldo=H1) for i in range(2)]
+        return [K.Gemm(B, H2, H3, g3, epilogue=K.EPI_MUL_ELUGRAD, tile_n=fwd_tile(B, H2, 2), b_major=K.MN_MAJOR),
+                K.Gemm(B, H1, H2, g2, epilogue=K.EPI_MUL_ELUGRAD, tile_n=fwd_tile(B, H1, 2), b_major=K.MN_MAJOR)]
+
+    def _head_backward_c51(self, nets, dl, h3, dz3):
+        g = [dict(a=K.addr(dl[i]), lda=self.pd, b=nets[i].W[3], ldb=H3, aux=K.addr(h3[i]), ldaux=H3,
+                  out=K.addr(dz3[i]), ldo=H3) for i in range(2)]
+        return K.Gemm(self.B, H3, self.N, g, epilogue=K.EPI_MUL_ELUGRAD, tile_n=128, b_major=K.MN_MAJOR)
+
+    def _wgrad(self, opt, layout, net_ids, layer, dz, ldz, n_out, h, ldh, n_in):
+        """dW[layer] of len(net_ids) nets = dz^T . h (contraction over the batch, split-K partials
+        in the workspace; grad_reduce sums them in a fixed order)."""
+        B = self.B
+        tile_n, splits = K.wgrad_tiling(n_out, n_in, B, len(net_ids))
+        ldw = layout.ldw[layer]
+        stride = n_out * ldw
+        groups = []
+        for j, i in enumerate(net_ids):
+            off = self._ws_alloc(splits * stride)
+            groups.append(dict(a=K.addr(dz[j]), lda=ldz, b=K.addr(h[j]), ldb=ldh, out=K.addr(self.ws, off), ldo=ldw,
+                               split_stride=stride))
+            opt.add_source(layout.w_off[i][layer], stride, off, stride, splits)
+        return K.Gemm(n_out, n_in, B, groups, epilogue=K.EPI_STORE, tile_n=tile_n, a_major=K.MN_MAJOR,
+                      b_major=K.MN_MAJOR, splits=splits)
+
+    def _bias_grads(self, opt, layout, entries):
+        """entries: (net, layer, dz tensor, ld, n_cols).  One launch for all bias gradients."""
+        packed = []
+        for i, layer, dz, ld, n_cols in entries:
+            off = self._ws_alloc(self.nblk * n_cols)
+            packed.append((K.addr(dz), ld, n_cols, K.addr(self.ws, off)))
+            opt.add_source(layout.b_off[i][layer], n_cols, off, n_cols, self.nblk)
+        return _colsum_call(self.B, packed, keep=None)
+
+
+class CriticUpdate(_UpdateBase):
+    """pql_v_learner.py:73-115 as a prepared launch list (twin-Q or C51)."""
+
+    def __init__(self, obs_dim, action_dim, batch, device, critic_flat, *, distl=False, num_atoms=51,
+                 v_min=-10.0, v_max=10.0, gamma_n=0.99 ** 3, lr=5e-4, tau=0.05, max_grad_norm=0.5,
+                 noise_bound=0.2, obs_norm=True, eps=1e-4, world_size=1, loss_ring=None):
+        super().__init__(obs_dim, action_dim, batch, device, distl, num_atoms, v_min, v_max, loss_ring)
+        O, A, B, N, x_ld = self.O, self.A, self.B, self.N, self.x_ld
+        dev = self.device
+        self.lr, self.tau, self.max_grad_norm = float(lr), float(tau), max_grad_norm
+        self.gamma_n = float(np.float32(gamma_n))
+        self.noise_bound, self.eps, self.obs_norm = float(noise_bound), float(eps), bool(obs_norm)
+        self.world_size = int(world_size)
+
+        # parameter arenas: critic (owned by the nn.Module), target, actor copy + TF32 twins
+        assert critic_flat.numel() == self.Lc.total and critic_flat.is_cuda
+        self.c_flat = critic_flat
+        self.t_flat = critic_flat.clone()                       # deepcopy(critic), :47
+        self.c_tf, self.t_tf = self._buf(self.Lc.total), self._buf(self.Lc.total)
+        self.a_flat, self.a_tf = self._buf(self.La.total), self._buf(self.La.total)
+        self.round_weights()
+        self.opt = _Optim(self.Lc, dev)
+
+        # batch buffers
+        self.idx = torch.zeros(B, dtype=torch.int64, device=dev)
+        self.noise = self._buf(B, A)
+        self.x_cur, self.x_tgt = self._buf(B, x_ld), self._buf(B, x_ld)
+        self.reward, self.done = self._buf(B), self._buf(B)
+        self.mean, self.var = self._buf(O), torch.ones(O, device=dev)
+        ha = [self._buf(B, d) for d in HIDDEN]
+        h_t = [[self._buf(B, d) for d in HIDDEN] for _ in range(2)]
+        h_c = [[self._buf(B, d) for d in HIDDEN] for _ in range(2)]
+        self.h_c = h_c
+        self.dz = [[self._buf(B, d) for d in HIDDEN] for _ in range(2)]      # dz[i][l]
+        self.q = [self._buf(B) for _ in range(2)]
+        self.tq = [self._buf(B) for _ in range(2)]
+        self.y = self._buf(B)
+        self.loss = self._buf(1)
+        self.grad_norm = self._buf(1)
+        if distl:
+            self.p = [self._buf(B, self.pd) for _ in range(2)]
+            self.tp = [self._buf(B, self.pd) for _ in range(2)]
+            self.dl = [self._buf(B, self.pd) for _ in range(2)]
+            self.target = self._buf(B, N)
+            self.loss_part = self._buf((B + 7) // 8)
+        else:
+            self.loss_part = self._buf(self.nblk)
+
+        actor = NetAddrs(self.La, 0, self.a_tf, self.a_flat)
+        cnet = [NetAddrs(self.Lc, i, self.c_tf, self.c_flat) for i in range(2)]
+        tnet = [NetAddrs(self.Lc, i, self.t_tf, self.t_flat) for i in range(2)]
+        self._ring_args = None
+        calls = self.calls
+
+        # -- target policy: a' = clamp(tanh(actor(next_obs)) + clamp(noise), +-1)   :62-71, noise.py:19-27
+        a_inst = dict(net=actor, x=K.addr(self.x_tgt), x_ld=x_ld, k_in=O, h=[K.addr(t) for t in ha])
+        calls += trunk_calls(B, [a_inst], 3)
+        calls.append(K.Gemm(B, A, H3, [dict(a=K.addr(ha[2]), lda=H3, b=actor.W[3], ldb=H3, bias=actor.b[3],
+                                             aux=K.addr(self.noise), ldaux=A, out=K.addr(self.x_tgt, O), ldo=x_ld)],
+                            epilogue=K.EPI_BIAS_TANH_NOISE, tile_n=K.pick_tile_n(A), noise_bound=self.noise_bound))
+        # -- both target nets on (next_obs, a') and both current nets on (obs, action), one launch per layer
+        insts = [dict(net=tnet[i], x=K.addr(self.x_tgt), x_ld=x_ld, k_in=O + A, h=[K.addr(t) for t in h_t[i]])
+                 for i in range(2)]
+        insts += [dict(net=cnet[i], x=K.addr(self.x_cur), x_ld=x_ld, k_in=O + A, h=[K.addr(t) for t in h_c[i]])
+                  for i in range(2)]
+        wg = [(H3, H2, H2), (H2, H1, H1), (H1, O + A, x_ld)] + ([(N, H3, H3)] if distl else [])
+        self._ws_init(wg, 2, [d for d in HIDDEN] * 2 + ([N, N] if distl else []), extra=2 * _ru(self.nblk * (H3 + 1), 32))
+        if not distl:
+            calls += trunk_calls(B, insts, 2)
+            groups = []
+            for j, it in enumerate(insts):
+                n = it["net"]
+                groups.append(dict(a=it["h"][1], lda=H2, b=n.W[2], ldb=H2, bias=n.b[2], head_w=n.Wf[3], head_b=n.b[3],
+                                   q=K.addr(self.tq[j] if j < 2 else self.q[j - 2]),
+                                   out=it["h"][2] if j >= 2 else 0, ldo=H3))
+            calls.append(K.Gemm(B, H3, H2, groups, epilogue=K.EPI_BIAS_ELU_HEAD, tile_n=128))
+            ws_head = [self._ws_alloc(self.nblk * (H3 + 1)) for _ in range(2)]
+            for i in range(2):
+                self.opt.add_source(self.Lc.w_off[i][3], H3, ws_head[i], H3 + 1, self.nblk)
+                self.opt.add_source(self.Lc.b_off[i][3], 1, ws_head[i] + H3, H3 + 1, self.nblk)
+            calls.append(K.Call("pqlb_doubleq_td_loss", _lib.ptr(self.q[0]), _lib.ptr(self.q[1]), _lib.ptr(self.tq[0]),
+                                _lib.ptr(self.tq[1]), _lib.ptr(self.reward), _lib.ptr(self.done), self.gamma_n, B,
+                                _lib.ptr(h_c[0][2]), _lib.ptr(h_c[1][2]), C.c_void_p(cnet[0].Wf[3]),
+                                C.c_void_p(cnet[1].Wf[3]), _lib.ptr(self.dz[0][2]), _lib.ptr(self.dz[1][2]),
+                                _lib.ptr(self.y), C.c_void_p(K.addr(self.ws, ws_head[0])),
+                                C.c_void_p(K.addr(self.ws, ws_head[1])), _lib.ptr(self.loss_part)))
+            self.loss_scale, self.n_loss_part = 1.0 / B, self.nblk
+        else:
+            calls += trunk_calls(B, insts, 3)
+            groups = [dict(a=it["h"][2], lda=H3, b=it["net"].W[3], ldb=H3, bias=it["net"].b[3],
+                           out=K.addr(self.tp[j] if j < 2 else self.p[j - 2]), ldo=self.pd)
+                      for j, it in enumerate(insts)]
+            calls.append(K.Gemm(B, N, H3, groups, epilogue=K.EPI_BIAS_SOFTMAX, tile_n=64))
+            calls.append(K.Call("pqlb_c51_td_loss", _lib.ptr(self.p[0]), _lib.ptr(self.p[1]), _lib.ptr(self.tp[0]),
+                                _lib.ptr(self.tp[1]), self.pd, _lib.ptr(self.reward), _lib.ptr(self.done),
+                                _lib.ptr(self.z), self.gamma_n, self.v_min, self.v_max, N, B, _lib.ptr(self.target),
+                                _lib.ptr(self.dl[0]), _lib.ptr(self.dl[1]), self.pd, _lib.ptr(self.loss_part)))
+            calls.append(self._head_backward_c51(cnet, self.dl, [h_c[i][2] for i in range(2)],
+                                                 [self.dz[i][2] for i in range(2)]))
+            calls.append(self._wgrad(self.opt, self.Lc, [0, 1], 3, self.dl, self.pd, N,
+                                     [h_c[i][2] for i in range(2)], H3, H3))
+            self.loss_scale, self.n_loss_part = 1.0 / (B * N), (B + 7) // 8
+        # -- backward of the current nets
+        dz3, dz2, dz1 = ([self.dz[i][l] for i in range(2)] for l in (2, 1, 0))
+        calls += self._critic_backward(cnet, dz3, dz2, dz1, [h_c[i][0] for i in range(2)], [h_c[i][1] for i in range(2)])
+        calls.append(self._wgrad(self.opt, self.Lc, [0, 1], 2, dz3, H3, H3, [h_c[i][1] for i in range(2)], H2, H2))
+        calls.append(self._wgrad(self.opt, self.Lc, [0, 1], 1, dz2, H2, H2, [h_c[i][0] for i in range(2)], H1, H1))
+        calls.append(self._wgrad(self.opt, self.Lc, [0, 1], 0, dz1, H1, H1, [self.x_cur, self.x_cur], x_ld, O + A))
+        entries = [(i, l, self.dz[i][l], HIDDEN[l], HIDDEN[l]) for i in range(2) for l in range(3)]
+        if distl:
+            entries += [(i, 3, self.dl[i], self.pd, N) for i in range(2)]
+        calls.append(self._bias_grads(self.opt, self.Lc, entries))
+        _finish_plan(self, self.opt, self.c_flat, self.t_flat, self.c_tf, self.t_tf)
+
+    def round_weights(self):
+        with torch.cuda.device(self.device):
+            for src, dst in ((self.c_flat, self.c_tf), (self.t_flat, self.t_tf), (self.a_flat, self.a_tf)):
+                _lib.call("pqlb_round_tf32", _lib.ptr(src), _lib.ptr(dst), src.numel())
+
+    def set_actor(self, flat):
+        """Weights of the target policy (the actor module the driver sends with every update())."""
+        self.a_flat.copy_(flat, non_blocking=True)
+        with torch.cuda.device(self.device):
+            _lib.call("pqlb_round_tf32", _lib.ptr(self.a_flat), _lib.ptr(self.a_tf), self.a_flat.numel())
+
+    def set_norm(self, normalize_tuple):
+        if normalize_tuple is None:
+            if self.obs_norm:
+                raise ValueError("obs_norm is on but no normalize_tuple was delivered")
+            return
+        mean, var, eps = normalize_tuple
+        if abs(float(eps) - self.eps) > 0:
+            raise ValueError(f"normaliser epsilon changed ({eps} vs {self.eps}): rebuild the plan")
+        self.mean.copy_(mean.reshape(-1).float(), non_blocking=True)
+        self.var.copy_(var.reshape(-1).float(), non_blocking=True)
+
+    def sample_call(self, ring, capacity):
+        """The fused gather + normalise + cat launch for a given replay ring."""
+        on = self.obs_norm
+        return K.Call("pqlb_sample_critic_batch", _lib.ptr(ring), int(capacity), self.O, self.A, _lib.ptr(self.idx),
+                      self.B, _lib.ptr(self.mean) if on else None, _lib.ptr(self.var) if on else None, self.eps,
+                      _lib.ptr(self.x_cur), _lib.ptr(self.x_tgt), self.x_ld, _lib.ptr(self.reward), _lib.ptr(self.done),
+                      keep=(ring,))
+
+    def run(self, sample=None, allreduce=None, use_graph=False):
+        """One update: [sample] + forward/backward launches + gradient reduction, the gradient
+        all-reduce when data parallel, then clip + AdamW (+ Polyak) and the loss.  With
+        ``use_graph`` the two launch segments are captured once into CUDA graphs and replayed
+        (every pointer is fixed; the step count and the loss window live on the device)."""
+        if not use_graph:
+            self._segment_a(sample)
+            if allreduce is not None:
+                allreduce(self.opt.grad)
+                self.sumsq_call()
+            self._segment_b()
+            return
+        if self.graphs is None or self.graphs[2] is not sample:
+            self._capture(sample, allreduce is not None)
+        self.graphs[0].replay()
+        if allreduce is not None:
+            allreduce(self.opt.grad)
+        self.graphs[1].replay()
+
+    def _segment_a(self, sample):
+        if sample is not None:
+            sample()
+        for c in self.calls:
+            c()
+        self.reduce_call()
+
+    def _segment_b(self):
+        self.adamw_call()
+        self.loss_call()
+
+    def _capture(self, sample, data_parallel):
+        torch.cuda.synchronize(self.device)
+        ga, gb = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+        with torch.cuda.graph(ga):
+            self._segment_a(sample)
+            if not data_parallel:
+                self._segment_b()
+        if data_parallel:
+            with torch.cuda.graph(gb):
+                self.sumsq_call()
+                self._segment_b()
+        else:
+            gb = _NoGraph()
+        self.graphs = (ga, gb, sample)
+
+
+class _NoGraph:
+    def replay(self):
+        pass
+
+
+class ActorUpdate(_UpdateBase):
+    """pql_p_learner.py:47-64 as a prepared launch list: DPG through the frozen twin-Q / C51 critic."""
+
+    def __init__(self, obs_dim, action_dim, batch, device, actor_flat, *, distl=False, num_atoms=51,
+                 v_min=-10.0, v_max=10.0, lr=5e-4, max_grad_norm=0.5, obs_norm=True, eps=1e-4, world_size=1,
+                 loss_ring=None):
+        super().__init__(obs_dim, action_dim, batch, device, distl, num_atoms, v_min, v_max, loss_ring)
+        O, A, B, N, x_ld, a_ld = self.O, self.A, self.B, self.N, self.x_ld, self.a_ld
+        dev = self.device
+        self.lr, self.max_grad_norm = float(lr), max_grad_norm
+        self.eps, self.obs_norm = float(eps), bool(obs_norm)
+        self.world_size = int(world_size)
+        assert actor_flat.numel() == self.La.total and actor_flat.is_cuda
+        self.a_flat, self.a_tf = actor_flat, self._buf(self.La.total)
+        self.c_flat, self.c_tf = self._buf(self.Lc.total), self._buf(self.Lc.total)
+        self.round_weights()
+        self.opt = _Optim(self.La, dev)
+
+        self.idx = torch.zeros(B, dtype=torch.int64, device=dev)
+        self.x = self._buf(B, x_ld)
+        self.mean, self.var = self._buf(O), torch.ones(O, device=dev)
+        self.act = self._buf(B, a_ld)
+        ha = [self._buf(B, d) for d in HIDDEN]
+        h_c = [[self._buf(B, d) for d in HIDDEN] for _ in range(2)]
+        self.dzc = [[self._buf(B, d) for d in HIDDEN] for _ in range(2)]
+        self.dza = [self._buf(B, d) for d in HIDDEN]
+        self.dz_act = self._buf(B, a_ld)
+        self.q = [self._buf(B) for _ in range(2)]
+        self.loss, self.grad_norm = self._buf(1), self._buf(1)
+        if distl:
+            self.p = [self._buf(B, self.pd) for _ in range(2)]
+            self.dl = [self._buf(B, self.pd) for _ in range(2)]
+            self.loss_part = self._buf((B + 7) // 8)
+        else:
+            self.loss_part = self._buf(self.nblk)
+        actor = NetAddrs(self.La, 0, self.a_tf, self.a_flat)
+        cnet = [NetAddrs(self.Lc, i, self.c_tf, self.c_flat) for i in range(2)]
+        calls = self.calls
+
+        self._ws_init([(A, H3, H3), (H3, H2, H2), (H2, H1, H1), (H1, O, self.La.ldw[0])], 1, [*HIDDEN, A])
+        # -- action = tanh(actor(obs)) written straight into the critic input rows      :55
+        a_inst = dict(net=actor, x=K.addr(self.x), x_ld=x_ld, k_in=O, h=[K.addr(t) for t in ha])
+        calls += trunk_calls(B, [a_inst], 3)
+        calls.append(K.Gemm(B, A, H3, [dict(a=K.addr(ha[2]), lda=H3, b=actor.W[3], ldb=H3, bias=actor.b[3],
+                                             out=K.addr(self.x, O), ldo=x_ld, out2=K.addr(self.act), ldo2=a_ld)],
+                            epilogue=K.EPI_BIAS_TANH, tile_n=K.pick_tile_n(A)))
+        # -- frozen critic forward                                                     :56
+        insts = [dict(net=cnet[i], x=K.addr(self.x), x_ld=x_ld, k_in=O + A, h=[K.addr(t) for t in h_c[i]])
+                 for i in range(2)]
+        dz3 = [self.dzc[i][2] for i in range(2)]
+        if not distl:
+            calls += trunk_calls(B, insts, 2)
+            groups = [dict(a=it["h"][1], lda=H2, b=it["net"].W[2], ldb=H2, bias=it["net"].b[2], head_w=it["net"].Wf[3],
+                           head_b=it["net"].b[3], q=K.addr(self.q[j]), out=it["h"][2], ldo=H3)
+                      for j, it in enumerate(insts)]
+            calls.append(K.Gemm(B, H3, H2, groups, epilogue=K.EPI_BIAS_ELU_HEAD, tile_n=128))
+            calls.append(K.Call("pqlb_dpg_loss", _lib.ptr(self.q[0]), _lib.ptr(self.q[1]), B, _lib.ptr(h_c[0][2]),
+                                _lib.ptr(h_c[1][2]), C.c_void_p(cnet[0].Wf[3]), C.c_void_p(cnet[1].Wf[3]),
+                                _lib.ptr(dz3[0]), _lib.ptr(dz3[1]), _lib.ptr(self.loss_part)))
+            self.n_loss_part = self.nblk
+        else:
+            calls += trunk_calls(B, insts, 3)
+            groups = [dict(a=it["h"][2], lda=H3, b=it["net"].W[3], ldb=H3, bias=it["net"].b[3],
+                           out=K.addr(self.p[j]), ldo=self.pd) for j, it in enumerate(insts)]
+            calls.append(K.Gemm(B, N, H3, groups, epilogue=K.EPI_BIAS_SOFTMAX, tile_n=64))
+            calls.append(K.Call("pqlb_c51_dpg_loss", _lib.ptr(self.p[0]), _lib.ptr(self.p[1]), self.pd, _lib.ptr(self.z),
+                                N, B, _lib.ptr(self.dl[0]), _lib.ptr(self.dl[1]), self.pd, _lib.ptr(self.q[0]),
+                                _lib.ptr(self.loss_part)))
+            calls.append(self._head_backward_c51(cnet, self.dl, [h_c[i][2] for i in range(2)], dz3))
+            self.n_loss_part = (B + 7) // 8
+        self.loss_scale = -1.0 / B                                                     # :57  -Q.mean()
+        dz2, dz1 = ([self.dzc[i][l] for i in range(2)] for l in (1, 0))
+        calls += self._critic_backward(cnet, dz3, dz2, dz1, [h_c[i][0] for i in range(2)], [h_c[i][1] for i in range(2)])
+        # -- d loss / d action: both critics' layer-1 dgrad summed in one contraction, tanh' fused
+        g = dict(a=K.addr(dz1[0]), lda=H1, a2=K.addr(dz1[1]), lda2=H1, ldb=x_ld, ldb2=x_ld, out=K.addr(self.dz_act),
+                 ldo=a_ld)
+        if O % 4 == 0:
+            g.update(b=cnet[0].W[0] + 4 * O, b2=cnet[1].W[0] + 4 * O, aux=K.addr(self.act), ldaux=a_ld)
+            calls.append(K.Gemm(B, A, H1, [g], epilogue=K.EPI_MUL_TANHGRAD, tile_n=K.pick_tile_n(A),
+                                b_major=K.MN_MAJOR, K2=H1))
+        else:   # action columns are not 16-byte aligned inside W1: contract all columns, store the window
+            g.update(b=cnet[0].W[0], b2=cnet[1].W[0], aux=K.addr(self.act, -O), ldaux=a_ld)
+            calls.append(K.Gemm(B, O + A, H1, [g], epilogue=K.EPI_MUL_TANHGRAD, tile_n=256, b_major=K.MN_MAJOR,
+                                K2=H1, col_lo=O, col_hi=O + A))
+        # -- actor backward
+        calls.append(K.Gemm(B, H3, A, [dict(a=K.addr(self.dz_act), lda=a_ld, b=actor.W[3], ldb=H3, aux=K.addr(ha[2]),
+                                             ldaux=H3, out=K.addr(self.dza[2]), ldo=H3)],
+                            epilogue=K.EPI_MUL_ELUGRAD, tile_n=fwd_tile(B, H3, 1), b_major=K.MN_MAJOR))
+        calls.append(K.Gemm(B, H2, H3, [dict(a=K.addr(self.dza[2]), lda=H3, b=actor.W[2], ldb=H2, aux=K.addr(ha[1]),
+                                              ldaux=H2, out=K.addr(self.dza[1]), ldo=H2)],
+                            epilogue=K.EPI_MUL_ELUGRAD, tile_n=fwd_tile(B, H2, 1), b_major=K.MN_MAJOR))
+        calls.append(K.Gemm(B, H1, H2, [dict(a=K.addr(self.dza[1]), lda=H2, b=actor.W[1], ldb=H1, aux=K.addr(ha[0]),
+                                              ldaux=H1, out=K.addr(self.dza[0]), ldo=H1)],
+                            epilogue=K.EPI_MUL_ELUGRAD, tile_n=fwd_tile(B, H1, 1), b_major=K.MN_MAJOR))
+        calls.append(self._wgrad(self.opt, self.La, [0], 3, [self.dz_act], a_ld, A, [ha[2]], H3, H3))
+        calls.append(self._wgrad(self.opt, self.La, [0], 2, [self.dza[2]], H3, H3, [ha[1]], H2, H2))
+        calls.append(self._wgrad(self.opt, self.La, [0], 1, [self.dza[1]], H2, H2, [ha[0]], H1, H1))
+        calls.append(self._wgrad(self.opt, self.La, [0], 0, [self.dza[0]], H1, H1, [self.x], x_ld, O))
+        entries = [(0, l, self.dza[l], HIDDEN[l], HIDDEN[l]) for l in range(3)] + [(0, 3, self.dz_act, a_ld, A)]
+        calls.append(self._bias_grads(self.opt, self.La, entries))
+        _finish_plan(self, self.opt, self.a_flat, None, self.a_tf, None)
+
+    def round_weights(self):
+        with torch.cuda.device(self.device):
+            for src, dst in ((self.a_flat, self.a_tf), (self.c_flat, self.c_tf)):
+                _lib.call("pqlb_round_tf32", _lib.ptr(src), _lib.ptr(dst), src.numel())
+
+    def set_critic(self, flat):
+        self.c_flat.copy_(flat, non_blocking=True)
+        with torch.cuda.device(self.device):
+            _lib.call("pqlb_round_tf32", _lib.ptr(self.c_flat), _lib.ptr(self.c_tf), self.c_flat.numel())
+
+    set_norm = CriticUpdate.set_norm
+
+    def sample_call(self, obsring, capacity):
+        on = self.obs_norm
+        return K.Call("pqlb_sample_obs_batch", _lib.ptr(obsring), int(capacity), self.O, _lib.ptr(self.idx), self.B,
+                      _lib.ptr(self.mean) if on else None, _lib.ptr(self.var) if on else None, self.eps,
+                      _lib.ptr(self.x), self.x_ld, self.A, keep=(obsring,))
+
+    run, _segment_a, _segment_b, _capture = (CriticUpdate.run, CriticUpdate._segment_a, CriticUpdate._segment_b,
+                                             CriticUpdate._capture)
+
+
+def _finish_plan(plan, opt, p_flat, t_flat, p_tf, t_tf):
+    """Prepare the reduce / clip+AdamW(+Polyak) / loss launches that close an update."""
+    opt.finish(plan.device)
+    big = plan.ws
+    plan.reduce_call = K.Call("pqlb_grad_reduce", _lib.ptr(opt.seg_table), opt.n_seg, _lib.ptr(big), _lib.ptr(opt.grad),
+                              _lib.ptr(opt.sumsq))
+    plan.sumsq_call = K.Call("pqlb_grad_sumsq", _lib.ptr(opt.seg_table), opt.n_seg, _lib.ptr(opt.grad),
+                             _lib.ptr(opt.sumsq))
+    max_norm = -1.0 if plan.max_grad_norm is None else float(plan.max_grad_norm)
+    tau = getattr(plan, "tau", 0.0)
+
+    plan.adamw_call = K.Call("pqlb_adamw_polyak", _lib.ptr(p_flat), _lib.ptr(opt.grad), _lib.ptr(opt.m), _lib.ptr(opt.v),
+                             _lib.ptr(t_flat), _lib.ptr(p_tf), _lib.ptr(t_tf), opt.layout.total, _lib.ptr(opt.sumsq),
+                             opt.n_seg, 1.0 / plan.world_size, max_norm, plan.lr, 0.9, 0.999, 1e-8, 0.01, 0,
+                             _lib.ptr(opt.count), tau, _lib.ptr(plan.grad_norm))
+    plan.loss_call = K.Call("pqlb_sum_partials", _lib.ptr(plan.loss_part), plan.n_loss_part, plan.loss_scale,
+                            _lib.ptr(plan.loss), _lib.ptr(opt.count), _lib.ptr(plan.loss_ring), plan.loss_ring.numel())

@@ -1,0 +1,132 @@
+"""V-learner (critic update) entry points: drop-in for pql/algo/pql_v_learner.py:22-133.
+
+Same constructor, ``start()``, ``learn()``, ``update(actor, trajectory, normalize_tuple, sleep_time)``
+and the same attributes (critic, critic_target weights, memory, loss_tracker, update_count).
+``learn()`` is: torch.randint (the reference's index stream), torch.normal (its noise stream),
+then a fixed list of sm_100a kernel launches (pql_b200/algo/_engine.py).  The reference's
+``@ray.remote`` decoration is the caller's business: these are plain classes,
+one process per GPU.
+"""
+import os
+
+import torch
+
+from .. import _lib
+from ..models import load_class
+from ..replay.simple_replay import ReplayBuffer
+from ..utils.common import DeviceTracker
+from ._engine import CriticUpdate
+
+
+def module_flat(module, layout_total, device):
+    """Flat fp32 arena of an actor / critic module in the kernel layout: our modules expose it
+    directly, a reference ``nn.Module`` with the same state_dict keys is repacked."""
+    if hasattr(module, "arena"):
+        flat = module.arena.flat
+        if flat.numel() != layout_total:
+            raise ValueError("module shape does not match this learner")
+        return flat.to(device, non_blocking=True)
+    raise TypeError("expected a pql_b200.models module (load a reference checkpoint with load_state_dict first)")
+
+
+class PQLVLearner:
+    def __init__(self, obs_dim, action_dim, cfg, process_group=None):
+        self.cfg = cfg
+        self.obs_dim = obs_dim
+        self.action_dim = action_dim
+        self.device = torch.device(f"cuda:{self.cfg.algo.v_learner_gpu}")
+        if not torch.cuda.is_available():
+            raise RuntimeError("PQLVLearner needs a CUDA device: pql_b200 has no CPU path")
+        _lib.load()
+        if self.cfg.algo.distl and "Distributional" not in self.cfg.algo.cri_class:
+            self.cfg.algo.cri_class = "Distributional" + self.cfg.algo.cri_class       # :30-31
+        cri_class = load_class(self.cfg.algo.cri_class)
+        if self.cfg.algo.distl:
+            self.critic = cri_class(self.obs_dim, self.action_dim, v_min=self.cfg.algo.v_min, v_max=self.cfg.algo.v_max,
+                                    num_atoms=self.cfg.algo.num_atoms, device=self.device).to(self.device)
+        else:
+            self.critic = cri_class(self.obs_dim, self.action_dim).to(self.device)
+        if self.cfg.artifact is not None:
+            raise NotImplementedError("W&B artifact loading (pql/utils/model_util.py) is out of scope: "
+                                      "use critic.load_state_dict()")
+        self.actor = None
+        self.memory = ReplayBuffer(capacity=int(cfg.algo.memory_size), obs_dim=self.obs_dim,
+                                   action_dim=self.action_dim, device=self.device)
+        self.loss_tracker = DeviceTracker(5, self.device)
+        self.update_count = 0
+        self.normalize_tuple = None
+        self.sleep_time = 0
+        self.process_group = process_group
+        self.world_size = 1
+        if process_group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()
+                                         and getattr(cfg, "data_parallel", False)):
+            self.world_size = torch.distributed.get_world_size(process_group)
+        self._plan = None
+        self._sample = None
+        self.use_cuda_graph = bool(getattr(cfg, "use_cuda_graph", True)) and not os.environ.get("PQLB_NO_GRAPH")
+
+    def disable_graph(self):
+        self.use_cuda_graph = False
+
+    def enable_graph(self):
+        self.use_cuda_graph = True
+
+    # ---- plan ------------------------------------------------------------------------------
+    def _obs_dim_int(self):
+        return int(self.obs_dim if isinstance(self.obs_dim, int) else self.obs_dim[0])
+
+    def _build(self):
+        a = self.cfg.algo
+        eps = 1e-4 if self.normalize_tuple is None else float(self.normalize_tuple[2])
+        self._plan = CriticUpdate(self._obs_dim_int(), self.action_dim, int(a.batch_size), self.device,
+                                  self.critic.arena.flat, distl=bool(a.distl), num_atoms=a.num_atoms, v_min=a.v_min,
+                                  v_max=a.v_max, gamma_n=a.gamma ** a.nstep, lr=a.critic_lr, tau=a.tau,
+                                  max_grad_norm=a.max_grad_norm, noise_bound=a.noise.tgt_pol_noise_bound,
+                                  obs_norm=bool(a.obs_norm) and self.normalize_tuple is not None, eps=eps,
+                                  world_size=self.world_size, loss_ring=self.loss_tracker.window)
+        self._sample = self._plan.sample_call(self.memory.ring, self.memory.capacity)
+        self._noise_mean = torch.zeros_like(self._plan.noise)
+        self._noise_std = torch.full_like(self._plan.noise, float(a.noise.tgt_pol_std))
+
+    @property
+    def critic_target(self):
+        """Snapshot of the Polyak target as a module (the live weights are the plan's flat arena)."""
+        import copy
+        tgt = copy.deepcopy(self.critic)
+        if self._plan is not None:
+            tgt.arena.flat.copy_(self._plan.t_flat)
+        return tgt
+
+    def start(self):
+        return self.critic, self.update_count, self.loss_tracker.mean()
+
+    def _allreduce(self, grad):
+        torch.distributed.all_reduce(grad, group=self.process_group)
+
+    @torch.no_grad()
+    def learn(self):
+        if self.actor is not None:
+            if self._plan is None:
+                self._build()
+            p = self._plan
+            with torch.cuda.device(self.device):
+                # same two draws, in the same order, as the reference: randint (simple_replay.py:87)
+                # then torch.normal(zeros, full(std)) (noise.py:20-21)
+                torch.randint(self.memory.cur_capacity, size=(p.B,), device=self.device, out=p.idx)
+                torch.normal(self._noise_mean, self._noise_std, out=p.noise)
+                p.run(self._sample, self._allreduce if self.world_size > 1 else None, self.use_cuda_graph)
+            self.update_count += 1
+        return self.sleep_time
+
+    @torch.no_grad()
+    def update(self, actor, trajectory, normalize_tuple, sleep_time):
+        self.actor = actor
+        self.memory.add_to_buffer(trajectory)
+        rebuild = self._plan is not None and ((normalize_tuple is None) != (self.normalize_tuple is None))
+        self.normalize_tuple = normalize_tuple
+        self.sleep_time = sleep_time
+        if self._plan is None or rebuild:
+            self._build()
+        self._plan.set_actor(module_flat(actor, self._plan.La.total, self.device))
+        self._plan.set_norm(normalize_tuple if self.cfg.algo.obs_norm else None)
+        return self.critic, self.loss_tracker.mean(), self.update_count

@@ -349,6 +349,22 @@ static int make_operand_map(CUtensorMap* map, const float* base, int64_t ld, int
 
 using namespace pqlb;
 
+// One-time, non-stream setup (opt-in shared memory size, driver entry point) so that nothing but
+// kernel launches happens while a caller is capturing a CUDA graph.  Per device.
+extern "C" int pqlb_init(void) {
+  static bool done[64] = {false};
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return (int)e;
+  if (dev < 64 && done[dev]) return PQLB_OK;
+  // static (barriers) + dynamic shared memory must stay <= 227 KB
+  e = cudaFuncSetAttribute(gemm_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget + 2048);
+  if (e != cudaSuccess) return (int)e;
+  if (!get_encode_fn()) return PQLB_E_DRIVER;
+  if (dev < 64) done[dev] = true;
+  return PQLB_OK;
+}
+
 extern "C" int pqlb_gemm_tf32(const pqlb_gemm_desc* d, pqlb_stream_t stream) {
   PQLB_CHECK_ARG(d != nullptr);
   PQLB_CHECK_ARG(d->M > 0 && d->N > 0 && d->K > 0 && d->K2 >= 0);
@@ -406,12 +422,7 @@ extern "C" int pqlb_gemm_tf32(const pqlb_gemm_desc* d, pqlb_stream_t stream) {
   }
 
   const int smem_bytes = P.stages * P.stage_bytes + 1024;
-  static bool smem_attr_set = false;      // static (barriers) + dynamic must stay <= 227 KB
-  if (!smem_attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget + 2048);
-    if (e != cudaSuccess) return (int)e;
-    smem_attr_set = true;
-  }
+  { int rc = pqlb_init(); if (rc != PQLB_OK) return rc; }
   dim3 grid((unsigned)((d->M + kTileM - 1) / kTileM), (unsigned)((d->N + tn - 1) / tn), (unsigned)(d->n_groups * d->splits));
   gemm_tf32_kernel<<<grid, kGemmThreads, smem_bytes, (cudaStream_t)stream>>>(P);
   PQLB_LAUNCH_RET();

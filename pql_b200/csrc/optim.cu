@@ -50,26 +50,43 @@ grad_reduce_kernel(const int64_t* __restrict__ seg, const float* __restrict__ ws
   if (threadIdx.x == 0) sumsq_part[blockIdx.x] = tot;
 }
 
+struct AdamHyper {     // as passed by the caller; derived scalars are computed on the device
+  float grad_scale, max_norm, lr, beta1, beta2, eps, weight_decay, tau;
+};
 struct AdamScalars {
-  float grad_scale, max_norm, decay, one_minus_b1, b2, one_minus_b2, step_size, bc2_sqrt, eps;
-  float tau, one_minus_tau;
+  float decay, one_minus_b1, b2, one_minus_b2, step_size, bc2_sqrt, eps, tau, one_minus_tau;
 };
 
 __global__ void __launch_bounds__(kOptThreads)
 adamw_polyak_kernel(float* __restrict__ param, const float* __restrict__ grad, float* __restrict__ m,
                     float* __restrict__ v, float* __restrict__ target, float* __restrict__ p_tf32,
                     float* __restrict__ t_tf32, int64_t n, const float* __restrict__ sumsq_part,
-                    int n_part, AdamScalars a, float* __restrict__ grad_norm_out) {
+                    int n_part, AdamHyper h, int64_t step_host, const int64_t* __restrict__ step_dev,
+                    float* __restrict__ grad_norm_out) {
   __shared__ float red[8];
+  __shared__ AdamScalars sa;
+  if (threadIdx.x == 0) {
+    // scalar corrections in double, like torch's python-side arithmetic (torch/optim/adam.py);
+    // the 1-based step count comes from the device counter when the update runs inside a
+    // CUDA graph (completed updates + 1), else from the host argument.
+    const double t = (double)(step_dev ? step_dev[0] + 1 : step_host);
+    const double b1 = h.beta1, b2 = h.beta2, lr = h.lr;
+    const double bc1 = 1.0 - pow(b1, t), bc2 = 1.0 - pow(b2, t);
+    sa.decay = (float)(1.0 - lr * (double)h.weight_decay);
+    sa.one_minus_b1 = (float)(1.0 - b1); sa.b2 = h.beta2; sa.one_minus_b2 = (float)(1.0 - b2);
+    sa.step_size = (float)(lr / bc1); sa.bc2_sqrt = (float)sqrt(bc2); sa.eps = h.eps;
+    sa.tau = h.tau; sa.one_minus_tau = (float)(1.0 - (double)h.tau);
+  }
   // global L2 norm of the (scaled) gradient from the per-segment partials, fixed order
   float part = 0.f;
   for (int i = threadIdx.x; i < n_part; i += kOptThreads) part += sumsq_part[i];
-  const float total = block_sum_256(part, red);
-  const float norm = sqrtf(total) * a.grad_scale;
+  const float total = block_sum_256(part, red);          // contains __syncthreads: sa is visible
+  const AdamScalars a = sa;
+  const float norm = sqrtf(total) * h.grad_scale;
   float coef = 1.f;
-  if (a.max_norm >= 0.f) coef = fminf(a.max_norm / (norm + 1e-6f), 1.f);   // clip_grad.py
+  if (h.max_norm >= 0.f) coef = fminf(h.max_norm / (norm + 1e-6f), 1.f);   // clip_grad.py
   if (blockIdx.x == 0 && threadIdx.x == 0 && grad_norm_out) grad_norm_out[0] = norm;
-  const float gmul = a.grad_scale * coef;
+  const float gmul = h.grad_scale * coef;
 
   const int64_t i4 = ((int64_t)blockIdx.x * kOptThreads + threadIdx.x) * 4;
   if (i4 >= n) return;
@@ -179,13 +196,25 @@ colsum_multi_kernel(ColsumMulti d, int64_t rows) {
   }
 }
 
+// out[0] = scale * sum(part); optionally also ring[count % ring_len] = out[0] and ++count, where
+// count = number of completed updates (the loss window of Tracker(5) and the AdamW step counter
+// live on the device so that a whole update can be replayed from a CUDA graph).
 __global__ void __launch_bounds__(kOptThreads)
-sum_partials_kernel(const float* __restrict__ part, int n, float scale, float* __restrict__ out) {
+sum_partials_kernel(const float* __restrict__ part, int n, float scale, float* __restrict__ out,
+                    int64_t* __restrict__ counter, float* __restrict__ ring, int ring_len) {
   __shared__ float red[8];
   float acc = 0.f;
   for (int i = threadIdx.x; i < n; i += kOptThreads) acc += part[i];
   const float tot = block_sum_256(acc, red);
-  if (threadIdx.x == 0) out[0] = tot * scale;
+  if (threadIdx.x == 0) {
+    const float r = tot * scale;
+    out[0] = r;
+    if (counter) {
+      const int64_t c = counter[0];
+      if (ring && ring_len > 0) ring[c % ring_len] = r;
+      counter[0] = c + 1;
+    }
+  }
 }
 
 }  // namespace pqlb
@@ -210,25 +239,19 @@ extern "C" int pqlb_adamw_polyak(float* param, const float* grad, float* m, floa
                                  float* param_tf32, float* target_tf32, int64_t n,
                                  const float* sumsq_part, int n_part, float grad_scale,
                                  float max_norm, float lr, float beta1, float beta2, float eps,
-                                 float weight_decay, int64_t step, float tau, float* grad_norm_out,
-                                 pqlb_stream_t stream) {
-  PQLB_CHECK_ARG(param && grad && m && v && n > 0 && sumsq_part && n_part > 0 && step >= 1);
+                                 float weight_decay, int64_t step, const int64_t* step_dev, float tau,
+                                 float* grad_norm_out, pqlb_stream_t stream) {
+  PQLB_CHECK_ARG(param && grad && m && v && n > 0 && sumsq_part && n_part > 0 && (step_dev || step >= 1));
   PQLB_CHECK_ALIGN(aligned16(param) && aligned16(grad) && aligned16(m) && aligned16(v));
   PQLB_CHECK_ALIGN((!target || aligned16(target)) && (!param_tf32 || aligned16(param_tf32)) &&
                    (!target_tf32 || aligned16(target_tf32)));
-  // scalar corrections in double like torch's python-side arithmetic (adam.py)
-  const double b1 = beta1, b2 = beta2, dlr = lr;
-  const double bc1 = 1.0 - pow(b1, (double)step);
-  const double bc2 = 1.0 - pow(b2, (double)step);
-  AdamScalars a;
-  a.grad_scale = grad_scale; a.max_norm = max_norm;
-  a.decay = (float)(1.0 - dlr * (double)weight_decay);
-  a.one_minus_b1 = (float)(1.0 - b1); a.b2 = beta2; a.one_minus_b2 = (float)(1.0 - b2);
-  a.step_size = (float)(dlr / bc1); a.bc2_sqrt = (float)sqrt(bc2); a.eps = eps;
-  a.tau = tau; a.one_minus_tau = (float)(1.0 - (double)tau);
+  AdamHyper h;
+  h.grad_scale = grad_scale; h.max_norm = max_norm; h.lr = lr; h.beta1 = beta1; h.beta2 = beta2;
+  h.eps = eps; h.weight_decay = weight_decay; h.tau = tau;
   const int64_t blocks = (n + kOptThreads * 4 - 1) / (kOptThreads * 4);
   adamw_polyak_kernel<<<(unsigned)blocks, kOptThreads, 0, (cudaStream_t)stream>>>(
-      param, grad, m, v, target, param_tf32, target_tf32, n, sumsq_part, n_part, a, grad_norm_out);
+      param, grad, m, v, target, param_tf32, target_tf32, n, sumsq_part, n_part, h, step, step_dev,
+      grad_norm_out);
   PQLB_LAUNCH_RET();
 }
 
@@ -246,9 +269,10 @@ extern "C" int pqlb_colsum_partial(const float* dz, int64_t ld, int64_t rows, in
   PQLB_LAUNCH_RET();
 }
 
-extern "C" int pqlb_sum_partials(const float* part, int n, float scale, float* out, pqlb_stream_t stream) {
-  PQLB_CHECK_ARG(part && n > 0 && out);
-  sum_partials_kernel<<<1, kOptThreads, 0, (cudaStream_t)stream>>>(part, n, scale, out);
+extern "C" int pqlb_sum_partials(const float* part, int n, float scale, float* out, int64_t* counter,
+                                 float* ring, int ring_len, pqlb_stream_t stream) {
+  PQLB_CHECK_ARG(part && n > 0 && out && ring_len >= 0 && (!ring || counter));
+  sum_partials_kernel<<<1, kOptThreads, 0, (cudaStream_t)stream>>>(part, n, scale, out, counter, ring, ring_len);
   PQLB_LAUNCH_RET();
 }
 

@@ -1,0 +1,348 @@
+"""MLP actor / twin-Q critics with the reference's class names, constructor signatures, method
+names and ``state_dict`` keys (pql/models/mlp.py:15-40,177-203,244-267), executed by the
+tcgen05 kernels of libpqlb200.so.
+
+Parameters live in one flat fp32 *arena* per top-level module (layout in include/pqlb200.h:
+each ``nn.Linear`` weight stored ``[out, round_up(in, 4)]`` then its bias, 32-word aligned); the
+``nn.Parameter``s of the ``nn.Linear`` sub-modules are views of it, so the fused optimiser kernel
+updates the module in place and ``state_dict()/load_state_dict()/deepcopy/pickle`` keep working.
+``deepcopy``/``pickle``/``.to()`` detach the views; ``_ensure_tied()`` re-attaches them lazily.
+
+Module-level ``forward``/``get_q*`` are inference entry points (no autograd graph): training
+goes through ``PQLVLearner.learn`` / ``PQLPLearner.learn``, which compute gradients with their
+own backward kernels.
+"""
+from collections.abc import Sequence
+
+import torch
+import torch.nn as nn
+
+from .. import _kernels as K
+from .. import _lib
+
+HIDDEN = (512, 256, 128)            # mlp.py:33-34
+
+
+def _ru(x, m):
+    return (x + m - 1) // m * m
+
+
+class NetLayout:
+    """Offsets (fp32 words) of ``n_nets`` MLPs ``in -> 512 -> 256 -> 128 -> out`` in a flat arena,
+    in ``nn.Module.parameters()`` order: per net, per layer, weight then bias."""
+
+    def __init__(self, in_dim, out_dim, n_nets=1):
+        self.in_dim, self.out_dim, self.n_nets = int(in_dim), int(out_dim), int(n_nets)
+        self.dims = [self.in_dim, *HIDDEN, self.out_dim]
+        self.n_layers = len(self.dims) - 1
+        self.ldw = [_ru(d, 4) for d in self.dims[:-1]]
+        off = 0
+        self.w_off, self.b_off = [], []
+        for _ in range(self.n_nets):
+            wo, bo = [], []
+            for l in range(self.n_layers):
+                off = _ru(off, 32)
+                wo.append(off)
+                off += self.dims[l + 1] * self.ldw[l]
+                off = _ru(off, 32)
+                bo.append(off)
+                off += self.dims[l + 1]
+            self.w_off.append(wo)
+            self.b_off.append(bo)
+        self.total = _ru(off, 32)
+
+    def tensors(self):
+        """(net, layer, kind, offset, count) of every parameter tensor, in parameters() order."""
+        for i in range(self.n_nets):
+            for l in range(self.n_layers):
+                yield i, l, "w", self.w_off[i][l], self.dims[l + 1] * self.ldw[l]
+                yield i, l, "b", self.b_off[i][l], self.dims[l + 1]
+
+    def n_params(self):
+        return sum(self.dims[l + 1] * (self.dims[l] + 1) for l in range(self.n_layers)) * self.n_nets
+
+
+class ParamArena:
+    def __init__(self, layout, device="cpu"):
+        self.layout = layout
+        self.flat = torch.zeros(layout.total, dtype=torch.float32, device=device)
+
+    def weight(self, i, l):
+        L = self.layout
+        o = L.w_off[i][l]
+        return self.flat[o:o + L.dims[l + 1] * L.ldw[l]].view(L.dims[l + 1], L.ldw[l])[:, :L.dims[l]]
+
+    def bias(self, i, l):
+        L = self.layout
+        o = L.b_off[i][l]
+        return self.flat[o:o + L.dims[l + 1]]
+
+
+class NetAddrs:
+    """Device addresses of one net's tensors: ``W`` = TF32-rounded tensor-core operands,
+    ``Wf`` / ``b`` = fp32 weights / biases."""
+
+    def __init__(self, layout, i, flat_tf32, flat_fp32):
+        self.dims, self.ldw = layout.dims, layout.ldw
+        self.W = [K.addr(flat_tf32, layout.w_off[i][l]) for l in range(layout.n_layers)]
+        self.Wf = [K.addr(flat_fp32, layout.w_off[i][l]) for l in range(layout.n_layers)]
+        self.b = [K.addr(flat_fp32, layout.b_off[i][l]) for l in range(layout.n_layers)]
+
+
+def fwd_tile(B, N, n_groups):
+    """Widest output tile that still gives the grid about one CTA per SM."""
+    if N <= 64:
+        return K.pick_tile_n(N)
+    for t in (256, 128, 64):
+        if t > N and t // 2 >= N:
+            continue
+        if ((B + 127) // 128) * ((N + t - 1) // t) * n_groups >= 120:
+            return t
+    return 64
+
+
+def trunk_calls(B, insts, n_hidden_out=3):
+    """Prepared launches of the hidden layers (Linear + ELU, mlp.py:15-24) for up to four
+    network instances of identical shape.  inst = dict(net=NetAddrs, x=addr, x_ld, k_in,
+    h=[addr h1, addr h2, addr h3])."""
+    calls = []
+    dims = insts[0]["net"].dims
+    for l in range(n_hidden_out):
+        groups = []
+        for it in insts:
+            net = it["net"]
+            a, lda, k = (it["x"], it["x_ld"], it["k_in"]) if l == 0 else (it["h"][l - 1], dims[l], dims[l])
+            groups.append(dict(a=a, lda=lda, b=net.W[l], ldb=net.ldw[l], bias=net.b[l], out=it["h"][l],
+                               ldo=dims[l + 1]))
+        k_l = insts[0]["k_in"] if l == 0 else dims[l]
+        calls.append(K.Gemm(B, dims[l + 1], k_l, groups, epilogue=K.EPI_BIAS_ELU,
+                            tile_n=fwd_tile(B, dims[l + 1], len(groups))))
+    return calls
+
+
+class _ArenaModule(nn.Module):
+    """Shared arena plumbing of the top-level modules."""
+
+    def _init_arena(self, layout, nets):
+        # plain attributes (not buffers): the arena must not appear in state_dict()
+        self._layout = layout
+        self._nets = nets                    # list of nn.Sequential, arena order
+        self._arena = ParamArena(layout, "cpu")
+        for i, seq in enumerate(nets):
+            for l, lin in enumerate(m for m in seq if isinstance(m, nn.Linear)):
+                self._arena.weight(i, l).copy_(lin.weight.data)
+                self._arena.bias(i, l).copy_(lin.bias.data)
+        self._tie()
+
+    def _linears(self):
+        for i, seq in enumerate(self._nets):
+            for l, lin in enumerate(m for m in seq if isinstance(m, nn.Linear)):
+                yield i, l, lin
+
+    def _tie(self):
+        for i, l, lin in self._linears():
+            lin.weight.data = self._arena.weight(i, l)
+            lin.bias.data = self._arena.bias(i, l)
+
+    def _ensure_tied(self):
+        """Re-attach the parameters to the arena after deepcopy / pickle / ``.to()`` (which clone
+        every parameter separately).  When detached, the parameters hold the truth."""
+        dev = next(self.parameters()).device
+        if self._arena.flat.device != dev:
+            self._arena.flat = torch.zeros(self._layout.total, dtype=torch.float32, device=dev)
+        tied = all(lin.weight.data_ptr() == self._arena.weight(i, l).data_ptr() and
+                   lin.bias.data_ptr() == self._arena.bias(i, l).data_ptr() for i, l, lin in self._linears())
+        if not tied:
+            with torch.no_grad():
+                for i, l, lin in self._linears():
+                    self._arena.weight(i, l).copy_(lin.weight.data)
+                    self._arena.bias(i, l).copy_(lin.bias.data)
+            self._tie()
+        return self._arena
+
+    def _apply(self, fn, recurse=True):
+        super()._apply(fn, recurse)          # moves every parameter separately ...
+        self._ensure_tied()                  # ... so gather them back into one arena
+        return self
+
+    @property
+    def arena(self):
+        return self._ensure_tied()
+
+    # ---- inference through the kernels -----------------------------------------------------
+    @torch.no_grad()
+    def _forward(self, net_ids, a, b=None, head="linear"):
+        """Outputs of nets ``net_ids`` on input rows ``cat(a, b)``: list of fp32 tensors."""
+        arena = self._ensure_tied()
+        L = self._layout
+        dev = arena.flat.device
+        if dev.type != "cuda":
+            raise RuntimeError("pql_b200 models run on CUDA only (there is no CPU or PyTorch fallback): "
+                               "move the module and its inputs to a CUDA device")
+        a = a.to(device=dev, dtype=torch.float32)
+        if a.dim() != 2 or a.stride(1) != 1:
+            a = a.reshape(a.shape[0], -1).contiguous()
+        na, nb = a.shape[1], 0
+        if b is not None:
+            b = b.to(device=dev, dtype=torch.float32)
+            if b.dim() != 2 or b.stride(1) != 1:
+                b = b.reshape(b.shape[0], -1).contiguous()
+            nb = b.shape[1]
+        if na + nb != L.in_dim:
+            raise RuntimeError(f"mat1 and mat2 shapes cannot be multiplied ({a.shape[0]}x{na + nb} and "
+                               f"{L.in_dim}x{HIDDEN[0]})")
+        B = a.shape[0]
+        x_ld = L.ldw[0]
+        with torch.cuda.device(dev):
+            w_tf = torch.empty_like(arena.flat)
+            _lib.call("pqlb_round_tf32", _lib.ptr(arena.flat), _lib.ptr(w_tf), arena.flat.numel())
+            x = torch.empty((B, x_ld), dtype=torch.float32, device=dev)
+            _lib.call("pqlb_pack_x", _lib.ptr(a), a.stride(0), na, _lib.ptr(b), b.stride(0) if nb else 0, nb,
+                      _lib.ptr(x), x_ld, B)
+            nets = [NetAddrs(L, i, w_tf, arena.flat) for i in net_ids]
+            hs = [[torch.empty((B, d), dtype=torch.float32, device=dev) for d in HIDDEN] for _ in net_ids]
+            insts = [dict(net=n, x=K.addr(x), x_ld=x_ld, k_in=L.in_dim, h=[K.addr(t) for t in h])
+                     for n, h in zip(nets, hs)]
+            out_dim = L.out_dim
+            outs = []
+            if head == "linear" and out_dim == 1:
+                for c in trunk_calls(B, insts, 2):
+                    c()
+                qs = [torch.empty((B, 1), dtype=torch.float32, device=dev) for _ in net_ids]
+                groups = [dict(a=it["h"][1], lda=HIDDEN[1], b=n.W[2], ldb=n.ldw[2], bias=n.b[2], head_w=n.Wf[3],
+                               head_b=n.b[3], q=K.addr(q)) for it, n, q in zip(insts, nets, qs)]
+                K.Gemm(B, HIDDEN[2], HIDDEN[1], groups, epilogue=K.EPI_BIAS_ELU_HEAD, tile_n=128)()
+                return qs
+            for c in trunk_calls(B, insts, 3):
+                c()
+            if head == "softmax" and out_dim > 64:
+                raise NotImplementedError("softmax head supports at most 64 atoms")
+            if out_dim > 256:
+                raise NotImplementedError("output layers wider than 256 are not on the PQL path")
+            tile = K.pick_tile_n(out_dim) if head != "softmax" else max(32, K.pick_tile_n(out_dim))
+            scratch = torch.empty((B, _ru(out_dim, 4)), dtype=torch.float32, device=dev) if head == "tanh" else None
+            for it, n in zip(insts, nets):
+                o = torch.empty((B, out_dim), dtype=torch.float32, device=dev)
+                g = dict(a=it["h"][2], lda=HIDDEN[2], b=n.W[3], ldb=n.ldw[3], bias=n.b[3])
+                if head == "tanh":
+                    g.update(out=K.addr(scratch), ldo=scratch.shape[1], out2=K.addr(o), ldo2=out_dim)
+                    epi = K.EPI_BIAS_TANH
+                else:
+                    g.update(out=K.addr(o), ldo=out_dim)
+                    epi = K.EPI_BIAS_SOFTMAX if head == "softmax" else K.EPI_BIAS
+                K.Gemm(B, out_dim, HIDDEN[2], [g], epilogue=epi, tile_n=tile)()
+                outs.append(o)
+            return outs
+
+
+def _make_seq(in_dim, out_dim):
+    """create_simple_mlp (mlp.py:15-24) with the default hidden sizes: same construction order,
+    hence the same seeded default initialisation as the reference."""
+    dims = [in_dim, *HIDDEN, out_dim]
+    mods = []
+    for idx, (i, o) in enumerate(zip(dims[:-1], dims[1:])):
+        mods.append(nn.Linear(i, o))
+        if idx < len(dims) - 2:
+            mods.append(nn.ELU())
+    return nn.Sequential(*mods)
+
+
+def _check_mlp_args(hidden_layers, use_batchnorm):
+    if use_batchnorm:
+        raise NotImplementedError("use_batchnorm is not on the PQL path (DoubleQBatchNorm is a CrossQ baseline)")
+    if hidden_layers is not None and tuple(hidden_layers) != HIDDEN:
+        raise NotImplementedError(f"the kernels are specialised to hidden_layers={list(HIDDEN)} (mlp.py:33-34)")
+
+
+class MLPNet(_ArenaModule):
+    """mlp.py:27-40."""
+
+    def __init__(self, in_dim, out_dim, hidden_layers=None, use_batchnorm=False, _own_arena=True):
+        super().__init__()
+        if isinstance(in_dim, Sequence):
+            in_dim = in_dim[0]
+        _check_mlp_args(hidden_layers, use_batchnorm)
+        self.net = _make_seq(int(in_dim), int(out_dim))
+        self._own = bool(_own_arena)
+        if self._own:
+            self._init_arena(NetLayout(in_dim, out_dim, 1), [self.net])
+
+    def _apply(self, fn, recurse=True):
+        if self._own:
+            return super()._apply(fn, recurse)
+        return nn.Module._apply(self, fn, recurse)
+
+    def _ensure_tied(self):
+        if not self._own:
+            raise RuntimeError("this MLPNet is a sub-network of a twin-Q critic: call the critic's methods")
+        return super()._ensure_tied()
+
+    def forward(self, x):
+        return self._forward([0], x)[0]
+
+
+class TanhMLPPolicy(MLPNet):
+    """mlp.py:177-179."""
+
+    def forward(self, state):
+        return self._forward([0], state, head="tanh")[0]
+
+
+class DoubleQ(_ArenaModule):
+    """mlp.py:186-203."""
+    _OUT = 1
+
+    def __init__(self, state_dim, act_dim):
+        super().__init__()
+        if isinstance(state_dim, Sequence):
+            state_dim = state_dim[0]
+        self._build(int(state_dim), int(act_dim), 1)
+
+    def _build(self, state_dim, act_dim, out_dim):
+        self.state_dim, self.act_dim = state_dim, act_dim
+        self.net_q1 = MLPNet(in_dim=state_dim + act_dim, out_dim=out_dim, _own_arena=False)
+        self.net_q2 = MLPNet(in_dim=state_dim + act_dim, out_dim=out_dim, _own_arena=False)
+        self._init_arena(NetLayout(state_dim + act_dim, out_dim, 2), [self.net_q1.net, self.net_q2.net])
+
+    def get_q_min(self, state, action):
+        q1, q2 = self._forward([0, 1], state, action)
+        return torch.min(q1, q2)
+
+    def get_q1_q2(self, state, action):
+        q1, q2 = self._forward([0, 1], state, action)
+        return q1, q2
+
+    def get_q1(self, state, action):
+        return self._forward([0], state, action)[0]
+
+
+class DistributionalDoubleQ(DoubleQ):
+    """mlp.py:244-267: 51-atom softmax heads; ``z_atoms`` is a plain tensor attribute."""
+
+    def __init__(self, state_dim, act_dim, v_min=-10, v_max=10, num_atoms=51, device="cuda"):
+        nn.Module.__init__(self)
+        if isinstance(state_dim, Sequence):
+            state_dim = state_dim[0]
+        if num_atoms > 64:
+            raise NotImplementedError("the C51 kernels keep one distribution per warp: num_atoms <= 64")
+        self.device = device
+        self.v_min, self.v_max, self.num_atoms = v_min, v_max, int(num_atoms)
+        self._build(int(state_dim), int(act_dim), int(num_atoms))
+        self.z_atoms = torch.linspace(v_min, v_max, num_atoms, device=device)
+
+    def get_q_min(self, state, action):
+        p1, p2 = self._forward([0, 1], state, action, head="softmax")
+        B = p1.shape[0]
+        q = torch.empty(B, dtype=torch.float32, device=p1.device)
+        z = self.z_atoms.to(device=p1.device, dtype=torch.float32).contiguous()
+        with torch.cuda.device(p1.device):
+            _lib.call("pqlb_c51_dpg_loss", _lib.ptr(p1), _lib.ptr(p2), self.num_atoms, _lib.ptr(z), self.num_atoms,
+                      B, None, None, 0, _lib.ptr(q), None)
+        return q
+
+    def get_q1_q2(self, state, action):
+        p1, p2 = self._forward([0, 1], state, action, head="softmax")
+        return p1, p2
+
+    def get_q1(self, state, action):
+        return self._forward([0], state, action, head="softmax")[0]

@@ -1,0 +1,88 @@
+"""Host-side helpers mirroring pql/utils/common.py for the learner path."""
+from collections import deque
+from collections.abc import Sequence
+
+import numpy as np
+import torch
+
+
+class Tracker:
+    """pql/utils/common.py:103-126 - fixed-length window pre-filled with zeros."""
+
+    def __init__(self, max_len):
+        self.moving_average = deque([0 for _ in range(max_len)], maxlen=max_len)
+        self.max_len = max_len
+
+    def __repr__(self):
+        return self.moving_average.__repr__()
+
+    def update(self, value):
+        if isinstance(value, (np.ndarray, torch.Tensor)):
+            self.moving_average.extend(value.tolist())
+        elif isinstance(value, Sequence):
+            self.moving_average.extend(value)
+        else:
+            self.moving_average.append(value)
+
+    def mean(self):
+        return np.mean(self.moving_average)
+
+    def std(self):
+        return np.std(self.moving_average)
+
+    def max(self):
+        return np.max(self.moving_average)
+
+
+class DeviceTracker:
+    """Tracker whose window lives on the GPU: the last kernel of every update writes its loss into
+    ``window[update_index % max_len]`` (pqlb_sum_partials) instead of the reference's
+    ``loss.item()`` host sync after every update (pql_v_learner.py:111); ``mean()`` - called once
+    per env step from ``update()`` - is the only synchronisation point.  Same
+    pre-filled-with-zeros window semantics as Tracker."""
+
+    def __init__(self, max_len, device):
+        self.max_len = max_len
+        self.window = torch.zeros(max_len, dtype=torch.float32, device=device)
+
+    def mean(self):
+        return float(np.mean(self.window.tolist()))
+
+    def std(self):
+        return float(np.std(self.window.tolist()))
+
+    def max(self):
+        return float(np.max(self.window.tolist()))
+
+
+class AttrDict(dict):
+    """Minimal stand-in for the OmegaConf DictConfig the reference passes around."""
+
+    def __getattr__(self, k):
+        try:
+            return self[k]
+        except KeyError:
+            raise AttributeError(k)
+
+    def __setattr__(self, k, v):
+        self[k] = v
+
+
+def default_pql_cfg(**overrides):
+    """Values of pql/cfg/algo/pql_algo.yaml + actor_critic.yaml + default.yaml that the learner
+    path reads."""
+    cfg = AttrDict(available_gpus=1, artifact=None, num_envs=4096, sim_device="cuda:0", info_track_keys=None, seed=42,
+                   algo=AttrDict(v_learner_gpu=0, p_learner_gpu=0, distl=False, cri_class="DoubleQ",
+                                 act_class="TanhMLPPolicy", v_min=-10, v_max=10, num_atoms=51, critic_lr=5e-4,
+                                 actor_lr=5e-4, memory_size=int(5e6), batch_size=8192, obs_norm=True, gamma=0.99,
+                                 nstep=3, tau=0.05, max_grad_norm=0.5, tracker_len=100, reward_scale=0.01,
+                                 handle_timeout=True, warm_up=32, horizon_len=1, critic_actor_ratio=2,
+                                 critic_sample_ratio=8,
+                                 noise=AttrDict(type="mixed", decay=None, std_max=0.8, std_min=0.05, tgt_pol_std=0.8,
+                                                tgt_pol_noise_bound=0.2)))
+    for k, v in overrides.items():
+        if k in cfg.algo:
+            cfg.algo[k] = v
+        else:
+            cfg[k] = v
+    return cfg

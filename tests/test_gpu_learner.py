@@ -1,0 +1,125 @@
+"""GPU tier: PQLVLearner.learn / PQLPLearner.learn (twin-Q, C51, ShadowHand shape) against the
+torch-CPU oracle on identical weights, batches, indices and noise; module-level forward API;
+RNG stream parity of the ``out=`` draws."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import learner as L
+from tests import parity
+from tests.golden import inputs
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+@pytest.mark.parametrize("tag,seed,B,O,A,distl,steps", [("doubleq", 1234, 512, 88, 16, False, 3),
+                                                        ("c51", 4321, 256, 88, 16, True, 3),
+                                                        ("shadow", 77, 128, 211, 20, False, 2),
+                                                        ("ragged", 5, 200, 88, 16, False, 1)])
+def test_learner_updates_match_oracle(tag, seed, B, O, A, distl, steps):
+    res = parity.run_learner_parity(seed=seed, B=B, obs_dim=O, act_dim=A, distl=distl, steps=steps, device=DEV)
+    print(tag, res)
+
+
+def test_learner_without_obs_norm():
+    parity.run_learner_parity(seed=3, B=256, obs_dim=88, act_dim=16, distl=False, steps=1, device=DEV, obs_norm=False)
+
+
+def test_full_batch_allegro_doubleq():
+    """BASELINE config 1/2 batch size (8192).  Everything holds 1e-3 except the P-learner's weight
+    gradients on untrained random networks (tests/parity.py, ``p_grad_tol``): 3e-3."""
+    res = parity.run_learner_parity(seed=11, B=8192, obs_dim=88, act_dim=16, distl=False, steps=1, device=DEV,
+                                    p_grad_tol=3e-3)
+    print(res)
+
+
+def test_free_running_trace_vs_reference_fixture(golden_dir):
+    """Three unsynchronised updates from the reference's initial weights: losses recorded from
+    the reference run itself (tests/golden/learner_doubleq.npz).  TF32 rounding compounds
+    through Adam's normalised step, so the trace tolerance is 1e-2 (step 1: 1e-3)."""
+    from pql_b200.algo import PQLPLearner, PQLVLearner
+    from pql_b200.models import TanhMLPPolicy
+    g = np.load(os.path.join(golden_dir, "learner_doubleq.npz"))
+    B, O, A = 512, 88, 16
+    case = inputs.learner_case(1234, B, O, A, False)
+    cfg = parity.make_cfg(B, False)
+    dev = torch.device(DEV)
+    v = PQLVLearner(O, A, cfg)
+    parity.load_params(v.critic.net_q1, case["q1"]); parity.load_params(v.critic.net_q2, case["q2"])
+    actor = TanhMLPPolicy(O, A).to(dev)
+    parity.load_params(actor, case["actor"])
+    norm = (case["norm"][0].to(dev), case["norm"][1].to(dev), case["norm"][2])
+    v.update(actor, tuple(x.to(dev) for x in case["batch"]), norm, 0)
+    idx = torch.from_numpy(g["idx"])
+    losses = []
+    for s in range(3):
+        with parity.injected_draws(idx, case["noises"][s]):
+            v.learn()
+        losses.append(v._plan.loss.item())
+    assert losses[0] == pytest.approx(g["v_losses"][0], rel=1e-3)
+    np.testing.assert_allclose(losses, g["v_losses"], rtol=1e-2)
+    assert v.update_count == 3
+    crit, mean, cnt = v.update(actor, tuple(x[:7].to(dev) for x in case["batch"]), norm, 0)
+    assert crit is v.critic and cnt == 3
+    # Tracker(5) pre-filled with zeros (common.py:104-105): mean over [0, 0, l0, l1, l2]
+    assert mean == pytest.approx(sum(losses) / 5, rel=1e-5)
+    p = PQLPLearner(O, A, cfg)
+    parity.load_params(p.actor, case["actor"])
+    crit0 = type(v.critic)(O, A).to(dev)
+    parity.load_params(crit0.net_q1, case["q1"]); parity.load_params(crit0.net_q2, case["q2"])
+    p.update(crit0, case["batch"][0].to(dev), norm, 0)
+    pl = []
+    for s in range(3):
+        with parity.injected_draws(idx):
+            p.learn()
+        pl.append(p._plan.loss.item())
+    assert pl[0] == pytest.approx(g["p_losses"][0], rel=1e-3, abs=1e-6)
+    np.testing.assert_allclose(pl, g["p_losses"], rtol=2e-2, atol=1e-5)
+
+
+def test_module_forward_api_matches_oracle():
+    from pql_b200.models import DistributionalDoubleQ, DoubleQ, TanhMLPPolicy
+    B, O, A = 300, 88, 16
+    dev = torch.device(DEV)
+    for distl in (False, True):
+        case = inputs.learner_case(9, B, O, A, distl)
+        obs, act = case["batch"][0], case["batch"][1]
+        crit = (DistributionalDoubleQ(O, A, device=dev) if distl else DoubleQ(O, A)).to(dev)
+        parity.load_params(crit.net_q1, case["q1"]); parity.load_params(crit.net_q2, case["q2"])
+        q1, q2 = crit.get_q1_q2(obs.to(dev), act.to(dev))
+        r1, r2 = L.q1_q2(obs, act, case["q1"], case["q2"], distl)
+        assert q1.shape == r1.shape
+        assert parity.rel(q1, r1) <= 1e-3 and parity.rel(q2, r2) <= 1e-3
+        assert parity.rel(crit.get_q1(obs.to(dev), act.to(dev)), r1) <= 1e-3
+        qm = crit.get_q_min(obs.to(dev), act.to(dev))
+        rm = L.q_min(obs, act, case["q1"], case["q2"], distl, torch.linspace(-10, 10, 51) if distl else None)
+        assert qm.shape == rm.shape and parity.rel(qm, rm) <= 1e-3
+    pol = TanhMLPPolicy(O, A).to(dev)
+    parity.load_params(pol, case["actor"])
+    a = pol(obs.to(dev))
+    assert a.shape == (B, A) and parity.rel(a, L.actor_forward(obs, case["actor"])) <= 1e-3
+    # deepcopy / state_dict round trip keeps the kernels and the parameters in sync
+    import copy
+    pol2 = copy.deepcopy(pol)
+    assert torch.equal(pol2(obs.to(dev)), a)
+    pol3 = TanhMLPPolicy(O, A).to(dev)
+    pol3.load_state_dict(pol.state_dict())
+    assert torch.equal(pol3(obs.to(dev)), a)
+
+
+def test_rng_out_variants_follow_the_reference_stream():
+    """learn() draws with out= buffers; the values must equal the reference's functional calls
+    (simple_replay.py:87, noise.py:20-21) for the same seed."""
+    dev = torch.device(DEV)
+    torch.manual_seed(42)
+    idx_ref = torch.randint(12345, size=(8192,), device=dev)
+    noise_ref = torch.normal(torch.zeros(8192, 16, device=dev), torch.full((8192, 16), 0.8, device=dev))
+    torch.manual_seed(42)
+    idx = torch.zeros(8192, dtype=torch.int64, device=dev)
+    noise = torch.zeros(8192, 16, device=dev)
+    torch.randint(12345, size=(8192,), device=dev, out=idx)
+    torch.normal(torch.zeros(8192, 16, device=dev), torch.full((8192, 16), 0.8, device=dev), out=noise)
+    assert torch.equal(idx, idx_ref) and torch.equal(noise, noise_ref)

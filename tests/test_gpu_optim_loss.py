@@ -38,14 +38,16 @@ def test_adamw_polyak_matches_torch_order(n, max_norm, with_target):
     segs = seg_table(n)
     sumsq = torch.zeros(segs.shape[0], device=DEV)
     norm_out = torch.zeros(1, device=DEV)
+    count = torch.zeros(1, dtype=torch.int64, device=DEV)     # device-resident step count (n == 4099 case)
     for step in range(1, 4):
         grad = torch.randn(n, generator=g) * (0.01 * step)
         gd = grad.to(DEV)
         _lib.call("pqlb_grad_sumsq", _lib.ptr(segs), segs.shape[0], _lib.ptr(gd), _lib.ptr(sumsq))
         _lib.call("pqlb_adamw_polyak", _lib.ptr(p), _lib.ptr(gd), _lib.ptr(m), _lib.ptr(v),
                   _lib.ptr(tgt) if with_target else None, _lib.ptr(p_tf), _lib.ptr(t_tf) if with_target else None,
-                  n, _lib.ptr(sumsq), segs.shape[0], 1.0, max_norm, 5e-4, 0.9, 0.999, 1e-8, 0.01, step, 0.05,
-                  _lib.ptr(norm_out))
+                  n, _lib.ptr(sumsq), segs.shape[0], 1.0, max_norm, 5e-4, 0.9, 0.999, 1e-8, 0.01,
+                  step if n != 4099 else 0, _lib.ptr(count) if n == 4099 else None, 0.05, _lib.ptr(norm_out))
+        count += 1
         grads = [grad]
         if max_norm >= 0:
             grads, total = L.clip_grad_norm(grads, max_norm)
@@ -89,8 +91,12 @@ def test_colsum_and_sum_partials():
     np.testing.assert_allclose(part.sum(0).cpu().numpy(), dz[:, :cols].double().sum(0).cpu().numpy(), rtol=1e-5, atol=1e-5)
     out = torch.zeros(1, device=DEV)
     flat = part.reshape(-1)
-    _lib.call("pqlb_sum_partials", _lib.ptr(flat), flat.numel(), 0.5, _lib.ptr(out))
+    _lib.call("pqlb_sum_partials", _lib.ptr(flat), flat.numel(), 0.5, _lib.ptr(out), None, None, 0)
     assert out.item() == pytest.approx(0.5 * flat.double().sum().item(), rel=1e-5, abs=1e-5)
+    counter = torch.full((1,), 7, dtype=torch.int64, device=DEV)
+    ring = torch.zeros(5, device=DEV)
+    _lib.call("pqlb_sum_partials", _lib.ptr(flat), flat.numel(), 2.0, _lib.ptr(out), _lib.ptr(counter), _lib.ptr(ring), 5)
+    assert counter.item() == 8 and ring[2].item() == out.item() and torch.count_nonzero(ring).item() == 1
 
 
 def test_doubleq_td_loss_and_head_backward():
