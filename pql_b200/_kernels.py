@@ -28,6 +28,8 @@ def _p(a):
     return C.c_void_p(a if a else None)
 
 
+import os as _os
+TRACE = bool(_os.environ.get("PQLB_TRACE"))     # debug: synchronise after every launch and name the failing one
 PROFILE = None      # bench.py sets this to {} to collect (start, end) CUDA events per entry point
 
 
@@ -38,6 +40,20 @@ class Call:
         self.name, self.args, self._keep = name, args, keep
 
     def __call__(self):
+        if TRACE:
+            _lib.call(self.name, *self.args)
+            try:
+                torch.cuda.synchronize()
+            except Exception:
+                d = getattr(self, "desc", None)
+                if d is not None:
+                    print(f"[pqlb trace] FAILED {self.name}: M={d.M} N={d.N} K={d.K} K2={d.K2} a_major={d.a_major} "
+                          f"b_major={d.b_major} epi={d.epilogue} tile_n={d.tile_n} splits={d.splits} groups={d.n_groups} "
+                          f"col=[{d.col_lo},{d.col_hi})", flush=True)
+                else:
+                    print(f"[pqlb trace] FAILED {self.name}", flush=True)
+                raise
+            return
         if PROFILE is None:
             _lib.call(self.name, *self.args)
             return

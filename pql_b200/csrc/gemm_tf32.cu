@@ -5,9 +5,14 @@
 //     full/empty mbarrier ring;
 //   * one elected thread issues tcgen05.mma.cta_group::1.kind::tf32 (M=128, N=tile_n, K=8) with
 //     shared-memory descriptors; the fp32 accumulator lives in TMEM;
-//   * four epilogue warps read the accumulator back with tcgen05.ld (32 lanes x 32 columns per
-//     warp) and apply the fused epilogue (bias / ELU / tanh+noise / softmax / ELU' / tanh' /
-//     scalar Q head / split-K partial store).
+//   * eight epilogue warps (two per TMEM lane quarter, each owning half of the tile's columns)
+//     read the accumulator back with tcgen05.ld (32 lanes x 32 columns per chunk), apply the
+//     fused epilogue (bias / ELU / tanh+noise / softmax / ELU' / tanh' / scalar Q head /
+//     split-K partial store) and hand every 32x32 chunk to a TMA store through a swizzled
+//     shared-memory staging buffer (the operand ring, idle by then), so that global writes are
+//     full 128-byte lines; the ELU'/tanh' operand tile is prefetched by TMA the same way;
+//   * shared memory is sized for two CTAs per SM, so one tile's epilogue overlaps the next
+//     tile's TMA + MMA main loop.
 //
 // Both operands may be K-major (memory [rows][K], forward + the A side of dgrad) or MN-major
 // (memory [K][rows], the weight side of dgrad and both sides of wgrad), so no transposed copy
@@ -22,18 +27,22 @@
 
 namespace pqlb {
 
-constexpr int kGemmThreads = 192;       // warp 0: TMA, warp 1: TMEM alloc + MMA, warps 2-5: epilogue
+constexpr int kEpiWarps = 8;
+constexpr int kGemmThreads = 64 + 32 * kEpiWarps;   // warp 0: TMA, warp 1: TMEM alloc + MMA, warps 2-9: epilogue
 constexpr int kTileM = 128;
 constexpr int kTileK = 32;              // fp32 words per k-block = one 128-byte swizzle row
 constexpr int kATileBytes = kTileM * 128;
 constexpr int kMaxStages = 8;
-constexpr int kSmemBudget = 200 * 1024;
+constexpr int kRingBudget = 96 * 1024;  // operand ring; leaves room for two CTAs per SM
+constexpr int kChunkBytes = 32 * 128;   // one warp's 32-row x 32-column staging chunk
+constexpr int kSmemMax = 200 * 1024;
 
 struct alignas(64) GroupDev {
-  CUtensorMap tmA, tmB, tmA2, tmB2;
+  CUtensorMap tmA, tmB, tmA2, tmB2, tmOut, tmAux;
   const float* bias; const float* aux; const float* head_w; const float* head_b;
   float* q; float* out; float* out2;
   long long ldaux, ldo, ldo2, split_stride;
+  int out_tma, aux_tma;
 };
 
 struct alignas(64) GemmDev {
@@ -42,7 +51,7 @@ struct alignas(64) GemmDev {
   int a_mn, b_mn, epi, tile_n;
   int splits, kb1, kb_total, kb_per_split;
   int stages, stage_bytes, b_tile_bytes, tmem_cols;
-  int col_lo, col_hi;
+  int col_lo, col_hi, ring_bytes, aux_bytes;
   float noise_bound;
   unsigned idesc;
 };
@@ -129,14 +138,54 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+      ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%1, %2, %3}], [%4];"
+               ::"l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(src) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void named_bar_sync(int id, int threads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory"); }
+__device__ __forceinline__ void sts128(uint32_t addr, float a, float b, float c, float d) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+// ELU (alpha = 1) for the epilogue: the accumulator is about to be rounded to TF32 (2^-11), so
+// expm1 is evaluated as ex2.approx - 1 (abs. error < 3e-7) away from zero and as a 4-term Taylor
+// polynomial near zero (rel. error < 2e-7): ~6 instructions instead of expm1f's ~30.
+__device__ __forceinline__ float elu_fast(float v) {
+  float e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(v * 1.4426950408889634f));
+  const float t = v * (1.f + v * (0.5f + v * (0.16666667f + v * 0.041666668f)));
+  return v > 0.f ? v : (v > -0.0625f ? t : e - 1.f);
+}
+
 // ------------------------------------------------------------------------------ the kernel
-__global__ void __launch_bounds__(kGemmThreads, 1)
+template <int EPI> struct EpiTraits {
+  static constexpr bool kBias = EPI == PQLB_EPI_BIAS || EPI == PQLB_EPI_BIAS_ELU || EPI == PQLB_EPI_BIAS_ELU_HEAD ||
+                                EPI == PQLB_EPI_BIAS_TANH || EPI == PQLB_EPI_BIAS_TANH_NOISE || EPI == PQLB_EPI_BIAS_SOFTMAX;
+  static constexpr bool kAux = EPI == PQLB_EPI_MUL_ELUGRAD || EPI == PQLB_EPI_MUL_TANHGRAD || EPI == PQLB_EPI_BIAS_TANH_NOISE;
+};
+
+template <int EPI>
+__global__ void __launch_bounds__(kGemmThreads, 2)
 gemm_tf32_kernel(const __grid_constant__ GemmDev P) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t full_bar[kMaxStages];
   __shared__ __align__(8) uint64_t empty_bar[kMaxStages];
   __shared__ __align__(8) uint64_t accum_bar;
+  __shared__ __align__(8) uint64_t aux_bar[kEpiWarps];
   __shared__ uint32_t tmem_slot;
+  __shared__ float s_q[kTileM];
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -149,15 +198,27 @@ gemm_tf32_kernel(const __grid_constant__ GemmDev P) {
   const int kb_end = min(kb_begin + P.kb_per_split, P.kb_total);
 
   const uint32_t tiles = (smem_u32(smem_raw) + 1023u) & ~1023u;   // SWIZZLE_128B wants 1024-B alignment
+  const uint32_t aux_stage = tiles + P.ring_bytes;                 // kEpiWarps chunks (aux_bytes = 0 without an epilogue operand)
+  float* s_vec = reinterpret_cast<float*>(smem_raw + (tiles - smem_u32(smem_raw)) + P.ring_bytes + P.aux_bytes);
+  float* s_bias = s_vec;                 // [tile_n]
+  float* s_head = s_vec + P.tile_n;      // [tile_n]
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < P.stages; ++s) { mbar_init(smem_u32(&full_bar[s]), 1); mbar_init(smem_u32(&empty_bar[s]), 1); }
     mbar_init(smem_u32(&accum_bar), 1);
+    for (int w = 0; w < kEpiWarps; ++w) mbar_init(smem_u32(&aux_bar[w]), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"((uint32_t)P.tmem_cols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (EpiTraits<EPI>::kBias || EPI == PQLB_EPI_BIAS_ELU_HEAD) {
+    for (int j = threadIdx.x; j < P.tile_n; j += kGemmThreads) {
+      const int n = n0 + j;
+      s_bias[j] = (EpiTraits<EPI>::kBias && n < P.N) ? G.bias[n] : 0.f;
+      if (EPI == PQLB_EPI_BIAS_ELU_HEAD) s_head[j] = n < P.N ? G.head_w[n] : 0.f;
+    }
   }
   tcgen05_fence_before();
   __syncthreads();
@@ -216,86 +277,150 @@ gemm_tf32_kernel(const __grid_constant__ GemmDev P) {
       umma_commit(smem_u32(&accum_bar));                    // accumulator complete
     }
   } else {
-    // ===================== epilogue (warps 2..5) =====================
+    // ===================== epilogue (warps 2..9) =====================
+    const int e = warp - 2;
     const int quarter = warp & 3;                           // TMEM lanes [32q, 32q+32) belong to warp%4 == q
-    const int row = m0 + quarter * 32 + lane;
+    const int half = e >> 2;                                // which half of the tile's column chunks
+    const int row0 = m0 + quarter * 32;
+    const int row = row0 + lane;
     const bool row_ok = row < P.M;
+    const int chunkw = P.tile_n >= 32 ? 32 : 16;
+    const int n_chunks = max(0, (min(P.tile_n, P.col_hi - n0) + 31) / 32);   // chunks that reach below col_hi
+    int c_begin, c_end;
+    if (EPI == PQLB_EPI_BIAS_SOFTMAX) { c_begin = 0; c_end = half == 0 ? n_chunks : 0; }
+    else { const int per = (n_chunks + 1) >> 1; c_begin = half * per; c_end = min(n_chunks, c_begin + per); }
+    const bool out_tma = G.out_tma && chunkw == 32;
+    const bool aux_tma = EpiTraits<EPI>::kAux && G.aux_tma && chunkw == 32;
+    const uint32_t my_aux = aux_stage + e * kChunkBytes;
+    const uint32_t my_aux_bar = smem_u32(&aux_bar[e]);
+    const uint32_t my_out = tiles + e * 2 * kChunkBytes;    // two staging chunks in the (idle) operand ring
+    const uint32_t swz = (uint32_t)(lane & 7) << 4;
+    const uint32_t row_off = (uint32_t)lane * 128u;
+    uint32_t aux_phase = 0;
+
+    if (aux_tma && c_begin < c_end && lane == 0) {           // prefetch the first ELU'/tanh' chunk under the main loop
+      mbar_expect_tx(my_aux_bar, kChunkBytes);
+      tma_load_3d(my_aux, &G.tmAux, n0 + c_begin * 32, row0, 0, my_aux_bar);
+    }
     mbar_wait(smem_u32(&accum_bar), 0);
     tcgen05_fence_after();
     const uint32_t taddr = tmem_d + ((uint32_t)(quarter * 32) << 16);
-    const int col_lo = P.col_lo, col_hi = P.col_hi;
-    const int epi = P.epi;
 
-    if (epi == PQLB_EPI_BIAS_SOFTMAX) {
+    float qacc = 0.f;
+    float sm_v[EPI == PQLB_EPI_BIAS_SOFTMAX ? 64 : 1];
+    if (EPI == PQLB_EPI_BIAS_SOFTMAX && half == 0) {
       // all N (<= 64) logits of a row live in this thread: softmax in registers
-      float v[64];
-      tmem_ld32(taddr, v);
-      if (P.tile_n > 32) tmem_ld32(taddr + 32, v + 32);
+      tmem_ld32(taddr, sm_v);
+      if (P.tile_n > 32) tmem_ld32(taddr + 32, sm_v + 32);
       float mx = -INFINITY;
 #pragma unroll
-      for (int j = 0; j < 64; ++j) if (j < P.N) { v[j] += G.bias[j]; mx = fmaxf(mx, v[j]); }
+      for (int j = 0; j < 64; ++j) if (j < P.N) { sm_v[j] += s_bias[j]; mx = fmaxf(mx, sm_v[j]); }
       float sum = 0.f;
 #pragma unroll
-      for (int j = 0; j < 64; ++j) if (j < P.N) { v[j] = expf(v[j] - mx); sum += v[j]; }
-      if (row_ok) {
+      for (int j = 0; j < 64; ++j) if (j < P.N) { sm_v[j] = __expf(sm_v[j] - mx); sum += sm_v[j]; }
+      const float inv = 1.f / sum;
 #pragma unroll
-        for (int j = 0; j < 64; ++j) if (j < P.N) G.out[(long long)row * G.ldo + j] = v[j] / sum;
-      }
-    } else {
-      float qacc = 0.f;
-      const int chunk = P.tile_n >= 32 ? 32 : 16;
-      for (int c0 = 0; c0 < P.tile_n; c0 += chunk) {
-        float v[32];
-        if (chunk == 32) tmem_ld32(taddr + c0, v); else tmem_ld16(taddr + c0, v);
-        const int nb = n0 + c0;
-        if (!row_ok) continue;
-        float* orow = nullptr;
-        if (G.out) orow = G.out + (long long)row * G.ldo + (epi == PQLB_EPI_STORE ? (long long)split * G.split_stride : 0ll);
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          if (j >= chunk) break;
-          const int n = nb + j;
-          if (n >= P.N) break;
-          float x = v[j];
-          switch (epi) {
-            case PQLB_EPI_STORE: break;
-            case PQLB_EPI_BIAS: x += G.bias[n]; break;
-            case PQLB_EPI_BIAS_ELU: x = rn_tf32(elu1(x + G.bias[n])); break;
-            case PQLB_EPI_BIAS_ELU_HEAD: { const float h = elu1(x + G.bias[n]); qacc = fmaf(h, G.head_w[n], qacc); x = rn_tf32(h); } break;
-            case PQLB_EPI_BIAS_TANH: { const float a = tanhf(x + G.bias[n]); if (G.out2) G.out2[(long long)row * G.ldo2 + n] = a; x = rn_tf32(a); } break;
-            case PQLB_EPI_BIAS_TANH_NOISE: {
-              const float a = tanhf(x + G.bias[n]);
-              const float z = fminf(fmaxf(G.aux[(long long)row * G.ldaux + n], -P.noise_bound), P.noise_bound);
-              x = rn_tf32(fminf(fmaxf(a + z, -1.f), 1.f));
-            } break;
-            case PQLB_EPI_MUL_ELUGRAD: { const float h = G.aux[(long long)row * G.ldaux + n]; x = rn_tf32(x * (h > 0.f ? 1.f : h + 1.f)); } break;
-            case PQLB_EPI_MUL_TANHGRAD: { const float a = G.aux[(long long)row * G.ldaux + n]; x = rn_tf32(x * (1.f - a * a)); } break;
-            default: break;
-          }
-          v[j] = x;
-        }
-        if (orow) {
-          // vector path when the 32-column chunk is fully inside [col_lo, col_hi) and 16-B aligned
-          const int lo = max(nb, col_lo), hi = min(min(nb + chunk, P.N), col_hi);
-          float* dst = orow + (nb - col_lo);
-          if (lo == nb && hi == nb + chunk && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              if (j >= chunk) break;
-              *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-            }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              if (j >= chunk) break;
-              const int n = nb + j;
-              if (n >= lo && n < hi) dst[j] = v[j];
-            }
-          }
-        }
-      }
-      if (epi == PQLB_EPI_BIAS_ELU_HEAD && row_ok) G.q[row] = qacc + G.head_b[0];
+      for (int j = 0; j < 64; ++j) sm_v[j] = j < P.N ? sm_v[j] * inv : 0.f;
     }
+
+    int n_stores = 0;
+    for (int c = c_begin; c < c_end; ++c) {
+      const int c0 = c * 32;
+      const int nb = n0 + c0;
+      if (nb + 32 <= P.col_lo) continue;                       // chunk left of the stored column window
+      float v[32];
+      if (EPI == PQLB_EPI_BIAS_SOFTMAX) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = sm_v[(c & 1) * 32 + j];
+      } else if (chunkw == 32) tmem_ld32(taddr + c0, v);
+      else tmem_ld16(taddr + c0, v);
+
+      // ---- second epilogue operand (h for ELU', a for tanh', noise): one 32x32 chunk
+      float a[EpiTraits<EPI>::kAux ? 32 : 1];
+      if (EpiTraits<EPI>::kAux) {
+        if (aux_tma) {
+          mbar_wait(my_aux_bar, aux_phase); aux_phase ^= 1u;
+#pragma unroll
+          for (int j4 = 0; j4 < 8; ++j4) {
+            const float4 t = lds128(my_aux + row_off + (((uint32_t)j4 << 4) ^ swz));
+            a[4 * j4] = t.x; a[4 * j4 + 1] = t.y; a[4 * j4 + 2] = t.z; a[4 * j4 + 3] = t.w;
+          }
+          __syncwarp();
+          if (c + 1 < c_end && lane == 0) {                  // next chunk lands while this one is computed
+            mbar_expect_tx(my_aux_bar, kChunkBytes);
+            tma_load_3d(my_aux, &G.tmAux, nb + 32, row0, 0, my_aux_bar);
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int n = nb + j;
+            a[j] = (row_ok && j < chunkw && n < P.N && n >= P.col_lo && n < P.col_hi) ? G.aux[(long long)row * G.ldaux + n] : 0.f;
+          }
+        }
+      }
+      // ---- element-wise epilogue
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        float x = v[j];
+        if (EPI == PQLB_EPI_BIAS) x += s_bias[c0 + j];
+        else if (EPI == PQLB_EPI_BIAS_ELU) x = rn_tf32(elu_fast(x + s_bias[c0 + j]));
+        else if (EPI == PQLB_EPI_BIAS_ELU_HEAD) { const float h = elu_fast(x + s_bias[c0 + j]); qacc = fmaf(h, s_head[c0 + j], qacc); x = rn_tf32(h); }
+        else if (EPI == PQLB_EPI_BIAS_TANH) x = tanhf(x + s_bias[c0 + j]);      // rounded below (out2 keeps fp32)
+        else if (EPI == PQLB_EPI_BIAS_TANH_NOISE) {
+          const float t = tanhf(x + s_bias[c0 + j]);
+          const float z = fminf(fmaxf(a[EpiTraits<EPI>::kAux ? j : 0], -P.noise_bound), P.noise_bound);
+          x = rn_tf32(fminf(fmaxf(t + z, -1.f), 1.f));
+        }
+        else if (EPI == PQLB_EPI_MUL_ELUGRAD) { const float h = a[EpiTraits<EPI>::kAux ? j : 0]; x = rn_tf32(x * (h > 0.f ? 1.f : h + 1.f)); }
+        else if (EPI == PQLB_EPI_MUL_TANHGRAD) { const float t = a[EpiTraits<EPI>::kAux ? j : 0]; x = rn_tf32(x * (1.f - t * t)); }
+        v[j] = x;
+      }
+      if (EPI == PQLB_EPI_BIAS_TANH) {
+        if (G.out2 && row_ok) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) { const int n = nb + j; if (j < chunkw && n < P.N) G.out2[(long long)row * G.ldo2 + n] = v[j]; }
+        }
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = rn_tf32(v[j]);
+      }
+      // ---- store the chunk
+      if (G.out == nullptr) continue;
+      if (out_tma) {
+        const uint32_t buf = my_out + (uint32_t)(n_stores & 1) * kChunkBytes;
+        if (n_stores >= 2) { if (lane == 0) bulk_wait_read<1>(); __syncwarp(); }   // staging buffer free again
+#pragma unroll
+        for (int j4 = 0; j4 < 8; ++j4)
+          sts128(buf + row_off + (((uint32_t)j4 << 4) ^ swz), v[4 * j4], v[4 * j4 + 1], v[4 * j4 + 2], v[4 * j4 + 3]);
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) { tma_store_3d(&G.tmOut, buf, nb - P.col_lo, row0, split); bulk_commit(); }
+        ++n_stores;
+      } else if (row_ok) {
+        float* orow = G.out + (long long)row * G.ldo + (EPI == PQLB_EPI_STORE ? (long long)split * G.split_stride : 0ll);
+        const int lo = max(nb, P.col_lo), hi = min(min(nb + chunkw, P.N), P.col_hi);
+        float* dst = orow + (nb - P.col_lo);
+        if (lo == nb && hi == nb + chunkw && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            if (j >= chunkw) break;
+            *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int n = nb + j;
+            if (j < chunkw && n >= lo && n < hi) dst[j] = v[j];
+          }
+        }
+      }
+    }
+    if (EPI == PQLB_EPI_BIAS_ELU_HEAD) {
+      // the two warps of a lane quarter each hold the dot product over their half of the columns
+      if (half == 1) s_q[quarter * 32 + lane] = qacc;
+      named_bar_sync(1 + quarter, 64);
+      if (half == 0 && row_ok) G.q[row] = (qacc + s_q[quarter * 32 + lane]) + G.head_b[0];
+    }
+    if (n_stores > 0 && lane == 0) bulk_wait_read<0>();       // staging memory must outlive the bulk reads
   }
 
   tcgen05_fence_before();
@@ -303,6 +428,22 @@ gemm_tf32_kernel(const __grid_constant__ GemmDev P) {
   if (warp == 1) {
     tcgen05_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"((uint32_t)P.tmem_cols) : "memory");
+  }
+}
+
+typedef void (*GemmKernel)(const GemmDev);
+static GemmKernel kernel_for(int epi) {
+  switch (epi) {
+    case PQLB_EPI_STORE: return gemm_tf32_kernel<PQLB_EPI_STORE>;
+    case PQLB_EPI_BIAS: return gemm_tf32_kernel<PQLB_EPI_BIAS>;
+    case PQLB_EPI_BIAS_ELU: return gemm_tf32_kernel<PQLB_EPI_BIAS_ELU>;
+    case PQLB_EPI_BIAS_ELU_HEAD: return gemm_tf32_kernel<PQLB_EPI_BIAS_ELU_HEAD>;
+    case PQLB_EPI_BIAS_TANH: return gemm_tf32_kernel<PQLB_EPI_BIAS_TANH>;
+    case PQLB_EPI_BIAS_TANH_NOISE: return gemm_tf32_kernel<PQLB_EPI_BIAS_TANH_NOISE>;
+    case PQLB_EPI_BIAS_SOFTMAX: return gemm_tf32_kernel<PQLB_EPI_BIAS_SOFTMAX>;
+    case PQLB_EPI_MUL_ELUGRAD: return gemm_tf32_kernel<PQLB_EPI_MUL_ELUGRAD>;
+    case PQLB_EPI_MUL_TANHGRAD: return gemm_tf32_kernel<PQLB_EPI_MUL_TANHGRAD>;
+    default: return nullptr;
   }
 }
 
@@ -337,6 +478,22 @@ static int make_map(CUtensorMap* map, const float* base, uint64_t dim0, uint64_t
   return r == CUDA_SUCCESS ? PQLB_OK : PQLB_E_DRIVER;
 }
 
+// Output / epilogue-operand map: [splits][rows][cols] fp32, 32x32 boxes, 128-byte swizzle (matches
+// the staging chunks the epilogue warps write / read).  Returns false when TMA cannot address it.
+static bool make_tile_map(CUtensorMap* map, const float* base, uint64_t cols, uint64_t rows, int64_t ld_words,
+                          uint64_t splits, int64_t split_stride_words) {
+  PFN_cuTensorMapEncodeTiled enc = get_encode_fn();
+  if (!enc || !base || !aligned16(base) || (ld_words % 4) != 0 || ld_words < (int64_t)cols) return false;
+  if (splits > 1 && ((split_stride_words % 4) != 0 || split_stride_words <= 0)) return false;
+  cuuint64_t gdim[3] = {cols, rows, splits};
+  cuuint64_t gstr[2] = {(cuuint64_t)ld_words * 4, (cuuint64_t)(splits > 1 ? split_stride_words : ld_words * (int64_t)rows) * 4};
+  cuuint32_t box[3] = {32, 32, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), gdim, gstr, box, estr,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 static int make_operand_map(CUtensorMap* map, const float* base, int64_t ld, int major, int rows, int k,
                             int tile_rows) {
   if (major == PQLB_K_MAJOR)   // memory [rows][k]
@@ -358,8 +515,10 @@ extern "C" int pqlb_init(void) {
   if (e != cudaSuccess) return (int)e;
   if (dev < 64 && done[dev]) return PQLB_OK;
   // static (barriers) + dynamic shared memory must stay <= 227 KB
-  e = cudaFuncSetAttribute(gemm_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget + 2048);
-  if (e != cudaSuccess) return (int)e;
+  for (int epi = PQLB_EPI_STORE; epi <= PQLB_EPI_MUL_TANHGRAD; ++epi) {
+    e = cudaFuncSetAttribute(kernel_for(epi), cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax);
+    if (e != cudaSuccess) return (int)e;
+  }
   if (!get_encode_fn()) return PQLB_E_DRIVER;
   if (dev < 64) done[dev] = true;
   return PQLB_OK;
@@ -386,11 +545,17 @@ extern "C" int pqlb_gemm_tf32(const pqlb_gemm_desc* d, pqlb_stream_t stream) {
   P.kb_per_split = P.kb_total / d->splits;
   P.b_tile_bytes = P.b_mn ? ((tn + 31) / 32) * 4096 : tn * 128;
   P.stage_bytes = kATileBytes + ((P.b_tile_bytes + 1023) / 1024) * 1024;
-  int stages = kSmemBudget / P.stage_bytes;
+  const bool wants_aux = d->epilogue == PQLB_EPI_MUL_ELUGRAD || d->epilogue == PQLB_EPI_MUL_TANHGRAD ||
+                         d->epilogue == PQLB_EPI_BIAS_TANH_NOISE;
+  int stages = (kRingBudget - (wants_aux ? kEpiWarps * kChunkBytes : 0)) / P.stage_bytes;
   if (stages > kMaxStages) stages = kMaxStages;
   if (stages > P.kb_per_split) stages = P.kb_per_split < 2 ? 2 : P.kb_per_split;
   if (stages < 2) stages = 2;
   P.stages = stages;
+  // the operand ring doubles as the epilogue's staging area: two 4 KB chunks per epilogue warp
+  P.ring_bytes = stages * P.stage_bytes;
+  if (P.ring_bytes < 2 * kEpiWarps * kChunkBytes) P.ring_bytes = 2 * kEpiWarps * kChunkBytes;
+  P.aux_bytes = wants_aux ? kEpiWarps * kChunkBytes : 0;
   P.tmem_cols = tn < 32 ? 32 : tn;
   P.col_lo = d->col_lo; P.col_hi = d->col_hi > 0 ? d->col_hi : d->N;
   PQLB_CHECK_SHAPE(P.col_lo >= 0 && P.col_lo < P.col_hi && P.col_hi <= d->N);
@@ -419,11 +584,20 @@ extern "C" int pqlb_gemm_tf32(const pqlb_gemm_desc* d, pqlb_stream_t stream) {
     G.bias = s.bias; G.aux = s.aux; G.head_w = s.head_w; G.head_b = s.head_b; G.q = s.q;
     G.out = s.out; G.out2 = s.out2; G.ldaux = s.ldaux; G.ldo = s.ldo; G.ldo2 = s.ldo2;
     G.split_stride = s.split_stride;
+    // TMA paths of the epilogue (fall back to per-thread accesses when the layout is not addressable)
+    const int n_store = P.col_hi - P.col_lo;
+    G.out_tma = s.out && P.col_lo == 0 && make_tile_map(&G.tmOut, s.out, (uint64_t)n_store, (uint64_t)d->M, s.ldo,
+                                       (uint64_t)d->splits, s.split_stride) ? 1 : 0;
+    G.aux_tma = wants_aux && P.col_lo == 0 && P.col_hi == d->N &&
+                make_tile_map(&G.tmAux, s.aux, (uint64_t)d->N, (uint64_t)d->M, s.ldaux, 1, 0) ? 1 : 0;
+    if (!G.out_tma) G.tmOut = G.tmA;
+    if (!G.aux_tma) G.tmAux = G.tmA;
   }
 
-  const int smem_bytes = P.stages * P.stage_bytes + 1024;
+  const int smem_bytes = 1024 + P.ring_bytes + P.aux_bytes + 2 * tn * (int)sizeof(float);
+  PQLB_CHECK_SHAPE(smem_bytes <= kSmemMax);
   { int rc = pqlb_init(); if (rc != PQLB_OK) return rc; }
   dim3 grid((unsigned)((d->M + kTileM - 1) / kTileM), (unsigned)((d->N + tn - 1) / tn), (unsigned)(d->n_groups * d->splits));
-  gemm_tf32_kernel<<<grid, kGemmThreads, smem_bytes, (cudaStream_t)stream>>>(P);
+  kernel_for(d->epilogue)<<<grid, kGemmThreads, smem_bytes, (cudaStream_t)stream>>>(P);
   PQLB_LAUNCH_RET();
 }
