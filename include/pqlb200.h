@@ -152,7 +152,9 @@ typedef struct {
   int n_groups;               /* 1..PQLB_MAX_GROUPS                            */
   int col_lo, col_hi;         /* only output columns [col_lo,col_hi) are stored, at out[row*ldo + n-col_lo];
                                  col_hi == 0 means [0, N).  aux/bias are indexed with the absolute n. */
-  float noise_bound;          /* BIAS_TANH_NOISE                               */
+  float noise_bound;          /* BIAS_TANH_NOISE: clamp(noise_std * aux, +-noise_bound)         */
+  float noise_std;            /* aux holds N(0,1) draws (out.normal_()), scaled here like
+                                 torch.normal(zeros, full(std)) does (mul_(std).add_(mean))     */
   pqlb_gemm_group g[PQLB_MAX_GROUPS];
 } pqlb_gemm_desc;
 
@@ -167,8 +169,9 @@ int pqlb_round_tf32(const float* src, float* dst, int64_t n, pqlb_stream_t strea
  * Replaces pql/algo/pql_v_learner.py:104-108 (torch.min, TD target, 2x mse_loss) and the
  * backward of the scalar head: y = r + (1-d)*gamma_n*min(tq1,tq2); loss = mean((q1-y)^2) +
  * mean((q2-y)^2); dq_i = 2(q_i-y)/B; dz3_i = rn_tf32(dq_i * w4_i * elu'(h3_i)).
- * Per-block partials (block = 128 rows): loss_part[nblk], and gw4/gb4 partials written to
- * ws_i[blk*129 + {0..127, 128}] for the deterministic reduction in pqlb_grad_reduce. */
+ * Per-block partials (block = 64 rows of one net, nblk = ceil(B/64)): loss_part[2*nblk], and
+ * gw4/gb4 partials written to ws_i[blk*129 + {0..127, 128}] for the deterministic reduction in
+ * pqlb_grad_reduce. */
 int pqlb_doubleq_td_loss(const float* q1, const float* q2, const float* tq1, const float* tq2,
                          const float* reward, const float* done, float gamma_n, int64_t batch,
                          const float* h3_1, const float* h3_2, const float* w4_1, const float* w4_2,

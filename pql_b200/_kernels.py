@@ -75,12 +75,12 @@ class Gemm(Call):
     INTS = ("lda", "ldb", "lda2", "ldb2", "ldaux", "ldo", "ldo2", "split_stride")
 
     def __init__(self, M, N, K, groups, *, epilogue, tile_n, a_major=K_MAJOR, b_major=K_MAJOR,
-                 splits=1, K2=0, col_lo=0, col_hi=0, noise_bound=0.0, keep=()):
+                 splits=1, K2=0, col_lo=0, col_hi=0, noise_bound=0.0, noise_std=1.0, keep=()):
         d = _lib.GemmDesc()
         d.M, d.N, d.K, d.K2 = int(M), int(N), int(K), int(K2)
         d.a_major, d.b_major, d.epilogue, d.tile_n = a_major, b_major, epilogue, int(tile_n)
         d.splits, d.n_groups = int(splits), len(groups)
-        d.col_lo, d.col_hi, d.noise_bound = int(col_lo), int(col_hi), float(noise_bound)
+        d.col_lo, d.col_hi, d.noise_bound, d.noise_std = int(col_lo), int(col_hi), float(noise_bound), float(noise_std)
         if not 1 <= len(groups) <= _lib.MAX_GROUPS:
             raise ValueError("1..%d groups per launch" % _lib.MAX_GROUPS)
         for i, g in enumerate(groups):

@@ -18,7 +18,7 @@ from .. import _lib
 from ..models.mlp import HIDDEN, NetAddrs, NetLayout, _ru, fwd_tile, trunk_calls
 
 H1, H2, H3 = HIDDEN
-SEG = 1024
+SEG = 256
 
 
 class _Optim:
@@ -76,6 +76,7 @@ class _UpdateBase:
         self.x_ld = _ru(self.O + self.A, 4)
         self.a_ld = _ru(self.A, 4)
         self.nblk = (self.B + 127) // 128
+        self.nblk_head = (self.B + 63) // 64        # head_loss_kernel: 64 rows of one net per block
         self.Lc = NetLayout(self.O + self.A, self.N, 2)
         self.La = NetLayout(self.O, self.A, 1)
         self.pd = 64 if distl else 0           # row stride of the probability / dlogit buffers
@@ -154,13 +155,14 @@ class CriticUpdate(_UpdateBase):
 
     def __init__(self, obs_dim, action_dim, batch, device, critic_flat, *, distl=False, num_atoms=51,
                  v_min=-10.0, v_max=10.0, gamma_n=0.99 ** 3, lr=5e-4, tau=0.05, max_grad_norm=0.5,
-                 noise_bound=0.2, obs_norm=True, eps=1e-4, world_size=1, loss_ring=None):
+                 noise_bound=0.2, noise_std=0.8, obs_norm=True, eps=1e-4, world_size=1, loss_ring=None):
         super().__init__(obs_dim, action_dim, batch, device, distl, num_atoms, v_min, v_max, loss_ring)
         O, A, B, N, x_ld = self.O, self.A, self.B, self.N, self.x_ld
         dev = self.device
         self.lr, self.tau, self.max_grad_norm = float(lr), float(tau), max_grad_norm
         self.gamma_n = float(np.float32(gamma_n))
         self.noise_bound, self.eps, self.obs_norm = float(noise_bound), float(eps), bool(obs_norm)
+        self.noise_std = float(noise_std)
         self.world_size = int(world_size)
 
         # parameter arenas: critic (owned by the nn.Module), target, actor copy + TF32 twins
@@ -195,7 +197,7 @@ class CriticUpdate(_UpdateBase):
             self.target = self._buf(B, N)
             self.loss_part = self._buf((B + 7) // 8)
         else:
-            self.loss_part = self._buf(self.nblk)
+            self.loss_part = self._buf(2 * self.nblk_head)
 
         actor = NetAddrs(self.La, 0, self.a_tf, self.a_flat)
         cnet = [NetAddrs(self.Lc, i, self.c_tf, self.c_flat) for i in range(2)]
@@ -208,14 +210,15 @@ class CriticUpdate(_UpdateBase):
         calls += trunk_calls(B, [a_inst], 3)
         calls.append(K.Gemm(B, A, H3, [dict(a=K.addr(ha[2]), lda=H3, b=actor.W[3], ldb=H3, bias=actor.b[3],
                                              aux=K.addr(self.noise), ldaux=A, out=K.addr(self.x_tgt, O), ldo=x_ld)],
-                            epilogue=K.EPI_BIAS_TANH_NOISE, tile_n=K.pick_tile_n(A), noise_bound=self.noise_bound))
+                            epilogue=K.EPI_BIAS_TANH_NOISE, tile_n=K.pick_tile_n(A), noise_bound=self.noise_bound,
+                            noise_std=self.noise_std))
         # -- both target nets on (next_obs, a') and both current nets on (obs, action), one launch per layer
         insts = [dict(net=tnet[i], x=K.addr(self.x_tgt), x_ld=x_ld, k_in=O + A, h=[K.addr(t) for t in h_t[i]])
                  for i in range(2)]
         insts += [dict(net=cnet[i], x=K.addr(self.x_cur), x_ld=x_ld, k_in=O + A, h=[K.addr(t) for t in h_c[i]])
                   for i in range(2)]
         wg = [(H3, H2, H2), (H2, H1, H1), (H1, O + A, x_ld)] + ([(N, H3, H3)] if distl else [])
-        self._ws_init(wg, 2, [d for d in HIDDEN] * 2 + ([N, N] if distl else []), extra=2 * _ru(self.nblk * (H3 + 1), 32))
+        self._ws_init(wg, 2, [d for d in HIDDEN] * 2 + ([N, N] if distl else []), extra=2 * _ru(self.nblk_head * (H3 + 1), 32))
         if not distl:
             calls += trunk_calls(B, insts, 2)
             groups = []
@@ -225,17 +228,17 @@ class CriticUpdate(_UpdateBase):
                                    q=K.addr(self.tq[j] if j < 2 else self.q[j - 2]),
                                    out=it["h"][2] if j >= 2 else 0, ldo=H3))
             calls.append(K.Gemm(B, H3, H2, groups, epilogue=K.EPI_BIAS_ELU_HEAD, tile_n=128))
-            ws_head = [self._ws_alloc(self.nblk * (H3 + 1)) for _ in range(2)]
+            ws_head = [self._ws_alloc(self.nblk_head * (H3 + 1)) for _ in range(2)]
             for i in range(2):
-                self.opt.add_source(self.Lc.w_off[i][3], H3, ws_head[i], H3 + 1, self.nblk)
-                self.opt.add_source(self.Lc.b_off[i][3], 1, ws_head[i] + H3, H3 + 1, self.nblk)
+                self.opt.add_source(self.Lc.w_off[i][3], H3, ws_head[i], H3 + 1, self.nblk_head)
+                self.opt.add_source(self.Lc.b_off[i][3], 1, ws_head[i] + H3, H3 + 1, self.nblk_head)
             calls.append(K.Call("pqlb_doubleq_td_loss", _lib.ptr(self.q[0]), _lib.ptr(self.q[1]), _lib.ptr(self.tq[0]),
                                 _lib.ptr(self.tq[1]), _lib.ptr(self.reward), _lib.ptr(self.done), self.gamma_n, B,
                                 _lib.ptr(h_c[0][2]), _lib.ptr(h_c[1][2]), C.c_void_p(cnet[0].Wf[3]),
                                 C.c_void_p(cnet[1].Wf[3]), _lib.ptr(self.dz[0][2]), _lib.ptr(self.dz[1][2]),
                                 _lib.ptr(self.y), C.c_void_p(K.addr(self.ws, ws_head[0])),
                                 C.c_void_p(K.addr(self.ws, ws_head[1])), _lib.ptr(self.loss_part)))
-            self.loss_scale, self.n_loss_part = 1.0 / B, self.nblk
+            self.loss_scale, self.n_loss_part = 1.0 / B, 2 * self.nblk_head
         else:
             calls += trunk_calls(B, insts, 3)
             groups = [dict(a=it["h"][2], lda=H3, b=it["net"].W[3], ldb=H3, bias=it["net"].b[3],
@@ -378,7 +381,7 @@ class ActorUpdate(_UpdateBase):
             self.dl = [self._buf(B, self.pd) for _ in range(2)]
             self.loss_part = self._buf((B + 7) // 8)
         else:
-            self.loss_part = self._buf(self.nblk)
+            self.loss_part = self._buf(2 * self.nblk_head)
         actor = NetAddrs(self.La, 0, self.a_tf, self.a_flat)
         cnet = [NetAddrs(self.Lc, i, self.c_tf, self.c_flat) for i in range(2)]
         calls = self.calls
@@ -403,7 +406,7 @@ class ActorUpdate(_UpdateBase):
             calls.append(K.Call("pqlb_dpg_loss", _lib.ptr(self.q[0]), _lib.ptr(self.q[1]), B, _lib.ptr(h_c[0][2]),
                                 _lib.ptr(h_c[1][2]), C.c_void_p(cnet[0].Wf[3]), C.c_void_p(cnet[1].Wf[3]),
                                 _lib.ptr(dz3[0]), _lib.ptr(dz3[1]), _lib.ptr(self.loss_part)))
-            self.n_loss_part = self.nblk
+            self.n_loss_part = 2 * self.nblk_head
         else:
             calls += trunk_calls(B, insts, 3)
             groups = [dict(a=it["h"][2], lda=H3, b=it["net"].W[3], ldb=H3, bias=it["net"].b[3],

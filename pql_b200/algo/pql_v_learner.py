@@ -82,11 +82,10 @@ class PQLVLearner:
                                   self.critic.arena.flat, distl=bool(a.distl), num_atoms=a.num_atoms, v_min=a.v_min,
                                   v_max=a.v_max, gamma_n=a.gamma ** a.nstep, lr=a.critic_lr, tau=a.tau,
                                   max_grad_norm=a.max_grad_norm, noise_bound=a.noise.tgt_pol_noise_bound,
+                                  noise_std=a.noise.tgt_pol_std,
                                   obs_norm=bool(a.obs_norm) and self.normalize_tuple is not None, eps=eps,
                                   world_size=self.world_size, loss_ring=self.loss_tracker.window)
         self._sample = self._plan.sample_call(self.memory.ring, self.memory.capacity)
-        self._noise_mean = torch.zeros_like(self._plan.noise)
-        self._noise_std = torch.full_like(self._plan.noise, float(a.noise.tgt_pol_std))
 
     @property
     def critic_target(self):
@@ -111,9 +110,12 @@ class PQLVLearner:
             p = self._plan
             with torch.cuda.device(self.device):
                 # same two draws, in the same order, as the reference: randint (simple_replay.py:87)
-                # then torch.normal(zeros, full(std)) (noise.py:20-21)
+                # then torch.normal(zeros, full(std)) (noise.py:20-21), which ATen evaluates as
+                # out.normal_(0, 1).mul_(std).add_(mean): we draw the N(0,1) part with the same
+                # generator call and apply std inside the actor-head epilogue (this also avoids
+                # torch.normal's std.min() >= 0 check, a device->host sync per update).
                 torch.randint(self.memory.cur_capacity, size=(p.B,), device=self.device, out=p.idx)
-                torch.normal(self._noise_mean, self._noise_std, out=p.noise)
+                p.noise.normal_()
                 p.run(self._sample, self._allreduce if self.world_size > 1 else None, self.use_cuda_graph)
             self.update_count += 1
         return self.sleep_time

@@ -7,14 +7,15 @@
 
 namespace pqlb {
 
-constexpr int kRowsPerBlock = 128;
+constexpr int kRowsPerBlock = 64;
 constexpr int kLossThreads = 256;
 constexpr int kHeadN = 128;          // width of the last hidden layer (mlp.py:33-34)
 
-// Phase A: per-row scalars; Phase B: dz3 rows + per-column partial sums of dq*h3 (head weight
-// gradient) for one 128-row block.
-//   mode 0 (critic): dq_i = 2 (q_i - y) / B,  loss partial = sum (q1-y)^2 + (q2-y)^2
+// One block = 64 batch rows of ONE of the two nets (blockIdx.y).  Phase A: per-row scalars;
+// phase B: dz3 rows + per-column partial sums of dq*h3 (head weight gradient) for the block.
+//   mode 0 (critic): dq_i = 2 (q_i - y) / B,  loss partial = sum (q_i - y)^2
 //   mode 1 (actor):  dq_i = -(1/B) [q_i is the min] (1/2 each on ties), loss partial = sum min(q1,q2)
+// Partials: loss_part[2*blockIdx.x + net]; head weight/bias gradient ws_net[blockIdx.x*129 + {0..127, 128}].
 __global__ void __launch_bounds__(kLossThreads)
 head_loss_kernel(int mode, const float* __restrict__ q1, const float* __restrict__ q2,
                  const float* __restrict__ tq1, const float* __restrict__ tq2,
@@ -23,33 +24,34 @@ head_loss_kernel(int mode, const float* __restrict__ q1, const float* __restrict
                  const float* __restrict__ w4_1, const float* __restrict__ w4_2,
                  float* __restrict__ dz3_1, float* __restrict__ dz3_2, float* __restrict__ y_out,
                  float* __restrict__ ws1, float* __restrict__ ws2, float* __restrict__ loss_part) {
-  __shared__ float s_dq[2][kRowsPerBlock];
+  __shared__ float s_dq[kRowsPerBlock];
   __shared__ float s_red[8], s_redb[8];
-  __shared__ float s_col[2][8][kHeadN];
+  __shared__ float s_col[8][kHeadN];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int net = blockIdx.y;
   const long long r0 = (long long)blockIdx.x * kRowsPerBlock;
   const float invB = 1.f / (float)B;
 
   float lpart = 0.f;
   if (tid < kRowsPerBlock) {
     const long long r = r0 + tid;
-    float d1 = 0.f, d2 = 0.f;
+    float dq = 0.f;
     if (r < B) {
       const float a = q1[r], b = q2[r];
+      const float mine = net ? b : a, other = net ? a : b;
       if (mode == 0) {
         // pql_v_learner.py:104-105: y = reward + (1 - done) * gamma^n * min(tq1, tq2)
         const float y = __fadd_rn(reward[r], __fmul_rn(__fmul_rn(1.f - done[r], gamma_n), fminf(tq1[r], tq2[r])));
-        if (y_out) y_out[r] = y;
-        const float e1 = a - y, e2 = b - y;
-        lpart = e1 * e1 + e2 * e2;
-        d1 = 2.f * e1 * invB; d2 = 2.f * e2 * invB;
+        if (y_out && net == 0) y_out[r] = y;
+        const float e = mine - y;
+        lpart = e * e;
+        dq = 2.f * e * invB;
       } else {
-        lpart = fminf(a, b);
-        d1 = a < b ? -invB : (a == b ? -0.5f * invB : 0.f);
-        d2 = b < a ? -invB : (a == b ? -0.5f * invB : 0.f);
+        lpart = net == 0 ? fminf(a, b) : 0.f;
+        dq = mine < other ? -invB : (mine == other ? -0.5f * invB : 0.f);
       }
     }
-    s_dq[0][tid] = d1; s_dq[1][tid] = d2;
+    s_dq[tid] = dq;
   }
   // deterministic block sum of the loss partials
   float v = lpart;
@@ -57,49 +59,51 @@ head_loss_kernel(int mode, const float* __restrict__ q1, const float* __restrict
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   if (lane == 0) s_red[warp] = v;
   __syncthreads();
-  if (tid == 0) { float t = 0.f; for (int i = 0; i < 8; ++i) t += s_red[i]; loss_part[blockIdx.x] = t; }
+  if (tid == 0) { float t = 0.f; for (int i = 0; i < 8; ++i) t += s_red[i]; loss_part[2 * blockIdx.x + net] = t; }
 
-  // Phase B: warp w owns rows [16w, 16w+16); lane owns columns 4*lane .. 4*lane+3
+  // Phase B: warp w owns rows [8w, 8w+8); lane owns columns 4*lane .. 4*lane+3
   const int c = lane * 4;
-  for (int net = 0; net < 2; ++net) {
-    const float* h3 = net ? h3_2 : h3_1;
-    const float* w4 = net ? w4_2 : w4_1;
-    float* dz3 = net ? dz3_2 : dz3_1;
-    const float4 w = *reinterpret_cast<const float4*>(w4 + c);
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    float accb = 0.f;
-#pragma unroll 4
-    for (int i = 0; i < 16; ++i) {
-      const int lr = warp * 16 + i;
-      const long long r = r0 + lr;
-      if (r >= B) break;
-      const float dq = s_dq[net][lr];
-      const float4 h = *reinterpret_cast<const float4*>(h3 + r * kHeadN + c);
-      float4 o;
-      o.x = rn_tf32(dq * w.x * (h.x > 0.f ? 1.f : h.x + 1.f));
-      o.y = rn_tf32(dq * w.y * (h.y > 0.f ? 1.f : h.y + 1.f));
-      o.z = rn_tf32(dq * w.z * (h.z > 0.f ? 1.f : h.z + 1.f));
-      o.w = rn_tf32(dq * w.w * (h.w > 0.f ? 1.f : h.w + 1.f));
-      *reinterpret_cast<float4*>(dz3 + r * kHeadN + c) = o;
-      acc.x += dq * h.x; acc.y += dq * h.y; acc.z += dq * h.z; acc.w += dq * h.w;
-      accb += dq;
-    }
-    if (mode == 0) {
-      *reinterpret_cast<float4*>(&s_col[net][warp][c]) = acc;
-      if (lane == 0) s_redb[warp] = accb;
-      __syncthreads();
-      float* ws = net ? ws2 : ws1;
-      if (tid < kHeadN) {
-        float t = 0.f;
+  const float* h3 = net ? h3_2 : h3_1;
+  const float* w4 = net ? w4_2 : w4_1;
+  float* dz3 = net ? dz3_2 : dz3_1;
+  const float4 w = *reinterpret_cast<const float4*>(w4 + c);
+  float4 h[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) t += s_col[net][i][tid];
-        ws[(long long)blockIdx.x * (kHeadN + 1) + tid] = t;
-      } else if (tid == kHeadN) {
-        float t = 0.f;
-        for (int i = 0; i < 8; ++i) t += s_redb[i];
-        ws[(long long)blockIdx.x * (kHeadN + 1) + kHeadN] = t;
-      }
-      __syncthreads();
+  for (int i = 0; i < 8; ++i) {
+    const long long r = r0 + warp * 8 + i;
+    h[i] = r < B ? *reinterpret_cast<const float4*>(h3 + r * kHeadN + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  float accb = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int lr = warp * 8 + i;
+    const long long r = r0 + lr;
+    if (r >= B) break;
+    const float dq = s_dq[lr];
+    float4 o;
+    o.x = rn_tf32(dq * w.x * (h[i].x > 0.f ? 1.f : h[i].x + 1.f));
+    o.y = rn_tf32(dq * w.y * (h[i].y > 0.f ? 1.f : h[i].y + 1.f));
+    o.z = rn_tf32(dq * w.z * (h[i].z > 0.f ? 1.f : h[i].z + 1.f));
+    o.w = rn_tf32(dq * w.w * (h[i].w > 0.f ? 1.f : h[i].w + 1.f));
+    *reinterpret_cast<float4*>(dz3 + r * kHeadN + c) = o;
+    acc.x += dq * h[i].x; acc.y += dq * h[i].y; acc.z += dq * h[i].z; acc.w += dq * h[i].w;
+    accb += dq;
+  }
+  if (mode == 0) {
+    *reinterpret_cast<float4*>(&s_col[warp][c]) = acc;
+    if (lane == 0) s_redb[warp] = accb;
+    __syncthreads();
+    float* ws = net ? ws2 : ws1;
+    if (tid < kHeadN) {
+      float t = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) t += s_col[i][tid];
+      ws[(long long)blockIdx.x * (kHeadN + 1) + tid] = t;
+    } else if (tid == kHeadN) {
+      float t = 0.f;
+      for (int i = 0; i < 8; ++i) t += s_redb[i];
+      ws[(long long)blockIdx.x * (kHeadN + 1) + kHeadN] = t;
     }
   }
 }
@@ -249,7 +253,7 @@ extern "C" int pqlb_doubleq_td_loss(const float* q1, const float* q2, const floa
   PQLB_CHECK_ARG(h3_1 && h3_2 && w4_1 && w4_2 && dz3_1 && dz3_2 && ws_head1 && ws_head2 && loss_part);
   PQLB_CHECK_ALIGN(aligned16(h3_1) && aligned16(h3_2) && aligned16(w4_1) && aligned16(w4_2) &&
                    aligned16(dz3_1) && aligned16(dz3_2));
-  const unsigned blocks = (unsigned)((batch + kRowsPerBlock - 1) / kRowsPerBlock);
+  const dim3 blocks((unsigned)((batch + kRowsPerBlock - 1) / kRowsPerBlock), 2);
   head_loss_kernel<<<blocks, kLossThreads, 0, (cudaStream_t)stream>>>(
       0, q1, q2, tq1, tq2, reward, done, gamma_n, batch, h3_1, h3_2, w4_1, w4_2, dz3_1, dz3_2, y_out,
       ws_head1, ws_head2, loss_part);
@@ -262,7 +266,7 @@ extern "C" int pqlb_dpg_loss(const float* q1, const float* q2, int64_t batch, co
   PQLB_CHECK_ARG(q1 && q2 && batch > 0 && h3_1 && h3_2 && w4_1 && w4_2 && dz3_1 && dz3_2 && loss_part);
   PQLB_CHECK_ALIGN(aligned16(h3_1) && aligned16(h3_2) && aligned16(w4_1) && aligned16(w4_2) &&
                    aligned16(dz3_1) && aligned16(dz3_2));
-  const unsigned blocks = (unsigned)((batch + kRowsPerBlock - 1) / kRowsPerBlock);
+  const dim3 blocks((unsigned)((batch + kRowsPerBlock - 1) / kRowsPerBlock), 2);
   head_loss_kernel<<<blocks, kLossThreads, 0, (cudaStream_t)stream>>>(
       1, q1, q2, nullptr, nullptr, nullptr, nullptr, 0.f, batch, h3_1, h3_2, w4_1, w4_2, dz3_1, dz3_2,
       nullptr, nullptr, nullptr, loss_part);

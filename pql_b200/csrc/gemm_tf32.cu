@@ -52,7 +52,7 @@ struct alignas(64) GemmDev {
   int splits, kb1, kb_total, kb_per_split;
   int stages, stage_bytes, b_tile_bytes, tmem_cols;
   int col_lo, col_hi, ring_bytes, aux_bytes;
-  float noise_bound;
+  float noise_bound, noise_std;
   unsigned idesc;
 };
 
@@ -368,7 +368,7 @@ gemm_tf32_kernel(const __grid_constant__ GemmDev P) {
         else if (EPI == PQLB_EPI_BIAS_TANH) x = tanhf(x + s_bias[c0 + j]);      // rounded below (out2 keeps fp32)
         else if (EPI == PQLB_EPI_BIAS_TANH_NOISE) {
           const float t = tanhf(x + s_bias[c0 + j]);
-          const float z = fminf(fmaxf(a[EpiTraits<EPI>::kAux ? j : 0], -P.noise_bound), P.noise_bound);
+          const float z = fminf(fmaxf(a[EpiTraits<EPI>::kAux ? j : 0] * P.noise_std, -P.noise_bound), P.noise_bound);
           x = rn_tf32(fminf(fmaxf(t + z, -1.f), 1.f));
         }
         else if (EPI == PQLB_EPI_MUL_ELUGRAD) { const float h = a[EpiTraits<EPI>::kAux ? j : 0]; x = rn_tf32(x * (h > 0.f ? 1.f : h + 1.f)); }
@@ -559,7 +559,7 @@ extern "C" int pqlb_gemm_tf32(const pqlb_gemm_desc* d, pqlb_stream_t stream) {
   P.tmem_cols = tn < 32 ? 32 : tn;
   P.col_lo = d->col_lo; P.col_hi = d->col_hi > 0 ? d->col_hi : d->N;
   PQLB_CHECK_SHAPE(P.col_lo >= 0 && P.col_lo < P.col_hi && P.col_hi <= d->N);
-  P.noise_bound = d->noise_bound;
+  P.noise_bound = d->noise_bound; P.noise_std = d->noise_std;
   // instruction descriptor (cute::UMMA::InstrDescriptor): c=F32 [4,6), a/b=TF32 [7,10)/[10,13),
   // a_major [15], b_major [16], N>>3 [17,23), M>>4 [24,29)
   P.idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((unsigned)P.a_mn << 15) | ((unsigned)P.b_mn << 16) |

@@ -27,6 +27,9 @@ __device__ __forceinline__ float block_sum_256(float v, float* smem8) {
   return tot;
 }
 
+// One block per segment of <= 256 elements (one per thread): the n_part partial sums of an
+// element are loaded eight at a time (independent loads in flight) and added in index order, so
+// the result does not depend on the launch shape.
 __global__ void __launch_bounds__(kOptThreads)
 grad_reduce_kernel(const int64_t* __restrict__ seg, const float* __restrict__ ws,
                    float* __restrict__ grad, float* __restrict__ sumsq_part, bool reduce) {
@@ -39,7 +42,15 @@ grad_reduce_kernel(const int64_t* __restrict__ seg, const float* __restrict__ ws
     if (reduce && n_part > 0) {
       g = 0.f;
       const float* p = ws + ws_off + i;
-      for (int64_t k = 0; k < n_part; ++k) g += p[k * ws_stride];
+      int64_t k = 0;
+      for (; k + 8 <= n_part; k += 8) {
+        float t[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) t[u] = p[(k + u) * ws_stride];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) g += t[u];
+      }
+      for (; k < n_part; ++k) g += p[k * ws_stride];
       grad[arena_off + i] = g;
     } else {
       g = grad[arena_off + i];

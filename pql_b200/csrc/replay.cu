@@ -215,13 +215,16 @@ __device__ __forceinline__ float norm_clamp(float x, float m, float v, float eps
 }
 
 // Fused V-learner batch: x_cur = [norm(obs)|action|0], x_tgt = [norm(next_obs)| (actor head) |0];
-// TF32-rounded because both are tensor-core operands.
+// TF32-rounded because both are tensor-core operands.  VEC = 4: one item = one float4 of one
+// output row (requires O % 4 == 0 and A % 4 == 0, so a float4 never straddles two fields).
+template <int VEC>
 __global__ void __launch_bounds__(kThreads)
 sample_critic_batch_kernel(const float* __restrict__ ring, RecGeom g, const int64_t* __restrict__ idx,
                            int64_t B, const float* __restrict__ mean, const float* __restrict__ var,
                            float eps, float* __restrict__ x_cur, float* __restrict__ x_tgt, int x_ld,
                            float* __restrict__ o_rew, float* __restrict__ o_done) {
-  const int per_row = g.O + x_ld;          // next_obs columns, then one full x_cur row
+  const int per_row = (g.O + x_ld) / VEC;  // next_obs columns, then one full x_cur row
+  const int ov = g.O / VEC;
   const int64_t total = B * per_row;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -229,17 +232,35 @@ sample_critic_batch_kernel(const float* __restrict__ ring, RecGeom g, const int6
     const int64_t b = item / per_row;
     const int sub = (int)(item - b * per_row);
     const float* rec = ring + __ldg(idx + b) * g.rec_ld;
-    if (sub < g.O) {
-      float v = rec[g.off_next + sub];
-      if (mean) v = norm_clamp(v, mean[sub], var[sub], eps);
-      x_tgt[b * x_ld + sub] = rn_tf32(v);
+    float v[VEC];
+    if (sub < ov) {
+      const int k = sub * VEC;
+      if (VEC == 4) *reinterpret_cast<float4*>(v) = *reinterpret_cast<const float4*>(rec + g.off_next + k);
+      else v[0] = rec[g.off_next + k];
+#pragma unroll
+      for (int u = 0; u < VEC; ++u) { if (mean) v[u] = norm_clamp(v[u], mean[k + u], var[k + u], eps); v[u] = rn_tf32(v[u]); }
+      if (VEC == 4) *reinterpret_cast<float4*>(x_tgt + b * x_ld + k) = *reinterpret_cast<float4*>(v);
+      else x_tgt[b * x_ld + k] = v[0];
     } else {
-      const int k = sub - g.O;             // column of x_cur
-      float v = 0.f;
-      if (k < g.O) { v = rec[g.off_obs + k]; if (mean) v = norm_clamp(v, mean[k], var[k], eps); }
-      else if (k < g.O + g.A) v = rec[g.off_act + (k - g.O)];
-      else x_tgt[b * x_ld + k] = 0.f;      // zero padding of the target input row
-      x_cur[b * x_ld + k] = rn_tf32(v);
+      const int k = (sub - ov) * VEC;      // first column of x_cur
+      if (k < g.O) {
+        if (VEC == 4) *reinterpret_cast<float4*>(v) = *reinterpret_cast<const float4*>(rec + g.off_obs + k);
+        else v[0] = rec[g.off_obs + k];
+#pragma unroll
+        for (int u = 0; u < VEC; ++u) { if (mean) v[u] = norm_clamp(v[u], mean[k + u], var[k + u], eps); v[u] = rn_tf32(v[u]); }
+      } else if (k < g.O + g.A) {
+        if (VEC == 4) *reinterpret_cast<float4*>(v) = *reinterpret_cast<const float4*>(rec + g.off_act + (k - g.O));
+        else v[0] = rec[g.off_act + (k - g.O)];
+#pragma unroll
+        for (int u = 0; u < VEC; ++u) v[u] = rn_tf32(v[u]);
+      } else {
+#pragma unroll
+        for (int u = 0; u < VEC; ++u) v[u] = 0.f;
+        if (VEC == 4) *reinterpret_cast<float4*>(x_tgt + b * x_ld + k) = make_float4(0.f, 0.f, 0.f, 0.f);
+        else x_tgt[b * x_ld + k] = 0.f;     // zero padding of the target input row
+      }
+      if (VEC == 4) *reinterpret_cast<float4*>(x_cur + b * x_ld + k) = *reinterpret_cast<float4*>(v);
+      else x_cur[b * x_ld + k] = v[0];
     }
   }
   for (int64_t b = tid; b < B; b += stride) {
@@ -406,8 +427,14 @@ extern "C" int pqlb_sample_critic_batch(const float* ring, int64_t capacity, int
   const RecGeom g = rec_geom(obs_dim, act_dim);
   PQLB_CHECK_SHAPE(x_ld >= obs_dim + act_dim && x_ld % 4 == 0);
   const int per_row = obs_dim + x_ld;
-  sample_critic_batch_kernel<<<grid_for(batch * per_row, kThreads, 2), kThreads, 0, (cudaStream_t)stream>>>(
-      ring, g, idx, batch, mean, var, eps, x_cur, x_tgt, x_ld, reward, done);
+  const bool vec4 = obs_dim % 4 == 0 && act_dim % 4 == 0 && aligned16(ring) && aligned16(x_cur) && aligned16(x_tgt) &&
+                    (!mean || (aligned16(mean) && aligned16(var)));
+  if (vec4)
+    sample_critic_batch_kernel<4><<<grid_for(batch * (per_row / 4), kThreads, 2), kThreads, 0, (cudaStream_t)stream>>>(
+        ring, g, idx, batch, mean, var, eps, x_cur, x_tgt, x_ld, reward, done);
+  else
+    sample_critic_batch_kernel<1><<<grid_for(batch * per_row, kThreads, 2), kThreads, 0, (cudaStream_t)stream>>>(
+        ring, g, idx, batch, mean, var, eps, x_cur, x_tgt, x_ld, reward, done);
   PQLB_LAUNCH_RET();
 }
 

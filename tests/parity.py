@@ -64,26 +64,27 @@ def unflatten(layout, flat, net, layer):
 
 
 @contextlib.contextmanager
-def injected_draws(idx, noise=None):
+def injected_draws(idx, noise=None, noise_std=0.8):
     """Replace torch.randint / torch.normal by the given draws (written into the learner's
     ``out=`` buffers) so oracle and CUDA path consume identical random numbers."""
-    real_randint, real_normal = torch.randint, torch.normal
+    real_randint, real_normal = torch.randint, torch.Tensor.normal_
 
     def fake_randint(*a, out=None, **k):
         out.copy_(idx.to(out.device))
         return out
 
-    def fake_normal(*a, out=None, **k):
-        out.copy_(noise.to(out.device))
-        return out
+    def fake_normal_(self, *a, **k):
+        # the learner draws N(0,1) and applies std in the kernel; ``noise`` is the N(0, std^2) draw
+        self.copy_((noise / noise_std).to(self.device))
+        return self
 
     torch.randint = fake_randint
     if noise is not None:
-        torch.normal = fake_normal
+        torch.Tensor.normal_ = fake_normal_
     try:
         yield
     finally:
-        torch.randint, torch.normal = real_randint, real_normal
+        torch.randint, torch.Tensor.normal_ = real_randint, real_normal
 
 
 def _clone_opt(opt, params):

@@ -137,11 +137,12 @@ def test_actor_head_tanh_and_noise(K):
     g = torch.Generator(device=DEV).manual_seed(9)
     h, w = mk((M, Kd), g), mk((A, Kd), g, 0.3)
     bias = torch.randn(A, generator=g, device=DEV) * 0.1
-    noise = torch.randn(M, A, generator=g, device=DEV) * 0.8
+    z01 = torch.randn(M, A, generator=g, device=DEV)
+    noise = z01 * 0.8
     x = torch.zeros(M, x_ld, device=DEV)
-    K.Gemm(M, A, Kd, [dict(a=K.addr(h), lda=Kd, b=K.addr(w), ldb=Kd, bias=K.addr(bias), aux=K.addr(noise), ldaux=A,
+    K.Gemm(M, A, Kd, [dict(a=K.addr(h), lda=Kd, b=K.addr(w), ldb=Kd, bias=K.addr(bias), aux=K.addr(z01), ldaux=A,
                            out=K.addr(x, O), ldo=x_ld)],
-           epilogue=K.EPI_BIAS_TANH_NOISE, tile_n=16, noise_bound=0.2)()
+           epilogue=K.EPI_BIAS_TANH_NOISE, tile_n=16, noise_bound=0.2, noise_std=0.8)()
     a = torch.tanh((h.double() @ w.double().t()).float() + bias)
     ref = torch.clamp(a + torch.clamp(noise, -0.2, 0.2), -1, 1)
     check(x[:, O:O + A], rn_tf32(ref), 1e-3, "tanh_noise")

@@ -110,10 +110,10 @@ def test_doubleq_td_loss_and_head_backward():
     w4 = [torch.randn(128, generator=g) * 0.1 for _ in range(2)]
     gamma_n = float(np.float32(0.99 ** 3))
     d = lambda x: x.to(DEV).contiguous()
-    nblk = (B + 127) // 128
+    nblk = (B + 63) // 64
     dz = [torch.zeros(B, 128, device=DEV) for _ in range(2)]
     ws = [torch.zeros(nblk, 129, device=DEV) for _ in range(2)]
-    y = torch.zeros(B, device=DEV); lp = torch.zeros(nblk, device=DEV)
+    y = torch.zeros(B, device=DEV); lp = torch.zeros(2 * nblk, device=DEV)
     dev_in = [d(x) for x in (q1, q2, tq1, tq2, reward, done)]
     dh3 = [d(x) for x in h3]; dw4 = [d(x) for x in w4]
     _lib.call("pqlb_doubleq_td_loss", *(_lib.ptr(x) for x in dev_in), gamma_n, B, _lib.ptr(dh3[0]), _lib.ptr(dh3[1]),
@@ -141,9 +141,9 @@ def test_dpg_loss_and_head_backward():
     h3 = [rn_tf32(F.elu(torch.randn(B, 128, generator=g))) for _ in range(2)]
     w4 = [torch.randn(128, generator=g) * 0.1 for _ in range(2)]
     d = lambda x: x.to(DEV).contiguous()
-    nblk = (B + 127) // 128
+    nblk = (B + 63) // 64
     dz = [torch.zeros(B, 128, device=DEV) for _ in range(2)]
-    lp = torch.zeros(nblk, device=DEV)
+    lp = torch.zeros(2 * nblk, device=DEV)
     dh3 = [d(x) for x in h3]; dw4 = [d(x) for x in w4]
     dq1, dq2 = d(q1), d(q2)
     _lib.call("pqlb_dpg_loss", _lib.ptr(dq1), _lib.ptr(dq2), B, _lib.ptr(dh3[0]), _lib.ptr(dh3[1]), _lib.ptr(dw4[0]),
