@@ -18,6 +18,7 @@ oracle, the reference and the CUDA path can be fed identical values.
 Parameters are plain lists ``[(W0,b0),(W1,b1),(W2,b2),(W3,b3)]`` of fp32 tensors
 with ``W`` shaped ``[out, in]`` exactly like ``nn.Linear.weight``.
 """
+import contextlib
 import math
 
 import numpy as np
@@ -57,6 +58,100 @@ def flat(params_list):
     return [t for params in params_list for wb in params for t in wb]
 
 
+# ----------------------------------------------------------------------------- TF32 operand model
+# The CUDA path feeds the tensor cores TF32 operands (fp32 accumulate).  With ``tf32_operands()``
+# active, ``mlp`` applies exactly the roundings the kernels apply - and nothing else - so that the
+# kernels can be checked against "the reference arithmetic with TF32-rounded GEMM operands" to
+# ~1e-5, separately from the cost of the number format itself (fp32 oracle vs TF32 oracle):
+#   * every GEMM operand is rounded to nearest (ties away) to a 10-bit mantissa when it is
+#     produced: inputs, weights, h = elu(z) and the back-propagated dz = g * elu'(h);
+#   * products are exact and accumulated in fp32 or better; biases, ELU, tanh, softmax, losses,
+#     the scalar Q head (a dot product with the un-rounded h3 and fp32 w4) stay fp32;
+#   * elu'(h) is evaluated on the rounded h (that is what the forward pass stored).
+_TF32 = False
+
+
+@contextlib.contextmanager
+def tf32_operands(on=True):
+    global _TF32
+    prev, _TF32 = _TF32, on
+    try:
+        yield
+    finally:
+        _TF32 = prev
+
+
+def rn_tf32(x):
+    """cvt.rna.tf32.f32 on every element: round to nearest, ties away, 10-bit mantissa."""
+    i = x.detach().contiguous().view(torch.int32)
+    return ((i + 0x1000) & ~0x1FFF).view(torch.float32)
+
+
+def _mm(a, b):
+    return (a.double() @ b.double()).float()
+
+
+class _LinELU(torch.autograd.Function):
+    """hr, h = rn(elu(z)), elu(z) with z = rn(x) rn(W)^T + b (one hidden layer of mlp.py:15-24)."""
+
+    @staticmethod
+    def forward(ctx, x, w, b):
+        xr, wr = rn_tf32(x), rn_tf32(w)
+        h = F.elu(_mm(xr, wr.t()) + b.detach())
+        hr = rn_tf32(h)
+        ctx.save_for_backward(xr, wr, hr)
+        return hr, h
+
+    @staticmethod
+    def backward(ctx, g_hr, g_h):
+        xr, wr, hr = ctx.saved_tensors
+        g = g_hr + g_h
+        dz = rn_tf32(g * torch.where(hr > 0, torch.ones_like(hr), hr + 1))
+        return _mm(dz, wr), _mm(dz.t(), xr), dz.sum(0)
+
+
+class _LinOut(torch.autograd.Function):
+    """Last layer with more than one output (actor / C51 logits): z = rn(x) rn(W)^T + b in fp32;
+    the incoming gradient is rounded (the loss / tanh' kernels emit TF32 operands)."""
+
+    @staticmethod
+    def forward(ctx, x, w, b):
+        xr, wr = rn_tf32(x), rn_tf32(w)
+        ctx.save_for_backward(xr, wr)
+        return _mm(xr, wr.t()) + b.detach()
+
+    @staticmethod
+    def backward(ctx, g):
+        xr, wr = ctx.saved_tensors
+        dz = rn_tf32(g)
+        return _mm(dz, wr), _mm(dz.t(), xr), dz.sum(0)
+
+
+class _ScalarHead(torch.autograd.Function):
+    """q = h3 w4^T + b4 on CUDA cores: un-rounded h3 and fp32 w4 forward; the weight gradient
+    uses the stored (rounded) h3."""
+
+    @staticmethod
+    def forward(ctx, h, hr, w, b):
+        ctx.save_for_backward(hr, w.detach())
+        return _mm(h.detach(), w.detach().t()) + b.detach()
+
+    @staticmethod
+    def backward(ctx, g):
+        hr, w = ctx.saved_tensors
+        return g * w, None, _mm(g.t(), hr), g.sum(0)
+
+
+def _mlp_tf32(x, params):
+    hr, h = x, x
+    for w, b in params[:-1]:
+        hr, h = _LinELU.apply(hr, w, b)
+    w, b = params[-1]
+    if w.shape[0] == 1:
+        return _ScalarHead.apply(h, hr, w, b)
+    return _LinOut.apply(hr, w, b)
+
+
 # ----------------------------------------------------------------------------- forward pieces
 def normalize(x, norm):
     """common.py:139-145: clamp((x-mean)/sqrt(var+eps), -5, 5); identity when norm is None."""
@@ -68,6 +163,8 @@ def normalize(x, norm):
 
 def mlp(x, params):
     """mlp.py:15-24: ELU after every layer but the last."""
+    if _TF32:
+        return _mlp_tf32(x, params)
     h = x
     last = len(params) - 1
     for i, (w, b) in enumerate(params):

@@ -1,24 +1,32 @@
 """Learner parity harness (test infrastructure): runs the CUDA V-/P-learner and the torch-CPU
 oracle (oracle/learner.py, itself pinned to reference-generated fixtures) on identical weights,
-batches, indices and noise, and returns the relative errors.
+batches, indices and noise, and returns the relative errors.  Two oracles are used per step:
 
-Tolerances (BASELINE.json north_star: 1e-3 relative, fp32 reference vs TF32 tensor cores), all
-norm-wise per tensor, ||x - ref||_2 / ||ref||_2:
-    loss, Q-values, TD target / projected distribution   <= 1e-3
-    every parameter gradient tensor                       <= 1e-3
-        * the 1-element bias of the scalar Q head is sum_b dq_b, a sum of signed residuals that
-          cancels almost completely; it is judged as |delta| <= 1e-3 * sum_b |dq_b|.
-        * ``p_grad_tol``: the P-learner's weight gradients on UNTRAINED random networks are the
-          mean of nearly uncorrelated per-sample gradients, so their norm shrinks like
-          1/sqrt(B) while the effect of rounding the forward operands to TF32 (a fixed
-          perturbation of the function) does not: a CPU emulation of single-pass TF32
-          (numerics) gives 5e-4 at B=512 and 1.7e-3..2.2e-3 at B=8192, exactly what
-          the kernels measure.  The full-batch test therefore states 3e-3 for those tensors.
-    the fused clip+AdamW+Polyak itself                    <= 1e-6 of the tensor, against the oracle's
-        clip_grad_norm + AdamW + polyak applied to the SAME (CUDA-computed) gradients: Adam's
-        normalised step m/sqrt(v) turns a 1e-3 gradient difference into sign flips of near-zero
-        entries, so the optimiser kernel is judged on identical inputs.  The parameters after
-        the step versus the oracle's own step are reported (v_param, p_param) but not asserted.
+(1) ``tf32`` - the reference arithmetic with GEMM operands rounded to TF32 exactly where the
+    kernels round them (oracle.learner.tf32_operands): products exact, fp32 accumulation,
+    everything else fp32.  The CUDA path must match it to 3e-4 on EVERY quantity (loss,
+    Q-values / distributions, TD target / projected distribution, every gradient tensor).  What
+    remains is not the operand format but its chaos: a ~3e-6 difference in a GEMM output
+    (accumulation order inside the tensor core, ex2.approx in ELU) flips the TF32 rounding of
+    ~0.5% of the activations by one 2^-11 ulp, ~4e-5 per rounding stage, ~2e-4 after the ten
+    stages of an update (measured 0.5e-4 .. 2.4e-4; a tensor whose sum cancels - see (2) -
+    amplifies this like any other perturbation, so the bound is max(3e-4, half the TF32-format
+    error of that tensor)).  This is the test that the kernels compute what they claim.
+(2) ``fp32`` - the reference arithmetic as the reference runs it (fp32 SGEMM).  BASELINE.json
+    north_star: 1e-3 relative.  All norm-wise per tensor, ||x - ref||_2 / ||ref||_2:
+        loss, Q-values, TD target / projected distribution, actions   <= 1e-3, asserted
+        gradient tensors                                                <= 1e-3, asserted, unless
+            the TF32 number format itself (oracle tf32 vs oracle fp32, no CUDA involved) already
+            exceeds 7e-4 on that tensor - then <= 1.5 x that.  This happens for sums that cancel:
+            bias gradients sum_b dz_b of a critic whose mean TD error is near zero, and the
+            P-learner's gradients on untrained random networks at large batch (the mean of
+            nearly uncorrelated per-sample gradients shrinks like 1/sqrt(B); the effect of
+            rounding the forward operands does not).  Measured values are returned and printed.
+(3) the fused clip+AdamW+Polyak is judged on identical inputs: against the oracle's
+    clip_grad_norm + AdamW + polyak applied to the SAME (CUDA-computed) gradients, <= 1e-6 of the
+    tensor.  (Adam's normalised step m/sqrt(v) turns a 1e-3 gradient difference into sign flips
+    of near-zero entries, so parameters after the step versus the oracle's own step are
+    reported - v_param, p_param - but not asserted.)
 """
 import contextlib
 
@@ -115,10 +123,45 @@ def make_cfg(B, distl, device_index=0, memory=None, obs_norm=True):
                            p_learner_gpu=device_index, obs_norm=obs_norm)
 
 
+def _record(case, res):
+    """Append the measured errors to gpurun_out/parity_results.jsonl (kept under profiles/)."""
+    import json
+    import os
+    try:
+        os.makedirs("gpurun_out", exist_ok=True)
+        with open("gpurun_out/parity_results.jsonl", "a") as f:
+            f.write(json.dumps(dict(case=case, errors=res)) + "\n")
+    except OSError:
+        pass
+
+
+def _grad_report(got_list, fp32_grads, tf32_grads, tag, out, per_tensor, check, scalar_scale=None):
+    """Per-tensor gradient errors of the CUDA path against both oracles."""
+    for gi, got in enumerate(got_list):
+        rf, rt = fp32_grads[gi], tf32_grads[gi]
+        if rf.numel() == 1 and scalar_scale is not None:
+            # 1-element bias of the scalar Q head = sum_b dq_b: judged against sum_b |dq_b|
+            sc = scalar_scale[gi]
+            e_t = (got.reshape(-1)[0] - rt.reshape(-1)[0]).abs().item() / sc
+            e_f = (got.reshape(-1)[0] - rf.reshape(-1)[0]).abs().item() / sc
+            fmt = (rt.reshape(-1)[0] - rf.reshape(-1)[0]).abs().item() / sc
+        else:
+            e_t, e_f, fmt = rel(got, rt), rel(got, rf), rel(rt, rf)
+        per_tensor.setdefault(tag, []).append((float(f"{e_t:.1e}"), float(f"{e_f:.1e}"), float(f"{fmt:.1e}")))
+        out[f"{tag}_grad_vs_tf32"] = max(out.get(f"{tag}_grad_vs_tf32", 0.0), e_t)
+        out[f"{tag}_grad_vs_fp32"] = max(out.get(f"{tag}_grad_vs_fp32", 0.0), e_f)
+        if check:
+            assert e_t <= max(3e-4, 0.5 * fmt), f"{tag} grad tensor {gi}: {e_t:.3e} vs the TF32-operand oracle"
+            assert e_f <= max(1e-3, 1.5 * fmt if fmt > 7e-4 else 0.0), \
+                f"{tag} grad tensor {gi}: {e_f:.3e} vs fp32 oracle (TF32 format alone: {fmt:.3e})"
+
+
 def run_learner_parity(seed=1234, B=512, obs_dim=88, act_dim=16, distl=False, steps=2, device="cuda:0",
-                       check=True, obs_norm=True, p_grad_tol=1e-3):
-    """Returns a dict of worst-case relative errors over ``steps`` synchronised updates of both
-    learners; raises AssertionError when ``check`` and a tolerance is exceeded."""
+                       check=True, obs_norm=True):
+    """Runs ``steps`` synchronised updates of both learners (before every step the CUDA learner is
+    loaded with the fp32 oracle's state) and returns the worst relative errors; raises
+    AssertionError when ``check`` and a tolerance from the module docstring is exceeded."""
+    import copy
     from pql_b200.algo import PQLPLearner, PQLVLearner
     from pql_b200.models import TanhMLPPolicy
     dev = torch.device(device)
@@ -127,7 +170,10 @@ def run_learner_parity(seed=1234, B=512, obs_dim=88, act_dim=16, distl=False, st
     cfg = make_cfg(B, distl, dev.index or 0, obs_norm=obs_norm)
     idx = torch.arange(B - 1, -1, -1)
     batch = tuple(x[idx] for x in case["batch"])
-    out = {}
+    out, per_tensor = {}, {}
+
+    def upd(key, val):
+        out[key] = max(out.get(key, 0.0), val)
 
     # ------------------------------------------------------------------ V-learner
     v = PQLVLearner(obs_dim, act_dim, cfg)
@@ -137,10 +183,7 @@ def run_learner_parity(seed=1234, B=512, obs_dim=88, act_dim=16, distl=False, st
     norm_dev = None if norm is None else (norm[0].to(dev), norm[1].to(dev), norm[2])
     v.update(actor, tuple(x.to(dev) for x in case["batch"]), norm_dev, 0)
     Lc = v._plan.Lc
-    worst = dict(v_loss=0.0, v_q=0.0, v_target=0.0, v_grad=0.0, v_param=0.0, v_tparam=0.0, v_k4=0.0)
-    per_tensor = {}
     for s in range(steps):
-        # synchronise the CUDA learner to the oracle's state
         plan = v._plan
         plan.c_flat.copy_(flat_of(v.critic, [ov.q1, ov.q2]).to(dev))
         plan.t_flat.copy_(flat_of(v.critic, [ov.tq1, ov.tq2]).to(dev))
@@ -153,17 +196,22 @@ def run_learner_parity(seed=1234, B=512, obs_dim=88, act_dim=16, distl=False, st
         before = [t.detach().clone() for t in L.flat([ov.q1, ov.q2])]
         tbefore = [t.detach().clone() for t in L.flat([ov.tq1, ov.tq2])]
         shadow = _clone_opt(ov.opt, before)
+        ot = copy.deepcopy(ov)                                   # TF32-operand oracle on the same state
+        with L.tf32_operands():
+            tf_loss = ot.learn(batch, case["noises"][s], case["actor"], norm)
         ref_loss = ov.learn(batch, case["noises"][s], case["actor"], norm)
         with injected_draws(idx, case["noises"][s]):
             v.learn()
         torch.cuda.synchronize(dev)
-        worst["v_loss"] = max(worst["v_loss"], abs(plan.loss.item() - ref_loss) / abs(ref_loss))
+        got_loss = plan.loss.item()
         if distl:
-            worst["v_q"] = max(worst["v_q"], rel(plan.p[0][:, :plan.N], ov.last["q1"]), rel(plan.p[1][:, :plan.N], ov.last["q2"]))
-            worst["v_target"] = max(worst["v_target"], rel(plan.target, ov.last["target"]))
+            got_q = (plan.p[0][:, :plan.N], plan.p[1][:, :plan.N]); got_y = plan.target
         else:
-            worst["v_q"] = max(worst["v_q"], rel(plan.q[0], ov.last["q1"]), rel(plan.q[1], ov.last["q2"]))
-            worst["v_target"] = max(worst["v_target"], rel(plan.y, ov.last["target"]))
+            got_q = (plan.q[0], plan.q[1]); got_y = plan.y
+        for tag, o, l in (("tf32", ot, tf_loss), ("fp32", ov, ref_loss)):
+            upd(f"v_loss_vs_{tag}", abs(got_loss - l) / abs(l))
+            upd(f"v_q_vs_{tag}", max(rel(got_q[0], o.last["q1"]), rel(got_q[1], o.last["q2"])))
+            upd(f"v_target_vs_{tag}", rel(got_y, o.last["target"]))
         triples = []
         for net in range(2):
             for layer in range(4):
@@ -171,24 +219,15 @@ def run_learner_parity(seed=1234, B=512, obs_dim=88, act_dim=16, distl=False, st
                 pw, pb = unflatten(Lc, plan.c_flat, net, layer)
                 tw, tb = unflatten(Lc, plan.t_flat, net, layer)
                 triples += [(gw, pw, tw), (gb, pb, tb)]
-        # the optimiser kernel on identical inputs: oracle clip + AdamW + polyak on the CUDA gradients
+        scale = None
+        if not distl:
+            scale = {gi: (2 * ((ov.last["q1"] if gi < 8 else ov.last["q2"]) - ov.last["target"]).abs() / B).sum().item()
+                     for gi in (7, 15)}
+        _grad_report([g for g, _, _ in triples], ov.last["grads"], ot.last["grads"], "v", out, per_tensor, check, scale)
         exp_p, exp_t = _expected_step(shadow, [g.clone() for g, _, _ in triples], tbefore, ov.max_grad_norm, ov.tau)
-        for gi, (got, gotp, gott) in enumerate(triples):
-            ref_g = ov.last["grads"][gi]
-            e = rel(got, ref_g)
-            per_tensor.setdefault("v", []).append(float(f"{e:.2e}"))
-            if ref_g.numel() > 1:
-                worst["v_grad"] = max(worst["v_grad"], e)
-            else:       # scalar head bias: sum of signed residuals, judged against sum |dq_b|
-                q_ref = ov.last["q1"] if gi < 8 else ov.last["q2"]
-                scale = (2 * (q_ref - ov.last["target"]).abs() / B).sum().item()
-                worst["v_grad"] = max(worst["v_grad"], (got.reshape(-1)[0] - ref_g.reshape(-1)[0]).abs().item() / scale)
-            ref_p = L.flat([ov.q1, ov.q2])[gi].detach()
-            ref_t = L.flat([ov.tq1, ov.tq2])[gi].detach()
-            worst["v_param"] = max(worst["v_param"], rel(gotp, ref_p))
-            worst["v_tparam"] = max(worst["v_tparam"], rel(gott, ref_t))
-            worst["v_k4"] = max(worst["v_k4"], rel(gotp, exp_p[gi]), rel(gott, exp_t[gi]))
-    out.update(worst)
+        for gi, (_, gotp, gott) in enumerate(triples):
+            upd("v_param", rel(gotp, L.flat([ov.q1, ov.q2])[gi].detach()))
+            upd("v_k4", max(rel(gotp, exp_p[gi]), rel(gott, exp_t[gi])))
 
     # ------------------------------------------------------------------ P-learner
     p = PQLPLearner(obs_dim, act_dim, cfg)
@@ -198,7 +237,6 @@ def run_learner_parity(seed=1234, B=512, obs_dim=88, act_dim=16, distl=False, st
     load_params(critic.net_q1, case["q1"]); load_params(critic.net_q2, case["q2"])
     p.update(critic, case["batch"][0].to(dev), norm_dev, 0)
     La = p._plan.La
-    worst = dict(p_loss=0.0, p_action=0.0, p_grad=0.0, p_param=0.0, p_k4=0.0)
     for s in range(steps):
         plan = p._plan
         plan.a_flat.copy_(flat_of(p.actor, [op.actor]).to(dev))
@@ -208,31 +246,35 @@ def run_learner_parity(seed=1234, B=512, obs_dim=88, act_dim=16, distl=False, st
         plan.round_weights()
         before = [t.detach().clone() for t in L.flat([op.actor])]
         shadow = _clone_opt(op.opt, before)
+        ot = copy.deepcopy(op)
+        with L.tf32_operands():
+            tf_loss = ot.learn(batch[0], case["q1"], case["q2"], norm)
         ref_loss = op.learn(batch[0], case["q1"], case["q2"], norm)
         with injected_draws(idx):
             p.learn()
         torch.cuda.synchronize(dev)
-        worst["p_loss"] = max(worst["p_loss"], abs(plan.loss.item() - ref_loss) / abs(ref_loss))
-        worst["p_action"] = max(worst["p_action"], rel(plan.act[:, :act_dim], op.last["action"]))
+        got_loss = plan.loss.item()
+        for tag, o, l in (("tf32", ot, tf_loss), ("fp32", op, ref_loss)):
+            # the loss is -mean(Q): judged against mean |Q| (a mean of signed values may cancel)
+            upd(f"p_loss_vs_{tag}", abs(got_loss - l) / o.last["q"].abs().mean().item())
+            upd(f"p_action_vs_{tag}", rel(plan.act[:, :act_dim], o.last["action"]))
         pairs = []
         for layer in range(4):
             gw, gb = unflatten(La, plan.opt.grad, 0, layer)
             pw, pb = unflatten(La, plan.a_flat, 0, layer)
             pairs += [(gw, pw), (gb, pb)]
+        _grad_report([g for g, _ in pairs], op.last["grads"], ot.last["grads"], "p", out, per_tensor, check)
         exp_p, _ = _expected_step(shadow, [g.clone() for g, _ in pairs], None, op.max_grad_norm, None)
-        for gi, (got, gotp) in enumerate(pairs):
-            e = rel(got, op.last["grads"][gi])
-            per_tensor.setdefault("p", []).append(float(f"{e:.2e}"))
-            worst["p_grad"] = max(worst["p_grad"], e)
-            worst["p_param"] = max(worst["p_param"], rel(gotp, L.flat([op.actor])[gi].detach()))
-            worst["p_k4"] = max(worst["p_k4"], rel(gotp, exp_p[gi]))
-    out.update(worst)
+        for gi, (_, gotp) in enumerate(pairs):
+            upd("p_param", rel(gotp, L.flat([op.actor])[gi].detach()))
+            upd("p_k4", rel(gotp, exp_p[gi]))
     if check:
         for k, val in out.items():
-            if k.endswith("_param") or k.endswith("_tparam"):
+            if k.endswith("_param") or "_grad_" in k:
                 continue
-            tol = 1e-6 if k.endswith("_k4") else (p_grad_tol if k == "p_grad" else 1e-3)
-            assert val <= tol, f"{k}: {val:.3e} > {tol:g}  ({out}) per-tensor grad errors {per_tensor}"
+            tol = 1e-6 if k.endswith("_k4") else (3e-4 if k.endswith("_vs_tf32") else 1e-3)
+            assert val <= tol, f"{k}: {val:.3e} > {tol:g}  ({out})"
     res = {k: float(f"{x:.3e}") for k, x in out.items()}
-    res["per_tensor_grad"] = per_tensor
+    _record(dict(seed=seed, B=B, obs_dim=obs_dim, act_dim=act_dim, distl=distl, steps=steps, obs_norm=obs_norm), res)
+    res["per_tensor_grad (vs tf32 oracle, vs fp32 oracle, tf32 oracle vs fp32 oracle)"] = per_tensor
     return res
