@@ -10,6 +10,7 @@ import torch
 from .. import _lib
 from ..models import load_class
 from ..utils.common import DeviceTracker
+from . import _dp
 from ._engine import ActorUpdate
 from .pql_v_learner import module_flat
 
@@ -72,7 +73,7 @@ class PQLPLearner:
         return self.actor, self.update_count, self.loss_tracker.mean()
 
     def _allreduce(self, grad):
-        torch.distributed.all_reduce(grad, group=self.process_group)
+        _dp.allreduce_sum_(grad, self.process_group)
 
     @torch.no_grad()
     def learn(self):

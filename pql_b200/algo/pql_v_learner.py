@@ -15,6 +15,7 @@ from .. import _lib
 from ..models import load_class
 from ..replay.simple_replay import ReplayBuffer
 from ..utils.common import DeviceTracker
+from . import _dp
 from ._engine import CriticUpdate
 
 
@@ -100,7 +101,7 @@ class PQLVLearner:
         return self.critic, self.update_count, self.loss_tracker.mean()
 
     def _allreduce(self, grad):
-        torch.distributed.all_reduce(grad, group=self.process_group)
+        _dp.allreduce_sum_(grad, self.process_group)
 
     @torch.no_grad()
     def learn(self):
