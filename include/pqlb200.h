@@ -162,6 +162,25 @@ typedef struct {
  * 177-179, 197-199, 261-263 and their autograd backward (cuBLAS sgemm + ATen elementwise). */
 int pqlb_gemm_tf32(const pqlb_gemm_desc* desc, pqlb_stream_t stream);
 
+/* ---- K3f: layer-fused MLP trunk forward -------------------------------------------------------
+ * x[M,k_in] -> ELU(Linear 512) -> ELU(Linear 256) -> ELU(Linear 128) [-> scalar head q[M]] for up
+ * to PQLB_MAX_GROUPS network instances in one launch; activations stay in tensor memory between
+ * layers (tcgen05.mma with the A operand in TMEM) and h1/h2/h3 are written only where non-NULL
+ * (the networks whose backward pass needs them).  Replaces the Linear+ELU launches of
+ * pql/models/mlp.py:15-24 as used by pql/algo/pql_v_learner.py:81-107 and pql_p_learner.py:55-56.
+ * All operands TF32-rounded fp32; w1 [512, ldw1], w2 [512-in: 256 x 512], w3 [128 x 256] row-major
+ * (nn.Linear layout); k_in <= 128 (wider inputs: PQLB_E_UNSUPPORTED, use pqlb_gemm_tf32). */
+typedef struct {
+  const float* x; int64_t ldx;
+  const float* w1; int64_t ldw1;
+  const float* w2; const float* w3;
+  const float* b1; const float* b2; const float* b3;
+  const float* head_w; const float* head_b; float* q;     /* q == NULL: no scalar head */
+  float* h1; float* h2; float* h3;                         /* [M,512] [M,256] [M,128] or NULL */
+} pqlb_mlp_group;
+typedef struct { int M, k_in, n_groups; pqlb_mlp_group g[PQLB_MAX_GROUPS]; } pqlb_mlp_desc;
+int pqlb_mlp_forward(const pqlb_mlp_desc* desc, pqlb_stream_t stream);
+
 /* dst = rn_tf32(src) elementwise (tensor-core operand copies of weights). */
 int pqlb_round_tf32(const float* src, float* dst, int64_t n, pqlb_stream_t stream);
 

@@ -95,6 +95,26 @@ class Gemm(Call):
         super().__init__("pqlb_gemm_tf32", C.byref(d), keep=keep)
 
 
+class MlpForward(Call):
+    """Layer-fused trunk forward (pqlb_mlp_forward) for up to four network instances.
+    ``groups``: dicts with x, ldx, w1, ldw1, w2, w3, b1, b2, b3, [head_w, head_b, q], [h1, h2, h3]."""
+
+    FIELDS = ("x", "w1", "w2", "w3", "b1", "b2", "b3", "head_w", "head_b", "q", "h1", "h2", "h3")
+
+    def __init__(self, M, k_in, groups):
+        d = _lib.MlpDesc()
+        d.M, d.k_in, d.n_groups = int(M), int(k_in), len(groups)
+        for i, g in enumerate(groups):
+            unknown = set(g) - set(self.FIELDS) - {"ldx", "ldw1"}
+            if unknown:
+                raise KeyError(f"unknown mlp group fields {sorted(unknown)}")
+            for k in self.FIELDS:
+                setattr(d.g[i], k, g.get(k, 0) or None)
+            d.g[i].ldx, d.g[i].ldw1 = int(g["ldx"]), int(g["ldw1"])
+        self.desc = d
+        super().__init__("pqlb_mlp_forward", C.byref(d))
+
+
 def pick_tile_n(N):
     for t in (16, 32, 64, 128, 256):
         if N <= t:
@@ -102,7 +122,7 @@ def pick_tile_n(N):
     return 256
 
 
-def wgrad_tiling(M, N, K, n_groups, target_ctas=148):
+def wgrad_tiling(M, N, K, n_groups, target_ctas=int(_os.environ.get("PQLB_WGRAD_CTAS", 296))):
     """Tile width and split-K factor of a weight-gradient GEMM (contraction over the batch):
     the smallest split count that still fills the SMs, with kb_total % splits == 0."""
     kb = (K + 31) // 32

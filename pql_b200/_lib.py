@@ -8,7 +8,7 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libpqlb200.so")
+LIB_PATH = os.environ.get("PQLB_LIB") or os.path.join(_HERE, "libpqlb200.so")   # PQLB_LIB: kernel-variant experiments
 
 MAX_GROUPS = 4
 (EPI_STORE, EPI_BIAS, EPI_BIAS_ELU, EPI_BIAS_ELU_HEAD, EPI_BIAS_TANH, EPI_BIAS_TANH_NOISE,
@@ -46,6 +46,16 @@ class GemmDesc(C.Structure):
                 ("noise_bound", _flt), ("noise_std", _flt), ("g", GemmGroup * MAX_GROUPS)]
 
 
+class MlpGroup(C.Structure):
+    _fields_ = [("x", _f), ("ldx", _i64), ("w1", _f), ("ldw1", _i64), ("w2", _f), ("w3", _f),
+                ("b1", _f), ("b2", _f), ("b3", _f), ("head_w", _f), ("head_b", _f), ("q", _f),
+                ("h1", _f), ("h2", _f), ("h3", _f)]
+
+
+class MlpDesc(C.Structure):
+    _fields_ = [("M", _int), ("k_in", _int), ("n_groups", _int), ("g", MlpGroup * MAX_GROUPS)]
+
+
 _PROTOS = {
     "pqlb_version": (_int, []),
     "pqlb_error_string": (C.c_char_p, [_int]),
@@ -63,6 +73,7 @@ _PROTOS = {
                                         _f, _f, _st]),
     "pqlb_sample_obs_batch": (_int, [_f, _i64, _int, _f, _i64, _f, _f, _flt, _f, _int, _int, _st]),
     "pqlb_gemm_tf32": (_int, [C.POINTER(GemmDesc), _st]),
+    "pqlb_mlp_forward": (_int, [C.POINTER(MlpDesc), _st]),
     "pqlb_round_tf32": (_int, [_f, _f, _i64, _st]),
     "pqlb_doubleq_td_loss": (_int, [_f, _f, _f, _f, _f, _f, _flt, _i64, _f, _f, _f, _f, _f, _f, _f,
                                     _f, _f, _f, _st]),

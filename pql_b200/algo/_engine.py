@@ -15,7 +15,7 @@ import torch
 
 from .. import _kernels as K
 from .. import _lib
-from ..models.mlp import HIDDEN, NetAddrs, NetLayout, _ru, fwd_tile, trunk_calls
+from ..models.mlp import HIDDEN, NetAddrs, NetLayout, _ru, forward_calls, fwd_tile
 
 H1, H2, H3 = HIDDEN
 SEG = 256
@@ -206,28 +206,22 @@ class CriticUpdate(_UpdateBase):
         calls = self.calls
 
         # -- target policy: a' = clamp(tanh(actor(next_obs)) + clamp(noise), +-1)   :62-71, noise.py:19-27
-        a_inst = dict(net=actor, x=K.addr(self.x_tgt), x_ld=x_ld, k_in=O, h=[K.addr(t) for t in ha])
-        calls += trunk_calls(B, [a_inst], 3)
+        a_inst = dict(net=actor, x=K.addr(self.x_tgt), x_ld=x_ld, k_in=O, h=[K.addr(t) for t in ha],
+                      store=(False, False, True))
+        calls += forward_calls(B, [a_inst], False)
         calls.append(K.Gemm(B, A, H3, [dict(a=K.addr(ha[2]), lda=H3, b=actor.W[3], ldb=H3, bias=actor.b[3],
                                              aux=K.addr(self.noise), ldaux=A, out=K.addr(self.x_tgt, O), ldo=x_ld)],
                             epilogue=K.EPI_BIAS_TANH_NOISE, tile_n=K.pick_tile_n(A), noise_bound=self.noise_bound,
                             noise_std=self.noise_std))
         # -- both target nets on (next_obs, a') and both current nets on (obs, action), one launch per layer
-        insts = [dict(net=tnet[i], x=K.addr(self.x_tgt), x_ld=x_ld, k_in=O + A, h=[K.addr(t) for t in h_t[i]])
-                 for i in range(2)]
-        insts += [dict(net=cnet[i], x=K.addr(self.x_cur), x_ld=x_ld, k_in=O + A, h=[K.addr(t) for t in h_c[i]])
-                  for i in range(2)]
+        insts = [dict(net=tnet[i], x=K.addr(self.x_tgt), x_ld=x_ld, k_in=O + A, h=[K.addr(t) for t in h_t[i]],
+                      store=(False, False, distl), q=K.addr(self.tq[i])) for i in range(2)]
+        insts += [dict(net=cnet[i], x=K.addr(self.x_cur), x_ld=x_ld, k_in=O + A, h=[K.addr(t) for t in h_c[i]],
+                       store=(True, True, True), q=K.addr(self.q[i])) for i in range(2)]
         wg = [(H3, H2, H2), (H2, H1, H1), (H1, O + A, x_ld)] + ([(N, H3, H3)] if distl else [])
         self._ws_init(wg, 2, [d for d in HIDDEN] * 2 + ([N, N] if distl else []), extra=2 * _ru(self.nblk_head * (H3 + 1), 32))
+        calls += forward_calls(B, insts, not distl)
         if not distl:
-            calls += trunk_calls(B, insts, 2)
-            groups = []
-            for j, it in enumerate(insts):
-                n = it["net"]
-                groups.append(dict(a=it["h"][1], lda=H2, b=n.W[2], ldb=H2, bias=n.b[2], head_w=n.Wf[3], head_b=n.b[3],
-                                   q=K.addr(self.tq[j] if j < 2 else self.q[j - 2]),
-                                   out=it["h"][2] if j >= 2 else 0, ldo=H3))
-            calls.append(K.Gemm(B, H3, H2, groups, epilogue=K.EPI_BIAS_ELU_HEAD, tile_n=128))
             ws_head = [self._ws_alloc(self.nblk_head * (H3 + 1)) for _ in range(2)]
             for i in range(2):
                 self.opt.add_source(self.Lc.w_off[i][3], H3, ws_head[i], H3 + 1, self.nblk_head)
@@ -240,7 +234,6 @@ class CriticUpdate(_UpdateBase):
                                 C.c_void_p(K.addr(self.ws, ws_head[1])), _lib.ptr(self.loss_part)))
             self.loss_scale, self.n_loss_part = 1.0 / B, 2 * self.nblk_head
         else:
-            calls += trunk_calls(B, insts, 3)
             groups = [dict(a=it["h"][2], lda=H3, b=it["net"].W[3], ldb=H3, bias=it["net"].b[3],
                            out=K.addr(self.tp[j] if j < 2 else self.p[j - 2]), ldo=self.pd)
                       for j, it in enumerate(insts)]
@@ -389,26 +382,21 @@ class ActorUpdate(_UpdateBase):
         self._ws_init([(A, H3, H3), (H3, H2, H2), (H2, H1, H1), (H1, O, self.La.ldw[0])], 1, [*HIDDEN, A])
         # -- action = tanh(actor(obs)) written straight into the critic input rows      :55
         a_inst = dict(net=actor, x=K.addr(self.x), x_ld=x_ld, k_in=O, h=[K.addr(t) for t in ha])
-        calls += trunk_calls(B, [a_inst], 3)
+        calls += forward_calls(B, [a_inst], False)
         calls.append(K.Gemm(B, A, H3, [dict(a=K.addr(ha[2]), lda=H3, b=actor.W[3], ldb=H3, bias=actor.b[3],
                                              out=K.addr(self.x, O), ldo=x_ld, out2=K.addr(self.act), ldo2=a_ld)],
                             epilogue=K.EPI_BIAS_TANH, tile_n=K.pick_tile_n(A)))
         # -- frozen critic forward                                                     :56
-        insts = [dict(net=cnet[i], x=K.addr(self.x), x_ld=x_ld, k_in=O + A, h=[K.addr(t) for t in h_c[i]])
-                 for i in range(2)]
+        insts = [dict(net=cnet[i], x=K.addr(self.x), x_ld=x_ld, k_in=O + A, h=[K.addr(t) for t in h_c[i]],
+                      q=K.addr(self.q[i])) for i in range(2)]
         dz3 = [self.dzc[i][2] for i in range(2)]
+        calls += forward_calls(B, insts, not distl)
         if not distl:
-            calls += trunk_calls(B, insts, 2)
-            groups = [dict(a=it["h"][1], lda=H2, b=it["net"].W[2], ldb=H2, bias=it["net"].b[2], head_w=it["net"].Wf[3],
-                           head_b=it["net"].b[3], q=K.addr(self.q[j]), out=it["h"][2], ldo=H3)
-                      for j, it in enumerate(insts)]
-            calls.append(K.Gemm(B, H3, H2, groups, epilogue=K.EPI_BIAS_ELU_HEAD, tile_n=128))
             calls.append(K.Call("pqlb_dpg_loss", _lib.ptr(self.q[0]), _lib.ptr(self.q[1]), B, _lib.ptr(h_c[0][2]),
                                 _lib.ptr(h_c[1][2]), C.c_void_p(cnet[0].Wf[3]), C.c_void_p(cnet[1].Wf[3]),
                                 _lib.ptr(dz3[0]), _lib.ptr(dz3[1]), _lib.ptr(self.loss_part)))
             self.n_loss_part = 2 * self.nblk_head
         else:
-            calls += trunk_calls(B, insts, 3)
             groups = [dict(a=it["h"][2], lda=H3, b=it["net"].W[3], ldb=H3, bias=it["net"].b[3],
                            out=K.addr(self.p[j]), ldo=self.pd) for j, it in enumerate(insts)]
             calls.append(K.Gemm(B, N, H3, groups, epilogue=K.EPI_BIAS_SOFTMAX, tile_n=64))

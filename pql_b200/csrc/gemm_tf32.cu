@@ -20,10 +20,7 @@
 //
 // Replaces: nn.Linear / nn.ELU / tanh / softmax forward and autograd backward launches of
 // pql/models/mlp.py:15-24,177-179,197-199,261-263 (cuBLAS fp32 sgemm + ATen elementwise).
-#include <cuda.h>
-#include <cudaTypedefs.h>
-
-#include "common.cuh"
+#include "tcgen05_utils.cuh"
 
 namespace pqlb {
 
@@ -56,119 +53,6 @@ struct alignas(64) GemmDev {
   unsigned idesc;
 };
 
-// ------------------------------------------------------------------------------ PTX wrappers
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
-  return ok != 0;
-}
-// Bounded wait: a protocol bug must surface as a launch failure, never as a hung GPU.
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  if (mbar_try_wait(bar, parity)) return;
-  const long long t0 = clock64();
-  while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > 4000000000LL) __trap();
-  }
-}
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
-      ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(bar) : "memory");
-}
-__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-// Shared-memory matrix descriptor (sm_100 format, cute/arch/mma_sm100_desc.hpp):
-// start>>4 [0,14), LBO>>4 [16,30), SBO>>4 [32,46), version=1 [46,48), layout type [61,64):
-// SWIZZLE_128B = 2 (K-major tiles), SWIZZLE_128B_BASE32B = 1 (the only layout the tensor core
-// accepts for MN-major 32-bit operands: 32-byte chunks swizzled inside 128-byte rows, 4-row atoms).
-constexpr uint32_t kLayoutSw128 = 2, kLayoutSw128Base32 = 1;
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout) {
-  uint64_t d = 0;
-  d |= (uint64_t)((addr >> 4) & 0x3FFF);
-  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
-  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
-  d |= (uint64_t)1 << 46;
-  d |= (uint64_t)layout << 61;
-  return d;
-}
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
-  uint32_t* r = reinterpret_cast<uint32_t*>(v);
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
-        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
-        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
-  uint32_t* r = reinterpret_cast<uint32_t*>(v);
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-      : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
-
-__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, uint32_t bar) {
-  asm volatile(
-      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
-      ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(bar) : "memory");
-}
-__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2) {
-  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%1, %2, %3}], [%4];"
-               ::"l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(src) : "memory");
-}
-__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-template <int N> __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void named_bar_sync(int id, int threads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory"); }
-__device__ __forceinline__ void sts128(uint32_t addr, float a, float b, float c, float d) {
-  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
-}
-__device__ __forceinline__ float4 lds128(uint32_t addr) {
-  float4 v;
-  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
-  return v;
-}
-// ELU (alpha = 1) for the epilogue: the accumulator is about to be rounded to TF32 (2^-11), so
-// expm1 is evaluated as ex2.approx - 1 (abs. error < 3e-7) away from zero and as a 4-term Taylor
-// polynomial near zero (rel. error < 2e-7): ~6 instructions instead of expm1f's ~30.
-__device__ __forceinline__ float elu_fast(float v) {
-  float e;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(v * 1.4426950408889634f));
-  const float t = v * (1.f + v * (0.5f + v * (0.16666667f + v * 0.041666668f)));
-  return v > 0.f ? v : (v > -0.0625f ? t : e - 1.f);
-}
-
 // ------------------------------------------------------------------------------ the kernel
 template <int EPI> struct EpiTraits {
   static constexpr bool kBias = EPI == PQLB_EPI_BIAS || EPI == PQLB_EPI_BIAS_ELU || EPI == PQLB_EPI_BIAS_ELU_HEAD ||
@@ -184,10 +68,11 @@ gemm_tf32_kernel(const __grid_constant__ GemmDev P) {
   __shared__ __align__(8) uint64_t empty_bar[kMaxStages];
   __shared__ __align__(8) uint64_t accum_bar;
   __shared__ __align__(8) uint64_t aux_bar[kEpiWarps];
+  __shared__ __align__(8) uint64_t aux_free[kEpiWarps];       // all 32 lanes have read their aux chunk out of shared memory
   __shared__ uint32_t tmem_slot;
   __shared__ float s_q[kTileM];
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = uniform_warp_idx();
   const int lane = threadIdx.x & 31;
   const int grp = blockIdx.z / P.splits;
   const int split = blockIdx.z - grp * P.splits;
@@ -206,7 +91,7 @@ gemm_tf32_kernel(const __grid_constant__ GemmDev P) {
   if (threadIdx.x == 0) {
     for (int s = 0; s < P.stages; ++s) { mbar_init(smem_u32(&full_bar[s]), 1); mbar_init(smem_u32(&empty_bar[s]), 1); }
     mbar_init(smem_u32(&accum_bar), 1);
-    for (int w = 0; w < kEpiWarps; ++w) mbar_init(smem_u32(&aux_bar[w]), 1);
+    for (int w = 0; w < kEpiWarps; ++w) { mbar_init(smem_u32(&aux_bar[w]), 1); mbar_init(smem_u32(&aux_free[w]), 32); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -223,59 +108,73 @@ gemm_tf32_kernel(const __grid_constant__ GemmDev P) {
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
-  const uint32_t tmem_d = tmem_slot;
+  const uint32_t tmem_d = uniform_u32(tmem_slot);
 
+  // Warps 0 and 1 run their loops with all 32 lanes and issue from one elected lane, so every
+  // TMA / MMA operand stays in uniform registers (see elect_one()).
   if (warp == 0) {
     // ===================== TMA producer =====================
-    if (lane == 0) {
-      const uint32_t tx_bytes = kATileBytes + P.b_tile_bytes;
-      int stage = 0; uint32_t phase = 0;
-      for (int kb = kb_begin; kb < kb_end; ++kb) {
-        mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1u);
-        const uint32_t bar = smem_u32(&full_bar[stage]);
+    const uint32_t tx_bytes = kATileBytes + P.b_tile_bytes;
+    int stage = 0; uint32_t phase = 0;
+    for (int kb = kb_begin; kb < kb_end; ++kb) {
+      mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1u);
+      const uint32_t bar = smem_u32(&full_bar[stage]);
+      const bool second = kb >= P.kb1;
+      const int k0 = (second ? kb - P.kb1 : kb) * kTileK;
+      const CUtensorMap* mapA = second ? &G.tmA2 : &G.tmA;
+      const CUtensorMap* mapB = second ? &G.tmB2 : &G.tmB;
+      const uint32_t sa = tiles + stage * P.stage_bytes;
+      const uint32_t sb = sa + kATileBytes;
+      if (elect_one()) {
         mbar_expect_tx(bar, tx_bytes);
-        const bool second = kb >= P.kb1;
-        const int k0 = (second ? kb - P.kb1 : kb) * kTileK;
-        const CUtensorMap* mapA = second ? &G.tmA2 : &G.tmA;
-        const CUtensorMap* mapB = second ? &G.tmB2 : &G.tmB;
-        const uint32_t sa = tiles + stage * P.stage_bytes;
-        const uint32_t sb = sa + kATileBytes;
         if (!P.a_mn) tma_load_2d(sa, mapA, k0, m0, bar);
         else for (int cb = 0; cb < kTileM / 32; ++cb) tma_load_2d(sa + cb * 4096, mapA, m0 + cb * 32, k0, bar);
         if (!P.b_mn) tma_load_2d(sb, mapB, k0, n0, bar);
         else for (int cb = 0; cb < (P.tile_n + 31) / 32; ++cb) tma_load_2d(sb + cb * 4096, mapB, n0 + cb * 32, k0, bar);
-        if (++stage == P.stages) { stage = 0; phase ^= 1u; }
       }
+      __syncwarp();
+      if (++stage == P.stages) { stage = 0; phase ^= 1u; }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
-      int stage = 0; uint32_t phase = 0; uint32_t accumulate = 0;
-      for (int kb = kb_begin; kb < kb_end; ++kb) {
-        mbar_wait(smem_u32(&full_bar[stage]), phase);
-        tcgen05_fence_after();
-        const bool second = kb >= P.kb1;
-        const int kseg = second ? P.K2 : P.K;
-        const int krem = kseg - (second ? kb - P.kb1 : kb) * kTileK;
-        const int ksteps = krem >= kTileK ? 4 : (krem + 7) / 8;
-        const uint32_t sa = tiles + stage * P.stage_bytes;
-        const uint32_t sb = sa + kATileBytes;
-        // K-major: 8-row groups 1024 B apart (SBO), k-step = 32 B inside the swizzle row.
-        // MN-major: 32-element column blocks 4096 B apart (LBO), 4-k-row swizzle atoms 512 B
-        // apart (SBO); one MMA (K = 8) consumes two atoms = 1024 B per k-step.
-        const uint64_t adesc = P.a_mn ? make_smem_desc(sa, 4096, 512, kLayoutSw128Base32) : make_smem_desc(sa, 16, 1024, kLayoutSw128);
-        const uint64_t bdesc = P.b_mn ? make_smem_desc(sb, 4096, 512, kLayoutSw128Base32) : make_smem_desc(sb, 16, 1024, kLayoutSw128);
-        const uint32_t a_step = P.a_mn ? (1024u >> 4) : (32u >> 4);
-        const uint32_t b_step = P.b_mn ? (1024u >> 4) : (32u >> 4);
-        for (int k = 0; k < ksteps; ++k) {
-          umma_tf32(tmem_d, adesc + (uint64_t)(a_step * k), bdesc + (uint64_t)(b_step * k), P.idesc, accumulate);
-          accumulate = 1;
+    int stage = 0; uint32_t phase = 0; uint32_t accumulate = 0;
+    // K-major: 8-row groups 1024 B apart (SBO), k-step = 32 B inside the swizzle row.
+    // MN-major: 32-element column blocks 4096 B apart (LBO), 4-k-row swizzle atoms 512 B
+    // apart (SBO); one MMA (K = 8) consumes two atoms = 1024 B per k-step.
+    const uint64_t adesc0 = P.a_mn ? make_smem_desc(0, 4096, 512, kLayoutSw128Base32) : make_smem_desc(0, 16, 1024, kLayoutSw128);
+    const uint64_t bdesc0 = P.b_mn ? make_smem_desc(0, 4096, 512, kLayoutSw128Base32) : make_smem_desc(0, 16, 1024, kLayoutSw128);
+    const uint32_t a_step = P.a_mn ? (1024u >> 4) : (32u >> 4);
+    const uint32_t b_step = P.b_mn ? (1024u >> 4) : (32u >> 4);
+    const uint32_t idesc = P.idesc;
+    for (int kb = kb_begin; kb < kb_end; ++kb) {
+      mbar_wait(smem_u32(&full_bar[stage]), phase);
+      tcgen05_fence_after();
+      const bool second = kb >= P.kb1;
+      const int kseg = second ? P.K2 : P.K;
+      const int krem = kseg - (second ? kb - P.kb1 : kb) * kTileK;
+      const uint32_t sa = tiles + stage * P.stage_bytes;
+      const uint32_t sb = sa + kATileBytes;
+      const uint64_t adesc = adesc0 | (uint64_t)((sa >> 4) & 0x3FFF);
+      const uint64_t bdesc = bdesc0 | (uint64_t)((sb >> 4) & 0x3FFF);
+      if (elect_one()) {
+        if (krem >= kTileK) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            umma_tf32(tmem_d, adesc + (uint64_t)(a_step * k), bdesc + (uint64_t)(b_step * k), idesc, k ? 1u : accumulate);
+          }
+        } else {
+          const int ksteps = (krem + 7) / 8;
+          for (int k = 0; k < ksteps; ++k)
+            umma_tf32(tmem_d, adesc + (uint64_t)(a_step * k), bdesc + (uint64_t)(b_step * k), idesc, k ? 1u : accumulate);
         }
         umma_commit(smem_u32(&empty_bar[stage]));          // frees the smem slot when the MMAs retire
-        if (++stage == P.stages) { stage = 0; phase ^= 1u; }
       }
-      umma_commit(smem_u32(&accum_bar));                    // accumulator complete
+      __syncwarp();
+      accumulate = 1;
+      if (++stage == P.stages) { stage = 0; phase ^= 1u; }
     }
+    if (elect_one()) umma_commit(smem_u32(&accum_bar));       // accumulator complete
+    __syncwarp();
   } else {
     // ===================== epilogue (warps 2..9) =====================
     const int e = warp - 2;
@@ -293,14 +192,18 @@ gemm_tf32_kernel(const __grid_constant__ GemmDev P) {
     const bool aux_tma = EpiTraits<EPI>::kAux && G.aux_tma && chunkw == 32;
     const uint32_t my_aux = aux_stage + e * kChunkBytes;
     const uint32_t my_aux_bar = smem_u32(&aux_bar[e]);
+    const uint32_t my_aux_free = smem_u32(&aux_free[e]);
     const uint32_t my_out = tiles + e * 2 * kChunkBytes;    // two staging chunks in the (idle) operand ring
     const uint32_t swz = (uint32_t)(lane & 7) << 4;
     const uint32_t row_off = (uint32_t)lane * 128u;
     uint32_t aux_phase = 0;
 
-    if (aux_tma && c_begin < c_end && lane == 0) {           // prefetch the first ELU'/tanh' chunk under the main loop
-      mbar_expect_tx(my_aux_bar, kChunkBytes);
-      tma_load_3d(my_aux, &G.tmAux, n0 + c_begin * 32, row0, 0, my_aux_bar);
+    if (aux_tma && c_begin < c_end) {                        // prefetch the first ELU'/tanh' chunk under the main loop
+      if (elect_one()) {
+        mbar_expect_tx(my_aux_bar, kChunkBytes);
+        tma_load_3d(my_aux, &G.tmAux, n0 + c_begin * 32, row0, 0, my_aux_bar);
+      }
+      __syncwarp();
     }
     mbar_wait(smem_u32(&accum_bar), 0);
     tcgen05_fence_after();
@@ -345,10 +248,18 @@ gemm_tf32_kernel(const __grid_constant__ GemmDev P) {
             const float4 t = lds128(my_aux + row_off + (((uint32_t)j4 << 4) ^ swz));
             a[4 * j4] = t.x; a[4 * j4 + 1] = t.y; a[4 * j4 + 2] = t.z; a[4 * j4 + 3] = t.w;
           }
-          __syncwarp();
-          if (c + 1 < c_end && lane == 0) {                  // next chunk lands while this one is computed
-            mbar_expect_tx(my_aux_bar, kChunkBytes);
-            tma_load_3d(my_aux, &G.tmAux, nb + 32, row0, 0, my_aux_bar);
+          // The refill below overwrites the buffer through the async proxy, and nothing orders it
+          // after the loads above (they may still sit in the LSU queue when a second CTA shares the
+          // SM; __syncwarp compiles to nothing in converged code): every lane releases its reads
+          // on aux_free and the refill is issued only once that phase completes.
+          mbar_arrive(my_aux_free);
+          if (c + 1 < c_end) {                               // next chunk lands while this one is computed
+            mbar_wait(my_aux_free, aux_phase ^ 1u);
+            if (elect_one()) {
+              mbar_expect_tx(my_aux_bar, kChunkBytes);
+              tma_load_3d(my_aux, &G.tmAux, nb + 32, row0, 0, my_aux_bar);
+            }
+            __syncwarp();
           }
         } else {
 #pragma unroll
@@ -387,13 +298,13 @@ gemm_tf32_kernel(const __grid_constant__ GemmDev P) {
       if (G.out == nullptr) continue;
       if (out_tma) {
         const uint32_t buf = my_out + (uint32_t)(n_stores & 1) * kChunkBytes;
-        if (n_stores >= 2) { if (lane == 0) bulk_wait_read<1>(); __syncwarp(); }   // staging buffer free again
+        if (n_stores >= 2) { if (elect_one()) bulk_wait_read<1>(); __syncwarp(); }   // staging buffer free again
 #pragma unroll
         for (int j4 = 0; j4 < 8; ++j4)
           sts128(buf + row_off + (((uint32_t)j4 << 4) ^ swz), v[4 * j4], v[4 * j4 + 1], v[4 * j4 + 2], v[4 * j4 + 3]);
         fence_proxy_async();
         __syncwarp();
-        if (lane == 0) { tma_store_3d(&G.tmOut, buf, nb - P.col_lo, row0, split); bulk_commit(); }
+        if (elect_one()) { tma_store_3d(&G.tmOut, buf, nb - P.col_lo, row0, split); bulk_commit(); }
         ++n_stores;
       } else if (row_ok) {
         float* orow = G.out + (long long)row * G.ldo + (EPI == PQLB_EPI_STORE ? (long long)split * G.split_stride : 0ll);
@@ -420,7 +331,7 @@ gemm_tf32_kernel(const __grid_constant__ GemmDev P) {
       named_bar_sync(1 + quarter, 64);
       if (half == 0 && row_ok) G.q[row] = (qacc + s_q[quarter * 32 + lane]) + G.head_b[0];
     }
-    if (n_stores > 0 && lane == 0) bulk_wait_read<0>();       // staging memory must outlive the bulk reads
+    if (n_stores > 0) { if (elect_one()) bulk_wait_read<0>(); __syncwarp(); }   // staging memory must outlive the bulk reads
   }
 
   tcgen05_fence_before();
@@ -448,7 +359,7 @@ static GemmKernel kernel_for(int epi) {
 }
 
 // ------------------------------------------------------------------------------ host side
-static PFN_cuTensorMapEncodeTiled get_encode_fn() {
+PFN_cuTensorMapEncodeTiled get_encode_fn() {
   static PFN_cuTensorMapEncodeTiled fn = nullptr;
   static bool tried = false;
   if (!tried) {
@@ -463,7 +374,7 @@ static PFN_cuTensorMapEncodeTiled get_encode_fn() {
 }
 
 // 2-D fp32 tensor map with 128-byte swizzle; dim0 is the contiguous dimension.
-static int make_map(CUtensorMap* map, const float* base, uint64_t dim0, uint64_t dim1, int64_t ld_words,
+int make_map(CUtensorMap* map, const float* base, uint64_t dim0, uint64_t dim1, int64_t ld_words,
                     uint32_t box0, uint32_t box1, CUtensorMapSwizzle swizzle) {
   PFN_cuTensorMapEncodeTiled enc = get_encode_fn();
   if (!enc) return PQLB_E_DRIVER;
@@ -480,7 +391,7 @@ static int make_map(CUtensorMap* map, const float* base, uint64_t dim0, uint64_t
 
 // Output / epilogue-operand map: [splits][rows][cols] fp32, 32x32 boxes, 128-byte swizzle (matches
 // the staging chunks the epilogue warps write / read).  Returns false when TMA cannot address it.
-static bool make_tile_map(CUtensorMap* map, const float* base, uint64_t cols, uint64_t rows, int64_t ld_words,
+bool make_tile_map(CUtensorMap* map, const float* base, uint64_t cols, uint64_t rows, int64_t ld_words,
                           uint64_t splits, int64_t split_stride_words) {
   PFN_cuTensorMapEncodeTiled enc = get_encode_fn();
   if (!enc || !base || !aligned16(base) || (ld_words % 4) != 0 || ld_words < (int64_t)cols) return false;
@@ -506,6 +417,8 @@ static int make_operand_map(CUtensorMap* map, const float* base, int64_t ld, int
 
 using namespace pqlb;
 
+extern "C" int pqlb_mlp_forward_init(void);
+
 // One-time, non-stream setup (opt-in shared memory size, driver entry point) so that nothing but
 // kernel launches happens while a caller is capturing a CUDA graph.  Per device.
 extern "C" int pqlb_init(void) {
@@ -520,6 +433,7 @@ extern "C" int pqlb_init(void) {
     if (e != cudaSuccess) return (int)e;
   }
   if (!get_encode_fn()) return PQLB_E_DRIVER;
+  { int rc = pqlb_mlp_forward_init(); if (rc != PQLB_OK) return rc; }
   if (dev < 64) done[dev] = true;
   return PQLB_OK;
 }

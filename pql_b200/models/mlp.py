@@ -89,14 +89,18 @@ class NetAddrs:
         self.b = [K.addr(flat_fp32, layout.b_off[i][l]) for l in range(layout.n_layers)]
 
 
+import os as _os
+_FWD_CTAS = int(_os.environ.get("PQLB_FWD_CTAS", 250))
+
+
 def fwd_tile(B, N, n_groups):
-    """Widest output tile that still gives the grid about one CTA per SM."""
+    """Widest output tile that still gives the grid enough CTAs to fill the SMs."""
     if N <= 64:
         return K.pick_tile_n(N)
     for t in (256, 128, 64):
         if t > N and t // 2 >= N:
             continue
-        if ((B + 127) // 128) * ((N + t - 1) // t) * n_groups >= 120:
+        if ((B + 127) // 128) * ((N + t - 1) // t) * n_groups >= _FWD_CTAS:
             return t
     return 64
 
@@ -117,6 +121,41 @@ def trunk_calls(B, insts, n_hidden_out=3):
         k_l = insts[0]["k_in"] if l == 0 else dims[l]
         calls.append(K.Gemm(B, dims[l + 1], k_l, groups, epilogue=K.EPI_BIAS_ELU,
                             tile_n=fwd_tile(B, dims[l + 1], len(groups))))
+    return calls
+
+
+FUSED_MAX_IN = 128        # pqlb_mlp_forward keeps a 128-row input tile of at most 128 columns in shared memory
+
+
+def forward_calls(B, insts, scalar_head):
+    """Prepared launches of the trunk (three Linear+ELU layers) for up to four network instances.
+    inst = dict(net, x, x_ld, k_in, h=[h1, h2, h3 addresses], store=(s1, s2, s3), q=addr or 0).
+    Inputs up to 128 wide take ONE layer-fused launch (activations stay in tensor memory, only the
+    flagged ones are written); wider inputs (ShadowHand) run layer by layer.  With ``scalar_head``
+    the twin-Q head q = h3 . w4 + b4 is fused into the last epilogue."""
+    k_in = insts[0]["k_in"]
+    if k_in <= FUSED_MAX_IN:
+        groups = []
+        for it in insts:
+            n = it["net"]
+            st = it.get("store", (True, True, True))
+            g = dict(x=it["x"], ldx=it["x_ld"], w1=n.W[0], ldw1=n.ldw[0], w2=n.W[1], w3=n.W[2], b1=n.b[0], b2=n.b[1],
+                     b3=n.b[2], h1=it["h"][0] if st[0] else 0, h2=it["h"][1] if st[1] else 0,
+                     h3=it["h"][2] if st[2] else 0)
+            if scalar_head:
+                g.update(head_w=n.Wf[3], head_b=n.b[3], q=it["q"])
+            groups.append(g)
+        return [K.MlpForward(B, k_in, groups)]
+    if not scalar_head:
+        return trunk_calls(B, insts, 3)
+    calls = trunk_calls(B, insts, 2)
+    groups = []
+    for it in insts:
+        n = it["net"]
+        st = it.get("store", (True, True, True))
+        groups.append(dict(a=it["h"][1], lda=HIDDEN[1], b=n.W[2], ldb=n.ldw[2], bias=n.b[2], head_w=n.Wf[3],
+                           head_b=n.b[3], q=it["q"], out=it["h"][2] if st[2] else 0, ldo=HIDDEN[2]))
+    calls.append(K.Gemm(B, HIDDEN[2], HIDDEN[1], groups, epilogue=K.EPI_BIAS_ELU_HEAD, tile_n=128))
     return calls
 
 

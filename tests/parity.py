@@ -278,3 +278,59 @@ def run_learner_parity(seed=1234, B=512, obs_dim=88, act_dim=16, distl=False, st
     _record(dict(seed=seed, B=B, obs_dim=obs_dim, act_dim=act_dim, distl=distl, steps=steps, obs_norm=obs_norm), res)
     res["per_tensor_grad (vs tf32 oracle, vs fp32 oracle, tf32 oracle vs fp32 oracle)"] = per_tensor
     return res
+
+
+def plan_divergence(B, distl, which="critic", repeats=4, obs_dim=88, act_dim=16, device="cuda:0", seed=3):
+    """Run the prepared launch list of one update ``repeats`` + 1 times from the same state and
+    return a description of the first launch after which any plan buffer differs bitwise from the
+    first run (None = bit-reproducible).  Catches shared-memory / TMEM races in the kernels: the
+    whole update is deterministic by construction (fixed-order split-K and partial-sum
+    reductions, no atomics), so ANY differing word is a bug."""
+    import torch
+    from pql_b200.algo._engine import ActorUpdate, CriticUpdate
+    from pql_b200.models.mlp import NetLayout
+    g = torch.Generator(device=device).manual_seed(seed)
+    N = 51 if distl else 1
+    if which == "critic":
+        flat = torch.randn(NetLayout(obs_dim + act_dim, N, 2).total, device=device, generator=g) * 0.05
+        up = CriticUpdate(obs_dim, act_dim, B, device, flat, distl=bool(distl))
+        up.a_flat.copy_(torch.randn(up.a_flat.numel(), device=device, generator=g) * 0.05)
+        inputs = [up.x_cur, up.x_tgt, up.reward, up.noise]
+    else:
+        flat = torch.randn(NetLayout(obs_dim, act_dim, 1).total, device=device, generator=g) * 0.05
+        up = ActorUpdate(obs_dim, act_dim, B, device, flat, distl=bool(distl))
+        up.c_flat.copy_(torch.randn(up.c_flat.numel(), device=device, generator=g) * 0.05)
+        inputs = [up.x]
+    up.round_weights()
+    for t in inputs:
+        t.copy_(torch.randn(t.shape, device=device, generator=g))
+        t.copy_(((t.view(torch.int32) + 0x1000) & ~0x1FFF).view(torch.float32))
+    bufs = up._bufs + [up.opt.grad]
+    init = [b.clone() for b in bufs]
+    calls = up.calls + [up.reduce_call]
+
+    def run():
+        for b, i in zip(bufs, init):
+            b.copy_(i)
+        sigs = []
+        for c in calls:
+            c()
+            sigs.append(torch.stack([b.view(torch.int32).to(torch.int64).sum() for b in bufs]))
+        torch.cuda.synchronize()
+        return torch.stack(sigs).cpu()
+
+    ref = run()
+    for rep in range(repeats):
+        cur = run()
+        diff = (cur != ref).any(dim=1).nonzero()
+        if diff.numel():
+            ci = int(diff[0])
+            c = calls[ci]
+            d = getattr(c, "desc", None)
+            extra = ""
+            if d is not None and hasattr(d, "epilogue"):
+                extra = (f" M={d.M} N={d.N} K={d.K} epi={d.epilogue} tile_n={d.tile_n} splits={d.splits} "
+                         f"a_major={d.a_major} b_major={d.b_major}")
+            shapes = [tuple(bufs[i].shape) for i in (cur[ci] != ref[ci]).nonzero().flatten().tolist()]
+            return f"repeat {rep}: launch {ci} ({c.name}{extra}) is not reproducible; buffers {shapes}"
+    return None

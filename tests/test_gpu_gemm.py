@@ -173,3 +173,76 @@ def test_round_tf32(K):
     y = torch.empty_like(x)
     _lib.call("pqlb_round_tf32", _lib.ptr(x), _lib.ptr(y), x.numel())
     assert torch.equal(y, rn_tf32(x))
+
+
+@pytest.mark.parametrize("M,k_in,n_groups", [(128, 104, 1), (200, 88, 1), (8192, 104, 4), (300, 104, 2)])
+def test_fused_trunk_forward(K, M, k_in, n_groups):
+    """pqlb_mlp_forward: three Linear+ELU layers with activations kept in tensor memory, optional
+    stores of h1/h2/h3 and the fused scalar head, against an fp64 evaluation with the same TF32
+    roundings (h rounded after every ELU)."""
+    g = torch.Generator(device=DEV).manual_seed(M + k_in)
+    ld = (k_in + 3) // 4 * 4
+    groups, checks, keep = [], [], []
+    for i in range(n_groups):
+        x = torch.zeros(M, ld, device=DEV); x[:, :k_in] = mk((M, k_in), g)
+        w1 = torch.zeros(512, ld, device=DEV); w1[:, :k_in] = mk((512, k_in), g, 1.0 / k_in ** 0.5)
+        w2, w3 = mk((256, 512), g, 1.0 / 512 ** 0.5), mk((128, 256), g, 1.0 / 16)
+        b1, b2, b3 = (torch.randn(n, generator=g, device=DEV) * 0.1 for n in (512, 256, 128))
+        w4, b4 = torch.randn(128, generator=g, device=DEV) * 0.1, torch.randn(1, generator=g, device=DEV)
+        store = i % 2 == 0
+        h = [torch.zeros(M, n, device=DEV) if store else None for n in (512, 256, 128)]
+        q = torch.zeros(M, device=DEV) if (i < 2 or not store) else None
+        groups.append(dict(x=K.addr(x), ldx=ld, w1=K.addr(w1), ldw1=ld, w2=K.addr(w2), w3=K.addr(w3), b1=K.addr(b1),
+                           b2=K.addr(b2), b3=K.addr(b3), head_w=K.addr(w4), head_b=K.addr(b4), q=K.addr(q),
+                           h1=K.addr(h[0]), h2=K.addr(h[1]), h3=K.addr(h[2])))
+        r1 = rn_tf32(elu((x[:, :k_in].double() @ w1[:, :k_in].double().t()).float() + b1))
+        r2 = rn_tf32(elu((r1.double() @ w2.double().t()).float() + b2))
+        z3 = elu((r2.double() @ w3.double().t()).float() + b3)
+        checks.append((h, q, (r1, r2, rn_tf32(z3)), z3.double() @ w4.double() + b4.double()))
+        keep += [x, w1, w2, w3, b1, b2, b3, w4, b4]
+    K.MlpForward(M, k_in, groups)()
+    torch.cuda.synchronize()
+    for h, q, refs, qref in checks:
+        if q is not None:
+            check(q, qref, 3e-4, "fused head q")     # rounding flips of h1/h2 (one TF32 ulp) propagate
+        for got, ref, name in zip(h, refs, ("h1", "h2", "h3")):
+            if got is not None:
+                check(got, ref, 1e-3, "fused " + name)
+
+
+@pytest.mark.parametrize("M,k_in,n_groups", [(128, 104, 1), (8192, 104, 4), (16384, 104, 4), (8192, 88, 1)])
+def test_fused_trunk_equals_layerwise(K, M, k_in, n_groups):
+    """The layer-fused trunk accumulates every output element over k in the same order as the
+    per-layer GEMMs (k-blocks ascending into one fp32 TMEM accumulator), so h1/h2/h3 must be
+    BIT-IDENTICAL between the two paths — a sharper check than any tolerance: a race on the
+    in-place TMEM conversion or a staging-buffer hazard shows up as a handful of differing words."""
+    g = torch.Generator(device=DEV).manual_seed(7 * M + k_in)
+    ld = (k_in + 3) // 4 * 4
+    groups, lw, outs = [], [[], [], []], []
+    for i in range(n_groups):
+        x = torch.zeros(M, ld, device=DEV); x[:, :k_in] = mk((M, k_in), g)
+        w1 = torch.zeros(512, ld, device=DEV); w1[:, :k_in] = mk((512, k_in), g, 1.0 / k_in ** 0.5)
+        w2, w3 = mk((256, 512), g, 1.0 / 512 ** 0.5), mk((128, 256), g, 1.0 / 16)
+        b1, b2, b3 = (torch.randn(n, generator=g, device=DEV) * 0.1 for n in (512, 256, 128))
+        hf = [torch.zeros(M, n, device=DEV) for n in (512, 256, 128)]
+        hl = [torch.zeros(M, n, device=DEV) for n in (512, 256, 128)]
+        groups.append(dict(x=K.addr(x), ldx=ld, w1=K.addr(w1), ldw1=ld, w2=K.addr(w2), w3=K.addr(w3), b1=K.addr(b1),
+                           b2=K.addr(b2), b3=K.addr(b3), h1=K.addr(hf[0]), h2=K.addr(hf[1]), h3=K.addr(hf[2])))
+        lw[0].append(dict(a=K.addr(x), lda=ld, b=K.addr(w1), ldb=ld, bias=K.addr(b1), out=K.addr(hl[0]), ldo=512))
+        lw[1].append(dict(a=K.addr(hl[0]), lda=512, b=K.addr(w2), ldb=512, bias=K.addr(b2), out=K.addr(hl[1]), ldo=256))
+        lw[2].append(dict(a=K.addr(hl[1]), lda=256, b=K.addr(w3), ldb=256, bias=K.addr(b3), out=K.addr(hl[2]), ldo=128))
+        outs.append((hf, hl, (x, w1, w2, w3, b1, b2, b3)))
+    for rep in range(3):                       # repeated launches: a race need not fire every time
+        K.MlpForward(M, k_in, groups)()
+        K.Gemm(M, 512, k_in, lw[0], epilogue=K.EPI_BIAS_ELU, tile_n=256)()
+        K.Gemm(M, 256, 512, lw[1], epilogue=K.EPI_BIAS_ELU, tile_n=128)()
+        K.Gemm(M, 128, 256, lw[2], epilogue=K.EPI_BIAS_ELU, tile_n=128)()
+        torch.cuda.synchronize()
+        for gi, (hf, hl, _) in enumerate(outs):
+            for name, a, b in zip(("h1", "h2", "h3"), hf, hl):
+                bad = (a.view(torch.int32) != b.view(torch.int32))
+                n_bad = int(bad.sum().item())
+                if n_bad:
+                    idx = bad.nonzero()[:8].tolist()
+                    raise AssertionError(f"rep {rep} group {gi} {name}: {n_bad} words differ, first at {idx}, "
+                                         f"fused {a[bad][:4].tolist()} layerwise {b[bad][:4].tolist()}")

@@ -128,3 +128,13 @@ def test_rng_out_variants_follow_the_reference_stream():
     torch.randint(12345, size=(8192,), device=dev, out=idx)
     noise.normal_()          # the kernel applies std: normal(zeros, full(std)) == normal_(0,1).mul_(std).add_(0)
     assert torch.equal(idx, idx_ref) and torch.equal(noise * 0.8, noise_ref)
+
+
+@pytest.mark.parametrize("B,distl,which", [(8192, False, "critic"), (8192, False, "actor"),
+                                           (16384, True, "critic"), (16384, True, "actor")])
+def test_update_launch_list_is_bit_reproducible(B, distl, which):
+    """Every launch of the update must reproduce its outputs bit for bit (fixed-order
+    reductions, no atomics).  Regression test for the dgrad-epilogue race found in round 1: the
+    refill of the ELU'-operand staging buffer could overtake the shared-memory reads of the
+    previous chunk when two CTAs shared an SM."""
+    assert parity.plan_divergence(B, distl, which, repeats=4, device=DEV) is None
