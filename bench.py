@@ -138,6 +138,8 @@ def config_dict(n_gpus):
             "step": f"1 n-step push + ring insert of {E} transitions, {V_PER_STEP} critic updates, {P_PER_STEP} actor updates",
             "critic_updates_per_step": V_PER_STEP, "actor_updates_per_step": P_PER_STEP, "batch_per_gpu": B,
             "num_envs_per_gpu": E, "replay_slots_per_gpu": CAP, "parallelism": f"dp{n_gpus}",
+            "learner_streams": "V-learner and P-learner each enqueue on their own CUDA stream (the reference runs them as "
+                               "two concurrent Ray actors); update() is the exchange/join point",
             "cache": "replay ring 800 MB per GPU > 126 MB L2 (random gathers miss L2); weights/activations are the "
                      "step's own working set and are not flushed"}
 
@@ -163,6 +165,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--one-stream", action="store_true", help="both learners on the caller's stream (no overlap)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
@@ -193,6 +196,7 @@ def main():
     cfg = default_pql_cfg(batch_size=B, memory_size=CAP, num_envs=E, v_learner_gpu=local, p_learner_gpu=local)
     cfg.data_parallel = world > 1
     cfg.use_cuda_graph = not args.no_graph
+    cfg.learner_streams = not args.one_stream      # V- and P-learner overlap like the reference's two Ray actors
     v = PQLVLearner(O, A, cfg)
     p = PQLPLearner(O, A, cfg)
     if world > 1:      # identical initial weights on every rank
@@ -241,6 +245,9 @@ def main():
         e0.record()
         for k in range(n):
             losses = super_step(base + k, host_inputs)
+        for lrn in (v, p):                       # the step ends when both learners' streams have drained
+            if lrn.stream is not None:
+                torch.cuda.current_stream(dev).wait_stream(lrn.stream)
         e1.record()
         torch.cuda.synchronize(dev)
         wall = time.perf_counter() - t0
@@ -271,7 +278,7 @@ def main():
         super_step(k, False)
     torch.cuda.synchronize(dev)
     per_kernel = {name: sum(a.elapsed_time(b) for a, b in evs) / prof_steps for name, evs in K.PROFILE.items()}
-    n_gemm = len(K.PROFILE.get("pqlb_gemm_tf32", [])) // prof_steps
+    n_gemm = (len(K.PROFILE.get("pqlb_gemm_tf32", [])) + len(K.PROFILE.get("pqlb_mlp_forward", []))) // prof_steps
     K.PROFILE = None
     v.enable_graph(); p.enable_graph()
 
@@ -321,7 +328,7 @@ def main():
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
     tf32_peak = peaks.get("bf16_tflops_sustained", 1400.0) / 2.0
     peak_src = "measured (MEASURED_PEAKS.json)" if peaks else "fallback (B200_PROFILING.md)"
-    gemm_ms = per_kernel.get("pqlb_gemm_tf32", float("nan"))
+    gemm_ms = per_kernel.get("pqlb_gemm_tf32", float("nan")) + per_kernel.get("pqlb_mlp_forward", 0.0)
     flops_step = B * (V_PER_STEP * FLOP_V + P_PER_STEP * FLOP_P)
     achieved = flops_step / (gemm_ms * 1e-3) / 1e12
     value = world * V_PER_STEP * args.steps / (ms * 1e-3)
@@ -333,7 +340,7 @@ def main():
             "e2e": {"value": e2e, "unit": "critic updates/s", "h2d_bytes_per_step": h2d_bytes,
                     "d2h_bytes_per_step": 2 * 5 * 4, "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": launches,
-            "roofline": {"kernel": "gemm_tf32_kernel (tcgen05 kind::tf32; all dense-layer launches of one step)",
+            "roofline": {"kernel": "gemm_tf32_kernel + mlp_fwd_kernel (tcgen05 kind::tf32; all dense-layer launches of one step)",
                          "bound": "tensor", "achieved": achieved, "peak": tf32_peak, "unit": "TFLOP/s",
                          "frac": achieved / tf32_peak, "traffic": None, "launches_per_step": n_gemm,
                          "ms_per_step_in_kernel": gemm_ms,

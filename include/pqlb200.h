@@ -180,6 +180,9 @@ typedef struct {
 } pqlb_mlp_group;
 typedef struct { int M, k_in, n_groups; pqlb_mlp_group g[PQLB_MAX_GROUPS]; } pqlb_mlp_desc;
 int pqlb_mlp_forward(const pqlb_mlp_desc* desc, pqlb_stream_t stream);
+/* Tuning / tests: force the thread-block-cluster size (1, 2 or 4 row tiles sharing every weight
+ * tile through TMA multicast) of pqlb_mlp_forward; 0 = default (1: no cluster, the fastest measured). */
+void pqlb_mlp_forward_cluster(int cluster);
 
 /* dst = rn_tf32(src) elementwise (tensor-core operand copies of weights). */
 int pqlb_round_tf32(const float* src, float* dst, int64_t n, pqlb_stream_t stream);

@@ -74,6 +74,7 @@ _PROTOS = {
     "pqlb_sample_obs_batch": (_int, [_f, _i64, _int, _f, _i64, _f, _f, _flt, _f, _int, _int, _st]),
     "pqlb_gemm_tf32": (_int, [C.POINTER(GemmDesc), _st]),
     "pqlb_mlp_forward": (_int, [C.POINTER(MlpDesc), _st]),
+    "pqlb_mlp_forward_cluster": (None, [_int]),
     "pqlb_round_tf32": (_int, [_f, _f, _i64, _st]),
     "pqlb_doubleq_td_loss": (_int, [_f, _f, _f, _f, _f, _f, _flt, _i64, _f, _f, _f, _f, _f, _f, _f,
                                     _f, _f, _f, _st]),

@@ -12,7 +12,7 @@ from ..models import load_class
 from ..utils.common import DeviceTracker
 from . import _dp
 from ._engine import ActorUpdate
-from .pql_v_learner import module_flat
+from .pql_v_learner import LearnerStream, module_flat
 
 
 class PQLPLearner:
@@ -51,6 +51,12 @@ class PQLPLearner:
         self._plan = None
         self._sample = None
         self.use_cuda_graph = bool(getattr(cfg, "use_cuda_graph", True)) and not os.environ.get("PQLB_NO_GRAPH")
+        self._ls = LearnerStream(cfg, self.device)
+        self._ls.tag(self.actor)
+
+    @property
+    def stream(self):
+        return self._ls.stream
 
     def disable_graph(self):
         self.use_cuda_graph = False
@@ -79,7 +85,7 @@ class PQLPLearner:
     def learn(self):
         if self.critic is not None:
             p = self._plan
-            with torch.cuda.device(self.device):
+            with torch.cuda.device(self.device), self._ls.ctx():
                 torch.randint(self.cur_capacity, size=(p.B,), device=self.device, out=p.idx)     # :49
                 p.run(self._sample, self._allreduce if self.world_size > 1 else None, self.use_cuda_graph)
             self.update_count += 1
@@ -92,23 +98,26 @@ class PQLPLearner:
         rebuild = self._plan is not None and ((normalize_tuple is None) != (self.normalize_tuple is None))
         self.normalize_tuple = normalize_tuple
         obs = obs.reshape(-1, self._O)
-        if obs.device != self.device or obs.dtype != torch.float32:
-            obs = obs.to(device=self.device, dtype=torch.float32, non_blocking=True)
-        obs = obs.contiguous()
-        self.add_capacity = obs.shape[0]
-        p = self.next_p + self.add_capacity
-        if p > self.memory_size and p - self.memory_size > self.memory_size:
-            raise RuntimeError(f"update: {self.add_capacity} observations do not fit a ring of {self.memory_size}")
         with torch.cuda.device(self.device):
-            _lib.call("pqlb_obsring_insert", _lib.ptr(self.memory), self.memory_size, self._O, _lib.ptr(obs),
-                      self.add_capacity, self.next_p)
-        if p > self.memory_size:                   # :73-77, strict
-            p = p - self.memory_size
-            self.if_full = True
-        self.next_p = p
-        self.cur_capacity = self.memory_size if self.if_full else self.next_p
-        if self._plan is None or rebuild:
-            self._build()
-        self._plan.set_critic(module_flat(critic, self._plan.Lc.total, self.device))
-        self._plan.set_norm(normalize_tuple if self.cfg.algo.obs_norm else None)
-        return self.actor, self.loss_tracker.mean(), self.update_count
+            self._ls.join(critic, (obs,) + (tuple(normalize_tuple[:2]) if normalize_tuple is not None else ()))
+            with self._ls.ctx():
+                if obs.device != self.device or obs.dtype != torch.float32:
+                    obs = obs.to(device=self.device, dtype=torch.float32, non_blocking=True)
+                obs = obs.contiguous()
+                self.add_capacity = obs.shape[0]
+                p = self.next_p + self.add_capacity
+                if p > self.memory_size and p - self.memory_size > self.memory_size:
+                    raise RuntimeError(f"update: {self.add_capacity} observations do not fit a ring of {self.memory_size}")
+                _lib.call("pqlb_obsring_insert", _lib.ptr(self.memory), self.memory_size, self._O, _lib.ptr(obs),
+                          self.add_capacity, self.next_p)
+                if p > self.memory_size:                   # :73-77, strict
+                    p = p - self.memory_size
+                    self.if_full = True
+                self.next_p = p
+                self.cur_capacity = self.memory_size if self.if_full else self.next_p
+                if self._plan is None or rebuild:
+                    self._build()
+                self._plan.set_critic(module_flat(critic, self._plan.Lc.total, self.device))
+                self._plan.set_norm(normalize_tuple if self.cfg.algo.obs_norm else None)
+                loss = self.loss_tracker.mean()          # the one host sync per env step (this learner's stream)
+        return self.actor, loss, self.update_count

@@ -7,7 +7,9 @@ then a fixed list of sm_100a kernel launches (pql_b200/algo/_engine.py).  The re
 ``@ray.remote`` decoration is the caller's business: these are plain classes,
 one process per GPU.
 """
+import contextlib
 import os
+import weakref
 
 import torch
 
@@ -17,6 +19,44 @@ from ..replay.simple_replay import ReplayBuffer
 from ..utils.common import DeviceTracker
 from . import _dp
 from ._engine import CriticUpdate
+
+
+_PRODUCER_STREAM = weakref.WeakKeyDictionary()     # module -> the learner stream that writes its weights
+
+
+class LearnerStream:
+    """Optional per-learner CUDA stream (``cfg.learner_streams = True``).
+
+    In the reference the V-learner and the P-learner are separate Ray actors (scripts/train_pql.py:
+    40-52), possibly on the same GPU, so their updates overlap.  A single process hosting both gets
+    the same concurrency by giving each learner its own stream: ``learn()`` enqueues there and
+    returns, ``update()`` is the exchange point and orders this learner's stream after the caller's
+    current stream (which produced the trajectory) and after the stream that produced the module it
+    is handed.  Off by default: then everything runs on the caller's current stream."""
+
+    def __init__(self, cfg, device):
+        self.device = device
+        self.stream = torch.cuda.Stream(device) if getattr(cfg, "learner_streams", False) else None
+
+    def ctx(self):
+        return torch.cuda.stream(self.stream) if self.stream is not None else contextlib.nullcontext()
+
+    def tag(self, module):
+        """Modules handed out by update()/start() remember which stream writes them."""
+        if self.stream is not None:
+            _PRODUCER_STREAM[module] = self.stream
+        return module
+
+    def join(self, module, tensors=()):
+        if self.stream is None:
+            return
+        self.stream.wait_stream(torch.cuda.current_stream(self.device))
+        src = _PRODUCER_STREAM.get(module) if module is not None else None
+        if src is not None and src is not self.stream:
+            self.stream.wait_stream(src)
+        for t in tensors:
+            if torch.is_tensor(t) and t.is_cuda:
+                t.record_stream(self.stream)
 
 
 def module_flat(module, layout_total, device):
@@ -65,6 +105,12 @@ class PQLVLearner:
         self._plan = None
         self._sample = None
         self.use_cuda_graph = bool(getattr(cfg, "use_cuda_graph", True)) and not os.environ.get("PQLB_NO_GRAPH")
+        self._ls = LearnerStream(cfg, self.device)
+        self._ls.tag(self.critic)
+
+    @property
+    def stream(self):
+        return self._ls.stream
 
     def disable_graph(self):
         self.use_cuda_graph = False
@@ -109,7 +155,7 @@ class PQLVLearner:
             if self._plan is None:
                 self._build()
             p = self._plan
-            with torch.cuda.device(self.device):
+            with torch.cuda.device(self.device), self._ls.ctx():
                 # same two draws, in the same order, as the reference: randint (simple_replay.py:87)
                 # then torch.normal(zeros, full(std)) (noise.py:20-21), which ATen evaluates as
                 # out.normal_(0, 1).mul_(std).add_(mean): we draw the N(0,1) part with the same
@@ -124,12 +170,16 @@ class PQLVLearner:
     @torch.no_grad()
     def update(self, actor, trajectory, normalize_tuple, sleep_time):
         self.actor = actor
-        self.memory.add_to_buffer(trajectory)
-        rebuild = self._plan is not None and ((normalize_tuple is None) != (self.normalize_tuple is None))
-        self.normalize_tuple = normalize_tuple
-        self.sleep_time = sleep_time
-        if self._plan is None or rebuild:
-            self._build()
-        self._plan.set_actor(module_flat(actor, self._plan.La.total, self.device))
-        self._plan.set_norm(normalize_tuple if self.cfg.algo.obs_norm else None)
-        return self.critic, self.loss_tracker.mean(), self.update_count
+        with torch.cuda.device(self.device):
+            self._ls.join(actor, tuple(trajectory) + (tuple(normalize_tuple[:2]) if normalize_tuple is not None else ()))
+            with self._ls.ctx():
+                self.memory.add_to_buffer(trajectory)
+                rebuild = self._plan is not None and ((normalize_tuple is None) != (self.normalize_tuple is None))
+                self.normalize_tuple = normalize_tuple
+                self.sleep_time = sleep_time
+                if self._plan is None or rebuild:
+                    self._build()
+                self._plan.set_actor(module_flat(actor, self._plan.La.total, self.device))
+                self._plan.set_norm(normalize_tuple if self.cfg.algo.obs_norm else None)
+                loss = self.loss_tracker.mean()          # the one host sync per env step (this learner's stream)
+        return self.critic, loss, self.update_count

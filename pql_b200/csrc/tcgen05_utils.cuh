@@ -53,6 +53,23 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
       ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(bar) : "memory");
 }
+// ---- thread-block clusters: weight tiles are fetched from L2 once per cluster and multicast into
+// every CTA's shared memory; the "slot free" barrier of each CTA collects one tcgen05.commit from
+// every CTA of the cluster (a multicast load overwrites the slot everywhere).
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_2d_mc(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%2, %3}], [%4], %5;"
+      ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(bar), "h"(mask) : "memory");
+}
+__device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"(mask) : "memory");
+}
 __device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
@@ -125,14 +142,17 @@ __device__ __forceinline__ float4 lds128(uint32_t addr) {
   asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
   return v;
 }
-// ELU (alpha = 1) for the epilogue: the accumulator is about to be rounded to TF32 (2^-11), so
-// expm1 is evaluated as ex2.approx - 1 (abs. error < 3e-7) away from zero and as a 4-term Taylor
-// polynomial near zero (rel. error < 2e-7): ~6 instructions instead of expm1f's ~30.
+// ELU (alpha = 1) for the epilogues: expm1(v) = ex2.approx(v log2 e) - 1, five instructions
+// instead of expm1f's ~30.  The absolute error stays below 3e-7 everywhere (ex2.approx is good to
+// 2^-22 of a result <= 1); the output is then rounded to TF32, whose half-ulp at the typical
+// activation magnitude (0.1 .. 1) is 3e-5 .. 2.4e-4, so the cancellation in e - 1 for v -> 0-
+// (relative, not absolute, growth of the error) is invisible to every consumer: the next layer's
+// dot product and ELU' = h + 1 both see absolute perturbations.  The epilogue is issue-bound
+// (ncu r1c: 14 FP32-pipe instructions per element with the former near-zero polynomial branch).
 __device__ __forceinline__ float elu_fast(float v) {
   float e;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(v * 1.4426950408889634f));
-  const float t = v * (1.f + v * (0.5f + v * (0.16666667f + v * 0.041666668f)));
-  return v > 0.f ? v : (v > -0.0625f ? t : e - 1.f);
+  return v > 0.f ? v : e - 1.f;
 }
 
 

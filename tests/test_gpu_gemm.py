@@ -210,8 +210,9 @@ def test_fused_trunk_forward(K, M, k_in, n_groups):
                 check(got, ref, 1e-3, "fused " + name)
 
 
-@pytest.mark.parametrize("M,k_in,n_groups", [(128, 104, 1), (8192, 104, 4), (16384, 104, 4), (8192, 88, 1)])
-def test_fused_trunk_equals_layerwise(K, M, k_in, n_groups):
+@pytest.mark.parametrize("M,k_in,n_groups,cluster", [(128, 104, 1, 0), (8192, 104, 4, 0), (16384, 104, 4, 2), (8192, 88, 1, 1),
+                                                     (300, 104, 2, 4), (700, 88, 3, 2), (8192, 104, 2, 4)])
+def test_fused_trunk_equals_layerwise(K, M, k_in, n_groups, cluster):
     """The layer-fused trunk accumulates every output element over k in the same order as the
     per-layer GEMMs (k-blocks ascending into one fp32 TMEM accumulator), so h1/h2/h3 must be
     BIT-IDENTICAL between the two paths — a sharper check than any tolerance: a race on the
@@ -232,8 +233,11 @@ def test_fused_trunk_equals_layerwise(K, M, k_in, n_groups):
         lw[1].append(dict(a=K.addr(hl[0]), lda=512, b=K.addr(w2), ldb=512, bias=K.addr(b2), out=K.addr(hl[1]), ldo=256))
         lw[2].append(dict(a=K.addr(hl[1]), lda=256, b=K.addr(w3), ldb=256, bias=K.addr(b3), out=K.addr(hl[2]), ldo=128))
         outs.append((hf, hl, (x, w1, w2, w3, b1, b2, b3)))
+    from pql_b200 import _lib
     for rep in range(3):                       # repeated launches: a race need not fire every time
+        _lib.load().pqlb_mlp_forward_cluster(cluster)     # 0 = automatic; M = 300 / 700 exercise the ghost tiles
         K.MlpForward(M, k_in, groups)()
+        _lib.load().pqlb_mlp_forward_cluster(0)
         K.Gemm(M, 512, k_in, lw[0], epilogue=K.EPI_BIAS_ELU, tile_n=256)()
         K.Gemm(M, 256, 512, lw[1], epilogue=K.EPI_BIAS_ELU, tile_n=128)()
         K.Gemm(M, 128, 256, lw[2], epilogue=K.EPI_BIAS_ELU, tile_n=128)()

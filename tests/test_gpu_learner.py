@@ -138,3 +138,45 @@ def test_update_launch_list_is_bit_reproducible(B, distl, which):
     refill of the ELU'-operand staging buffer could overtake the shared-memory reads of the
     previous chunk when two CTAs shared an SM."""
     assert parity.plan_divergence(B, distl, which, repeats=4, device=DEV) is None
+
+
+def _run_interleaved(streams, seed=9, B=512, steps=3):
+    """bench.py's loop in miniature: per env step one update() exchange, 4 critic + 2 actor updates."""
+    from pql_b200.algo import PQLPLearner, PQLVLearner
+    from pql_b200.replay import NStepReplay
+    from pql_b200.utils import default_pql_cfg
+    O, A, E = 88, 16, 256
+    torch.manual_seed(seed)
+    cfg = default_pql_cfg(batch_size=B, memory_size=4096, num_envs=E)
+    cfg.learner_streams = streams
+    v, p = PQLVLearner(O, A, cfg), PQLPLearner(O, A, cfg)
+    ns = NStepReplay(O, A, num_envs=E, nstep=3, device=DEV)
+    g = torch.Generator(device=DEV).manual_seed(seed)
+    norm = (torch.zeros(O, device=DEV), torch.ones(O, device=DEV), 1e-4)
+    critic, actor = v.start()[0], p.start()[0]
+    losses = []
+    for k in range(steps):
+        T = 8 if k == 0 else 1
+        blk = (torch.randn(E, T, O, device=DEV, generator=g), torch.rand(E, T, A, device=DEV, generator=g) * 2 - 1,
+               torch.randn(E, T, 1, device=DEV, generator=g) * 0.01, torch.randn(E, T, O, device=DEV, generator=g),
+               (torch.rand(E, T, 1, device=DEV, generator=g) < 0.05).float())
+        tr = ns.add_to_buffer(*blk)
+        critic, vl, _ = v.update(actor, tr, norm, 0)
+        actor, pl, _ = p.update(critic, tr[0], norm, 0)
+        losses.append((vl, pl))
+        for j in range(4):
+            v.learn()
+            if j % 2 == 1:
+                p.learn()
+    torch.cuda.synchronize()
+    return v.critic.arena.flat.clone(), p.actor.arena.flat.clone(), losses
+
+
+def test_learner_streams_match_single_stream():
+    """cfg.learner_streams only changes WHERE the launches are enqueued: with the update() exchange
+    as the join point, weights and reported losses must be bit-identical to the one-stream run."""
+    c0, a0, l0 = _run_interleaved(False)
+    c1, a1, l1 = _run_interleaved(True)
+    assert torch.equal(c0, c1) and torch.equal(a0, a1)
+    assert l0 == l1
+    assert torch.isfinite(c0).all() and torch.isfinite(a0).all()

@@ -21,6 +21,7 @@ for i in range(ng):
                        b3=K.addr(b[2]), head_w=K.addr(w4), head_b=K.addr(b4), q=K.addr(q),
                        h1=K.addr(h[0]) if st else 0, h2=K.addr(h[1]) if st else 0, h3=K.addr(h[2]) if st else 0))
     keep += [x, w1, w2, w3, b, h, q, w4, b4]
+lib.pqlb_mlp_forward_cluster(int(os.environ.get("CLUSTER", "0")))
 call = K.MlpForward(M, k_in, groups)
 call(); torch.cuda.synchronize()
 dbg = torch.zeros(64, dtype=torch.int64, device=dev)
@@ -31,7 +32,11 @@ e0.record(); call(); e1.record(); torch.cuda.synchronize()
 lib.pqlb_mlp_forward_debug(None)
 t = dbg.cpu().tolist()
 t0 = min(x for x in t if x > 0)
-print("kernel us", e0.elapsed_time(e1) * 1e3)
+print("kernel us (with timeline stamps)", e0.elapsed_time(e1) * 1e3)
+e0.record()
+for _ in range(20): call()
+e1.record(); torch.cuda.synchronize()
+print("kernel us (avg of 20)", e0.elapsed_time(e1) * 1e3 / 20)
 names_m = ["start", "x_full", "L1q0", "L1q1", "c0 wait", "c0 done", "L1q2", "c1 wait", "c1 done", "L1q3", "c2 wait", "c2 done", "c3 wait", "c3 done", "L3 done"]
 print("MMA thread:")
 for n, v in zip(names_m, t[:len(names_m)]):
