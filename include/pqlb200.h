@@ -10,7 +10,9 @@
  * Layouts
  * -------
  * Transition record (ring and n-step window), fp32 words, `rec_ld` words per record
- * (a multiple of 8 words = 32 B so that a record covers whole DRAM sectors):
+ * (the next power of two >= the words used: 256 words = 1 KB for obs 88 / act 16, 512 words for
+ * obs 211 / act 20 - random gathers of power-of-two-aligned records run ~1.4x faster than
+ * 800-byte ones on B200, see common.cuh):
  *     [0, O)                     obs
  *     [obs_pad, obs_pad+O)       next_obs          obs_pad = round_up(O, 4)
  *     [2*obs_pad, 2*obs_pad+A)   action
@@ -63,6 +65,10 @@ int pqlb_ring_insert(float* ring, int64_t capacity, int obs_dim, int act_dim,
                      const float* obs, const float* action, const float* reward,
                      const float* next_obs, const float* done,
                      int64_t n, int64_t next_p, pqlb_stream_t stream);
+
+/* Tests / measurements: 1 = force the LDG/STG insert kernel; 0 (default) = the TMA tile mover
+ * whenever obs_dim % 4 == 0, act_dim % 4 == 0, 16-byte aligned inputs and n <= capacity. */
+void pqlb_ring_insert_force_ldg(int on);
 
 /* Observation-only ring of the P-learner, pql/algo/pql_p_learner.py:66-83.  ring is [capacity, O]. */
 int pqlb_obsring_insert(float* ring, int64_t capacity, int obs_dim, const float* obs,

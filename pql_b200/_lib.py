@@ -65,6 +65,7 @@ _PROTOS = {
     "pqlb_record_ld": (_int, [_int, _int]),
     "pqlb_x_ld": (_int, [_int, _int]),
     "pqlb_ring_insert": (_int, [_f, _i64, _int, _int, _f, _f, _f, _f, _f, _i64, _i64, _st]),
+    "pqlb_ring_insert_force_ldg": (None, [_int]),
     "pqlb_obsring_insert": (_int, [_f, _i64, _int, _f, _i64, _i64, _st]),
     "pqlb_nstep_push": (_int, [_f, _int, _int, _int, _int, _f, _f, _f, _f, _f, _int, _i64,
                                C.POINTER(_flt), _f, _f, _f, _f, _f, _st]),

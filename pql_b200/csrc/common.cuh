@@ -34,7 +34,14 @@ __host__ __device__ inline RecGeom rec_geom(int O, int A) {
   g.off_act = 2 * g.obs_pad;
   g.off_rew = 2 * g.obs_pad + g.act_pad;
   g.off_done = g.off_rew + 1;
-  g.rec_ld = round_up(g.off_done + 1, 8);
+  // Record stride: the next power of two (words).  Measured on B200 (tools/gather_bench.cu,
+  // profiles/r1_gather_record_size.txt): gathering random 800-byte records out of an 800 MB table
+  // runs at 3.9-4.0 TB/s, 896-byte (128-B aligned) records at 4.2 TB/s, 1024-byte records at
+  // 5.8 TB/s - DRAM efficiency collapses when a record straddles a power-of-two block - so the
+  // ring trades 28 % more memory (1.02 GB for 1 M AllegroHand slots) for ~1.4x sample bandwidth.
+  int ld = 8;
+  while (ld < g.off_done + 1) ld <<= 1;
+  g.rec_ld = ld;
   return g;
 }
 

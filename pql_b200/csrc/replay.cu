@@ -10,7 +10,8 @@
 namespace pqlb {
 
 constexpr int kThreads = 256;
-constexpr int kUnroll = 4;
+constexpr int kUnroll = 8;          // independent 16-byte loads in flight per thread (tools/copy_bench.cu: U8 + 32 blocks/SM is the fastest copy)
+constexpr int kBlocksPerSM = 32;
 
 template <int VEC> struct VecT;
 template <> struct VecT<4> { using type = float4; };
@@ -23,7 +24,42 @@ template <int VEC> __host__ __device__ inline FieldMap field_map(const RecGeom& 
   FieldMap f; f.ov = g.O / VEC; f.av = g.A / VEC; f.per_row = 2 * f.ov + f.av; return f;
 }
 
+// Walks the flattened (row, sub-item) space with the grid stride WITHOUT a division per item: the
+// first item and the stride are decomposed once per thread, every step is two adds and a carry.
+// (The first version divided a 64-bit item index by per_row for every 16 bytes moved - ~100
+// instructions - which made these "HBM-bound" kernels issue-bound: 0.58-0.74 of the copy roofline.)
+struct ItemWalk {
+  int64_t row, drow;
+  int sub, dsub, per_row;
+  __device__ ItemWalk(int64_t first, int64_t stride, int per_row_) : per_row(per_row_) {
+    row = first / per_row; sub = (int)(first - row * per_row);
+    drow = stride / per_row; dsub = (int)(stride - drow * per_row);
+  }
+  __device__ __forceinline__ void next() {
+    sub += dsub; row += drow;
+    if (sub >= per_row) { sub -= per_row; ++row; }
+  }
+};
+
 // -------------------------------------------------------------------------------- K1 insert
+// One warp moves kRec records at a time: lane l handles items l, l + 32, ... of each record, so
+// the field decode depends on the item only (shared by the kRec records), every record pointer is
+// warp-uniform and a thread keeps kRec independent 16-byte loads in flight with ~50 registers
+// (the flat item-per-thread version needed 114 at 8 loads in flight and ran at 2 blocks per SM).
+constexpr int kRec = 4;
+
+// item -> (field, offset inside the field, offset inside the record), in VEC-word units.
+// field: 0 obs, 1 next_obs, 2 action, 3 reward/done (+ padding up to a whole 32-byte sector)
+template <int VEC> struct ItemDecode {
+  int field, fo, ro;
+  __device__ __forceinline__ ItemDecode(int it, const RecGeom& g, const FieldMap& f) {
+    if (it < f.ov)               { field = 0; fo = it * VEC;                ro = g.off_obs + fo; }
+    else if (it < 2 * f.ov)      { field = 1; fo = (it - f.ov) * VEC;       ro = g.off_next + fo; }
+    else if (it < f.per_row)     { field = 2; fo = (it - 2 * f.ov) * VEC;   ro = g.off_act + fo; }
+    else                         { field = 3; fo = (it - f.per_row) * VEC;  ro = g.off_rew + fo; }
+  }
+};
+
 template <int VEC>
 __global__ void __launch_bounds__(kThreads)
 ring_insert_kernel(float* __restrict__ ring, RecGeom g,
@@ -33,43 +69,49 @@ ring_insert_kernel(float* __restrict__ ring, RecGeom g,
                    int64_t tail) {
   using V = typename VecT<VEC>::type;
   const FieldMap f = field_map<VEC>(g);
-  const int64_t total = n * f.per_row;
-  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  // items of the tail: [rew, done] and zero padding up to the end of their 32-byte sector, so that
+  // every sector of a record is written whole (no read-modify-write of a partial sector in L2)
+  const int tail_words = ((g.off_rew + 2 + 7) & ~7) - g.off_rew;
+  const int items = f.per_row + tail_words / VEC;
 
   auto slot_of = [&](int64_t row) -> int64_t {
     if (row < head) { int64_t s = next_p + row; return s < tail ? -1 : s; }   // superseded by the wrapped tail
     return row - head;
   };
 
-  for (int64_t base = tid; base < total; base += stride * kUnroll) {
-    V val[kUnroll]; float* dst[kUnroll];
+  for (int64_t r0 = ((((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5)) * kRec; r0 < n; r0 += nwarps * kRec) {
+    float* dst[kRec];
 #pragma unroll
-    for (int u = 0; u < kUnroll; ++u) {
-      const int64_t item = base + (int64_t)u * stride;
-      dst[u] = nullptr;
-      if (item < total) {
-        const int64_t row = item / f.per_row;
-        const int sub = (int)(item - row * f.per_row);
-        const int64_t s = slot_of(row);
-        const float* src; int off;
-        if (sub < f.ov)            { src = obs  + row * g.O + sub * VEC;               off = g.off_obs  + sub * VEC; }
-        else if (sub < 2 * f.ov)   { src = nobs + row * g.O + (sub - f.ov) * VEC;      off = g.off_next + (sub - f.ov) * VEC; }
-        else                       { src = act  + row * g.A + (sub - 2 * f.ov) * VEC;  off = g.off_act  + (sub - 2 * f.ov) * VEC; }
-        val[u] = *reinterpret_cast<const V*>(src);
-        if (s >= 0) dst[u] = ring + s * g.rec_ld + off;
-      }
+    for (int r = 0; r < kRec; ++r) {
+      const int64_t s = r0 + r < n ? slot_of(r0 + r) : -1;
+      dst[r] = s >= 0 ? ring + s * g.rec_ld : nullptr;
     }
+    for (int it = lane; it < items; it += 32) {
+      const ItemDecode<VEC> d(it, g, f);
+      V val[kRec];
 #pragma unroll
-    for (int u = 0; u < kUnroll; ++u)
-      if (dst[u]) *reinterpret_cast<V*>(dst[u]) = val[u];
-  }
-  // reward + done: one float2 per row; done is stored as the reference's bool column (x != 0)
-  for (int64_t row = tid; row < n; row += stride) {
-    const int64_t s = slot_of(row);
-    if (s >= 0) {
-      float2 rd = make_float2(rew[row], done[row] != 0.f ? 1.f : 0.f);
-      *reinterpret_cast<float2*>(ring + s * g.rec_ld + g.off_rew) = rd;
+      for (int r = 0; r < kRec; ++r) {
+        if (!dst[r]) continue;
+        const int64_t row = r0 + r;
+        if (d.field == 0)      val[r] = __ldcs(reinterpret_cast<const V*>(obs + row * g.O + d.fo));
+        else if (d.field == 1) val[r] = __ldcs(reinterpret_cast<const V*>(nobs + row * g.O + d.fo));
+        else if (d.field == 2) val[r] = __ldcs(reinterpret_cast<const V*>(act + row * g.A + d.fo));
+        else {
+          // done is stored as the reference's bool column (x != 0)
+          float t[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+          for (int q = 0; q < VEC; ++q) {
+            const int wq = d.fo + q;
+            t[q] = wq == 0 ? rew[row] : (wq == 1 ? (done[row] != 0.f ? 1.f : 0.f) : 0.f);
+          }
+          val[r] = *reinterpret_cast<V*>(t);
+        }
+      }
+#pragma unroll
+      for (int r = 0; r < kRec; ++r)       // streaming stores: the ring must not evict the learner's working set from L2
+        if (dst[r]) __stcs(reinterpret_cast<V*>(dst[r] + d.ro), val[r]);
     }
   }
 }
@@ -80,26 +122,26 @@ obsring_insert_kernel(float* __restrict__ ring, int O, const float* __restrict__
                       int64_t next_p, int64_t head, int64_t tail) {
   using V = typename VecT<VEC>::type;
   const int ov = O / VEC;
-  const int64_t total = n * ov;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t base = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; base < total; base += stride * kUnroll) {
+  ItemWalk w((int64_t)blockIdx.x * blockDim.x + threadIdx.x, stride, ov);
+  while (w.row < n) {
     V val[kUnroll]; float* dst[kUnroll];
 #pragma unroll
     for (int u = 0; u < kUnroll; ++u) {
-      const int64_t item = base + (int64_t)u * stride;
       dst[u] = nullptr;
-      if (item < total) {
-        const int64_t row = item / ov;
-        const int sub = (int)(item - row * ov);
+      if (w.row < n) {
+        const int64_t row = w.row;
+        const int sub = w.sub;
         int64_t s;
         if (row < head) { s = next_p + row; if (s < tail) s = -1; } else s = row - head;
-        val[u] = *reinterpret_cast<const V*>(obs + row * O + sub * VEC);
+        val[u] = __ldcs(reinterpret_cast<const V*>(obs + row * O + sub * VEC));
         if (s >= 0) dst[u] = ring + s * O + sub * VEC;
       }
+      w.next();
     }
 #pragma unroll
     for (int u = 0; u < kUnroll; ++u)
-      if (dst[u]) *reinterpret_cast<V*>(dst[u]) = val[u];
+      if (dst[u]) __stcs(reinterpret_cast<V*>(dst[u]), val[u]);
   }
 }
 
@@ -180,31 +222,34 @@ sample_gather_kernel(const float* __restrict__ ring, RecGeom g, const int64_t* _
                      float* __restrict__ o_rew, float* __restrict__ o_nobs, float* __restrict__ o_done) {
   using V = typename VecT<VEC>::type;
   const FieldMap f = field_map<VEC>(g);
-  const int64_t total = B * f.per_row;
-  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  for (int64_t base = tid; base < total; base += stride * kUnroll) {
-    V val[kUnroll]; float* dst[kUnroll];
+  const int lane = threadIdx.x & 31;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const int items = f.per_row + (VEC == 4 ? 1 : 2);      // + [rew, done]
+  for (int64_t b0 = ((((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5)) * kRec; b0 < B; b0 += nwarps * kRec) {
+    const float* rec[kRec];
 #pragma unroll
-    for (int u = 0; u < kUnroll; ++u) {
-      const int64_t item = base + (int64_t)u * stride;
-      dst[u] = nullptr;
-      if (item < total) {
-        const int64_t b = item / f.per_row;
-        const int sub = (int)(item - b * f.per_row);
-        const float* rec = ring + __ldg(idx + b) * g.rec_ld;
-        if (sub < f.ov)          { val[u] = *reinterpret_cast<const V*>(rec + g.off_obs + sub * VEC);             dst[u] = o_obs + b * g.O + sub * VEC; }
-        else if (sub < 2 * f.ov) { val[u] = *reinterpret_cast<const V*>(rec + g.off_next + (sub - f.ov) * VEC);   dst[u] = o_nobs + b * g.O + (sub - f.ov) * VEC; }
-        else                     { val[u] = *reinterpret_cast<const V*>(rec + g.off_act + (sub - 2 * f.ov) * VEC); dst[u] = o_act + b * g.A + (sub - 2 * f.ov) * VEC; }
+    for (int r = 0; r < kRec; ++r) rec[r] = b0 + r < B ? ring + __ldg(idx + b0 + r) * g.rec_ld : nullptr;
+    for (int it = lane; it < items; it += 32) {
+      const ItemDecode<VEC> d(it, g, f);
+      V val[kRec];
+#pragma unroll
+      for (int r = 0; r < kRec; ++r)
+        if (rec[r]) val[r] = __ldcs(reinterpret_cast<const V*>(rec[r] + d.ro));
+#pragma unroll
+      for (int r = 0; r < kRec; ++r) {
+        if (!rec[r]) continue;
+        const int64_t b = b0 + r;
+        if (d.field == 0)      *reinterpret_cast<V*>(o_obs + b * g.O + d.fo) = val[r];
+        else if (d.field == 1) *reinterpret_cast<V*>(o_nobs + b * g.O + d.fo) = val[r];
+        else if (d.field == 2) *reinterpret_cast<V*>(o_act + b * g.A + d.fo) = val[r];
+        else {
+          const float* t = reinterpret_cast<const float*>(&val[r]);   // bool column -> .float() is 0.0 / 1.0 already
+          if (VEC == 4) { o_rew[b] = t[0]; o_done[b] = t[1]; }
+          else if (d.fo == 0) o_rew[b] = t[0];
+          else o_done[b] = t[0];
+        }
       }
     }
-#pragma unroll
-    for (int u = 0; u < kUnroll; ++u)
-      if (dst[u]) *reinterpret_cast<V*>(dst[u]) = val[u];
-  }
-  for (int64_t b = tid; b < B; b += stride) {
-    const float2 rd = *reinterpret_cast<const float2*>(ring + __ldg(idx + b) * g.rec_ld + g.off_rew);
-    o_rew[b] = rd.x; o_done[b] = rd.y;      // bool column -> .float() is 0.0 / 1.0 already
   }
 }
 
@@ -223,49 +268,64 @@ sample_critic_batch_kernel(const float* __restrict__ ring, RecGeom g, const int6
                            int64_t B, const float* __restrict__ mean, const float* __restrict__ var,
                            float eps, float* __restrict__ x_cur, float* __restrict__ x_tgt, int x_ld,
                            float* __restrict__ o_rew, float* __restrict__ o_done) {
-  const int per_row = (g.O + x_ld) / VEC;  // next_obs columns, then one full x_cur row
-  const int ov = g.O / VEC;
-  const int64_t total = B * per_row;
-  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  for (int64_t item = tid; item < total; item += stride) {
-    const int64_t b = item / per_row;
-    const int sub = (int)(item - b * per_row);
-    const float* rec = ring + __ldg(idx + b) * g.rec_ld;
-    float v[VEC];
-    if (sub < ov) {
-      const int k = sub * VEC;
-      if (VEC == 4) *reinterpret_cast<float4*>(v) = *reinterpret_cast<const float4*>(rec + g.off_next + k);
-      else v[0] = rec[g.off_next + k];
+  using V = typename VecT<VEC>::type;
+  const FieldMap f = field_map<VEC>(g);
+  const int lane = threadIdx.x & 31;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const int rd_items = VEC == 4 ? 1 : 2;
+  const int pad_items = (x_ld - g.O - g.A) / VEC;           // zero padding columns of both input rows
+  const int items = f.per_row + rd_items + pad_items;
+  for (int64_t b0 = ((((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5)) * kRec; b0 < B; b0 += nwarps * kRec) {
+    const float* rec[kRec];
 #pragma unroll
-      for (int u = 0; u < VEC; ++u) { if (mean) v[u] = norm_clamp(v[u], mean[k + u], var[k + u], eps); v[u] = rn_tf32(v[u]); }
-      if (VEC == 4) *reinterpret_cast<float4*>(x_tgt + b * x_ld + k) = *reinterpret_cast<float4*>(v);
-      else x_tgt[b * x_ld + k] = v[0];
-    } else {
-      const int k = (sub - ov) * VEC;      // first column of x_cur
-      if (k < g.O) {
-        if (VEC == 4) *reinterpret_cast<float4*>(v) = *reinterpret_cast<const float4*>(rec + g.off_obs + k);
-        else v[0] = rec[g.off_obs + k];
+    for (int r = 0; r < kRec; ++r) rec[r] = b0 + r < B ? ring + __ldg(idx + b0 + r) * g.rec_ld : nullptr;
+    for (int it = lane; it < items; it += 32) {
+      if (it >= f.per_row + rd_items) {                       // padding columns
+        const int k = g.O + g.A + (it - f.per_row - rd_items) * VEC;
+        float z[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-        for (int u = 0; u < VEC; ++u) { if (mean) v[u] = norm_clamp(v[u], mean[k + u], var[k + u], eps); v[u] = rn_tf32(v[u]); }
-      } else if (k < g.O + g.A) {
-        if (VEC == 4) *reinterpret_cast<float4*>(v) = *reinterpret_cast<const float4*>(rec + g.off_act + (k - g.O));
-        else v[0] = rec[g.off_act + (k - g.O)];
-#pragma unroll
-        for (int u = 0; u < VEC; ++u) v[u] = rn_tf32(v[u]);
-      } else {
-#pragma unroll
-        for (int u = 0; u < VEC; ++u) v[u] = 0.f;
-        if (VEC == 4) *reinterpret_cast<float4*>(x_tgt + b * x_ld + k) = make_float4(0.f, 0.f, 0.f, 0.f);
-        else x_tgt[b * x_ld + k] = 0.f;     // zero padding of the target input row
+        for (int r = 0; r < kRec; ++r)
+          if (rec[r]) {
+            *reinterpret_cast<V*>(x_cur + (b0 + r) * x_ld + k) = *reinterpret_cast<V*>(z);
+            *reinterpret_cast<V*>(x_tgt + (b0 + r) * x_ld + k) = *reinterpret_cast<V*>(z);
+          }
+        continue;
       }
-      if (VEC == 4) *reinterpret_cast<float4*>(x_cur + b * x_ld + k) = *reinterpret_cast<float4*>(v);
-      else x_cur[b * x_ld + k] = v[0];
+      const ItemDecode<VEC> d(it, g, f);
+      V val[kRec];
+#pragma unroll
+      for (int r = 0; r < kRec; ++r)
+        if (rec[r]) val[r] = __ldcs(reinterpret_cast<const V*>(rec[r] + d.ro));
+      float m[4] = {0.f, 0.f, 0.f, 0.f}, sd[4] = {1.f, 1.f, 1.f, 1.f};
+      if (mean && d.field <= 1) {
+#pragma unroll
+        for (int q = 0; q < VEC; ++q) { m[q] = mean[d.fo + q]; sd[q] = __fsqrt_rn(__fadd_rn(var[d.fo + q], eps)); }
+      }
+#pragma unroll
+      for (int r = 0; r < kRec; ++r) {
+        if (!rec[r]) continue;
+        const int64_t b = b0 + r;
+        float* t = reinterpret_cast<float*>(&val[r]);
+        if (d.field <= 1) {
+          // common.py:139-145: clamp((x - mean) / sqrt(var + eps), -5, 5), then the tensor-core operand rounding
+#pragma unroll
+          for (int q = 0; q < VEC; ++q) {
+            float y = t[q];
+            if (mean) y = fminf(fmaxf(__fdiv_rn(__fsub_rn(y, m[q]), sd[q]), -5.f), 5.f);
+            t[q] = rn_tf32(y);
+          }
+          *reinterpret_cast<V*>((d.field == 0 ? x_cur : x_tgt) + b * x_ld + d.fo) = val[r];
+        } else if (d.field == 2) {
+#pragma unroll
+          for (int q = 0; q < VEC; ++q) t[q] = rn_tf32(t[q]);
+          *reinterpret_cast<V*>(x_cur + b * x_ld + g.O + d.fo) = val[r];
+        } else {
+          if (VEC == 4) { o_rew[b] = t[0]; o_done[b] = t[1]; }
+          else if (d.fo == 0) o_rew[b] = t[0];
+          else o_done[b] = t[0];
+        }
+      }
     }
-  }
-  for (int64_t b = tid; b < B; b += stride) {
-    const float2 rd = *reinterpret_cast<const float2*>(ring + __ldg(idx + b) * g.rec_ld + g.off_rew);
-    o_rew[b] = rd.x; o_done[b] = rd.y;
   }
 }
 
@@ -273,11 +333,10 @@ __global__ void __launch_bounds__(kThreads)
 sample_obs_batch_kernel(const float* __restrict__ obsring, int O, const int64_t* __restrict__ idx,
                         int64_t B, const float* __restrict__ mean, const float* __restrict__ var,
                         float eps, float* __restrict__ x, int x_ld, int A) {
-  const int64_t total = B * x_ld;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t item = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; item < total; item += stride) {
-    const int64_t b = item / x_ld;
-    const int k = (int)(item - b * x_ld);
+  for (ItemWalk w((int64_t)blockIdx.x * blockDim.x + threadIdx.x, stride, x_ld); w.row < B; w.next()) {
+    const int64_t b = w.row;
+    const int k = w.sub;
     if (k < O) {
       float v = obsring[__ldg(idx + b) * O + k];
       if (mean) v = norm_clamp(v, mean[k], var[k], eps);
@@ -293,15 +352,14 @@ sample_obs_batch_kernel(const float* __restrict__ obsring, int O, const int64_t*
 __global__ void __launch_bounds__(kThreads)
 pack_x_kernel(const float* __restrict__ a, int64_t lda, int na, const float* __restrict__ b,
               int64_t ldb, int nb, float* __restrict__ x, int x_ld, int64_t rows) {
-  const int64_t total = rows * x_ld;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t item = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; item < total; item += stride) {
-    const int64_t r = item / x_ld;
-    const int k = (int)(item - r * x_ld);
+  for (ItemWalk w((int64_t)blockIdx.x * blockDim.x + threadIdx.x, stride, x_ld); w.row < rows; w.next()) {
+    const int64_t r = w.row;
+    const int k = w.sub;
     float v = 0.f;
     if (k < na) v = a[r * lda + k];
     else if (k < na + nb) v = b[r * ldb + (k - na)];
-    x[item] = rn_tf32(v);
+    x[r * x_ld + k] = rn_tf32(v);
   }
 }
 
@@ -314,6 +372,13 @@ static inline void split_insert(int64_t n, int64_t next_p, int64_t capacity, int
 }  // namespace pqlb
 
 using namespace pqlb;
+
+int pqlb_ring_insert_tma(float* ring, int64_t capacity, int obs_dim, int act_dim, const float* obs,
+                         const float* action, const float* reward, const float* next_obs,
+                         const float* done, int64_t n, int64_t next_p, cudaStream_t stream);
+static bool g_insert_ldg = false;
+/* Tests / measurements: 1 = force the LDG/STG insert kernel, 0 = TMA path when possible (default). */
+extern "C" void pqlb_ring_insert_force_ldg(int on) { g_insert_ldg = on != 0; }
 
 extern "C" int pqlb_obs_pad(int obs_dim) { return round_up(obs_dim, 4); }
 extern "C" int pqlb_record_ld(int obs_dim, int act_dim) { return rec_geom(obs_dim, act_dim).rec_ld; }
@@ -332,14 +397,16 @@ extern "C" int pqlb_ring_insert(float* ring, int64_t capacity, int obs_dim, int 
   PQLB_CHECK_ALIGN(aligned16(ring));
   const RecGeom g = rec_geom(obs_dim, act_dim);
   cudaStream_t st = (cudaStream_t)stream;
+  if (!g_insert_ldg) {         // TMA tile mover (replay_tma.cu) whenever shape and alignment allow
+    const int rc = pqlb_ring_insert_tma(ring, capacity, obs_dim, act_dim, obs, action, reward, next_obs, done, n, next_p, st);
+    if (rc != PQLB_E_UNSUPPORTED) return rc;
+  }
   const bool vec4 = obs_dim % 4 == 0 && act_dim % 4 == 0 && aligned16(obs) && aligned16(action) && aligned16(next_obs);
   if (vec4) {
-    const int64_t items = n * field_map<4>(g).per_row;
-    ring_insert_kernel<4><<<grid_for(items, kThreads, kUnroll), kThreads, 0, st>>>(
+    ring_insert_kernel<4><<<grid_for(n * 32, kThreads, kRec, kBlocksPerSM), kThreads, 0, st>>>(
         ring, g, obs, action, reward, next_obs, done, n, next_p, head, tail);
   } else {
-    const int64_t items = n * field_map<1>(g).per_row;
-    ring_insert_kernel<1><<<grid_for(items, kThreads, kUnroll), kThreads, 0, st>>>(
+    ring_insert_kernel<1><<<grid_for(n * 32, kThreads, kRec, kBlocksPerSM), kThreads, 0, st>>>(
         ring, g, obs, action, reward, next_obs, done, n, next_p, head, tail);
   }
   PQLB_LAUNCH_RET();
@@ -354,10 +421,10 @@ extern "C" int pqlb_obsring_insert(float* ring, int64_t capacity, int obs_dim, c
   PQLB_CHECK_SHAPE(tail <= capacity);
   cudaStream_t st = (cudaStream_t)stream;
   if (obs_dim % 4 == 0 && aligned16(obs) && aligned16(ring)) {
-    obsring_insert_kernel<4><<<grid_for(n * (obs_dim / 4), kThreads, kUnroll), kThreads, 0, st>>>(
+    obsring_insert_kernel<4><<<grid_for(n * (obs_dim / 4), kThreads, kUnroll, kBlocksPerSM), kThreads, 0, st>>>(
         ring, obs_dim, obs, n, next_p, head, tail);
   } else {
-    obsring_insert_kernel<1><<<grid_for(n * obs_dim, kThreads, kUnroll), kThreads, 0, st>>>(
+    obsring_insert_kernel<1><<<grid_for(n * obs_dim, kThreads, kUnroll, kBlocksPerSM), kThreads, 0, st>>>(
         ring, obs_dim, obs, n, next_p, head, tail);
   }
   PQLB_LAUNCH_RET();
@@ -409,10 +476,10 @@ extern "C" int pqlb_sample_gather(const float* ring, int64_t capacity, int obs_d
   const bool vec4 = obs_dim % 4 == 0 && act_dim % 4 == 0 && aligned16(ring) && aligned16(out_obs) &&
                     aligned16(out_action) && aligned16(out_next_obs);
   if (vec4) {
-    sample_gather_kernel<4><<<grid_for(batch * field_map<4>(g).per_row, kThreads, kUnroll), kThreads, 0, st>>>(
+    sample_gather_kernel<4><<<grid_for(batch * 32, kThreads, kRec, kBlocksPerSM), kThreads, 0, st>>>(
         ring, g, idx, batch, out_obs, out_action, out_reward, out_next_obs, out_done);
   } else {
-    sample_gather_kernel<1><<<grid_for(batch * field_map<1>(g).per_row, kThreads, kUnroll), kThreads, 0, st>>>(
+    sample_gather_kernel<1><<<grid_for(batch * 32, kThreads, kRec, kBlocksPerSM), kThreads, 0, st>>>(
         ring, g, idx, batch, out_obs, out_action, out_reward, out_next_obs, out_done);
   }
   PQLB_LAUNCH_RET();
@@ -430,10 +497,10 @@ extern "C" int pqlb_sample_critic_batch(const float* ring, int64_t capacity, int
   const bool vec4 = obs_dim % 4 == 0 && act_dim % 4 == 0 && aligned16(ring) && aligned16(x_cur) && aligned16(x_tgt) &&
                     (!mean || (aligned16(mean) && aligned16(var)));
   if (vec4)
-    sample_critic_batch_kernel<4><<<grid_for(batch * (per_row / 4), kThreads, 2), kThreads, 0, (cudaStream_t)stream>>>(
+    sample_critic_batch_kernel<4><<<grid_for(batch * 32, kThreads, kRec, kBlocksPerSM), kThreads, 0, (cudaStream_t)stream>>>(
         ring, g, idx, batch, mean, var, eps, x_cur, x_tgt, x_ld, reward, done);
   else
-    sample_critic_batch_kernel<1><<<grid_for(batch * per_row, kThreads, 2), kThreads, 0, (cudaStream_t)stream>>>(
+    sample_critic_batch_kernel<1><<<grid_for(batch * 32, kThreads, kRec, kBlocksPerSM), kThreads, 0, (cudaStream_t)stream>>>(
         ring, g, idx, batch, mean, var, eps, x_cur, x_tgt, x_ld, reward, done);
   PQLB_LAUNCH_RET();
 }

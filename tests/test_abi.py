@@ -33,8 +33,8 @@ def test_geometry_helpers(lib):
     assert lib.pqlb_version() >= 100
     assert lib.pqlb_obs_pad(88) == 88 and lib.pqlb_obs_pad(211) == 212
     # Allegro: 88 + 88 + 16 + reward + done = 194 words -> 200 (multiple of 8 words = 32 B)
-    assert lib.pqlb_record_ld(88, 16) == 200
-    assert lib.pqlb_record_ld(211, 20) == 448
+    assert lib.pqlb_record_ld(88, 16) == 256       # 194 words used, power-of-two stride
+    assert lib.pqlb_record_ld(211, 20) == 512
     assert lib.pqlb_x_ld(88, 16) == 104 and lib.pqlb_x_ld(211, 20) == 232
 
 

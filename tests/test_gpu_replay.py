@@ -103,9 +103,20 @@ def test_allegro_stream_digests(golden_dir):
     assert sha(*(x.cpu().numpy() for x in s)) == meta["sample_digest"]
 
 
-@pytest.mark.parametrize("O,A", [(88, 16), (211, 20), (5, 3)])
-def test_ring_random_inserts_vs_oracle(O, A):
-    """Ragged sizes, exact fill (p == capacity), wraps, an insert larger than the free tail."""
+@pytest.mark.parametrize("O,A,ldg", [(88, 16, False), (88, 16, True), (211, 20, False), (5, 3, False), (12, 4, False)])
+def test_ring_random_inserts_vs_oracle(O, A, ldg):
+    """Ragged sizes, exact fill (p == capacity), wraps, an insert larger than the free tail; both
+    insert kernels (the TMA tile mover takes O % 4 == A % 4 == 0 shapes, ``ldg`` forces the other)."""
+    from pql_b200 import _lib
+    from pql_b200.replay import ReplayBuffer
+    _lib.load().pqlb_ring_insert_force_ldg(int(ldg))
+    try:
+        _ring_random_inserts(O, A)
+    finally:
+        _lib.load().pqlb_ring_insert_force_ldg(0)
+
+
+def _ring_random_inserts(O, A):
     from pql_b200.replay import ReplayBuffer
     cap = 1000
     rb = ReplayBuffer(cap, O, A, device=dev())
