@@ -278,7 +278,7 @@ def main():
         super_step(k, False)
     torch.cuda.synchronize(dev)
     per_kernel = {name: sum(a.elapsed_time(b) for a, b in evs) / prof_steps for name, evs in K.PROFILE.items()}
-    n_gemm = (len(K.PROFILE.get("pqlb_gemm_tf32", [])) + len(K.PROFILE.get("pqlb_mlp_forward", []))) // prof_steps
+    n_gemm = sum(len(K.PROFILE.get(k, [])) for k in ("pqlb_gemm_tf32", "pqlb_mlp_forward", "pqlb_mlp_backward")) // prof_steps
     K.PROFILE = None
     v.enable_graph(); p.enable_graph()
 
@@ -328,7 +328,8 @@ def main():
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
     tf32_peak = peaks.get("bf16_tflops_sustained", 1400.0) / 2.0
     peak_src = "measured (MEASURED_PEAKS.json)" if peaks else "fallback (B200_PROFILING.md)"
-    gemm_ms = per_kernel.get("pqlb_gemm_tf32", float("nan")) + per_kernel.get("pqlb_mlp_forward", 0.0)
+    TC_KERNELS = ("pqlb_gemm_tf32", "pqlb_mlp_forward", "pqlb_mlp_backward")      # every tcgen05 launch of the step
+    gemm_ms = sum(per_kernel.get(k, 0.0) for k in TC_KERNELS)
     flops_step = B * (V_PER_STEP * FLOP_V + P_PER_STEP * FLOP_P)
     achieved = flops_step / (gemm_ms * 1e-3) / 1e12
     value = world * V_PER_STEP * args.steps / (ms * 1e-3)
@@ -340,7 +341,7 @@ def main():
             "e2e": {"value": e2e, "unit": "critic updates/s", "h2d_bytes_per_step": h2d_bytes,
                     "d2h_bytes_per_step": 2 * 5 * 4, "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": launches,
-            "roofline": {"kernel": "gemm_tf32_kernel + mlp_fwd_kernel (tcgen05 kind::tf32; all dense-layer launches of one step)",
+            "roofline": {"kernel": "gemm_tf32_kernel + mlp_fwd_kernel + mlp_bwd_kernel (tcgen05 kind::tf32; all dense-layer launches of one step)",
                          "bound": "tensor", "achieved": achieved, "peak": tf32_peak, "unit": "TFLOP/s",
                          "frac": achieved / tf32_peak, "traffic": None, "launches_per_step": n_gemm,
                          "ms_per_step_in_kernel": gemm_ms,

@@ -190,6 +190,24 @@ int pqlb_mlp_forward(const pqlb_mlp_desc* desc, pqlb_stream_t stream);
  * tile through TMA multicast) of pqlb_mlp_forward; 0 = default (1: no cluster, the fastest measured). */
 void pqlb_mlp_forward_cluster(int cluster);
 
+/* ---- K3b: layer-fused dgrad chain of the trunk ---------------------------------------------------
+ * dz2[M,256] = (dz3[M,128] . W3) * elu'(h2);  dz1[M,512] = (dz2 . W2) * elu'(h1), both TF32-rounded,
+ * for up to PQLB_MAX_GROUPS network instances in one launch; dz2 stays in tensor memory between the
+ * two contractions.  w3 [128 x 256] and w2 [256 x 512] are the nn.Linear weights (TF32 copies), read
+ * as [K][N] without a transpose.  bias_part2 / bias_part1 (optional) receive the per-128-row-tile
+ * column sums of dz2 / dz1: part[tile * n_cols + col], tile < ceil(M / 128) - the bias gradients'
+ * partials for pqlb_grad_reduce.  Replaces the autograd backward of the Linear + ELU layers 2 and 3
+ * (pql/models/mlp.py:15-24 under loss.backward(), pql_v_learner.py:125, pql_p_learner.py:60). */
+typedef struct {
+  const float* dz3;
+  const float* w3; const float* w2;
+  const float* h2; const float* h1;
+  float* dz2; float* dz1;
+  float* bias_part2; float* bias_part1;
+} pqlb_mlp_bwd_group;
+typedef struct { int M, n_groups; pqlb_mlp_bwd_group g[PQLB_MAX_GROUPS]; } pqlb_mlp_bwd_desc;
+int pqlb_mlp_backward(const pqlb_mlp_bwd_desc* desc, pqlb_stream_t stream);
+
 /* dst = rn_tf32(src) elementwise (tensor-core operand copies of weights). */
 int pqlb_round_tf32(const float* src, float* dst, int64_t n, pqlb_stream_t stream);
 

@@ -115,6 +115,25 @@ class MlpForward(Call):
         super().__init__("pqlb_mlp_forward", C.byref(d))
 
 
+class MlpBackward(Call):
+    """Layer-fused dgrad chain (pqlb_mlp_backward) for up to four network instances.
+    ``groups``: dicts with dz3, w3, w2, h2, h1, dz2, dz1, [bias_part2, bias_part1] device addresses."""
+
+    FIELDS = ("dz3", "w3", "w2", "h2", "h1", "dz2", "dz1", "bias_part2", "bias_part1")
+
+    def __init__(self, M, groups):
+        d = _lib.MlpBwdDesc()
+        d.M, d.n_groups = int(M), len(groups)
+        for i, g in enumerate(groups):
+            unknown = set(g) - set(self.FIELDS)
+            if unknown:
+                raise KeyError(f"unknown mlp backward group fields {sorted(unknown)}")
+            for k in self.FIELDS:
+                setattr(d.g[i], k, g.get(k, 0) or None)
+        self.desc = d
+        super().__init__("pqlb_mlp_backward", C.byref(d))
+
+
 def pick_tile_n(N):
     for t in (16, 32, 64, 128, 256):
         if N <= t:

@@ -52,6 +52,15 @@ class MlpGroup(C.Structure):
                 ("h1", _f), ("h2", _f), ("h3", _f)]
 
 
+class MlpBwdGroup(C.Structure):
+    _fields_ = [("dz3", _f), ("w3", _f), ("w2", _f), ("h2", _f), ("h1", _f), ("dz2", _f), ("dz1", _f),
+                ("bias_part2", _f), ("bias_part1", _f)]
+
+
+class MlpBwdDesc(C.Structure):
+    _fields_ = [("M", _int), ("n_groups", _int), ("g", MlpBwdGroup * MAX_GROUPS)]
+
+
 class MlpDesc(C.Structure):
     _fields_ = [("M", _int), ("k_in", _int), ("n_groups", _int), ("g", MlpGroup * MAX_GROUPS)]
 
@@ -76,6 +85,7 @@ _PROTOS = {
     "pqlb_gemm_tf32": (_int, [C.POINTER(GemmDesc), _st]),
     "pqlb_mlp_forward": (_int, [C.POINTER(MlpDesc), _st]),
     "pqlb_mlp_forward_cluster": (None, [_int]),
+    "pqlb_mlp_backward": (_int, [C.POINTER(MlpBwdDesc), _st]),
     "pqlb_round_tf32": (_int, [_f, _f, _i64, _st]),
     "pqlb_doubleq_td_loss": (_int, [_f, _f, _f, _f, _f, _f, _flt, _i64, _f, _f, _f, _f, _f, _f, _f,
                                     _f, _f, _f, _st]),

@@ -109,15 +109,23 @@ class _UpdateBase:
         return off
 
     # ---- pieces shared by both updates -----------------------------------------------------
-    def _critic_backward(self, nets, dz3, dz2, dz1, h1, h2):
-        """dgrad through layers 3 and 2 of both critics (weights read as [K][N], no transposes)."""
-        B = self.B
-        g3 = [dict(a=K.addr(dz3[i]), lda=H3, b=nets[i].W[2], ldb=H2, aux=K.addr(h2[i]), ldaux=H2,
-                   out=K.addr(dz2[i]), ldo=H2) for i in range(2)]
-        g2 = [dict(a=K.addr(dz2[i]), lda=H2, b=nets[i].W[1], ldb=H1, aux=K.addr(h1[i]), ldaux=H1,
-                   out=K.addr(dz1[i]), ldo=H1) for i in range(2)]
-        return [K.Gemm(B, H2, H3, g3, epilogue=K.EPI_MUL_ELUGRAD, tile_n=fwd_tile(B, H2, 2), b_major=K.MN_MAJOR),
-                K.Gemm(B, H1, H2, g2, epilogue=K.EPI_MUL_ELUGRAD, tile_n=fwd_tile(B, H1, 2), b_major=K.MN_MAJOR)]
+    def _dgrad_chain(self, nets, dz3, dz2, dz1, h1, h2, bias=None):
+        """dgrad through layers 3 and 2 of len(nets) networks in ONE launch (pqlb_mlp_backward): dz2
+        stays in tensor memory, weights are read as [K][N] (no transposes).  ``bias`` = (opt, layout,
+        net ids): the kernel also writes the per-128-row partial column sums of dz2 / dz1, i.e. the
+        bias gradients of layers 1 and 0, registered here as reduction sources."""
+        groups = []
+        for j, n in enumerate(nets):
+            g = dict(dz3=K.addr(dz3[j]), w3=n.W[2], w2=n.W[1], h2=K.addr(h2[j]), h1=K.addr(h1[j]), dz2=K.addr(dz2[j]),
+                     dz1=K.addr(dz1[j]))
+            if bias is not None:
+                opt, layout, ids = bias
+                for layer, key, n_cols in ((1, "bias_part2", H2), (0, "bias_part1", H1)):
+                    off = self._ws_alloc(self.nblk * n_cols)
+                    g[key] = K.addr(self.ws, off)
+                    opt.add_source(layout.b_off[ids[j]][layer], n_cols, off, n_cols, self.nblk)
+            groups.append(g)
+        return [K.MlpBackward(self.B, groups)]
 
     def _head_backward_c51(self, nets, dl, h3, dz3):
         g = [dict(a=K.addr(dl[i]), lda=self.pd, b=nets[i].W[3], ldb=H3, aux=K.addr(h3[i]), ldaux=H3,
@@ -249,11 +257,12 @@ class CriticUpdate(_UpdateBase):
             self.loss_scale, self.n_loss_part = 1.0 / (B * N), (B + 7) // 8
         # -- backward of the current nets
         dz3, dz2, dz1 = ([self.dz[i][l] for i in range(2)] for l in (2, 1, 0))
-        calls += self._critic_backward(cnet, dz3, dz2, dz1, [h_c[i][0] for i in range(2)], [h_c[i][1] for i in range(2)])
+        calls += self._dgrad_chain(cnet, dz3, dz2, dz1, [h_c[i][0] for i in range(2)], [h_c[i][1] for i in range(2)],
+                                   bias=(self.opt, self.Lc, [0, 1]))
         calls.append(self._wgrad(self.opt, self.Lc, [0, 1], 2, dz3, H3, H3, [h_c[i][1] for i in range(2)], H2, H2))
         calls.append(self._wgrad(self.opt, self.Lc, [0, 1], 1, dz2, H2, H2, [h_c[i][0] for i in range(2)], H1, H1))
         calls.append(self._wgrad(self.opt, self.Lc, [0, 1], 0, dz1, H1, H1, [self.x_cur, self.x_cur], x_ld, O + A))
-        entries = [(i, l, self.dz[i][l], HIDDEN[l], HIDDEN[l]) for i in range(2) for l in range(3)]
+        entries = [(i, 2, self.dz[i][2], H3, H3) for i in range(2)]      # layers 0 / 1: fused into the dgrad chain
         if distl:
             entries += [(i, 3, self.dl[i], self.pd, N) for i in range(2)]
         calls.append(self._bias_grads(self.opt, self.Lc, entries))
@@ -407,7 +416,7 @@ class ActorUpdate(_UpdateBase):
             self.n_loss_part = (B + 7) // 8
         self.loss_scale = -1.0 / B                                                     # :57  -Q.mean()
         dz2, dz1 = ([self.dzc[i][l] for i in range(2)] for l in (1, 0))
-        calls += self._critic_backward(cnet, dz3, dz2, dz1, [h_c[i][0] for i in range(2)], [h_c[i][1] for i in range(2)])
+        calls += self._dgrad_chain(cnet, dz3, dz2, dz1, [h_c[i][0] for i in range(2)], [h_c[i][1] for i in range(2)])
         # -- d loss / d action: both critics' layer-1 dgrad summed in one contraction, tanh' fused
         g = dict(a=K.addr(dz1[0]), lda=H1, a2=K.addr(dz1[1]), lda2=H1, ldb=x_ld, ldb2=x_ld, out=K.addr(self.dz_act),
                  ldo=a_ld)
@@ -423,17 +432,13 @@ class ActorUpdate(_UpdateBase):
         calls.append(K.Gemm(B, H3, A, [dict(a=K.addr(self.dz_act), lda=a_ld, b=actor.W[3], ldb=H3, aux=K.addr(ha[2]),
                                              ldaux=H3, out=K.addr(self.dza[2]), ldo=H3)],
                             epilogue=K.EPI_MUL_ELUGRAD, tile_n=fwd_tile(B, H3, 1), b_major=K.MN_MAJOR))
-        calls.append(K.Gemm(B, H2, H3, [dict(a=K.addr(self.dza[2]), lda=H3, b=actor.W[2], ldb=H2, aux=K.addr(ha[1]),
-                                              ldaux=H2, out=K.addr(self.dza[1]), ldo=H2)],
-                            epilogue=K.EPI_MUL_ELUGRAD, tile_n=fwd_tile(B, H2, 1), b_major=K.MN_MAJOR))
-        calls.append(K.Gemm(B, H1, H2, [dict(a=K.addr(self.dza[1]), lda=H2, b=actor.W[1], ldb=H1, aux=K.addr(ha[0]),
-                                              ldaux=H1, out=K.addr(self.dza[0]), ldo=H1)],
-                            epilogue=K.EPI_MUL_ELUGRAD, tile_n=fwd_tile(B, H1, 1), b_major=K.MN_MAJOR))
+        calls += self._dgrad_chain([actor], [self.dza[2]], [self.dza[1]], [self.dza[0]], [ha[0]], [ha[1]],
+                                   bias=(self.opt, self.La, [0]))
         calls.append(self._wgrad(self.opt, self.La, [0], 3, [self.dz_act], a_ld, A, [ha[2]], H3, H3))
         calls.append(self._wgrad(self.opt, self.La, [0], 2, [self.dza[2]], H3, H3, [ha[1]], H2, H2))
         calls.append(self._wgrad(self.opt, self.La, [0], 1, [self.dza[1]], H2, H2, [ha[0]], H1, H1))
         calls.append(self._wgrad(self.opt, self.La, [0], 0, [self.dza[0]], H1, H1, [self.x], x_ld, O))
-        entries = [(0, l, self.dza[l], HIDDEN[l], HIDDEN[l]) for l in range(3)] + [(0, 3, self.dz_act, a_ld, A)]
+        entries = [(0, 2, self.dza[2], H3, H3), (0, 3, self.dz_act, a_ld, A)]     # layers 0 / 1: fused into the dgrad chain
         calls.append(self._bias_grads(self.opt, self.La, entries))
         _finish_plan(self, self.opt, self.a_flat, None, self.a_tf, None)
 

@@ -250,3 +250,44 @@ def test_fused_trunk_equals_layerwise(K, M, k_in, n_groups, cluster):
                     idx = bad.nonzero()[:8].tolist()
                     raise AssertionError(f"rep {rep} group {gi} {name}: {n_bad} words differ, first at {idx}, "
                                          f"fused {a[bad][:4].tolist()} layerwise {b[bad][:4].tolist()}")
+
+
+@pytest.mark.parametrize("M,n_groups,with_bias", [(128, 1, True), (8192, 2, True), (16384, 2, False), (300, 3, True), (8192, 1, True)])
+def test_fused_dgrad_chain_equals_layerwise(K, M, n_groups, with_bias):
+    """pqlb_mlp_backward against the two per-layer dgrad GEMMs (EPI_MUL_ELUGRAD, weights read as
+    [K][N]): same accumulation order, so dz2 / dz1 must be BIT-IDENTICAL; the fused bias-gradient
+    partials against a float64 column sum of each 128-row tile."""
+    g = torch.Generator(device=DEV).manual_seed(11 * M + n_groups)
+    nblk = (M + 127) // 128
+    fused, lw2, lw1, outs = [], [], [], []
+    for i in range(n_groups):
+        dz3 = mk((M, 128), g)
+        w3, w2 = mk((128, 256), g, 1.0 / 16), mk((256, 512), g, 1.0 / 512 ** 0.5)
+        h2 = rn_tf32(elu(torch.randn(M, 256, generator=g, device=DEV)))
+        h1 = rn_tf32(elu(torch.randn(M, 512, generator=g, device=DEV)))
+        f2, f1 = torch.zeros(M, 256, device=DEV), torch.zeros(M, 512, device=DEV)
+        l2, l1 = torch.zeros(M, 256, device=DEV), torch.zeros(M, 512, device=DEV)
+        p2 = torch.full((nblk, 256), 7.0, device=DEV) if with_bias else None
+        p1 = torch.full((nblk, 512), 7.0, device=DEV) if with_bias else None
+        fused.append(dict(dz3=K.addr(dz3), w3=K.addr(w3), w2=K.addr(w2), h2=K.addr(h2), h1=K.addr(h1), dz2=K.addr(f2),
+                          dz1=K.addr(f1), bias_part2=K.addr(p2), bias_part1=K.addr(p1)))
+        lw2.append(dict(a=K.addr(dz3), lda=128, b=K.addr(w3), ldb=256, aux=K.addr(h2), ldaux=256, out=K.addr(l2), ldo=256))
+        lw1.append(dict(a=K.addr(l2), lda=256, b=K.addr(w2), ldb=512, aux=K.addr(h1), ldaux=512, out=K.addr(l1), ldo=512))
+        outs.append((f2, f1, l2, l1, p2, p1, (dz3, w3, w2, h2, h1)))
+    for rep in range(3):
+        K.MlpBackward(M, fused)()
+        K.Gemm(M, 256, 128, lw2, epilogue=K.EPI_MUL_ELUGRAD, tile_n=128, b_major=K.MN_MAJOR)()
+        K.Gemm(M, 512, 256, lw1, epilogue=K.EPI_MUL_ELUGRAD, tile_n=256, b_major=K.MN_MAJOR)()
+        torch.cuda.synchronize()
+        for gi, (f2, f1, l2, l1, p2, p1, _) in enumerate(outs):
+            for name, a, b in (("dz2", f2, l2), ("dz1", f1, l1)):
+                bad = a.view(torch.int32) != b.view(torch.int32)
+                n_bad = int(bad.sum().item())
+                assert n_bad == 0, (f"rep {rep} group {gi} {name}: {n_bad} words differ, first at {bad.nonzero()[:6].tolist()}, "
+                                    f"fused {a[bad][:4].tolist()} layerwise {b[bad][:4].tolist()}")
+            if with_bias:
+                for name, part, dz in (("bias2", p2, f2), ("bias1", p1, f1)):
+                    pad = torch.zeros(nblk * 128, dz.shape[1], device=DEV, dtype=torch.float64)
+                    pad[:M] = dz.double()
+                    ref = pad.view(nblk, 128, -1).sum(1)
+                    check(part, ref, 2e-6, f"rep {rep} group {gi} {name} partials")
