@@ -186,8 +186,8 @@ typedef struct {
 } pqlb_mlp_group;
 typedef struct { int M, k_in, n_groups; pqlb_mlp_group g[PQLB_MAX_GROUPS]; } pqlb_mlp_desc;
 int pqlb_mlp_forward(const pqlb_mlp_desc* desc, pqlb_stream_t stream);
-/* Tuning / tests: force the thread-block-cluster size (1, 2 or 4 row tiles sharing every weight
- * tile through TMA multicast) of pqlb_mlp_forward; 0 = default (1: no cluster, the fastest measured). */
+/* Tuning / tests: 1 = one CTA per 128-row tile, 2 = CTA pairs (cta_group::2 MMAs, M = 256, each SM
+ * streams half of every weight tile), 0 = the library default. */
 void pqlb_mlp_forward_cluster(int cluster);
 
 /* ---- K3b: layer-fused dgrad chain of the trunk ---------------------------------------------------

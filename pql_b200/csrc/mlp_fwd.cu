@@ -24,12 +24,12 @@ namespace pqlb {
 constexpr int kFH1 = 512, kFH2 = 256, kFH3 = 128;
 constexpr int kFEpiWarps = 16;             // four per TMEM lane quarter: one 32-column chunk each per 128-column region
 constexpr int kFThreads = 64 + 32 * kFEpiWarps;
-constexpr int kFStages = 5;                   // weight ring (16 KB tiles); the rest of shared memory is X + 16 store-staging chunks
-constexpr int kFStageBytes = 128 * 128;       // every weight tile: 128 rows x 32 k (W2 goes as two row halves)
+constexpr int kFRingBytes = 5 * 16384;        // weight ring; the rest of shared memory is X + 16 store-staging chunks
+constexpr int kFTileBytes = 128 * 128;        // every weight tile: 128 rows x 32 k (W2 goes as two row halves)
 constexpr int kFXKb = 4;                      // input width <= 128
 constexpr int kFXBytes = kFXKb * 128 * 128;
 constexpr int kFChunk = 32 * 128;
-constexpr int kFSmem = 1024 + kFXBytes + kFStages * kFStageBytes + kFEpiWarps * kFChunk + (kFH1 + kFH2 + 2 * kFH3) * 4;
+constexpr int kFSmem = 1024 + kFXBytes + kFRingBytes + kFEpiWarps * kFChunk + (kFH1 + kFH2 + 2 * kFH3) * 4;
 
 struct alignas(64) MlpGroupDev {
   CUtensorMap tmX, tmW1, tmW2, tmW3, tmH1, tmH2, tmH3;
@@ -39,7 +39,7 @@ struct alignas(64) MlpGroupDev {
 };
 struct alignas(64) MlpDev {
   MlpGroupDev g[PQLB_MAX_GROUPS];
-  int M, k_in, kb1, cluster;   // cluster = CTAs (consecutive row tiles of one network) sharing every weight tile
+  int M, k_in, kb1, pad;
   unsigned long long* dbg;     // optional timeline of CTA (0,0): clock64 stamps (PQLB_MLP_DEBUG)
 };
 
@@ -47,8 +47,20 @@ __host__ __device__ constexpr uint32_t idesc_tf32(int n) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((unsigned)(n >> 3) << 17) | ((unsigned)(128 >> 4) << 24);
 }
 
+// PAIR = false: one CTA per 128-row tile.  PAIR = true: two CTAs of a (2,1,1) cluster (row tiles
+// 2i, 2i + 1 of one network) run every contraction as one M = 256 cta_group::2 MMA issued by the
+// leader; each CTA streams only HALF of every weight tile (64 of its 128 rows), which halves the
+// L2 -> SM traffic that bounds the one-CTA version (~40 B/clk per SM, measured).
+template <bool PAIR>
 __global__ void __launch_bounds__(kFThreads, 1)
 mlp_fwd_kernel(const __grid_constant__ MlpDev P) {
+  // Ring stage = 16 KB either way.  One CTA per tile: every weight tile is 128 rows x 32 k.  Pair:
+  // layer 2 runs as N = 256 MMAs (the A operand is read from tensor memory once per k-step instead
+  // of once per 128-column half: TMEM delivers only 64 B/clk to tcgen05.ld and A-operand reads
+  // together), so a W2 tile is 256 rows x 32 k and each CTA holds 128 of them (16 KB); W1 / W3
+  // tiles are 128 rows, 64 per CTA (8 KB of the stage).
+  constexpr int kFStageBytes = kFTileBytes;
+  constexpr int kFStages = kFRingBytes / kFStageBytes;
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t x_full, full_bar[kFStages], empty_bar[kFStages];
   __shared__ __align__(8) uint64_t p_full[2], p_conv[2], y_full, y_conv[2], z_full;
@@ -63,29 +75,36 @@ mlp_fwd_kernel(const __grid_constant__ MlpDev P) {
   const uint32_t xs = base;
   const uint32_t ring = xs + kFXBytes;
   const uint32_t stage_buf = ring + kFStages * kFStageBytes;
-  float* s_vec = reinterpret_cast<float*>(smem_raw + (base - smem_u32(smem_raw)) + kFXBytes + kFStages * kFStageBytes + kFEpiWarps * kFChunk);
+  float* s_vec = reinterpret_cast<float*>(smem_raw + (base - smem_u32(smem_raw)) + kFXBytes + kFRingBytes + kFEpiWarps * kFChunk);
   float* s_b1 = s_vec; float* s_b2 = s_b1 + kFH1; float* s_b3 = s_b2 + kFH2; float* s_w4 = s_b3 + kFH3;
 
   if (threadIdx.x == 0) {
     mbar_init(smem_u32(&x_full), 1);
-    for (int s = 0; s < kFStages; ++s) { mbar_init(smem_u32(&full_bar[s]), 1); mbar_init(smem_u32(&empty_bar[s]), (uint32_t)P.cluster); }
-    for (int b = 0; b < 2; ++b) { mbar_init(smem_u32(&p_full[b]), 1); mbar_init(smem_u32(&p_conv[b]), kFEpiWarps); mbar_init(smem_u32(&y_conv[b]), kFEpiWarps); }
+    // "converted" barriers live in the leader and collect the epilogue warps of BOTH CTAs of a pair
+    constexpr uint32_t kConv = PAIR ? 2 * kFEpiWarps : kFEpiWarps;
+    for (int s = 0; s < kFStages; ++s) { mbar_init(smem_u32(&full_bar[s]), 1); mbar_init(smem_u32(&empty_bar[s]), 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(smem_u32(&p_full[b]), 1); mbar_init(smem_u32(&p_conv[b]), kConv); mbar_init(smem_u32(&y_conv[b]), kConv); }
     mbar_init(smem_u32(&y_full), 1); mbar_init(smem_u32(&z_full), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(512u) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   for (int j = threadIdx.x; j < kFH1; j += kFThreads) s_b1[j] = G.b1[j];
   for (int j = threadIdx.x; j < kFH2; j += kFThreads) s_b2[j] = G.b2[j];
   for (int j = threadIdx.x; j < kFH3; j += kFThreads) { s_b3[j] = G.b3[j]; s_w4[j] = G.q ? G.head_w[j] : 0.f; }
+  __syncthreads();
+  const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
+  if (PAIR) cluster_sync_all();             // both CTAs' barriers are initialised before any remote arrive / TMA completion
+  if (warp == 1) {                          // one warp of EACH CTA of a pair takes part in the cta_group::2 allocation
+    if (PAIR) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(512u) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(512u) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+  }
   tcgen05_fence_before();
   __syncthreads();
-  const int C = P.cluster;
-  const uint32_t rank = C > 1 ? cluster_ctarank() : 0u;
-  const uint16_t mc_mask = (uint16_t)((1u << C) - 1u);
-  if (C > 1) cluster_sync_all();            // every CTA's barriers are initialised before any remote arrive / multicast
+  if (PAIR) cluster_sync_all();             // the leader issues MMAs into the peer's tensor memory: both allocations are done
   tcgen05_fence_after();
   const uint32_t tmem = uniform_u32(tmem_slot);
   unsigned long long* dbg = (blockIdx.x == 0 && blockIdx.y == 0) ? P.dbg : nullptr;
@@ -98,51 +117,62 @@ mlp_fwd_kernel(const __grid_constant__ MlpDev P) {
   // the lowest digit).  kind 0 = layer-1 quarter q, 1 = layer-2 K-chunk c, 2 = layer 3; the loops
   // over it are fully unrolled, so every branch below folds to straight-line code.
   constexpr unsigned long long kKinds = 0x211010100ull, kArgs = 0x032312010ull;
-  constexpr uint32_t idesc = idesc_tf32(128);
+  // M = 256 for a pair (field M >> 4 at bit 24), N = 128 either way
+  constexpr uint32_t idesc = PAIR ? (idesc_tf32(128) & ~(0x1Fu << 24)) | ((256u >> 4) << 24) : idesc_tf32(128);
+  constexpr uint32_t idesc_n256 = (idesc_tf32(256) & ~(0x1Fu << 24)) | ((256u >> 4) << 24);       // pair, layer 2
   const uint64_t desc0 = make_smem_desc(0, 16, 1024, kLayoutSw128);
+  // barrier of the LEADER at the same offset (identity for the leader itself / without pairs)
+  auto leader = [&](uint32_t local_bar) -> uint32_t { return PAIR ? mapa_shared(local_bar, 0) : local_bar; };
+  auto mma_ss = [&](uint32_t d, uint64_t a, uint64_t b, uint32_t acc) { if (PAIR) umma_tf32_pair(d, a, b, idesc, acc); else umma_tf32(d, a, b, idesc, acc); };
+  auto mma_ts = [&](uint32_t d, uint32_t a, uint64_t b, uint32_t acc) { if (PAIR) umma_tf32_ts_pair(d, a, b, idesc, acc); else umma_tf32_ts(d, a, b, idesc, acc); };
+  auto commit = [&](uint32_t bar) { if (PAIR) umma_commit_pair(bar); else umma_commit(bar); };
 
   // Warps 0 and 1 run with all 32 lanes and issue from one elected lane (see elect_one()).
   if (warp == 0) {
     // ===================== TMA producer =====================
-    const uint32_t xb = smem_u32(&x_full);
+    const uint32_t xb = leader(smem_u32(&x_full));
     if (elect_one()) {
-      mbar_expect_tx(xb, (uint32_t)P.kb1 * 16384u);
-      for (int kb = 0; kb < P.kb1; ++kb) tma_load_2d(xs + kb * 16384, &G.tmX, kb * 32, m0, xb);
+      // the leader's barrier counts the X tiles of both CTAs and both halves of every weight tile
+      if (rank == 0) mbar_expect_tx(smem_u32(&x_full), (uint32_t)P.kb1 * 16384u * (PAIR ? 2u : 1u));
+      for (int kb = 0; kb < P.kb1; ++kb) {
+        if (PAIR) tma_load_2d_pair(xs + kb * 16384, &G.tmX, kb * 32, m0, xb);
+        else tma_load_2d(xs + kb * 16384, &G.tmX, kb * 32, m0, xb);
+      }
     }
     __syncwarp();
     int stage = 0; uint32_t phase = 0;
-    const int slice_rows = 128 / C;
+    const int r0 = PAIR ? (int)rank * 64 : 0;       // this CTA's rows of every 128-row weight tile (W1, W3)
 #pragma unroll
     for (int ph = 0; ph < 9; ++ph) {
       const int kind = (int)((kKinds >> (4 * ph)) & 15), arg = (int)((kArgs >> (4 * ph)) & 15);
-      const int n_tiles = kind == 0 ? P.kb1 : 8;
+      const int n_tiles = kind == 0 ? P.kb1 : (kind == 1 && PAIR ? 4 : 8);
 #pragma unroll 1
       for (int t = 0; t < n_tiles; ++t) {
         mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1u);
-        const uint32_t bar = smem_u32(&full_bar[stage]);
+        const uint32_t bar = leader(smem_u32(&full_bar[stage]));
+        const uint32_t dst = ring + stage * kFStageBytes;
         if (elect_one()) {
-          mbar_expect_tx(bar, 16384u);         // the whole tile: one slice from every CTA of the cluster
-          if (C == 1) {
-            const uint32_t dst = ring + stage * kFStageBytes;
-            if (kind == 0) tma_load_2d(dst, &G.tmW1, t * 32, arg * 128, bar);
-            else if (kind == 1) tma_load_2d(dst, &G.tmW2, arg * 128 + (t >> 1) * 32, (t & 1) * 128, bar);
-            else tma_load_2d(dst, &G.tmW3, t * 32, 0, bar);
-          } else {
-            // this CTA fetches rows [rank * 128 / C, +128 / C) of the tile and multicasts them
-            const int r0 = (int)rank * slice_rows;
-            const uint32_t dst = ring + stage * kFStageBytes + rank * (uint32_t)(slice_rows * 128);
-            if (kind == 0) tma_load_2d_mc(dst, &G.tmW1, t * 32, arg * 128 + r0, bar, mc_mask);
-            else if (kind == 1) tma_load_2d_mc(dst, &G.tmW2, arg * 128 + (t >> 1) * 32, (t & 1) * 128 + r0, bar, mc_mask);
-            else tma_load_2d_mc(dst, &G.tmW3, t * 32, r0, bar, mc_mask);
+          // the leader's barrier counts what BOTH CTAs of a pair load
+          if (rank == 0) mbar_expect_tx(smem_u32(&full_bar[stage]), (uint32_t)(PAIR && kind == 1 ? 2 * kFTileBytes : kFTileBytes));
+          const CUtensorMap* map; int c0, c1;
+          if (kind == 0) { map = &G.tmW1; c0 = t * 32; c1 = arg * 128 + r0; }
+          else if (kind == 1) {
+            map = &G.tmW2;
+            if (PAIR) { c0 = arg * 128 + t * 32; c1 = (int)rank * 128; }          // 128 of the 256 rows of W2
+            else { c0 = arg * 128 + (t >> 1) * 32; c1 = (t & 1) * 128; }
           }
+          else { map = &G.tmW3; c0 = t * 32; c1 = r0; }
+          if (PAIR) tma_load_2d_pair(dst, map, c0, c1, bar);
+          else tma_load_2d(dst, map, c0, c1, bar);
         }
         __syncwarp();
         if (++stage == kFStages) { stage = 0; phase ^= 1u; }
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    auto free_stage = [&](uint32_t bar) { if (C == 1) umma_commit(bar); else umma_commit_mc(bar, mc_mask); };
+    // ===================== MMA issuer (the leader CTA of a pair only) =====================
+    if (rank == 0) {
+    auto free_stage = [&](uint32_t bar) { commit(bar); };
     PQLB_STAMP(0);
     mbar_wait(smem_u32(&x_full), 0);
     tcgen05_fence_after();
@@ -163,17 +193,17 @@ mlp_fwd_kernel(const __grid_constant__ MlpDev P) {
           if (elect_one()) {
             if (krem >= 32) {
 #pragma unroll
-              for (int k = 0; k < 4; ++k) umma_tf32(tP, adesc + 2u * k, bdesc + 2u * k, idesc, (uint32_t)(kb | k) != 0u);
+              for (int k = 0; k < 4; ++k) mma_ss(tP, adesc + 2u * k, bdesc + 2u * k, (uint32_t)(kb | k) != 0u);
             } else {
               const int ksteps = (krem + 7) / 8;
-              for (int k = 0; k < ksteps; ++k) umma_tf32(tP, adesc + 2u * k, bdesc + 2u * k, idesc, (uint32_t)(kb | k) != 0u);
+              for (int k = 0; k < ksteps; ++k) mma_ss(tP, adesc + 2u * k, bdesc + 2u * k, (uint32_t)(kb | k) != 0u);
             }
             free_stage(smem_u32(&empty_bar[stage]));
           }
           __syncwarp();
           if (++stage == kFStages) { stage = 0; phase ^= 1u; }
         }
-        if (elect_one()) umma_commit(smem_u32(&p_full[arg & 1]));
+        if (elect_one()) commit(smem_u32(&p_full[arg & 1]));
         __syncwarp();
         PQLB_STAMP(0);
       } else if (kind == 1) {
@@ -182,23 +212,40 @@ mlp_fwd_kernel(const __grid_constant__ MlpDev P) {
         mbar_wait(smem_u32(&p_conv[b]), (uint32_t)(c >> 1) & 1u);      // quarter c converted in place
         tcgen05_fence_after();
         PQLB_STAMP(0);
+        if (PAIR) {
 #pragma unroll
-        for (int t = 0; t < 8; ++t) {          // (k-block t>>1 of the chunk) x (row half t&1 of W2)
-          mbar_wait(smem_u32(&full_bar[stage]), phase);
-          tcgen05_fence_after();
-          const uint64_t bdesc = desc0 | (uint64_t)(((ring + stage * kFStageBytes) >> 4) & 0x3FFF);
-          const int kk = t >> 1;
-          if (elect_one()) {
+          for (int kk = 0; kk < 4; ++kk) {       // k-block kk of the chunk, all 256 rows of W2 in one N = 256 MMA
+            mbar_wait(smem_u32(&full_bar[stage]), phase);
+            tcgen05_fence_after();
+            const uint64_t bdesc = desc0 | (uint64_t)(((ring + stage * kFStageBytes) >> 4) & 0x3FFF);
+            if (elect_one()) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
-              umma_tf32_ts(tY + (uint32_t)((t & 1) * 128), tP + (uint32_t)(kk * 32 + k * 8), bdesc + 2u * k,
-                           idesc, (uint32_t)((c | kk | k) != 0));
-            free_stage(smem_u32(&empty_bar[stage]));
+              for (int k = 0; k < 4; ++k)
+                umma_tf32_ts_pair(tY, tP + (uint32_t)(kk * 32 + k * 8), bdesc + 2u * k, idesc_n256, (uint32_t)((c | kk | k) != 0));
+              free_stage(smem_u32(&empty_bar[stage]));
+            }
+            __syncwarp();
+            if (++stage == kFStages) { stage = 0; phase ^= 1u; }
           }
-          __syncwarp();
-          if (++stage == kFStages) { stage = 0; phase ^= 1u; }
+        } else {
+#pragma unroll
+          for (int t = 0; t < 8; ++t) {          // (k-block t>>1 of the chunk) x (row half t&1 of W2)
+            mbar_wait(smem_u32(&full_bar[stage]), phase);
+            tcgen05_fence_after();
+            const uint64_t bdesc = desc0 | (uint64_t)(((ring + stage * kFStageBytes) >> 4) & 0x3FFF);
+            const int kk = t >> 1;
+            if (elect_one()) {
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                mma_ts(tY + (uint32_t)((t & 1) * 128), tP + (uint32_t)(kk * 32 + k * 8), bdesc + 2u * k,
+                       (uint32_t)((c | kk | k) != 0));
+              free_stage(smem_u32(&empty_bar[stage]));
+            }
+            __syncwarp();
+            if (++stage == kFStages) { stage = 0; phase ^= 1u; }
+          }
         }
-        if (c == 3) { if (elect_one()) umma_commit(smem_u32(&y_full)); __syncwarp(); }
+        if (c == 3) { if (elect_one()) commit(smem_u32(&y_full)); __syncwarp(); }
         PQLB_STAMP(0);
       } else {
 #pragma unroll
@@ -210,17 +257,18 @@ mlp_fwd_kernel(const __grid_constant__ MlpDev P) {
           if (elect_one()) {
 #pragma unroll
             for (int k = 0; k < 4; ++k)
-              umma_tf32_ts(tZ, tY + (uint32_t)(t * 32 + k * 8), bdesc + 2u * k, idesc, (uint32_t)((t | k) != 0));
+              mma_ts(tZ, tY + (uint32_t)(t * 32 + k * 8), bdesc + 2u * k, (uint32_t)((t | k) != 0));
             free_stage(smem_u32(&empty_bar[stage]));
           }
           __syncwarp();
           if (++stage == kFStages) { stage = 0; phase ^= 1u; }
         }
-        if (elect_one()) umma_commit(smem_u32(&z_full));
+        if (elect_one()) commit(smem_u32(&z_full));
         __syncwarp();
         PQLB_STAMP(0);
       }
     }
+    }   // rank == 0
   } else {
     // ===================== conversion / epilogue warps =====================
     // Warp e owns TMEM lanes [32 (warp % 4), +32) (hardware rule) and the 32-column chunk e >> 2
@@ -248,18 +296,21 @@ mlp_fwd_kernel(const __grid_constant__ MlpDev P) {
       if (elect_one()) { tma_store_3d(omap, my_stage, n_col, row0, 0); bulk_commit(); }
       pending = true;
     };
-    // converts this warp's chunk of a 128-column TMEM region in place: +bias, ELU, RN to TF32
-    auto convert = [&](uint32_t region, const float* bias, int n_base, const CUtensorMap* omap, bool store) {
+    // converts this warp's chunk of a 128-column TMEM region in place (+bias, ELU, RN to TF32), tells
+    // the MMA issuer (``done``, a barrier of the leader) and only then walks the HBM store path, so
+    // that the next contraction never waits for staging / TMA stores
+    auto convert = [&](uint32_t region, const float* bias, int n_base, const CUtensorMap* omap, bool store, uint32_t done) {
       const uint32_t taddr = region + lane_sel + (uint32_t)col;
       float v[32];
       tmem_ld32(taddr, v);
 #pragma unroll
       for (int j = 0; j < 32; ++j) v[j] = rn_tf32(elu_fast(v[j] + bias[n_base + col + j]));
       tmem_st32(taddr, v);
-      if (store) store_chunk(v, omap, n_base + col);
       tmem_wait_st();
       tcgen05_fence_before();
       __syncwarp();
+      if (lane == 0) { if (PAIR) mbar_arrive_cluster(leader(done)); else mbar_arrive(done); }
+      if (store) store_chunk(v, omap, n_base + col);
     };
 
     if (e != 0) dbg = nullptr;
@@ -269,16 +320,14 @@ mlp_fwd_kernel(const __grid_constant__ MlpDev P) {
       mbar_wait(smem_u32(&p_full[b]), (uint32_t)(q >> 1) & 1u);
       tcgen05_fence_after();
       PQLB_STAMP(32);
-      convert(tmem + (uint32_t)(b * 128), s_b1, q * 128, &G.tmH1, G.st1 != 0);
-      if (lane == 0) mbar_arrive(smem_u32(&p_conv[b]));
+      convert(tmem + (uint32_t)(b * 128), s_b1, q * 128, &G.tmH1, G.st1 != 0, smem_u32(&p_conv[b]));
       PQLB_STAMP(32);
     }
     mbar_wait(smem_u32(&y_full), 0);
     tcgen05_fence_after();
     PQLB_STAMP(32);
     for (int hh = 0; hh < 2; ++hh) {
-      convert(tY + (uint32_t)(hh * 128), s_b2, hh * 128, &G.tmH2, G.st2 != 0);
-      if (lane == 0) mbar_arrive(smem_u32(&y_conv[hh]));
+      convert(tY + (uint32_t)(hh * 128), s_b2, hh * 128, &G.tmH2, G.st2 != 0, smem_u32(&y_conv[hh]));
       PQLB_STAMP(32);
     }
     mbar_wait(smem_u32(&z_full), 0);
@@ -312,11 +361,12 @@ mlp_fwd_kernel(const __grid_constant__ MlpDev P) {
 
   tcgen05_fence_before();
   __syncthreads();
+  if (PAIR) cluster_sync_all();             // nobody frees tensor memory or leaves while the peer may still use / signal it
   if (warp == 1) {
     tcgen05_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
+    if (PAIR) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
+    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
   }
-  if (C > 1) cluster_sync_all();            // nobody leaves while a peer may still signal its barriers
 }
 
 }  // namespace pqlb
@@ -325,13 +375,15 @@ using namespace pqlb;
 
 static unsigned long long* g_mlp_debug = nullptr;
 static int g_mlp_cluster = 0;
-/* Experiments: force the cluster size (1, 2 or 4) of pqlb_mlp_forward; 0 = automatic. */
-extern "C" void pqlb_mlp_forward_cluster(int c) { g_mlp_cluster = (c == 1 || c == 2 || c == 4) ? c : 0; }
+constexpr int kFDefaultCluster = 1;
+/* 1 = one CTA per row tile, 2 = CTA pairs (cta_group::2), 0 = default. */
+extern "C" void pqlb_mlp_forward_cluster(int c) { g_mlp_cluster = (c == 1 || c == 2) ? c : 0; }
 /* Debug: device buffer of 64 uint64 receiving a clock64 timeline of CTA (0,0) (NULL = off). */
 extern "C" void pqlb_mlp_forward_debug(unsigned long long* buf) { g_mlp_debug = buf; }
 
 extern "C" int pqlb_mlp_forward_init(void) {
-  cudaError_t e = cudaFuncSetAttribute(mlp_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFSmem);
+  cudaError_t e = cudaFuncSetAttribute(mlp_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFSmem);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(mlp_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFSmem);
   return e == cudaSuccess ? PQLB_OK : (int)e;
 }
 
@@ -341,12 +393,9 @@ extern "C" int pqlb_mlp_forward(const pqlb_mlp_desc* d, pqlb_stream_t stream) {
   { int rc = pqlb_init(); if (rc != PQLB_OK) return rc; }
   static MlpDev P;
   P.M = d->M; P.k_in = d->k_in; P.kb1 = (d->k_in + 31) / 32;
-  const int tiles_m = (d->M + 127) / 128;
-  // Measured on B200 (M = 8192, 1 and 4 networks): multicast clusters of 2 / 4 row tiles are 0-7 % SLOWER
-  // than independent CTAs - the kernel is bound by the ~40 B/clk each SM can take in from L2, not by
-  // L2 read traffic - so the default is no cluster; the path stays for the cta_group::2 follow-up.
-  P.cluster = g_mlp_cluster > 0 ? g_mlp_cluster : 1;
   P.dbg = g_mlp_debug;
+  const int tiles_m = (d->M + 127) / 128;
+  const int cluster = g_mlp_cluster > 0 ? g_mlp_cluster : kFDefaultCluster;
   for (int i = 0; i < d->n_groups; ++i) {
     const pqlb_mlp_group& s = d->g[i];
     MlpGroupDev& G = P.g[i];
@@ -354,9 +403,9 @@ extern "C" int pqlb_mlp_forward(const pqlb_mlp_desc* d, pqlb_stream_t stream) {
     PQLB_CHECK_ARG(!s.q || (s.head_w && s.head_b));
     int rc;
     if ((rc = make_map(&G.tmX, s.x, (uint64_t)d->k_in, (uint64_t)d->M, s.ldx, 32, 128, CU_TENSOR_MAP_SWIZZLE_128B)) != PQLB_OK) return rc;
-    const uint32_t wrows = 128u / (uint32_t)P.cluster;      // rows of a weight tile each CTA of the cluster fetches
+    const uint32_t wrows = 128u / (uint32_t)cluster;         // rows of a weight tile each CTA fetches (a pair: half each)
     if ((rc = make_map(&G.tmW1, s.w1, (uint64_t)d->k_in, kFH1, s.ldw1, 32, wrows, CU_TENSOR_MAP_SWIZZLE_128B)) != PQLB_OK) return rc;
-    if ((rc = make_map(&G.tmW2, s.w2, kFH1, kFH2, kFH1, 32, wrows, CU_TENSOR_MAP_SWIZZLE_128B)) != PQLB_OK) return rc;
+    if ((rc = make_map(&G.tmW2, s.w2, kFH1, kFH2, kFH1, 32, 128, CU_TENSOR_MAP_SWIZZLE_128B)) != PQLB_OK) return rc;   // pair: half of a 256-row tile
     if ((rc = make_map(&G.tmW3, s.w3, kFH2, kFH3, kFH2, 32, wrows, CU_TENSOR_MAP_SWIZZLE_128B)) != PQLB_OK) return rc;
     G.st1 = s.h1 != nullptr; G.st2 = s.h2 != nullptr; G.st3 = s.h3 != nullptr;
     if (G.st1 && !make_tile_map(&G.tmH1, s.h1, kFH1, (uint64_t)d->M, kFH1, 1, 0)) return PQLB_E_ALIGN;
@@ -367,9 +416,9 @@ extern "C" int pqlb_mlp_forward(const pqlb_mlp_desc* d, pqlb_stream_t stream) {
     if (!G.st3) G.tmH3 = G.tmX;
     G.b1 = s.b1; G.b2 = s.b2; G.b3 = s.b3; G.head_w = s.head_w; G.head_b = s.head_b; G.q = s.q;
   }
-  // ghost CTAs round the row tiles up to whole clusters: their X tile is zero-filled and their
-  // stores are clipped by TMA, so they only take part in the weight multicast
-  const unsigned gx = (unsigned)((tiles_m + P.cluster - 1) / P.cluster * P.cluster);
+  // a ghost CTA rounds an odd number of row tiles up to whole pairs: its X tile is zero-filled and
+  // its stores are clipped by TMA
+  const unsigned gx = (unsigned)((tiles_m + cluster - 1) / cluster * cluster);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(gx, (unsigned)d->n_groups, 1);
   cfg.blockDim = dim3(kFThreads, 1, 1);
@@ -377,9 +426,9 @@ extern "C" int pqlb_mlp_forward(const pqlb_mlp_desc* d, pqlb_stream_t stream) {
   cfg.stream = (cudaStream_t)stream;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = (unsigned)P.cluster; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  attr[0].val.clusterDim.x = (unsigned)cluster; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr; cfg.numAttrs = 1;
-  cudaError_t le = cudaLaunchKernelEx(&cfg, mlp_fwd_kernel, P);
+  cudaError_t le = cluster == 2 ? cudaLaunchKernelEx(&cfg, mlp_fwd_kernel<true>, P) : cudaLaunchKernelEx(&cfg, mlp_fwd_kernel<false>, P);
   PQLB_COUNT_LAUNCH(1);
   return le == cudaSuccess ? PQLB_OK : (int)le;
 }

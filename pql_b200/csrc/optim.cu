@@ -76,6 +76,20 @@ adamw_polyak_kernel(float* __restrict__ param, const float* __restrict__ grad, f
                     float* __restrict__ grad_norm_out) {
   __shared__ float red[8];
   __shared__ AdamScalars sa;
+  // the element loads do not depend on the norm or the bias corrections: issue them first, so that
+  // they are in flight under the partial-sum reduction and thread 0's double-precision pow()
+  const int64_t i4 = ((int64_t)blockIdx.x * kOptThreads + threadIdx.x) * 4;
+  const int cnt = i4 >= n ? 0 : ((n - i4) >= 4 ? 4 : (int)(n - i4));
+  float p[4], g[4], mm[4], vv[4], tt[4];
+  if (cnt == 4) {
+    *reinterpret_cast<float4*>(p) = *reinterpret_cast<const float4*>(param + i4);
+    *reinterpret_cast<float4*>(g) = *reinterpret_cast<const float4*>(grad + i4);
+    *reinterpret_cast<float4*>(mm) = *reinterpret_cast<const float4*>(m + i4);
+    *reinterpret_cast<float4*>(vv) = *reinterpret_cast<const float4*>(v + i4);
+    if (target) *reinterpret_cast<float4*>(tt) = *reinterpret_cast<const float4*>(target + i4);
+  } else {
+    for (int k = 0; k < cnt; ++k) { p[k] = param[i4 + k]; g[k] = grad[i4 + k]; mm[k] = m[i4 + k]; vv[k] = v[i4 + k]; if (target) tt[k] = target[i4 + k]; }
+  }
   if (threadIdx.x == 0) {
     // scalar corrections in double, like torch's python-side arithmetic (torch/optim/adam.py);
     // the 1-based step count comes from the device counter when the update runs inside a
@@ -98,20 +112,7 @@ adamw_polyak_kernel(float* __restrict__ param, const float* __restrict__ grad, f
   if (h.max_norm >= 0.f) coef = fminf(h.max_norm / (norm + 1e-6f), 1.f);   // clip_grad.py
   if (blockIdx.x == 0 && threadIdx.x == 0 && grad_norm_out) grad_norm_out[0] = norm;
   const float gmul = h.grad_scale * coef;
-
-  const int64_t i4 = ((int64_t)blockIdx.x * kOptThreads + threadIdx.x) * 4;
-  if (i4 >= n) return;
-  const int cnt = (n - i4) >= 4 ? 4 : (int)(n - i4);
-  float p[4], g[4], mm[4], vv[4], tt[4];
-  if (cnt == 4) {
-    *reinterpret_cast<float4*>(p) = *reinterpret_cast<const float4*>(param + i4);
-    *reinterpret_cast<float4*>(g) = *reinterpret_cast<const float4*>(grad + i4);
-    *reinterpret_cast<float4*>(mm) = *reinterpret_cast<const float4*>(m + i4);
-    *reinterpret_cast<float4*>(vv) = *reinterpret_cast<const float4*>(v + i4);
-    if (target) *reinterpret_cast<float4*>(tt) = *reinterpret_cast<const float4*>(target + i4);
-  } else {
-    for (int k = 0; k < cnt; ++k) { p[k] = param[i4 + k]; g[k] = grad[i4 + k]; mm[k] = m[i4 + k]; vv[k] = v[i4 + k]; if (target) tt[k] = target[i4 + k]; }
-  }
+  if (cnt == 0) return;
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
     if (k >= cnt) break;
