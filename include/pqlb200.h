@@ -183,6 +183,16 @@ typedef struct {
   const float* b1; const float* b2; const float* b3;
   const float* head_w; const float* head_b; float* q;     /* q == NULL: no scalar head */
   float* h1; float* h2; float* h3;                         /* [M,512] [M,256] [M,128] or NULL */
+  /* Optional policy head (pql/models/mlp.py:177-179, tanh(Linear(128, act_n))) as a fourth contraction
+   * in the same launch: act_w [act_n, 128] (TF32 copy), act_b [act_n], act_n a multiple of 4 <= 16.
+   * act_out[row * act_ldo + j] = rn_tf32(tanh(.)) or, with act_noise (N(0,1) draws, [M, act_ldnoise]),
+   * rn_tf32(clamp(tanh(.) + clamp(noise_std * noise, +-noise_bound), +-1)) (pql/utils/noise.py:19-27);
+   * act_out2 (optional) keeps the fp32 tanh.  act_w == NULL: no policy head.  Mutually exclusive with q. */
+  const float* act_w; const float* act_b; const float* act_noise;
+  float* act_out; float* act_out2;
+  int64_t act_ldo, act_ldo2, act_ldnoise;
+  float noise_std, noise_bound;
+  int act_n;
 } pqlb_mlp_group;
 typedef struct { int M, k_in, n_groups; pqlb_mlp_group g[PQLB_MAX_GROUPS]; } pqlb_mlp_desc;
 int pqlb_mlp_forward(const pqlb_mlp_desc* desc, pqlb_stream_t stream);

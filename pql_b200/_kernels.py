@@ -99,17 +99,24 @@ class MlpForward(Call):
     """Layer-fused trunk forward (pqlb_mlp_forward) for up to four network instances.
     ``groups``: dicts with x, ldx, w1, ldw1, w2, w3, b1, b2, b3, [head_w, head_b, q], [h1, h2, h3]."""
 
-    FIELDS = ("x", "w1", "w2", "w3", "b1", "b2", "b3", "head_w", "head_b", "q", "h1", "h2", "h3")
+    FIELDS = ("x", "w1", "w2", "w3", "b1", "b2", "b3", "head_w", "head_b", "q", "h1", "h2", "h3",
+              "act_w", "act_b", "act_noise", "act_out", "act_out2")
+    INTS = ("act_ldo", "act_ldo2", "act_ldnoise", "act_n")
+    FLOATS = ("noise_std", "noise_bound")
 
     def __init__(self, M, k_in, groups):
         d = _lib.MlpDesc()
         d.M, d.k_in, d.n_groups = int(M), int(k_in), len(groups)
         for i, g in enumerate(groups):
-            unknown = set(g) - set(self.FIELDS) - {"ldx", "ldw1"}
+            unknown = set(g) - set(self.FIELDS) - set(self.INTS) - set(self.FLOATS) - {"ldx", "ldw1"}
             if unknown:
                 raise KeyError(f"unknown mlp group fields {sorted(unknown)}")
             for k in self.FIELDS:
                 setattr(d.g[i], k, g.get(k, 0) or None)
+            for k in self.INTS:
+                setattr(d.g[i], k, int(g.get(k, 0)))
+            for k in self.FLOATS:
+                setattr(d.g[i], k, float(g.get(k, 0.0)))
             d.g[i].ldx, d.g[i].ldw1 = int(g["ldx"]), int(g["ldw1"])
         self.desc = d
         super().__init__("pqlb_mlp_forward", C.byref(d))

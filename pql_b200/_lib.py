@@ -49,7 +49,10 @@ class GemmDesc(C.Structure):
 class MlpGroup(C.Structure):
     _fields_ = [("x", _f), ("ldx", _i64), ("w1", _f), ("ldw1", _i64), ("w2", _f), ("w3", _f),
                 ("b1", _f), ("b2", _f), ("b3", _f), ("head_w", _f), ("head_b", _f), ("q", _f),
-                ("h1", _f), ("h2", _f), ("h3", _f)]
+                ("h1", _f), ("h2", _f), ("h3", _f),
+                ("act_w", _f), ("act_b", _f), ("act_noise", _f), ("act_out", _f), ("act_out2", _f),
+                ("act_ldo", _i64), ("act_ldo2", _i64), ("act_ldnoise", _i64),
+                ("noise_std", _flt), ("noise_bound", _flt), ("act_n", _int)]
 
 
 class MlpBwdGroup(C.Structure):

@@ -215,12 +215,10 @@ class CriticUpdate(_UpdateBase):
 
         # -- target policy: a' = clamp(tanh(actor(next_obs)) + clamp(noise), +-1)   :62-71, noise.py:19-27
         a_inst = dict(net=actor, x=K.addr(self.x_tgt), x_ld=x_ld, k_in=O, h=[K.addr(t) for t in ha],
-                      store=(False, False, True))
+                      store=(False, False, False),
+                      act=dict(out=K.addr(self.x_tgt, O), ldo=x_ld, noise=K.addr(self.noise), ldnoise=A,
+                               noise_std=self.noise_std, noise_bound=self.noise_bound))
         calls += forward_calls(B, [a_inst], False)
-        calls.append(K.Gemm(B, A, H3, [dict(a=K.addr(ha[2]), lda=H3, b=actor.W[3], ldb=H3, bias=actor.b[3],
-                                             aux=K.addr(self.noise), ldaux=A, out=K.addr(self.x_tgt, O), ldo=x_ld)],
-                            epilogue=K.EPI_BIAS_TANH_NOISE, tile_n=K.pick_tile_n(A), noise_bound=self.noise_bound,
-                            noise_std=self.noise_std))
         # -- both target nets on (next_obs, a') and both current nets on (obs, action), one launch per layer
         insts = [dict(net=tnet[i], x=K.addr(self.x_tgt), x_ld=x_ld, k_in=O + A, h=[K.addr(t) for t in h_t[i]],
                       store=(False, False, distl), q=K.addr(self.tq[i])) for i in range(2)]
@@ -390,11 +388,9 @@ class ActorUpdate(_UpdateBase):
 
         self._ws_init([(A, H3, H3), (H3, H2, H2), (H2, H1, H1), (H1, O, self.La.ldw[0])], 1, [*HIDDEN, A])
         # -- action = tanh(actor(obs)) written straight into the critic input rows      :55
-        a_inst = dict(net=actor, x=K.addr(self.x), x_ld=x_ld, k_in=O, h=[K.addr(t) for t in ha])
+        a_inst = dict(net=actor, x=K.addr(self.x), x_ld=x_ld, k_in=O, h=[K.addr(t) for t in ha],
+                      act=dict(out=K.addr(self.x, O), ldo=x_ld, out2=K.addr(self.act), ldo2=a_ld))
         calls += forward_calls(B, [a_inst], False)
-        calls.append(K.Gemm(B, A, H3, [dict(a=K.addr(ha[2]), lda=H3, b=actor.W[3], ldb=H3, bias=actor.b[3],
-                                             out=K.addr(self.x, O), ldo=x_ld, out2=K.addr(self.act), ldo2=a_ld)],
-                            epilogue=K.EPI_BIAS_TANH, tile_n=K.pick_tile_n(A)))
         # -- frozen critic forward                                                     :56
         insts = [dict(net=cnet[i], x=K.addr(self.x), x_ld=x_ld, k_in=O + A, h=[K.addr(t) for t in h_c[i]],
                       q=K.addr(self.q[i])) for i in range(2)]

@@ -32,10 +32,15 @@ constexpr int kFChunk = 32 * 128;
 constexpr int kFSmem = 1024 + kFXBytes + kFRingBytes + kFEpiWarps * kFChunk + (kFH1 + kFH2 + 2 * kFH3) * 4;
 
 struct alignas(64) MlpGroupDev {
-  CUtensorMap tmX, tmW1, tmW2, tmW3, tmH1, tmH2, tmH3;
+  CUtensorMap tmX, tmW1, tmW2, tmW3, tmH1, tmH2, tmH3, tmW4;
   const float* b1; const float* b2; const float* b3; const float* head_w; const float* head_b;
   float* q;
-  int st1, st2, st3, pad;
+  // policy head (tanh): a fourth contraction [128 x 128] . W4^T -> [128 x act_n], act_n <= 16
+  const float* act_b; const float* act_noise; float* act_out; float* act_out2;
+  long long act_ldo, act_ldo2, act_ldnoise;
+  float noise_std, noise_bound;
+  int act_n;
+  int st1, st2, st3;
 };
 struct alignas(64) MlpDev {
   MlpGroupDev g[PQLB_MAX_GROUPS];
@@ -63,7 +68,7 @@ mlp_fwd_kernel(const __grid_constant__ MlpDev P) {
   constexpr int kFStages = kFRingBytes / kFStageBytes;
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t x_full, full_bar[kFStages], empty_bar[kFStages];
-  __shared__ __align__(8) uint64_t p_full[2], p_conv[2], y_full, y_conv[2], z_full;
+  __shared__ __align__(8) uint64_t p_full[2], p_conv[2], y_full, y_conv[2], z_full, z_conv, a_full;
   __shared__ uint32_t tmem_slot;
   __shared__ float s_q[4][128];
 
@@ -85,6 +90,7 @@ mlp_fwd_kernel(const __grid_constant__ MlpDev P) {
     for (int s = 0; s < kFStages; ++s) { mbar_init(smem_u32(&full_bar[s]), 1); mbar_init(smem_u32(&empty_bar[s]), 1); }
     for (int b = 0; b < 2; ++b) { mbar_init(smem_u32(&p_full[b]), 1); mbar_init(smem_u32(&p_conv[b]), kConv); mbar_init(smem_u32(&y_conv[b]), kConv); }
     mbar_init(smem_u32(&y_full), 1); mbar_init(smem_u32(&z_full), 1);
+    mbar_init(smem_u32(&z_conv), kFEpiWarps); mbar_init(smem_u32(&a_full), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   for (int j = threadIdx.x; j < kFH1; j += kFThreads) s_b1[j] = G.b1[j];
@@ -168,6 +174,16 @@ mlp_fwd_kernel(const __grid_constant__ MlpDev P) {
         __syncwarp();
         if (++stage == kFStages) { stage = 0; phase ^= 1u; }
       }
+    }
+    if (!PAIR && G.act_n > 0) {                 // policy head weights: 16 rows x 128 k as four 2 KB boxes in one stage
+      mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1u);
+      const uint32_t bar = smem_u32(&full_bar[stage]);
+      const uint32_t dst = ring + stage * kFStageBytes;
+      if (elect_one()) {
+        mbar_expect_tx(bar, 4u * 2048u);
+        for (int kb = 0; kb < 4; ++kb) tma_load_2d(dst + kb * 2048, &G.tmW4, kb * 32, 0, bar);
+      }
+      __syncwarp();
     }
   } else if (warp == 1) {
     // ===================== MMA issuer (the leader CTA of a pair only) =====================
@@ -268,6 +284,24 @@ mlp_fwd_kernel(const __grid_constant__ MlpDev P) {
         PQLB_STAMP(0);
       }
     }
+    if (!PAIR && G.act_n > 0) {
+      // policy head: h3 (converted in place in Z) . W4^T into 16 columns of P1, N = 16
+      mbar_wait(smem_u32(&z_conv), 0);
+      tcgen05_fence_after();
+      mbar_wait(smem_u32(&full_bar[stage]), phase);
+      tcgen05_fence_after();
+      if (elect_one()) {
+#pragma unroll
+        for (int kb = 0; kb < 4; ++kb) {
+          const uint64_t bdesc = desc0 | (uint64_t)(((ring + stage * kFStageBytes + kb * 2048) >> 4) & 0x3FFF);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_tf32_ts(tmem + 128u, tZ + (uint32_t)(kb * 32 + k * 8), bdesc + 2u * k, idesc_tf32(16), (uint32_t)((kb | k) != 0));
+        }
+        umma_commit(smem_u32(&a_full));
+      }
+      __syncwarp();
+    }
     }   // rank == 0
   } else {
     // ===================== conversion / epilogue warps =====================
@@ -343,7 +377,48 @@ mlp_fwd_kernel(const __grid_constant__ MlpDev P) {
         qacc = fmaf(h, s_w4[col + j], qacc);
         v[j] = rn_tf32(h);
       }
+      if (!PAIR && G.act_n > 0) {                // h3 back into Z: the A operand of the policy-head contraction
+        tmem_st32(tZ + lane_sel + (uint32_t)col, v);
+        tmem_wait_st();
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&z_conv));
+      }
       if (G.st3) store_chunk(v, &G.tmH3, col);
+      if (!PAIR && G.act_n > 0 && chunk == 0) {
+        // one warp per lane quarter finishes the head: + bias, tanh, (+ clipped noise, clamp), TF32 rounding
+        mbar_wait(smem_u32(&a_full), 0);
+        tcgen05_fence_after();
+        float a[16];
+        tmem_ld16(tmem + 128u + lane_sel, a);
+        if (row < P.M) {
+          float o[16], o2[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            float t = 0.f, r = 0.f;
+            if (j < G.act_n) {
+              t = tanhf(a[j] + G.act_b[j]);
+              r = t;
+              if (G.act_noise) {                   // noise.py:19-27 on N(0,1) draws scaled by std (see pqlb_gemm_tf32)
+                const float z = fminf(fmaxf(G.act_noise[(long long)row * G.act_ldnoise + j] * G.noise_std, -G.noise_bound), G.noise_bound);
+                r = fminf(fmaxf(t + z, -1.f), 1.f);
+              }
+              r = rn_tf32(r);
+            }
+            o[j] = r; o2[j] = t;
+          }
+          float* dst = G.act_out + (long long)row * G.act_ldo;
+#pragma unroll
+          for (int j = 0; j < 16; j += 4)
+            if (j < G.act_n) *reinterpret_cast<float4*>(dst + j) = make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]);
+          if (G.act_out2) {
+            float* dst2 = G.act_out2 + (long long)row * G.act_ldo2;
+#pragma unroll
+            for (int j = 0; j < 16; j += 4)
+              if (j < G.act_n) *reinterpret_cast<float4*>(dst2 + j) = make_float4(o2[j], o2[j + 1], o2[j + 2], o2[j + 3]);
+          }
+        }
+      }
       if (G.q) {
         // the four warps of a lane quarter each hold the dot product over their 32 columns;
         // summed in chunk order (fixed, so q is reproducible)
@@ -415,6 +490,18 @@ extern "C" int pqlb_mlp_forward(const pqlb_mlp_desc* d, pqlb_stream_t stream) {
     if (!G.st2) G.tmH2 = G.tmX;
     if (!G.st3) G.tmH3 = G.tmX;
     G.b1 = s.b1; G.b2 = s.b2; G.b3 = s.b3; G.head_w = s.head_w; G.head_b = s.head_b; G.q = s.q;
+    G.act_n = 0; G.tmW4 = G.tmX;
+    if (s.act_w) {
+      // policy head: act_n a multiple of 4 up to 16, 16-byte aligned output rows (else: pqlb_gemm_tf32)
+      PQLB_CHECK_ARG(!s.q && s.act_b && s.act_out && s.act_n > 0);
+      if (s.act_n > 16 || s.act_n % 4 || s.act_ldo % 4 || !aligned16(s.act_out) ||
+          (s.act_out2 && (s.act_ldo2 % 4 || !aligned16(s.act_out2)))) return PQLB_E_UNSUPPORTED;
+      if (cluster != 1) return PQLB_E_UNSUPPORTED;
+      if ((rc = make_map(&G.tmW4, s.act_w, kFH3, (uint64_t)s.act_n, kFH3, 32, 16, CU_TENSOR_MAP_SWIZZLE_128B)) != PQLB_OK) return rc;
+      G.act_n = s.act_n; G.act_b = s.act_b; G.act_noise = s.act_noise; G.act_out = s.act_out; G.act_out2 = s.act_out2;
+      G.act_ldo = s.act_ldo; G.act_ldo2 = s.act_ldo2; G.act_ldnoise = s.act_ldnoise;
+      G.noise_std = s.noise_std; G.noise_bound = s.noise_bound;
+    }
   }
   // a ghost CTA rounds an odd number of row tiles up to whole pairs: its X tile is zero-filled and
   // its stores are clipped by TMA

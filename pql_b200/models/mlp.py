@@ -129,13 +129,15 @@ FUSED_MAX_IN = 128        # pqlb_mlp_forward keeps a 128-row input tile of at mo
 
 def forward_calls(B, insts, scalar_head):
     """Prepared launches of the trunk (three Linear+ELU layers) for up to four network instances.
-    inst = dict(net, x, x_ld, k_in, h=[h1, h2, h3 addresses], store=(s1, s2, s3), q=addr or 0).
+    inst = dict(net, x, x_ld, k_in, h=[h1, h2, h3 addresses], store=(s1, s2, s3), q=addr or 0,
+    act=dict(out, ldo, [out2, ldo2], [noise, ldnoise, noise_std, noise_bound]) for a policy net).
     Inputs up to 128 wide take ONE layer-fused launch (activations stay in tensor memory, only the
-    flagged ones are written); wider inputs (ShadowHand) run layer by layer.  With ``scalar_head``
-    the twin-Q head q = h3 . w4 + b4 is fused into the last epilogue."""
+    flagged ones are written; the scalar twin-Q head or the tanh policy head ride in the same
+    launch); wider inputs (ShadowHand) run layer by layer."""
     k_in = insts[0]["k_in"]
+    calls = []
     if k_in <= FUSED_MAX_IN:
-        groups = []
+        groups, heads_left = [], []
         for it in insts:
             n = it["net"]
             st = it.get("store", (True, True, True))
@@ -144,10 +146,28 @@ def forward_calls(B, insts, scalar_head):
                      h3=it["h"][2] if st[2] else 0)
             if scalar_head:
                 g.update(head_w=n.Wf[3], head_b=n.b[3], q=it["q"])
+            act = it.get("act")
+            if act is not None:
+                A = n.dims[4]
+                if A <= 16 and A % 4 == 0 and act["ldo"] % 4 == 0 and act.get("ldo2", 0) % 4 == 0:
+                    g.update(act_w=n.W[3], act_b=n.b[3], act_n=A, act_out=act["out"], act_ldo=act["ldo"],
+                             act_out2=act.get("out2", 0), act_ldo2=act.get("ldo2", 0), act_noise=act.get("noise", 0),
+                             act_ldnoise=act.get("ldnoise", 0), noise_std=act.get("noise_std", 0.0),
+                             noise_bound=act.get("noise_bound", 0.0))
+                else:
+                    g["h3"] = it["h"][2]          # the separate head launch reads h3
+                    heads_left.append(it)
             groups.append(g)
-        return [K.MlpForward(B, k_in, groups)]
+        calls.append(K.MlpForward(B, k_in, groups))
+        for it in heads_left:
+            calls.append(policy_head_call(B, it))
+        return calls
     if not scalar_head:
-        return trunk_calls(B, insts, 3)
+        calls = trunk_calls(B, insts, 3)
+        for it in insts:
+            if it.get("act") is not None:
+                calls.append(policy_head_call(B, it))
+        return calls
     calls = trunk_calls(B, insts, 2)
     groups = []
     for it in insts:
@@ -157,6 +177,21 @@ def forward_calls(B, insts, scalar_head):
                            head_b=n.b[3], q=it["q"], out=it["h"][2] if st[2] else 0, ldo=HIDDEN[2]))
     calls.append(K.Gemm(B, HIDDEN[2], HIDDEN[1], groups, epilogue=K.EPI_BIAS_ELU_HEAD, tile_n=128))
     return calls
+
+
+def policy_head_call(B, it):
+    """tanh(Linear(128, A)) (+ clipped target-policy noise) as its own launch: the path for action
+    widths the fused kernel does not take (A > 16 or not a multiple of 4) and for wide inputs."""
+    n, act = it["net"], it["act"]
+    A, H3 = n.dims[4], HIDDEN[2]
+    g = dict(a=it["h"][2], lda=H3, b=n.W[3], ldb=H3, bias=n.b[3], out=act["out"], ldo=act["ldo"])
+    if act.get("noise"):
+        g.update(aux=act["noise"], ldaux=act["ldnoise"])
+        return K.Gemm(B, A, H3, [g], epilogue=K.EPI_BIAS_TANH_NOISE, tile_n=K.pick_tile_n(A),
+                      noise_bound=act["noise_bound"], noise_std=act["noise_std"])
+    if act.get("out2"):
+        g.update(out2=act["out2"], ldo2=act["ldo2"])
+    return K.Gemm(B, A, H3, [g], epilogue=K.EPI_BIAS_TANH, tile_n=K.pick_tile_n(A))
 
 
 class _ArenaModule(nn.Module):

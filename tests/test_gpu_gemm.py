@@ -291,3 +291,39 @@ def test_fused_dgrad_chain_equals_layerwise(K, M, n_groups, with_bias):
                     pad[:M] = dz.double()
                     ref = pad.view(nblk, 128, -1).sum(1)
                     check(part, ref, 2e-6, f"rep {rep} group {gi} {name} partials")
+
+
+@pytest.mark.parametrize("M,A,noisy", [(8192, 16, True), (300, 16, False), (1000, 8, True), (128, 4, False)])
+def test_fused_policy_head_equals_separate_launch(K, M, A, noisy):
+    """The tanh policy head as a fourth contraction inside pqlb_mlp_forward (h3 converted in place in
+    TMEM, N = 16 MMA) against the separate head GEMM on the stored h3: same operands, same k order,
+    so the actions (with and without clipped target-policy noise) and the fp32 tanh copy must be
+    bit-identical."""
+    g = torch.Generator(device=DEV).manual_seed(M + A)
+    k_in, O, x_ld = 88, 88, 104
+    x = torch.zeros(M, x_ld, device=DEV); x[:, :k_in] = mk((M, k_in), g)
+    w1 = mk((512, k_in), g, 1.0 / k_in ** 0.5)
+    w2, w3, w4 = mk((256, 512), g, 1.0 / 512 ** 0.5), mk((128, 256), g, 1.0 / 16), mk((A, 128), g, 0.3)
+    b1, b2, b3, b4 = (torch.randn(n, generator=g, device=DEV) * 0.1 for n in (512, 256, 128, A))
+    noise = torch.randn(M, A, generator=g, device=DEV)
+    h3 = torch.zeros(M, 128, device=DEV)
+    out_f, out_s = torch.zeros(M, x_ld, device=DEV), torch.zeros(M, x_ld, device=DEV)
+    act_f, act_s = torch.zeros(M, A, device=DEV), torch.zeros(M, A, device=DEV)
+    grp = dict(x=K.addr(x), ldx=x_ld, w1=K.addr(w1), ldw1=k_in, w2=K.addr(w2), w3=K.addr(w3), b1=K.addr(b1), b2=K.addr(b2),
+               b3=K.addr(b3), h3=K.addr(h3), act_w=K.addr(w4), act_b=K.addr(b4), act_n=A, act_out=K.addr(out_f, O), act_ldo=x_ld)
+    if noisy:
+        grp.update(act_noise=K.addr(noise), act_ldnoise=A, noise_std=0.8, noise_bound=0.2)
+    else:
+        grp.update(act_out2=K.addr(act_f), act_ldo2=A)
+    K.MlpForward(M, k_in, [grp])()
+    hd = dict(a=K.addr(h3), lda=128, b=K.addr(w4), ldb=128, bias=K.addr(b4), out=K.addr(out_s, O), ldo=x_ld)
+    if noisy:
+        hd.update(aux=K.addr(noise), ldaux=A)
+        K.Gemm(M, A, 128, [hd], epilogue=K.EPI_BIAS_TANH_NOISE, tile_n=K.pick_tile_n(A), noise_bound=0.2, noise_std=0.8)()
+    else:
+        hd.update(out2=K.addr(act_s), ldo2=A)
+        K.Gemm(M, A, 128, [hd], epilogue=K.EPI_BIAS_TANH, tile_n=K.pick_tile_n(A))()
+    torch.cuda.synchronize()
+    assert torch.equal(out_f, out_s), f"{int((out_f != out_s).sum())} action words differ"
+    assert torch.equal(act_f, act_s)
+    assert out_f[:, O:O + A].abs().max() > 0.1 and torch.count_nonzero(out_f[:, :O]) == 0
