@@ -263,10 +263,12 @@ def main():
         return ms, wall, losses
 
     timed(args.warmup, False, 0)
-    launches0 = _lib.launch_count()
+    def n_launches():      # C-ABI launches + the kernels replayed from the learners' CUDA graphs
+        return _lib.launch_count() + sum(getattr(l._plan, "graph_launches", 0) for l in (v, p) if l._plan is not None)
+    launches0 = n_launches()
     with ClockSampler(local) as clk:
         ms, wall, losses = timed(args.steps, False, args.warmup)
-    launches = _lib.launch_count() - launches0
+    launches = n_launches() - launches0
     clocks = clk.summary()
     timed(2, True, 0)
     ms_e2e, wall_e2e, _ = timed(args.steps, True, args.warmup)

@@ -234,6 +234,15 @@ int pqlb_doubleq_td_loss(const float* q1, const float* q2, const float* tq1, con
                          float* dz3_1, float* dz3_2, float* y_out,
                          float* ws_head1, float* ws_head2, float* loss_part, pqlb_stream_t stream);
 
+/* The same, additionally writing the column sums of dz3 per 64-row block (the bias gradient of the
+ * third hidden layer): bias3_part_i[blk * 128 + c]. */
+int pqlb_doubleq_td_loss_b3(const float* q1, const float* q2, const float* tq1, const float* tq2,
+                            const float* reward, const float* done, float gamma_n, int64_t batch,
+                            const float* h3_1, const float* h3_2, const float* w4_1, const float* w4_2,
+                            float* dz3_1, float* dz3_2, float* y_out,
+                            float* ws_head1, float* ws_head2, float* loss_part,
+                            float* bias3_part1, float* bias3_part2, pqlb_stream_t stream);
+
 /* DPG actor loss, pql/algo/pql_p_learner.py:55-57: loss = -mean(min(q1,q2));
  * dq_i = -(1/B) on the smaller head (split 1/2 on ties, torch.minimum backward);
  * dz3_i = rn_tf32(dq_i * w4_i * elu'(h3_i)). */
@@ -308,6 +317,23 @@ int pqlb_adamw_polyak(float* param, const float* grad, float* m, float* v, float
  * ++counter[0]. */
 int pqlb_sum_partials(const float* part, int n, float scale, float* out, int64_t* counter,
                       float* ring, int ring_len, pqlb_stream_t stream);
+
+/* ---- K4, fused tail (what the learners launch): two kernels instead of four ---------------------
+ * pqlb_grad_reduce_finish = pqlb_grad_reduce, whose last block also does pqlb_sum_partials' job
+ * (loss_out[0] = loss_scale * sum(loss_part[0..n_loss)), ring[counter[0] % ring_len] = loss_out[0])
+ * and precomputes the AdamW bias corrections of step counter[0] + 1 into scalars_out (16 floats).
+ * It does NOT advance the counter.  pqlb_adamw_polyak_pre = pqlb_adamw_polyak taking those scalars
+ * (no per-block double-precision pow) and advancing counter[0] by one when the step is applied. */
+int pqlb_grad_reduce_finish(const int64_t* seg_table, int n_seg, const float* ws, float* grad,
+                            float* sumsq_part, const float* loss_part, int n_loss, float loss_scale,
+                            float* loss_out, const int64_t* counter, float* ring, int ring_len,
+                            float lr, float beta1, float beta2, float eps, float weight_decay,
+                            float tau, float* scalars_out, pqlb_stream_t stream);
+int pqlb_adamw_polyak_pre(float* param, const float* grad, float* m, float* v, float* target,
+                          float* param_tf32, float* target_tf32, int64_t n,
+                          const float* sumsq_part, int n_part, float grad_scale, float max_norm,
+                          const float* scalars, int64_t* counter, float* grad_norm_out,
+                          pqlb_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -92,6 +92,8 @@ _PROTOS = {
     "pqlb_round_tf32": (_int, [_f, _f, _i64, _st]),
     "pqlb_doubleq_td_loss": (_int, [_f, _f, _f, _f, _f, _f, _flt, _i64, _f, _f, _f, _f, _f, _f, _f,
                                     _f, _f, _f, _st]),
+    "pqlb_doubleq_td_loss_b3": (_int, [_f, _f, _f, _f, _f, _f, _flt, _i64, _f, _f, _f, _f, _f, _f, _f,
+                                       _f, _f, _f, _f, _f, _st]),
     "pqlb_dpg_loss": (_int, [_f, _f, _i64, _f, _f, _f, _f, _f, _f, _f, _st]),
     "pqlb_c51_td_loss": (_int, [_f, _f, _f, _f, _int, _f, _f, _f, _flt, _flt, _flt, _int, _i64,
                                 _f, _f, _f, _int, _f, _st]),
@@ -103,6 +105,9 @@ _PROTOS = {
     "pqlb_grad_sumsq": (_int, [_f, _int, _f, _f, _st]),
     "pqlb_adamw_polyak": (_int, [_f, _f, _f, _f, _f, _f, _f, _i64, _f, _int, _flt, _flt, _flt, _flt,
                                  _flt, _flt, _flt, _i64, _f, _flt, _f, _st]),
+    "pqlb_grad_reduce_finish": (_int, [_f, _int, _f, _f, _f, _f, _int, _flt, _f, _f, _f, _int,
+                                       _flt, _flt, _flt, _flt, _flt, _flt, _f, _st]),
+    "pqlb_adamw_polyak_pre": (_int, [_f, _f, _f, _f, _f, _f, _f, _i64, _f, _int, _flt, _flt, _f, _f, _f, _st]),
     "pqlb_sum_partials": (_int, [_f, _int, _flt, _f, _f, _f, _int, _st]),
 }
 

@@ -69,6 +69,7 @@ class _UpdateBase:
             _lib.check(_lib.load().pqlb_init(), "pqlb_init")
         self.loss_ring = loss_ring if loss_ring is not None else torch.zeros(5, device=self.device)
         self.graphs = None
+        self.graph_launches = 0
         self._bufs = []
         self.distl = bool(distl)
         self.N = int(num_atoms) if distl else 1
@@ -225,19 +226,24 @@ class CriticUpdate(_UpdateBase):
         insts += [dict(net=cnet[i], x=K.addr(self.x_cur), x_ld=x_ld, k_in=O + A, h=[K.addr(t) for t in h_c[i]],
                        store=(True, True, True), q=K.addr(self.q[i])) for i in range(2)]
         wg = [(H3, H2, H2), (H2, H1, H1), (H1, O + A, x_ld)] + ([(N, H3, H3)] if distl else [])
-        self._ws_init(wg, 2, [d for d in HIDDEN] * 2 + ([N, N] if distl else []), extra=2 * _ru(self.nblk_head * (H3 + 1), 32))
+        self._ws_init(wg, 2, [d for d in HIDDEN] * 2 + ([N, N] if distl else []),
+                      extra=2 * _ru(self.nblk_head * (H3 + 1), 32) + 2 * _ru(self.nblk_head * H3, 32))
         calls += forward_calls(B, insts, not distl)
         if not distl:
             ws_head = [self._ws_alloc(self.nblk_head * (H3 + 1)) for _ in range(2)]
             for i in range(2):
                 self.opt.add_source(self.Lc.w_off[i][3], H3, ws_head[i], H3 + 1, self.nblk_head)
                 self.opt.add_source(self.Lc.b_off[i][3], 1, ws_head[i] + H3, H3 + 1, self.nblk_head)
-            calls.append(K.Call("pqlb_doubleq_td_loss", _lib.ptr(self.q[0]), _lib.ptr(self.q[1]), _lib.ptr(self.tq[0]),
+            b3 = [self._ws_alloc(self.nblk_head * H3) for _ in range(2)]       # layer-3 bias gradient partials
+            for i in range(2):
+                self.opt.add_source(self.Lc.b_off[i][2], H3, b3[i], H3, self.nblk_head)
+            calls.append(K.Call("pqlb_doubleq_td_loss_b3", _lib.ptr(self.q[0]), _lib.ptr(self.q[1]), _lib.ptr(self.tq[0]),
                                 _lib.ptr(self.tq[1]), _lib.ptr(self.reward), _lib.ptr(self.done), self.gamma_n, B,
                                 _lib.ptr(h_c[0][2]), _lib.ptr(h_c[1][2]), C.c_void_p(cnet[0].Wf[3]),
                                 C.c_void_p(cnet[1].Wf[3]), _lib.ptr(self.dz[0][2]), _lib.ptr(self.dz[1][2]),
                                 _lib.ptr(self.y), C.c_void_p(K.addr(self.ws, ws_head[0])),
-                                C.c_void_p(K.addr(self.ws, ws_head[1])), _lib.ptr(self.loss_part)))
+                                C.c_void_p(K.addr(self.ws, ws_head[1])), _lib.ptr(self.loss_part),
+                                C.c_void_p(K.addr(self.ws, b3[0])), C.c_void_p(K.addr(self.ws, b3[1]))))
             self.loss_scale, self.n_loss_part = 1.0 / B, 2 * self.nblk_head
         else:
             groups = [dict(a=it["h"][2], lda=H3, b=it["net"].W[3], ldb=H3, bias=it["net"].b[3],
@@ -260,10 +266,10 @@ class CriticUpdate(_UpdateBase):
         calls.append(self._wgrad(self.opt, self.Lc, [0, 1], 2, dz3, H3, H3, [h_c[i][1] for i in range(2)], H2, H2))
         calls.append(self._wgrad(self.opt, self.Lc, [0, 1], 1, dz2, H2, H2, [h_c[i][0] for i in range(2)], H1, H1))
         calls.append(self._wgrad(self.opt, self.Lc, [0, 1], 0, dz1, H1, H1, [self.x_cur, self.x_cur], x_ld, O + A))
-        entries = [(i, 2, self.dz[i][2], H3, H3) for i in range(2)]      # layers 0 / 1: fused into the dgrad chain
+        # bias gradients: layers 0 / 1 come out of the dgrad chain, layer 2 out of the twin-Q loss kernel
         if distl:
-            entries += [(i, 3, self.dl[i], self.pd, N) for i in range(2)]
-        calls.append(self._bias_grads(self.opt, self.Lc, entries))
+            entries = [(i, 2, self.dz[i][2], H3, H3) for i in range(2)] + [(i, 3, self.dl[i], self.pd, N) for i in range(2)]
+            calls.append(self._bias_grads(self.opt, self.Lc, entries))
         _finish_plan(self, self.opt, self.c_flat, self.t_flat, self.c_tf, self.t_tf)
 
     def round_weights(self):
@@ -310,6 +316,8 @@ class CriticUpdate(_UpdateBase):
             return
         if self.graphs is None or self.graphs[2] is not sample:
             self._capture(sample, allreduce is not None)
+        # kernels a replay launches without passing through the C ABI's own launch counter
+        self.graph_launches += len(self.calls) + (1 if sample is not None else 0) + 2 + (1 if allreduce is not None else 0)
         self.graphs[0].replay()
         if allreduce is not None:
             allreduce(self.opt.grad)
@@ -464,16 +472,19 @@ def _finish_plan(plan, opt, p_flat, t_flat, p_tf, t_tf):
     """Prepare the reduce / clip+AdamW(+Polyak) / loss launches that close an update."""
     opt.finish(plan.device)
     big = plan.ws
-    plan.reduce_call = K.Call("pqlb_grad_reduce", _lib.ptr(opt.seg_table), opt.n_seg, _lib.ptr(big), _lib.ptr(opt.grad),
-                              _lib.ptr(opt.sumsq))
-    plan.sumsq_call = K.Call("pqlb_grad_sumsq", _lib.ptr(opt.seg_table), opt.n_seg, _lib.ptr(opt.grad),
-                             _lib.ptr(opt.sumsq))
     max_norm = -1.0 if plan.max_grad_norm is None else float(plan.max_grad_norm)
     tau = getattr(plan, "tau", 0.0)
-
-    plan.adamw_call = K.Call("pqlb_adamw_polyak", _lib.ptr(p_flat), _lib.ptr(opt.grad), _lib.ptr(opt.m), _lib.ptr(opt.v),
+    plan.adam_scalars = torch.zeros(16, device=plan.device)
+    # reduction + loss sum + AdamW bias corrections in one launch; clip + AdamW (+ Polyak) + step
+    # count in the second (pqlb_sum_partials and the per-block pow() are gone from the update)
+    plan.reduce_call = K.Call("pqlb_grad_reduce_finish", _lib.ptr(opt.seg_table), opt.n_seg, _lib.ptr(big), _lib.ptr(opt.grad),
+                              _lib.ptr(opt.sumsq), _lib.ptr(plan.loss_part), plan.n_loss_part, plan.loss_scale,
+                              _lib.ptr(plan.loss), _lib.ptr(opt.count), _lib.ptr(plan.loss_ring), plan.loss_ring.numel(),
+                              plan.lr, 0.9, 0.999, 1e-8, 0.01, tau, _lib.ptr(plan.adam_scalars))
+    plan.sumsq_call = K.Call("pqlb_grad_sumsq", _lib.ptr(opt.seg_table), opt.n_seg, _lib.ptr(opt.grad),
+                             _lib.ptr(opt.sumsq))
+    plan.adamw_call = K.Call("pqlb_adamw_polyak_pre", _lib.ptr(p_flat), _lib.ptr(opt.grad), _lib.ptr(opt.m), _lib.ptr(opt.v),
                              _lib.ptr(t_flat), _lib.ptr(p_tf), _lib.ptr(t_tf), opt.layout.total, _lib.ptr(opt.sumsq),
-                             opt.n_seg, 1.0 / plan.world_size, max_norm, plan.lr, 0.9, 0.999, 1e-8, 0.01, 0,
-                             _lib.ptr(opt.count), tau, _lib.ptr(plan.grad_norm))
-    plan.loss_call = K.Call("pqlb_sum_partials", _lib.ptr(plan.loss_part), plan.n_loss_part, plan.loss_scale,
-                            _lib.ptr(plan.loss), _lib.ptr(opt.count), _lib.ptr(plan.loss_ring), plan.loss_ring.numel())
+                             opt.n_seg, 1.0 / plan.world_size, max_norm, _lib.ptr(plan.adam_scalars),
+                             _lib.ptr(opt.count), _lib.ptr(plan.grad_norm))
+    plan.loss_call = lambda: None

@@ -23,10 +23,12 @@ head_loss_kernel(int mode, const float* __restrict__ q1, const float* __restrict
                  long long B, const float* __restrict__ h3_1, const float* __restrict__ h3_2,
                  const float* __restrict__ w4_1, const float* __restrict__ w4_2,
                  float* __restrict__ dz3_1, float* __restrict__ dz3_2, float* __restrict__ y_out,
-                 float* __restrict__ ws1, float* __restrict__ ws2, float* __restrict__ loss_part) {
+                 float* __restrict__ ws1, float* __restrict__ ws2, float* __restrict__ loss_part,
+                 float* __restrict__ bz1, float* __restrict__ bz2) {
   __shared__ float s_dq[kRowsPerBlock];
   __shared__ float s_red[8], s_redb[8];
   __shared__ float s_col[8][kHeadN];
+  __shared__ float s_colz[8][kHeadN];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int net = blockIdx.y;
   const long long r0 = (long long)blockIdx.x * kRowsPerBlock;
@@ -73,7 +75,7 @@ head_loss_kernel(int mode, const float* __restrict__ q1, const float* __restrict
     const long long r = r0 + warp * 8 + i;
     h[i] = r < B ? *reinterpret_cast<const float4*>(h3 + r * kHeadN + c) : make_float4(0.f, 0.f, 0.f, 0.f);
   }
-  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f), accz = make_float4(0.f, 0.f, 0.f, 0.f);
   float accb = 0.f;
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
@@ -88,8 +90,11 @@ head_loss_kernel(int mode, const float* __restrict__ q1, const float* __restrict
     o.w = rn_tf32(dq * w.w * (h[i].w > 0.f ? 1.f : h[i].w + 1.f));
     *reinterpret_cast<float4*>(dz3 + r * kHeadN + c) = o;
     acc.x += dq * h[i].x; acc.y += dq * h[i].y; acc.z += dq * h[i].z; acc.w += dq * h[i].w;
+    accz.x += o.x; accz.y += o.y; accz.z += o.z; accz.w += o.w;      // column sums of dz3: the layer-3 bias gradient
     accb += dq;
   }
+  float* bz = net ? bz2 : bz1;
+  if (bz) *reinterpret_cast<float4*>(&s_colz[warp][c]) = accz;
   if (mode == 0) {
     *reinterpret_cast<float4*>(&s_col[warp][c]) = acc;
     if (lane == 0) s_redb[warp] = accb;
@@ -104,6 +109,13 @@ head_loss_kernel(int mode, const float* __restrict__ q1, const float* __restrict
       float t = 0.f;
       for (int i = 0; i < 8; ++i) t += s_redb[i];
       ws[(long long)blockIdx.x * (kHeadN + 1) + kHeadN] = t;
+    }
+    if (bz && tid >= kHeadN && tid < 2 * kHeadN) {       // the other half of the block sums the dz3 columns
+      const int cc = tid - kHeadN;
+      float t = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) t += s_colz[i][cc];
+      bz[(long long)blockIdx.x * kHeadN + cc] = t;
     }
   }
 }
@@ -256,7 +268,24 @@ extern "C" int pqlb_doubleq_td_loss(const float* q1, const float* q2, const floa
   const dim3 blocks((unsigned)((batch + kRowsPerBlock - 1) / kRowsPerBlock), 2);
   head_loss_kernel<<<blocks, kLossThreads, 0, (cudaStream_t)stream>>>(
       0, q1, q2, tq1, tq2, reward, done, gamma_n, batch, h3_1, h3_2, w4_1, w4_2, dz3_1, dz3_2, y_out,
-      ws_head1, ws_head2, loss_part);
+      ws_head1, ws_head2, loss_part, nullptr, nullptr);
+  PQLB_LAUNCH_RET();
+}
+
+extern "C" int pqlb_doubleq_td_loss_b3(const float* q1, const float* q2, const float* tq1, const float* tq2,
+                                       const float* reward, const float* done, float gamma_n, int64_t batch,
+                                       const float* h3_1, const float* h3_2, const float* w4_1, const float* w4_2,
+                                       float* dz3_1, float* dz3_2, float* y_out, float* ws_head1, float* ws_head2,
+                                       float* loss_part, float* bias3_part1, float* bias3_part2,
+                                       pqlb_stream_t stream) {
+  PQLB_CHECK_ARG(q1 && q2 && tq1 && tq2 && reward && done && batch > 0 && bias3_part1 && bias3_part2);
+  PQLB_CHECK_ARG(h3_1 && h3_2 && w4_1 && w4_2 && dz3_1 && dz3_2 && ws_head1 && ws_head2 && loss_part);
+  PQLB_CHECK_ALIGN(aligned16(h3_1) && aligned16(h3_2) && aligned16(w4_1) && aligned16(w4_2) &&
+                   aligned16(dz3_1) && aligned16(dz3_2));
+  const dim3 blocks((unsigned)((batch + kRowsPerBlock - 1) / kRowsPerBlock), 2);
+  head_loss_kernel<<<blocks, kLossThreads, 0, (cudaStream_t)stream>>>(
+      0, q1, q2, tq1, tq2, reward, done, gamma_n, batch, h3_1, h3_2, w4_1, w4_2, dz3_1, dz3_2, y_out,
+      ws_head1, ws_head2, loss_part, bias3_part1, bias3_part2);
   PQLB_LAUNCH_RET();
 }
 
@@ -269,7 +298,7 @@ extern "C" int pqlb_dpg_loss(const float* q1, const float* q2, int64_t batch, co
   const dim3 blocks((unsigned)((batch + kRowsPerBlock - 1) / kRowsPerBlock), 2);
   head_loss_kernel<<<blocks, kLossThreads, 0, (cudaStream_t)stream>>>(
       1, q1, q2, nullptr, nullptr, nullptr, nullptr, 0.f, batch, h3_1, h3_2, w4_1, w4_2, dz3_1, dz3_2,
-      nullptr, nullptr, nullptr, loss_part);
+      nullptr, nullptr, nullptr, loss_part, nullptr, nullptr);
   PQLB_LAUNCH_RET();
 }
 

@@ -27,12 +27,39 @@ __device__ __forceinline__ float block_sum_256(float v, float* smem8) {
   return tot;
 }
 
+struct AdamScalars {
+  float decay, one_minus_b1, b2, one_minus_b2, step_size, bc2_sqrt, eps, tau, one_minus_tau;
+};
+// scalar corrections in double, like torch's python-side arithmetic (torch/optim/adam.py), t 1-based
+__device__ __forceinline__ AdamScalars adam_scalars(double t, float lr_f, float beta1, float beta2, float eps, float wd, float tau) {
+  AdamScalars sa;
+  const double b1 = beta1, b2 = beta2, lr = lr_f;
+  const double bc1 = 1.0 - pow(b1, t), bc2 = 1.0 - pow(b2, t);
+  sa.decay = (float)(1.0 - lr * (double)wd);
+  sa.one_minus_b1 = (float)(1.0 - b1); sa.b2 = beta2; sa.one_minus_b2 = (float)(1.0 - b2);
+  sa.step_size = (float)(lr / bc1); sa.bc2_sqrt = (float)sqrt(bc2); sa.eps = eps;
+  sa.tau = tau; sa.one_minus_tau = (float)(1.0 - (double)tau);
+  return sa;
+}
+
+// Work the LAST block of the reduction does for the rest of the update (it used to be a launch of
+// its own plus a serial section at the top of every AdamW block): the loss = scale * sum of the loss
+// partials (fixed order), written to out[0] and to the Tracker window ring[count % ring_len], and the
+// AdamW bias corrections of step count + 1.  count (completed updates) is NOT advanced here: the
+// optimiser kernel does that when it has applied the step.
+struct FinishArgs {
+  const float* loss_part; int n_loss; float loss_scale; float* loss_out;
+  const long long* counter; float* ring; int ring_len;
+  float lr, beta1, beta2, eps, weight_decay, tau;
+  AdamScalars* scalars_out;
+};
+
 // One block per segment of <= 256 elements (one per thread): the n_part partial sums of an
-// element are loaded eight at a time (independent loads in flight) and added in index order, so
+// element are loaded sixteen at a time (independent loads in flight) and added in index order, so
 // the result does not depend on the launch shape.
 __global__ void __launch_bounds__(kOptThreads)
 grad_reduce_kernel(const int64_t* __restrict__ seg, const float* __restrict__ ws,
-                   float* __restrict__ grad, float* __restrict__ sumsq_part, bool reduce) {
+                   float* __restrict__ grad, float* __restrict__ sumsq_part, bool reduce, FinishArgs fin) {
   __shared__ float red[8];
   const int64_t* s = seg + (int64_t)blockIdx.x * 5;
   const int64_t arena_off = s[0], count = s[1], ws_off = s[2], ws_stride = s[3], n_part = s[4];
@@ -43,6 +70,13 @@ grad_reduce_kernel(const int64_t* __restrict__ seg, const float* __restrict__ ws
       g = 0.f;
       const float* p = ws + ws_off + i;
       int64_t k = 0;
+      for (; k + 16 <= n_part; k += 16) {
+        float t[16];
+#pragma unroll
+        for (int u = 0; u < 16; ++u) t[u] = p[(k + u) * ws_stride];
+#pragma unroll
+        for (int u = 0; u < 16; ++u) g += t[u];
+      }
       for (; k + 8 <= n_part; k += 8) {
         float t[8];
 #pragma unroll
@@ -59,21 +93,31 @@ grad_reduce_kernel(const int64_t* __restrict__ seg, const float* __restrict__ ws
   }
   const float tot = block_sum_256(sq, red);
   if (threadIdx.x == 0) sumsq_part[blockIdx.x] = tot;
+
+  if (fin.loss_part != nullptr && blockIdx.x == gridDim.x - 1) {
+    float acc = 0.f;
+    for (int i = threadIdx.x; i < fin.n_loss; i += kOptThreads) acc += fin.loss_part[i];
+    const float ltot = block_sum_256(acc, red);
+    if (threadIdx.x == 0) {
+      const long long c = fin.counter[0];
+      const float r = ltot * fin.loss_scale;
+      fin.loss_out[0] = r;
+      if (fin.ring && fin.ring_len > 0) fin.ring[c % fin.ring_len] = r;
+      *fin.scalars_out = adam_scalars((double)(c + 1), fin.lr, fin.beta1, fin.beta2, fin.eps, fin.weight_decay, fin.tau);
+    }
+  }
 }
 
 struct AdamHyper {     // as passed by the caller; derived scalars are computed on the device
   float grad_scale, max_norm, lr, beta1, beta2, eps, weight_decay, tau;
 };
-struct AdamScalars {
-  float decay, one_minus_b1, b2, one_minus_b2, step_size, bc2_sqrt, eps, tau, one_minus_tau;
-};
-
 __global__ void __launch_bounds__(kOptThreads)
 adamw_polyak_kernel(float* __restrict__ param, const float* __restrict__ grad, float* __restrict__ m,
                     float* __restrict__ v, float* __restrict__ target, float* __restrict__ p_tf32,
                     float* __restrict__ t_tf32, int64_t n, const float* __restrict__ sumsq_part,
                     int n_part, AdamHyper h, int64_t step_host, const int64_t* __restrict__ step_dev,
-                    float* __restrict__ grad_norm_out) {
+                    float* __restrict__ grad_norm_out, const AdamScalars* __restrict__ scal_dev,
+                    long long* __restrict__ counter_inc) {
   __shared__ float red[8];
   __shared__ AdamScalars sa;
   // the element loads do not depend on the norm or the bias corrections: issue them first, so that
@@ -91,16 +135,10 @@ adamw_polyak_kernel(float* __restrict__ param, const float* __restrict__ grad, f
     for (int k = 0; k < cnt; ++k) { p[k] = param[i4 + k]; g[k] = grad[i4 + k]; mm[k] = m[i4 + k]; vv[k] = v[i4 + k]; if (target) tt[k] = target[i4 + k]; }
   }
   if (threadIdx.x == 0) {
-    // scalar corrections in double, like torch's python-side arithmetic (torch/optim/adam.py);
-    // the 1-based step count comes from the device counter when the update runs inside a
-    // CUDA graph (completed updates + 1), else from the host argument.
-    const double t = (double)(step_dev ? step_dev[0] + 1 : step_host);
-    const double b1 = h.beta1, b2 = h.beta2, lr = h.lr;
-    const double bc1 = 1.0 - pow(b1, t), bc2 = 1.0 - pow(b2, t);
-    sa.decay = (float)(1.0 - lr * (double)h.weight_decay);
-    sa.one_minus_b1 = (float)(1.0 - b1); sa.b2 = h.beta2; sa.one_minus_b2 = (float)(1.0 - b2);
-    sa.step_size = (float)(lr / bc1); sa.bc2_sqrt = (float)sqrt(bc2); sa.eps = h.eps;
-    sa.tau = h.tau; sa.one_minus_tau = (float)(1.0 - (double)h.tau);
+    // bias corrections: precomputed by the reduction kernel's last block (scal_dev), else computed
+    // here from the device counter (completed updates + 1) or the host step argument
+    if (scal_dev) sa = *scal_dev;
+    else sa = adam_scalars((double)(step_dev ? step_dev[0] + 1 : step_host), h.lr, h.beta1, h.beta2, h.eps, h.weight_decay, h.tau);
   }
   // global L2 norm of the (scaled) gradient from the per-segment partials, fixed order
   float part = 0.f;
@@ -110,7 +148,10 @@ adamw_polyak_kernel(float* __restrict__ param, const float* __restrict__ grad, f
   const float norm = sqrtf(total) * h.grad_scale;
   float coef = 1.f;
   if (h.max_norm >= 0.f) coef = fminf(h.max_norm / (norm + 1e-6f), 1.f);   // clip_grad.py
-  if (blockIdx.x == 0 && threadIdx.x == 0 && grad_norm_out) grad_norm_out[0] = norm;
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    if (grad_norm_out) grad_norm_out[0] = norm;
+    if (counter_inc) counter_inc[0] += 1;          // nobody reads the counter in this kernel when scal_dev is used
+  }
   const float gmul = h.grad_scale * coef;
   if (cnt == 0) return;
 #pragma unroll
@@ -236,14 +277,32 @@ using namespace pqlb;
 extern "C" int pqlb_grad_reduce(const int64_t* seg_table, int n_seg, const float* ws, float* grad,
                                 float* sumsq_part, pqlb_stream_t stream) {
   PQLB_CHECK_ARG(seg_table && n_seg > 0 && ws && grad && sumsq_part);
-  grad_reduce_kernel<<<n_seg, kOptThreads, 0, (cudaStream_t)stream>>>(seg_table, ws, grad, sumsq_part, true);
+  FinishArgs fin = {};
+  grad_reduce_kernel<<<n_seg, kOptThreads, 0, (cudaStream_t)stream>>>(seg_table, ws, grad, sumsq_part, true, fin);
+  PQLB_LAUNCH_RET();
+}
+
+extern "C" int pqlb_grad_reduce_finish(const int64_t* seg_table, int n_seg, const float* ws, float* grad,
+                                       float* sumsq_part, const float* loss_part, int n_loss, float loss_scale,
+                                       float* loss_out, const int64_t* counter, float* ring, int ring_len,
+                                       float lr, float beta1, float beta2, float eps, float weight_decay,
+                                       float tau, float* scalars_out, pqlb_stream_t stream) {
+  PQLB_CHECK_ARG(seg_table && n_seg > 0 && ws && grad && sumsq_part);
+  PQLB_CHECK_ARG(loss_part && n_loss > 0 && loss_out && counter && scalars_out && ring_len >= 0);
+  FinishArgs fin;
+  fin.loss_part = loss_part; fin.n_loss = n_loss; fin.loss_scale = loss_scale; fin.loss_out = loss_out;
+  fin.counter = reinterpret_cast<const long long*>(counter); fin.ring = ring; fin.ring_len = ring_len;
+  fin.lr = lr; fin.beta1 = beta1; fin.beta2 = beta2; fin.eps = eps; fin.weight_decay = weight_decay; fin.tau = tau;
+  fin.scalars_out = reinterpret_cast<AdamScalars*>(scalars_out);
+  grad_reduce_kernel<<<n_seg, kOptThreads, 0, (cudaStream_t)stream>>>(seg_table, ws, grad, sumsq_part, true, fin);
   PQLB_LAUNCH_RET();
 }
 
 extern "C" int pqlb_grad_sumsq(const int64_t* seg_table, int n_seg, const float* grad,
                                float* sumsq_part, pqlb_stream_t stream) {
   PQLB_CHECK_ARG(seg_table && n_seg > 0 && grad && sumsq_part);
-  grad_reduce_kernel<<<n_seg, kOptThreads, 0, (cudaStream_t)stream>>>(seg_table, nullptr, const_cast<float*>(grad), sumsq_part, false);
+  FinishArgs fin = {};
+  grad_reduce_kernel<<<n_seg, kOptThreads, 0, (cudaStream_t)stream>>>(seg_table, nullptr, const_cast<float*>(grad), sumsq_part, false, fin);
   PQLB_LAUNCH_RET();
 }
 
@@ -263,7 +322,25 @@ extern "C" int pqlb_adamw_polyak(float* param, const float* grad, float* m, floa
   const int64_t blocks = (n + kOptThreads * 4 - 1) / (kOptThreads * 4);
   adamw_polyak_kernel<<<(unsigned)blocks, kOptThreads, 0, (cudaStream_t)stream>>>(
       param, grad, m, v, target, param_tf32, target_tf32, n, sumsq_part, n_part, h, step, step_dev,
-      grad_norm_out);
+      grad_norm_out, nullptr, nullptr);
+  PQLB_LAUNCH_RET();
+}
+
+extern "C" int pqlb_adamw_polyak_pre(float* param, const float* grad, float* m, float* v, float* target,
+                                     float* param_tf32, float* target_tf32, int64_t n,
+                                     const float* sumsq_part, int n_part, float grad_scale, float max_norm,
+                                     const float* scalars, int64_t* counter, float* grad_norm_out,
+                                     pqlb_stream_t stream) {
+  PQLB_CHECK_ARG(param && grad && m && v && n > 0 && sumsq_part && n_part > 0 && scalars && counter);
+  PQLB_CHECK_ALIGN(aligned16(param) && aligned16(grad) && aligned16(m) && aligned16(v));
+  PQLB_CHECK_ALIGN((!target || aligned16(target)) && (!param_tf32 || aligned16(param_tf32)) &&
+                   (!target_tf32 || aligned16(target_tf32)));
+  AdamHyper h = {};
+  h.grad_scale = grad_scale; h.max_norm = max_norm;
+  const int64_t blocks = (n + kOptThreads * 4 - 1) / (kOptThreads * 4);
+  adamw_polyak_kernel<<<(unsigned)blocks, kOptThreads, 0, (cudaStream_t)stream>>>(
+      param, grad, m, v, target, param_tf32, target_tf32, n, sumsq_part, n_part, h, 0, nullptr,
+      grad_norm_out, reinterpret_cast<const AdamScalars*>(scalars), reinterpret_cast<long long*>(counter));
   PQLB_LAUNCH_RET();
 }
 
