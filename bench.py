@@ -166,6 +166,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--one-stream", action="store_true", help="both learners on the caller's stream (no overlap)")
+    ap.add_argument("--eager-allreduce", action="store_true", help="data parallel: NCCL all-reduce between two graphs instead of inside one")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
@@ -199,8 +200,13 @@ def main():
     cfg.data_parallel = world > 1
     cfg.use_cuda_graph = not args.no_graph
     cfg.learner_streams = not args.one_stream      # V- and P-learner overlap like the reference's two Ray actors
-    v = PQLVLearner(O, A, cfg)
-    p = PQLPLearner(O, A, cfg)
+    cfg.dp_graph_allreduce = world > 1 and not args.eager_allreduce
+    # one communicator per learner: their updates replay on two streams, and an all-reduce captured in
+    # a CUDA graph must not share NCCL's per-communicator ordering with the other learner's
+    pg_v = dist.new_group(list(range(world))) if world > 1 else None
+    pg_p = dist.new_group(list(range(world))) if world > 1 else None
+    v = PQLVLearner(O, A, cfg, process_group=pg_v)
+    p = PQLPLearner(O, A, cfg, process_group=pg_p)
     if world > 1:      # identical initial weights on every rank
         dist.broadcast(v.critic.arena.flat, 0)
         dist.broadcast(p.actor.arena.flat, 0)
@@ -320,9 +326,21 @@ def main():
         t_ms = ev_time(fn, 200 if units <= 8 * B else 50)
         replay[name] = {"us": round(t_ms * 1e3, 2), "gbs": round(units * per / (t_ms * 1e-3) / 1e9, 1)}
 
-    if rank != 0:
+    def leave():
+        """Tear-down of a data-parallel run.  The learners' CUDA graphs hold captured NCCL kernels;
+        destroying the communicators under them hung in round 1, so: drop the graphs, drain the
+        device, meet at a barrier and leave without NCCL's destructor."""
         if world > 1:
-            dist.destroy_process_group()
+            for l in (v, p):
+                if l._plan is not None:
+                    l._plan.graphs = None
+            torch.cuda.synchronize(dev)
+            dist.barrier()
+            sys.stdout.flush(); sys.stderr.flush()
+            os._exit(0)
+
+    if rank != 0:
+        leave()
         return
     peaks = {}
     try:
@@ -361,8 +379,7 @@ def main():
         r = cpu_reference_rate(seconds_budget=15.0)
         line["cpu_baseline"] = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
     print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    leave()
 
 
 if __name__ == "__main__":

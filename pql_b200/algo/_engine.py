@@ -302,11 +302,14 @@ class CriticUpdate(_UpdateBase):
                       _lib.ptr(self.x_cur), _lib.ptr(self.x_tgt), self.x_ld, _lib.ptr(self.reward), _lib.ptr(self.done),
                       keep=(ring,))
 
-    def run(self, sample=None, allreduce=None, use_graph=False):
+    def run(self, sample=None, allreduce=None, use_graph=False, graph_allreduce=False):
         """One update: [sample] + forward/backward launches + gradient reduction, the gradient
         all-reduce when data parallel, then clip + AdamW (+ Polyak) and the loss.  With
-        ``use_graph`` the two launch segments are captured once into CUDA graphs and replayed
-        (every pointer is fixed; the step count and the loss window live on the device)."""
+        ``use_graph`` the launches are captured once into CUDA graphs and replayed (every pointer is
+        fixed; the step count and the loss window live on the device): one graph per update, or two
+        with the all-reduce issued eagerly between them; ``graph_allreduce`` captures the NCCL
+        all-reduce as well (one graph per update also when data parallel - the learner must then own
+        its communicator, because two learners replaying on two streams give NCCL no common order)."""
         if not use_graph:
             self._segment_a(sample)
             if allreduce is not None:
@@ -315,11 +318,11 @@ class CriticUpdate(_UpdateBase):
             self._segment_b()
             return
         if self.graphs is None or self.graphs[2] is not sample:
-            self._capture(sample, allreduce is not None)
+            self._capture(sample, allreduce, graph_allreduce)
         # kernels a replay launches without passing through the C ABI's own launch counter
         self.graph_launches += len(self.calls) + (1 if sample is not None else 0) + 2 + (1 if allreduce is not None else 0)
         self.graphs[0].replay()
-        if allreduce is not None:
+        if allreduce is not None and not self.graphs[3]:
             allreduce(self.opt.grad)
         self.graphs[1].replay()
 
@@ -334,20 +337,25 @@ class CriticUpdate(_UpdateBase):
         self.adamw_call()
         self.loss_call()
 
-    def _capture(self, sample, data_parallel):
+    def _capture(self, sample, allreduce, graph_allreduce):
         torch.cuda.synchronize(self.device)
+        data_parallel = allreduce is not None
+        fused = data_parallel and graph_allreduce
         ga, gb = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
         with torch.cuda.graph(ga):
             self._segment_a(sample)
-            if not data_parallel:
+            if fused:
+                allreduce(self.opt.grad)
+                self.sumsq_call()
+            if fused or not data_parallel:
                 self._segment_b()
-        if data_parallel:
+        if data_parallel and not fused:
             with torch.cuda.graph(gb):
                 self.sumsq_call()
                 self._segment_b()
         else:
             gb = _NoGraph()
-        self.graphs = (ga, gb, sample)
+        self.graphs = (ga, gb, sample, fused)
 
 
 class _NoGraph:

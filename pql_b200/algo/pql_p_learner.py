@@ -51,6 +51,9 @@ class PQLPLearner:
         self._plan = None
         self._sample = None
         self.use_cuda_graph = bool(getattr(cfg, "use_cuda_graph", True)) and not os.environ.get("PQLB_NO_GRAPH")
+        # capture the gradient all-reduce into the update's CUDA graph (needs a communicator of this
+        # learner's own: pass process_group=dist.new_group(...) per learner)
+        self.graph_allreduce = bool(getattr(cfg, "dp_graph_allreduce", False)) and process_group is not None
         self._ls = LearnerStream(cfg, self.device)
         self._ls.tag(self.actor)
 
@@ -87,7 +90,8 @@ class PQLPLearner:
             p = self._plan
             with torch.cuda.device(self.device), self._ls.ctx():
                 torch.randint(self.cur_capacity, size=(p.B,), device=self.device, out=p.idx)     # :49
-                p.run(self._sample, self._allreduce if self.world_size > 1 else None, self.use_cuda_graph)
+                p.run(self._sample, self._allreduce if self.world_size > 1 else None, self.use_cuda_graph,
+                      self.graph_allreduce)
             self.update_count += 1
         return self.sleep_time
 

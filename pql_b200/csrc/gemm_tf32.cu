@@ -463,7 +463,11 @@ extern "C" int pqlb_gemm_tf32(const pqlb_gemm_desc* d, pqlb_stream_t stream) {
   P.stage_bytes = kATileBytes + ((P.b_tile_bytes + 1023) / 1024) * 1024;
   const bool wants_aux = d->epilogue == PQLB_EPI_MUL_ELUGRAD || d->epilogue == PQLB_EPI_MUL_TANHGRAD ||
                          d->epilogue == PQLB_EPI_BIAS_TANH_NOISE;
-  int stages = (kRingBudget - (wants_aux ? kEpiWarps * kChunkBytes : 0)) / P.stage_bytes;
+  // Split-K weight gradients with 256-wide tiles stream 48 KB per k-block: two stages (what fits
+  // next to a second CTA) cannot keep the L2 -> SM pipe full, so these launches take the whole SM
+  // (one CTA, four stages).
+  const bool big_ring = d->epilogue == PQLB_EPI_STORE && d->splits > 1 && tn == 256;
+  int stages = ((big_ring ? 2 * kRingBudget : kRingBudget) - (wants_aux ? kEpiWarps * kChunkBytes : 0)) / P.stage_bytes;
   if (stages > kMaxStages) stages = kMaxStages;
   if (stages > P.kb_per_split) stages = P.kb_per_split < 2 ? 2 : P.kb_per_split;
   if (stages < 2) stages = 2;
