@@ -166,7 +166,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--one-stream", action="store_true", help="both learners on the caller's stream (no overlap)")
-    ap.add_argument("--eager-allreduce", action="store_true", help="data parallel: NCCL all-reduce between two graphs instead of inside one")
+    ap.add_argument("--dp", default="fused", choices=["fused", "nccl", "nccl-graph"],
+                    help="gradient exchange: fused into the optimiser kernel over symmetric memory (default), "
+                         "NCCL all-reduce between two CUDA graphs, or NCCL captured inside the update graph")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
@@ -200,7 +202,8 @@ def main():
     cfg.data_parallel = world > 1
     cfg.use_cuda_graph = not args.no_graph
     cfg.learner_streams = not args.one_stream      # V- and P-learner overlap like the reference's two Ray actors
-    cfg.dp_graph_allreduce = world > 1 and not args.eager_allreduce
+    cfg.dp_fused = world > 1 and args.dp == "fused"             # all-reduce inside the optimiser kernel (symmetric memory)
+    cfg.dp_graph_allreduce = world > 1 and args.dp == "nccl-graph"
     # one communicator per learner: their updates replay on two streams, and an all-reduce captured in
     # a CUDA graph must not share NCCL's per-communicator ordering with the other learner's
     pg_v = dist.new_group(list(range(world))) if world > 1 else None

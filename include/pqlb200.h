@@ -335,6 +335,27 @@ int pqlb_adamw_polyak_pre(float* param, const float* grad, float* m, float* v, f
                           const float* scalars, int64_t* counter, float* grad_norm_out,
                           pqlb_stream_t stream);
 
+/* ---- K4-DP: gradient all-reduce fused into the optimiser kernel (one process per GPU) ----------
+ * grad_peers[r] / red_peers[r] / ctl_peers[r]: rank r's gradient arena, reduced-gradient receive
+ * buffer (n floats each) and control block (32 words of flags + world * grid floats), all in
+ * peer-mapped (symmetric) memory; local: two int64 in local memory, zero-initialised.  Every rank
+ * launches the same grid (<= 148 blocks, all co-resident).  Replaces ncclAllReduce(grad) +
+ * pqlb_grad_sumsq + pqlb_adamw_polyak_pre: slice `rank` of the gradient is summed over ranks in rank
+ * order by its owner and delivered to every rank (two-shot all-reduce over NVLink), the global norm is
+ * assembled from the world x grid partial sums in a fixed order, and every rank applies the same
+ * clip + AdamW + Polyak step of the mean gradient (grad_scale = 1 / world) to its full arena. */
+typedef struct {
+  const float* grad_peers[8];
+  float* red_peers[8];
+  void* ctl_peers[8];
+  int64_t* local;
+  int rank, world, grid;
+} pqlb_dp_desc;
+int pqlb_adamw_polyak_dp(float* param, float* m, float* v, float* target, float* param_tf32,
+                         float* target_tf32, int64_t n, const pqlb_dp_desc* dp, float max_norm,
+                         const float* scalars, int64_t* counter, float* grad_norm_out,
+                         pqlb_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -55,6 +55,11 @@ class MlpGroup(C.Structure):
                 ("noise_std", _flt), ("noise_bound", _flt), ("act_n", _int)]
 
 
+class DpDesc(C.Structure):
+    _fields_ = [("grad_peers", _f * 8), ("red_peers", _f * 8), ("ctl_peers", _f * 8), ("local", _f),
+                ("rank", _int), ("world", _int), ("grid", _int)]
+
+
 class MlpBwdGroup(C.Structure):
     _fields_ = [("dz3", _f), ("w3", _f), ("w2", _f), ("h2", _f), ("h1", _f), ("dz2", _f), ("dz1", _f),
                 ("bias_part2", _f), ("bias_part1", _f)]
@@ -108,6 +113,7 @@ _PROTOS = {
     "pqlb_grad_reduce_finish": (_int, [_f, _int, _f, _f, _f, _f, _int, _flt, _f, _f, _f, _int,
                                        _flt, _flt, _flt, _flt, _flt, _flt, _f, _st]),
     "pqlb_adamw_polyak_pre": (_int, [_f, _f, _f, _f, _f, _f, _f, _i64, _f, _int, _flt, _flt, _f, _f, _f, _st]),
+    "pqlb_adamw_polyak_dp": (_int, [_f, _f, _f, _f, _f, _f, _i64, C.POINTER(DpDesc), _flt, _f, _f, _f, _st]),
     "pqlb_sum_partials": (_int, [_f, _int, _flt, _f, _f, _f, _int, _st]),
 }
 

@@ -38,3 +38,45 @@ def params_in_sync(flat_params, group=None, atol=0.0):
     dist.all_reduce(lo, op=dist.ReduceOp.MIN, group=group)
     dist.all_reduce(hi, op=dist.ReduceOp.MAX, group=group)
     return bool((hi - lo).abs().max().item() <= atol)
+
+
+class FusedExchange:
+    """Symmetric-memory state of the fused all-reduce + optimiser kernel (pqlb_adamw_polyak_dp): this
+    rank's gradient arena, the receive buffer of the reduced gradient and the control block (flags +
+    per-block sums of squares) are allocated in peer-mapped memory and exchanged once, at plan
+    construction (a collective: every rank builds its plans in the same order).
+
+    GRID is the launch width on every rank.  The kernel's blocks spin on flags written by the peers,
+    so they must not be able to starve the OTHER learner's kernels of SMs (two learners on two
+    streams, ranks at different points of their schedules: a full-width spinning grid could block the
+    kernel its peer is waiting for): 64 one-block-per-SM blocks leave 84 SMs to everything else."""
+
+    GRID = 64
+    FLAG_WORDS = 32
+
+    def __init__(self, n, device, group=None):
+        import torch.distributed._symmetric_memory as symm_mem
+        name = (group if group is not None else dist.group.WORLD).group_name
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        if self.world > 8:
+            raise RuntimeError("fused exchange: at most 8 ranks (one NVSwitch domain)")
+        self.grad = symm_mem.empty(n, dtype=torch.float32, device=device)
+        self.red = symm_mem.empty(n, dtype=torch.float32, device=device)
+        self.ctl = symm_mem.empty(self.FLAG_WORDS + self.world * self.GRID, dtype=torch.float32, device=device)
+        for t in (self.grad, self.red, self.ctl):
+            t.zero_()
+        self.handles = [symm_mem.rendezvous(t, name) for t in (self.grad, self.red, self.ctl)]
+        self.local = torch.zeros(2, dtype=torch.int64, device=device)
+        torch.cuda.synchronize(device)
+        dist.barrier(group)              # every rank's flags are zero before anybody can signal
+
+    def desc(self):
+        from .. import _lib
+        d = _lib.DpDesc()
+        for r in range(self.world):
+            d.grad_peers[r] = self.handles[0].buffer_ptrs[r]
+            d.red_peers[r] = self.handles[1].buffer_ptrs[r]
+            d.ctl_peers[r] = self.handles[2].buffer_ptrs[r]
+        d.local = self.local.data_ptr()
+        d.rank, d.world, d.grid = self.rank, self.world, self.GRID
+        return d

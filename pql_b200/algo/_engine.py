@@ -164,8 +164,10 @@ class CriticUpdate(_UpdateBase):
 
     def __init__(self, obs_dim, action_dim, batch, device, critic_flat, *, distl=False, num_atoms=51,
                  v_min=-10.0, v_max=10.0, gamma_n=0.99 ** 3, lr=5e-4, tau=0.05, max_grad_norm=0.5,
-                 noise_bound=0.2, noise_std=0.8, obs_norm=True, eps=1e-4, world_size=1, loss_ring=None):
+                 noise_bound=0.2, noise_std=0.8, obs_norm=True, eps=1e-4, world_size=1, loss_ring=None,
+                 process_group=None, dp_fused=False):
         super().__init__(obs_dim, action_dim, batch, device, distl, num_atoms, v_min, v_max, loss_ring)
+        self.process_group, self.dp_fused = process_group, bool(dp_fused)
         O, A, B, N, x_ld = self.O, self.A, self.B, self.N, self.x_ld
         dev = self.device
         self.lr, self.tau, self.max_grad_norm = float(lr), float(tau), max_grad_norm
@@ -368,8 +370,9 @@ class ActorUpdate(_UpdateBase):
 
     def __init__(self, obs_dim, action_dim, batch, device, actor_flat, *, distl=False, num_atoms=51,
                  v_min=-10.0, v_max=10.0, lr=5e-4, max_grad_norm=0.5, obs_norm=True, eps=1e-4, world_size=1,
-                 loss_ring=None):
+                 loss_ring=None, process_group=None, dp_fused=False):
         super().__init__(obs_dim, action_dim, batch, device, distl, num_atoms, v_min, v_max, loss_ring)
+        self.process_group, self.dp_fused = process_group, bool(dp_fused)
         O, A, B, N, x_ld, a_ld = self.O, self.A, self.B, self.N, self.x_ld, self.a_ld
         dev = self.device
         self.lr, self.max_grad_norm = float(lr), max_grad_norm
@@ -479,6 +482,13 @@ class ActorUpdate(_UpdateBase):
 def _finish_plan(plan, opt, p_flat, t_flat, p_tf, t_tf):
     """Prepare the reduce / clip+AdamW(+Polyak) / loss launches that close an update."""
     opt.finish(plan.device)
+    plan.dp = None
+    if plan.world_size > 1 and getattr(plan, "dp_fused", False):
+        # data parallel without NCCL on the path: the gradient arena lives in symmetric memory and the
+        # optimiser kernel does the two-shot all-reduce over NVLink itself (csrc/optim.cu)
+        from ._dp import FusedExchange
+        plan.dp = FusedExchange(opt.layout.total, plan.device, getattr(plan, "process_group", None))
+        opt.grad = plan.dp.grad
     big = plan.ws
     max_norm = -1.0 if plan.max_grad_norm is None else float(plan.max_grad_norm)
     tau = getattr(plan, "tau", 0.0)
@@ -495,4 +505,10 @@ def _finish_plan(plan, opt, p_flat, t_flat, p_tf, t_tf):
                              _lib.ptr(t_flat), _lib.ptr(p_tf), _lib.ptr(t_tf), opt.layout.total, _lib.ptr(opt.sumsq),
                              opt.n_seg, 1.0 / plan.world_size, max_norm, _lib.ptr(plan.adam_scalars),
                              _lib.ptr(opt.count), _lib.ptr(plan.grad_norm))
+    if plan.dp is not None:
+        desc = plan.dp.desc()
+        plan.adamw_call = K.Call("pqlb_adamw_polyak_dp", _lib.ptr(p_flat), _lib.ptr(opt.m), _lib.ptr(opt.v), _lib.ptr(t_flat),
+                                 _lib.ptr(p_tf), _lib.ptr(t_tf), opt.layout.total, C.byref(desc), max_norm,
+                                 _lib.ptr(plan.adam_scalars), _lib.ptr(opt.count), _lib.ptr(plan.grad_norm),
+                                 keep=(desc, plan.dp))
     plan.loss_call = lambda: None

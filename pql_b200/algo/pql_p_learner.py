@@ -54,6 +54,8 @@ class PQLPLearner:
         # capture the gradient all-reduce into the update's CUDA graph (needs a communicator of this
         # learner's own: pass process_group=dist.new_group(...) per learner)
         self.graph_allreduce = bool(getattr(cfg, "dp_graph_allreduce", False)) and process_group is not None
+        # cfg.dp_fused: no NCCL on the path - the optimiser kernel all-reduces over symmetric memory
+        self.dp_fused = bool(getattr(cfg, "dp_fused", False)) and self.world_size > 1
         self._ls = LearnerStream(cfg, self.device)
         self._ls.tag(self.actor)
 
@@ -75,7 +77,8 @@ class PQLPLearner:
                                  distl=distl, num_atoms=a.num_atoms, v_min=a.v_min, v_max=a.v_max, lr=a.actor_lr,
                                  max_grad_norm=a.max_grad_norm,
                                  obs_norm=bool(a.obs_norm) and self.normalize_tuple is not None, eps=eps,
-                                 world_size=self.world_size, loss_ring=self.loss_tracker.window)
+                                 world_size=self.world_size, loss_ring=self.loss_tracker.window,
+                                  process_group=self.process_group, dp_fused=self.dp_fused)
         self._sample = self._plan.sample_call(self.memory, self.memory_size)
 
     def start(self):
@@ -90,7 +93,7 @@ class PQLPLearner:
             p = self._plan
             with torch.cuda.device(self.device), self._ls.ctx():
                 torch.randint(self.cur_capacity, size=(p.B,), device=self.device, out=p.idx)     # :49
-                p.run(self._sample, self._allreduce if self.world_size > 1 else None, self.use_cuda_graph,
+                p.run(self._sample, self._allreduce if self.world_size > 1 and p.dp is None else None, self.use_cuda_graph,
                       self.graph_allreduce)
             self.update_count += 1
         return self.sleep_time

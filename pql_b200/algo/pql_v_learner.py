@@ -108,6 +108,8 @@ class PQLVLearner:
         # capture the gradient all-reduce into the update's CUDA graph (needs a communicator of this
         # learner's own: pass process_group=dist.new_group(...) per learner)
         self.graph_allreduce = bool(getattr(cfg, "dp_graph_allreduce", False)) and process_group is not None
+        # cfg.dp_fused: no NCCL on the path - the optimiser kernel all-reduces over symmetric memory
+        self.dp_fused = bool(getattr(cfg, "dp_fused", False)) and self.world_size > 1
         self._ls = LearnerStream(cfg, self.device)
         self._ls.tag(self.critic)
 
@@ -134,7 +136,8 @@ class PQLVLearner:
                                   max_grad_norm=a.max_grad_norm, noise_bound=a.noise.tgt_pol_noise_bound,
                                   noise_std=a.noise.tgt_pol_std,
                                   obs_norm=bool(a.obs_norm) and self.normalize_tuple is not None, eps=eps,
-                                  world_size=self.world_size, loss_ring=self.loss_tracker.window)
+                                  world_size=self.world_size, loss_ring=self.loss_tracker.window,
+                                  process_group=self.process_group, dp_fused=self.dp_fused)
         self._sample = self._plan.sample_call(self.memory.ring, self.memory.capacity)
 
     @property
@@ -166,7 +169,7 @@ class PQLVLearner:
                 # torch.normal's std.min() >= 0 check, a device->host sync per update).
                 torch.randint(self.memory.cur_capacity, size=(p.B,), device=self.device, out=p.idx)
                 p.noise.normal_()
-                p.run(self._sample, self._allreduce if self.world_size > 1 else None, self.use_cuda_graph,
+                p.run(self._sample, self._allreduce if self.world_size > 1 and p.dp is None else None, self.use_cuda_graph,
                       self.graph_allreduce)
             self.update_count += 1
         return self.sleep_time

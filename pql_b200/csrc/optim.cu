@@ -182,6 +182,143 @@ adamw_polyak_kernel(float* __restrict__ param, const float* __restrict__ grad, f
   }
 }
 
+// ---- data parallel: gradient all-reduce fused into the optimiser kernel -------------------------
+// Every rank's gradient arena, a receive buffer for the reduced gradient and a small control block
+// live in symmetric memory (peer-mapped over NVLink / NVSwitch).  One launch per update replaces
+// ncclAllReduce + the norm kernel + AdamW:
+//   A  wait until every rank's gradient is complete (flags in the peers' control blocks);
+//   B  two-shot all-reduce: this rank sums slice `rank` of all peers' gradients in rank order
+//      (deterministic) and stores the result, plus the per-block sums of squares of the slice, into
+//      EVERY rank's receive buffer / control block;
+//   C  wait until every rank has delivered its slice;
+//   D  global norm from the world x grid partials (same values, same order on every rank), clip,
+//      AdamW, Polyak, TF32 copies - on the full arena, redundantly on every rank, so parameters stay
+//      bit-identical without a broadcast.
+// All blocks of the grid must be co-resident (grid <= one block per SM); spins are bounded.
+constexpr int kDpMaxWorld = 8;
+constexpr int kDpFlagWords = 32;           // [0,16): phase-A flags by source rank, [16,32): phase-C flags
+struct DpArgs {
+  const float* grad_peers[kDpMaxWorld];
+  float* red_peers[kDpMaxWorld];
+  unsigned* ctl_peers[kDpMaxWorld];      // kDpFlagWords flags, then float sumsq[world][grid]
+  int rank, world;
+  unsigned long long* local;             // [0] epoch of the last completed exchange, [1] blocks done (monotonic)
+};
+
+__device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) { asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) { unsigned v; asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v; }
+__device__ __forceinline__ float4 ld_sys_f4(const float* p) {
+  float4 v; asm volatile("ld.relaxed.sys.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory"); return v;
+}
+__device__ __forceinline__ void st_sys_f4(float* p, float4 v) {
+  asm volatile("st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ float ld_sys_f(const float* p) { float v; asm volatile("ld.relaxed.sys.global.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory"); return v; }
+__device__ __forceinline__ void st_sys_f(float* p, float v) { asm volatile("st.relaxed.sys.global.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory"); }
+// bounded spin: a protocol bug or a dead peer must surface as a launch failure, not as a hung GPU
+__device__ __forceinline__ void wait_flag(const unsigned* p, unsigned epoch) {
+  const long long t0 = clock64();
+  while ((int)(ld_acquire_sys(p) - epoch) < 0) {
+    if (clock64() - t0 > 20000000000LL) __trap();
+  }
+}
+
+__global__ void __launch_bounds__(kOptThreads, 1)
+adamw_polyak_dp_kernel(float* __restrict__ param, float* __restrict__ m, float* __restrict__ v,
+                       float* __restrict__ target, float* __restrict__ p_tf32, float* __restrict__ t_tf32,
+                       int64_t n, DpArgs dp, float max_norm, const AdamScalars* __restrict__ scal_dev,
+                       long long* __restrict__ counter_inc, float* __restrict__ grad_norm_out) {
+  __shared__ float red[8];
+  __shared__ AdamScalars sa;
+  const unsigned G = gridDim.x;
+  const unsigned epoch = (unsigned)(dp.local[0] + 1ull);
+  unsigned* my_ctl = dp.ctl_peers[dp.rank];
+  if (threadIdx.x == 0) sa = *scal_dev;
+
+  // ---- A: every rank's gradient is complete (the kernel boundary before this launch made ours visible)
+  if (blockIdx.x == 0 && (int)threadIdx.x < dp.world) {
+    __threadfence_system();
+    st_release_sys(dp.ctl_peers[threadIdx.x] + dp.rank, epoch);
+  }
+  if ((int)threadIdx.x < dp.world) wait_flag(my_ctl + threadIdx.x, epoch);
+  __syncthreads();
+
+  // ---- B: reduce my slice in rank order, deliver it (and its sums of squares) to every rank
+  const int64_t n4 = n >> 2;
+  const int64_t s4 = (n4 + dp.world - 1) / dp.world;
+  const int64_t lo = (int64_t)dp.rank * s4, hi = lo + s4 < n4 ? lo + s4 : n4;
+  float sq = 0.f;
+  for (int64_t i = lo + (int64_t)blockIdx.x * kOptThreads + threadIdx.x; i < hi; i += (int64_t)G * kOptThreads) {
+    float4 acc = ld_sys_f4(dp.grad_peers[0] + 4 * i);
+    for (int r = 1; r < dp.world; ++r) {
+      const float4 t = ld_sys_f4(dp.grad_peers[r] + 4 * i);
+      acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
+    }
+    sq += acc.x * acc.x + acc.y * acc.y + acc.z * acc.z + acc.w * acc.w;
+    for (int q = 0; q < dp.world; ++q) st_sys_f4(dp.red_peers[q] + 4 * i, acc);
+  }
+  const float tot = block_sum_256(sq, red);
+  if (threadIdx.x == 0)
+    for (int q = 0; q < dp.world; ++q)
+      st_sys_f(reinterpret_cast<float*>(dp.ctl_peers[q] + kDpFlagWords) + (int64_t)dp.rank * G + blockIdx.x, tot);
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned long long done = atomicAdd(dp.local + 1, 1ull) + 1ull;
+    if (done == (unsigned long long)epoch * G) {       // last block of this rank: the slice is out
+      __threadfence_system();
+      for (int q = 0; q < dp.world; ++q) st_release_sys(dp.ctl_peers[q] + 16 + dp.rank, epoch);
+    }
+  }
+
+  // ---- C: every rank's slice has arrived
+  if ((int)threadIdx.x < dp.world) wait_flag(my_ctl + 16 + threadIdx.x, epoch);
+  __syncthreads();
+
+  // ---- D: global norm (world x G partials, fixed order), clip, AdamW, Polyak
+  const float* sumsq_all = reinterpret_cast<const float*>(my_ctl + kDpFlagWords);
+  float part = 0.f;
+  for (int i = threadIdx.x; i < dp.world * (int)G; i += kOptThreads) part += ld_sys_f(sumsq_all + i);
+  const float total = block_sum_256(part, red);
+  const AdamScalars a = sa;
+  const float grad_scale = 1.f / (float)dp.world;
+  const float norm = sqrtf(total) * grad_scale;
+  float coef = 1.f;
+  if (max_norm >= 0.f) coef = fminf(max_norm / (norm + 1e-6f), 1.f);   // clip_grad.py
+  const float gmul = grad_scale * coef;
+  const float* redl = dp.red_peers[dp.rank];
+  for (int64_t i = (int64_t)blockIdx.x * kOptThreads + threadIdx.x; i < n4; i += (int64_t)G * kOptThreads) {
+    const int64_t i4 = 4 * i;
+    float p[4], g[4], mm[4], vv[4], tt[4];
+    *reinterpret_cast<float4*>(g) = ld_sys_f4(redl + i4);
+    *reinterpret_cast<float4*>(p) = *reinterpret_cast<const float4*>(param + i4);
+    *reinterpret_cast<float4*>(mm) = *reinterpret_cast<const float4*>(m + i4);
+    *reinterpret_cast<float4*>(vv) = *reinterpret_cast<const float4*>(v + i4);
+    if (target) *reinterpret_cast<float4*>(tt) = *reinterpret_cast<const float4*>(target + i4);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float gk = g[k] * gmul;
+      p[k] = p[k] * a.decay;
+      mm[k] = mm[k] + a.one_minus_b1 * (gk - mm[k]);
+      vv[k] = vv[k] * a.b2 + a.one_minus_b2 * gk * gk;
+      const float denom = sqrtf(vv[k]) / a.bc2_sqrt + a.eps;
+      p[k] = p[k] - a.step_size * (mm[k] / denom);
+      if (target) tt[k] = p[k] * a.tau + tt[k] * a.one_minus_tau;
+    }
+    *reinterpret_cast<float4*>(param + i4) = *reinterpret_cast<float4*>(p);
+    *reinterpret_cast<float4*>(m + i4) = *reinterpret_cast<float4*>(mm);
+    *reinterpret_cast<float4*>(v + i4) = *reinterpret_cast<float4*>(vv);
+    if (target) *reinterpret_cast<float4*>(target + i4) = *reinterpret_cast<float4*>(tt);
+    if (p_tf32) *reinterpret_cast<float4*>(p_tf32 + i4) = make_float4(rn_tf32(p[0]), rn_tf32(p[1]), rn_tf32(p[2]), rn_tf32(p[3]));
+    if (target && t_tf32) *reinterpret_cast<float4*>(t_tf32 + i4) = make_float4(rn_tf32(tt[0]), rn_tf32(tt[1]), rn_tf32(tt[2]), rn_tf32(tt[3]));
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    if (grad_norm_out) grad_norm_out[0] = norm;
+    if (counter_inc) counter_inc[0] += 1;
+    dp.local[0] = epoch;          // every block of this rank passed phase C, i.e. has read the old value
+  }
+}
+
 __global__ void __launch_bounds__(kOptThreads)
 round_tf32_kernel(const float* __restrict__ src, float* __restrict__ dst, int64_t n) {
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -341,6 +478,29 @@ extern "C" int pqlb_adamw_polyak_pre(float* param, const float* grad, float* m, 
   adamw_polyak_kernel<<<(unsigned)blocks, kOptThreads, 0, (cudaStream_t)stream>>>(
       param, grad, m, v, target, param_tf32, target_tf32, n, sumsq_part, n_part, h, 0, nullptr,
       grad_norm_out, reinterpret_cast<const AdamScalars*>(scalars), reinterpret_cast<long long*>(counter));
+  PQLB_LAUNCH_RET();
+}
+
+extern "C" int pqlb_adamw_polyak_dp(float* param, float* m, float* v, float* target, float* param_tf32,
+                                    float* target_tf32, int64_t n, const pqlb_dp_desc* dp, float max_norm,
+                                    const float* scalars, int64_t* counter, float* grad_norm_out,
+                                    pqlb_stream_t stream) {
+  PQLB_CHECK_ARG(param && m && v && n > 0 && (n % 4) == 0 && dp && scalars && counter);
+  PQLB_CHECK_ARG(dp->world >= 2 && dp->world <= kDpMaxWorld && dp->rank >= 0 && dp->rank < dp->world && dp->local);
+  PQLB_CHECK_ARG(dp->grid >= 1 && dp->grid <= kNumSMs);
+  PQLB_CHECK_ALIGN(aligned16(param) && aligned16(m) && aligned16(v) && (!target || aligned16(target)) &&
+                   (!param_tf32 || aligned16(param_tf32)) && (!target_tf32 || aligned16(target_tf32)));
+  DpArgs a;
+  for (int r = 0; r < kDpMaxWorld; ++r) {
+    const bool on = r < dp->world;
+    if (on) PQLB_CHECK_ARG(dp->grad_peers[r] && dp->red_peers[r] && dp->ctl_peers[r] && aligned16(dp->grad_peers[r]) && aligned16(dp->red_peers[r]));
+    a.grad_peers[r] = on ? dp->grad_peers[r] : nullptr; a.red_peers[r] = on ? dp->red_peers[r] : nullptr;
+    a.ctl_peers[r] = on ? reinterpret_cast<unsigned*>(dp->ctl_peers[r]) : nullptr;
+  }
+  a.rank = dp->rank; a.world = dp->world; a.local = reinterpret_cast<unsigned long long*>(dp->local);
+  adamw_polyak_dp_kernel<<<(unsigned)dp->grid, kOptThreads, 0, (cudaStream_t)stream>>>(
+      param, m, v, target, param_tf32, target_tf32, n, a, max_norm, reinterpret_cast<const AdamScalars*>(scalars),
+      reinterpret_cast<long long*>(counter), grad_norm_out);
   PQLB_LAUNCH_RET();
 }
 
