@@ -47,43 +47,55 @@ def synth_block(rs, T=1):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+    """SM clock, power and throttle reasons sampled DURING the timed region through NVML (a thread
+    polling every 10 ms: the timed region of a default run is ~50 ms, too short for nvidia-smi -lms)."""
 
     def __init__(self, index):
-        self.rows, self.proc, self.index = [], None, index
+        self.rows, self.index, self.stop, self.th, self.max_mhz = [], index, False, None, None
 
     def __enter__(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.th = threading.Thread(target=self._read, daemon=True)
+            import pynvml as N
+            N.nvmlInit()
+            h = N.nvmlDeviceGetHandleByIndex(self._physical_index())
+            self.max_mhz = float(N.nvmlDeviceGetMaxClockInfo(h, N.NVML_CLOCK_SM))
+            names = {"hw_slowdown": N.nvmlClocksEventReasonHwSlowdown, "hw_thermal_slowdown": N.nvmlClocksEventReasonHwThermalSlowdown,
+                     "sw_thermal_slowdown": N.nvmlClocksEventReasonSwThermalSlowdown, "sw_power_cap": N.nvmlClocksEventReasonSwPowerCap}
+
+            def poll():
+                while not self.stop:
+                    try:
+                        mask = N.nvmlDeviceGetCurrentClocksEventReasons(h)
+                        self.rows.append((float(N.nvmlDeviceGetClockInfo(h, N.NVML_CLOCK_SM)), N.nvmlDeviceGetPowerUsage(h) / 1000.0,
+                                          [k for k, bit in names.items() if mask & bit]))
+                    except Exception:
+                        pass
+                    time.sleep(0.01)
+            self.th = threading.Thread(target=poll, daemon=True)
             self.th.start()
-        except OSError:
-            self.proc = None
+        except Exception:
+            self.th = None
         return self
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+    def _physical_index(self):
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
+            ids = [x for x in vis.split(",") if x.strip() != ""]
+            if self.index < len(ids) and ids[self.index].strip().isdigit():
+                return int(ids[self.index])
+        return self.index
 
     def __exit__(self, *a):
-        if self.proc is not None:
-            time.sleep(0.15)
-            self.proc.terminate()
-            self.th.join(timeout=2)
+        self.stop = True
+        if self.th is not None:
+            self.th.join(timeout=1)
 
     def summary(self):
-        sm = [float(r[0]) for r in self.rows if len(r) >= 8 and r[0].replace(".", "").isdigit()]
-        if not sm:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({n for r in self.rows if len(r) >= 8 for n, v in zip(names, r[4:8]) if v.lower().startswith("active")})
-        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(self.rows[0][1]), "reasons": reasons,
-                "power_w_max": max(float(r[2]) for r in self.rows if len(r) >= 8), "samples": len(sm)}
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["unavailable"]}
+        sm = [r[0] for r in self.rows]
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": self.max_mhz, "reasons": sorted({x for r in self.rows for x in r[2]}),
+                "power_w_max": max(r[1] for r in self.rows), "samples": len(sm)}
 
 
 def cpu_reference_rate(seconds_budget=20.0, threads=None):
@@ -138,9 +150,12 @@ def config_dict(n_gpus):
             "step": f"1 n-step push + ring insert of {E} transitions, {V_PER_STEP} critic updates, {P_PER_STEP} actor updates",
             "critic_updates_per_step": V_PER_STEP, "actor_updates_per_step": P_PER_STEP, "batch_per_gpu": B,
             "num_envs_per_gpu": E, "replay_slots_per_gpu": CAP, "parallelism": f"dp{n_gpus}",
+            "gradient_exchange": "none (1 GPU)" if n_gpus == 1 else "two-shot all-reduce over symmetric memory fused into the "
+                                 "optimiser kernel (pqlb_adamw_polyak_dp); --dp nccl / nccl-graph for the NCCL paths",
+            "settle_steps": 30,
             "learner_streams": "V-learner and P-learner each enqueue on their own CUDA stream (the reference runs them as "
                                "two concurrent Ray actors); update() is the exchange/join point",
-            "cache": "replay ring 800 MB per GPU > 126 MB L2 (random gathers miss L2); weights/activations are the "
+            "cache": "replay ring 1 GB per GPU > 126 MB L2 (random gathers miss L2); weights/activations are the "
                      "step's own working set and are not flushed"}
 
 
@@ -272,6 +287,11 @@ def main():
         return ms, wall, losses
 
     timed(args.warmup, False, 0)
+    # settling beyond the W warm-up steps (reported in config.settle_steps): GPUs 1..N-1 idle through
+    # the set-up and have not reached their boost clock, and the peer-memory / NCCL paths are cold;
+    # without it the first timed block of an 8-GPU run measured 6 % below the second
+    SETTLE = 30
+    timed(SETTLE, False, args.warmup)
     def n_launches():      # C-ABI launches + the kernels replayed from the learners' CUDA graphs
         return _lib.launch_count() + sum(getattr(l._plan, "graph_launches", 0) for l in (v, p) if l._plan is not None)
     launches0 = n_launches()
