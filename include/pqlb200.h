@@ -115,6 +115,34 @@ int pqlb_sample_obs_batch(const float* obsring, int64_t capacity, int obs_dim,
                           const float* mean, const float* var, float eps,
                           float* x, int x_ld, int act_dim, pqlb_stream_t stream);
 
+/* ---- Fused sampler RNG ---------------------------------------------------------------
+ * The same two fused gathers with the random draws of the update made INSIDE the kernel instead of
+ * by two torch launches: indices = torch.randint(cur_capacity, (batch,)) (simple_replay.py:87,
+ * pql_p_learner.py:49) and, for the V-learner, noise_out[noise_numel] = the N(0,1) draw behind
+ * torch.normal(zeros, full(std)) (pql/utils/noise.py:20-21), bit-identical to what ATen produces for
+ * the same generator state (csrc/rng.cuh: Philox4x32-10 / Box-Muller from cuRAND's device header,
+ * ATen's launch policy).  All state is device-resident so that the launch can be replayed from a
+ * CUDA graph: rng_state = {seed, base_offset, offset_increment_per_update}, counter = completed
+ * updates (the optimiser kernel advances it), cur_capacity = the ring's fill level (pqlb_store_i64
+ * after every insert).  The draw uses offset = base_offset + increment * counter[0] for the
+ * indices and + 4 for the noise; idx_out receives the indices.  PQLB_E_UNSUPPORTED: capacity >= 2^28
+ * (ATen switches to 64-bit draws) or a draw larger than one pass of ATen's grid. */
+int pqlb_sample_critic_batch_rng(const float* ring, int64_t capacity, int obs_dim, int act_dim,
+                                 int64_t* idx_out, int64_t batch,
+                                 const float* mean, const float* var, float eps,
+                                 float* x_cur, float* x_tgt, int x_ld, float* reward, float* done,
+                                 const int64_t* rng_state, const int64_t* counter,
+                                 const int64_t* cur_capacity, float* noise_out, int64_t noise_numel,
+                                 pqlb_stream_t stream);
+int pqlb_sample_obs_batch_rng(const float* obsring, int64_t capacity, int obs_dim,
+                              int64_t* idx_out, int64_t batch,
+                              const float* mean, const float* var, float eps,
+                              float* x, int x_ld, int act_dim,
+                              const int64_t* rng_state, const int64_t* counter,
+                              const int64_t* cur_capacity, pqlb_stream_t stream);
+/* *dst = value, stream-ordered (device-resident copies of host-side ring state). */
+int pqlb_store_i64(int64_t* dst, int64_t value, pqlb_stream_t stream);
+
 /* ---- K3: dense layers on tcgen05 (kind::tf32, fp32 accumulate in TMEM) ---------------------- */
 enum pqlb_epilogue {
   PQLB_EPI_STORE = 0,          /* out = acc                     (split-K partial, no rounding)  */

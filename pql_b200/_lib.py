@@ -90,6 +90,10 @@ _PROTOS = {
     "pqlb_sample_critic_batch": (_int, [_f, _i64, _int, _int, _f, _i64, _f, _f, _flt, _f, _f, _int,
                                         _f, _f, _st]),
     "pqlb_sample_obs_batch": (_int, [_f, _i64, _int, _f, _i64, _f, _f, _flt, _f, _int, _int, _st]),
+    "pqlb_sample_critic_batch_rng": (_int, [_f, _i64, _int, _int, _f, _i64, _f, _f, _flt, _f, _f, _int,
+                                            _f, _f, _f, _f, _f, _f, _i64, _st]),
+    "pqlb_sample_obs_batch_rng": (_int, [_f, _i64, _int, _f, _i64, _f, _f, _flt, _f, _int, _int, _f, _f, _f, _st]),
+    "pqlb_store_i64": (_int, [_f, _i64, _st]),
     "pqlb_gemm_tf32": (_int, [C.POINTER(GemmDesc), _st]),
     "pqlb_mlp_forward": (_int, [C.POINTER(MlpDesc), _st]),
     "pqlb_mlp_forward_cluster": (None, [_int]),

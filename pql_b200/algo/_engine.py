@@ -82,6 +82,7 @@ class _UpdateBase:
         self.La = NetLayout(self.O, self.A, 1)
         self.pd = 64 if distl else 0           # row stride of the probability / dlogit buffers
         self.calls = []
+        self.rng_state = None       # fused sampler RNG: int64 [seed, base_offset, increment] on the device
         self.z = torch.linspace(v_min, v_max, self.N, device=self.device) if distl else None
 
     def _buf(self, *shape):
@@ -91,6 +92,18 @@ class _UpdateBase:
         t = torch.zeros(*shape, dtype=torch.float32, device=self.device)
         self._bufs.append(t)
         return t
+
+    def enable_fused_rng(self, generator, draws_per_update):
+        """Draw the update's random numbers inside the gather kernel (csrc/rng.cuh) from
+        ``generator``'s Philox stream: update k uses offset = generator offset now + 4 * draws * (k -
+        completed updates now), i.e. exactly the values torch.randint / normal_ would return if they
+        were called with this generator once per update."""
+        inc = 4 * int(draws_per_update)
+        seed = int(generator.initial_seed())
+        if seed >= 1 << 63:
+            seed -= 1 << 64
+        base = int(generator.get_offset()) - inc * self.opt.step
+        self.rng_state = torch.tensor([seed, base, inc], dtype=torch.int64, device=self.device)
 
     def _ws_init(self, wgrads, n_nets, bias_cols, extra=0):
         """One workspace for every split-K / per-block partial sum of the update, sized up front
@@ -296,13 +309,17 @@ class CriticUpdate(_UpdateBase):
         self.mean.copy_(mean.reshape(-1).float(), non_blocking=True)
         self.var.copy_(var.reshape(-1).float(), non_blocking=True)
 
-    def sample_call(self, ring, capacity):
-        """The fused gather + normalise + cat launch for a given replay ring."""
+    def sample_call(self, ring, capacity, cur_capacity_dev=None):
+        """The fused gather + normalise + cat launch for a given replay ring; with the fused sampler
+        RNG enabled the same launch also draws the indices and the target-policy noise."""
         on = self.obs_norm
-        return K.Call("pqlb_sample_critic_batch", _lib.ptr(ring), int(capacity), self.O, self.A, _lib.ptr(self.idx),
-                      self.B, _lib.ptr(self.mean) if on else None, _lib.ptr(self.var) if on else None, self.eps,
-                      _lib.ptr(self.x_cur), _lib.ptr(self.x_tgt), self.x_ld, _lib.ptr(self.reward), _lib.ptr(self.done),
-                      keep=(ring,))
+        args = (_lib.ptr(ring), int(capacity), self.O, self.A, _lib.ptr(self.idx),
+                self.B, _lib.ptr(self.mean) if on else None, _lib.ptr(self.var) if on else None, self.eps,
+                _lib.ptr(self.x_cur), _lib.ptr(self.x_tgt), self.x_ld, _lib.ptr(self.reward), _lib.ptr(self.done))
+        if self.rng_state is None:
+            return K.Call("pqlb_sample_critic_batch", *args, keep=(ring,))
+        return K.Call("pqlb_sample_critic_batch_rng", *args, _lib.ptr(self.rng_state), _lib.ptr(self.opt.count),
+                      _lib.ptr(cur_capacity_dev), _lib.ptr(self.noise), self.noise.numel(), keep=(ring, cur_capacity_dev))
 
     def run(self, sample=None, allreduce=None, use_graph=False, graph_allreduce=False):
         """One update: [sample] + forward/backward launches + gradient reduction, the gradient
@@ -469,11 +486,15 @@ class ActorUpdate(_UpdateBase):
 
     set_norm = CriticUpdate.set_norm
 
-    def sample_call(self, obsring, capacity):
+    def sample_call(self, obsring, capacity, cur_capacity_dev=None):
         on = self.obs_norm
-        return K.Call("pqlb_sample_obs_batch", _lib.ptr(obsring), int(capacity), self.O, _lib.ptr(self.idx), self.B,
-                      _lib.ptr(self.mean) if on else None, _lib.ptr(self.var) if on else None, self.eps,
-                      _lib.ptr(self.x), self.x_ld, self.A, keep=(obsring,))
+        args = (_lib.ptr(obsring), int(capacity), self.O, _lib.ptr(self.idx), self.B,
+                _lib.ptr(self.mean) if on else None, _lib.ptr(self.var) if on else None, self.eps,
+                _lib.ptr(self.x), self.x_ld, self.A)
+        if self.rng_state is None:
+            return K.Call("pqlb_sample_obs_batch", *args, keep=(obsring,))
+        return K.Call("pqlb_sample_obs_batch_rng", *args, _lib.ptr(self.rng_state), _lib.ptr(self.opt.count),
+                      _lib.ptr(cur_capacity_dev), keep=(obsring, cur_capacity_dev))
 
     run, _segment_a, _segment_b, _capture = (CriticUpdate.run, CriticUpdate._segment_a, CriticUpdate._segment_b,
                                              CriticUpdate._capture)

@@ -12,7 +12,7 @@ from ..models import load_class
 from ..utils.common import DeviceTracker
 from . import _dp
 from ._engine import ActorUpdate
-from .pql_v_learner import LearnerStream, module_flat
+from .pql_v_learner import LearnerStream, make_generator, module_flat
 
 
 class PQLPLearner:
@@ -58,6 +58,8 @@ class PQLPLearner:
         self.dp_fused = bool(getattr(cfg, "dp_fused", False)) and self.world_size > 1
         self._ls = LearnerStream(cfg, self.device)
         self._ls.tag(self.actor)
+        self.generator, self.fused_rng = make_generator(cfg, self.device, salt=1)
+        self.cur_capacity_dev = torch.zeros(1, dtype=torch.int64, device=self.device)
 
     @property
     def stream(self):
@@ -79,7 +81,9 @@ class PQLPLearner:
                                  obs_norm=bool(a.obs_norm) and self.normalize_tuple is not None, eps=eps,
                                  world_size=self.world_size, loss_ring=self.loss_tracker.window,
                                   process_group=self.process_group, dp_fused=self.dp_fused)
-        self._sample = self._plan.sample_call(self.memory, self.memory_size)
+        if self.fused_rng and self.memory_size < (1 << 28):
+            self._plan.enable_fused_rng(self.generator, draws_per_update=1)      # randint
+        self._sample = self._plan.sample_call(self.memory, self.memory_size, self.cur_capacity_dev)
 
     def start(self):
         return self.actor, self.update_count, self.loss_tracker.mean()
@@ -92,7 +96,11 @@ class PQLPLearner:
         if self.critic is not None:
             p = self._plan
             with torch.cuda.device(self.device), self._ls.ctx():
-                torch.randint(self.cur_capacity, size=(p.B,), device=self.device, out=p.idx)     # :49
+                if p.rng_state is None:
+                    torch.randint(self.cur_capacity, size=(p.B,), device=self.device, out=p.idx,
+                                  generator=self.generator)                                          # :49
+                elif self.cur_capacity <= 0:
+                    raise RuntimeError("learn(): the observation ring is empty (random_ expects 'from' to be less than 'to')")
                 p.run(self._sample, self._allreduce if self.world_size > 1 and p.dp is None else None, self.use_cuda_graph,
                       self.graph_allreduce)
             self.update_count += 1
@@ -122,6 +130,7 @@ class PQLPLearner:
                     self.if_full = True
                 self.next_p = p
                 self.cur_capacity = self.memory_size if self.if_full else self.next_p
+                _lib.call("pqlb_store_i64", _lib.ptr(self.cur_capacity_dev), self.cur_capacity)
                 if self._plan is None or rebuild:
                     self._build()
                 self._plan.set_critic(module_flat(critic, self._plan.Lc.total, self.device))

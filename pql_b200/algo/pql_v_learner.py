@@ -59,6 +59,21 @@ class LearnerStream:
                 t.record_stream(self.stream)
 
 
+def make_generator(cfg, device, salt):
+    """The learner's own random stream.  In the reference every learner is a process of its own with
+    its own default CUDA generator (scripts/train_pql.py:40-52); here a learner owns a
+    ``torch.Generator`` seeded from the device's default generator (so ``torch.manual_seed`` governs it;
+    ``salt`` keeps the two learners of one process from drawing the same indices).  With
+    ``cfg.fused_rng`` (default) the draws are made inside the gather kernel from this generator's
+    (seed, offset) - bit-identical to calling torch.randint / normal_ with it (csrc/rng.cuh) - and two
+    torch launches per update disappear; ``cfg.fused_rng = False`` makes those torch calls instead."""
+    gen = torch.Generator(device=device)
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    gen.manual_seed((torch.cuda.default_generators[idx].initial_seed() + salt) % (1 << 63))
+    fused = bool(getattr(cfg, "fused_rng", True)) and not os.environ.get("PQLB_NO_FUSED_RNG")
+    return gen, fused
+
+
 def module_flat(module, layout_total, device):
     """Flat fp32 arena of an actor / critic module in the kernel layout: our modules expose it
     directly, a reference ``nn.Module`` with the same state_dict keys is repacked."""
@@ -112,6 +127,7 @@ class PQLVLearner:
         self.dp_fused = bool(getattr(cfg, "dp_fused", False)) and self.world_size > 1
         self._ls = LearnerStream(cfg, self.device)
         self._ls.tag(self.critic)
+        self.generator, self.fused_rng = make_generator(cfg, self.device, salt=0)
 
     @property
     def stream(self):
@@ -138,7 +154,9 @@ class PQLVLearner:
                                   obs_norm=bool(a.obs_norm) and self.normalize_tuple is not None, eps=eps,
                                   world_size=self.world_size, loss_ring=self.loss_tracker.window,
                                   process_group=self.process_group, dp_fused=self.dp_fused)
-        self._sample = self._plan.sample_call(self.memory.ring, self.memory.capacity)
+        if self.fused_rng and self.memory.capacity < (1 << 28):
+            self._plan.enable_fused_rng(self.generator, draws_per_update=2)      # randint, then normal
+        self._sample = self._plan.sample_call(self.memory.ring, self.memory.capacity, self.memory.cur_capacity_dev)
 
     @property
     def critic_target(self):
@@ -167,8 +185,12 @@ class PQLVLearner:
                 # out.normal_(0, 1).mul_(std).add_(mean): we draw the N(0,1) part with the same
                 # generator call and apply std inside the actor-head epilogue (this also avoids
                 # torch.normal's std.min() >= 0 check, a device->host sync per update).
-                torch.randint(self.memory.cur_capacity, size=(p.B,), device=self.device, out=p.idx)
-                p.noise.normal_()
+                if p.rng_state is None:
+                    torch.randint(self.memory.cur_capacity, size=(p.B,), device=self.device, out=p.idx,
+                                  generator=self.generator)
+                    p.noise.normal_(generator=self.generator)
+                elif self.memory.cur_capacity <= 0:       # what torch.randint(0, ...) raises in the reference
+                    raise RuntimeError("learn(): the replay buffer is empty (random_ expects 'from' to be less than 'to')")
                 p.run(self._sample, self._allreduce if self.world_size > 1 and p.dp is None else None, self.use_cuda_graph,
                       self.graph_allreduce)
             self.update_count += 1

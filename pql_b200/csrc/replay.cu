@@ -6,6 +6,7 @@
 // words of one field of one row, so that consecutive lanes touch consecutive addresses on both
 // the read and the write side, and each thread keeps UNROLL independent loads in flight.
 #include "common.cuh"
+#include "rng.cuh"
 
 namespace pqlb {
 
@@ -267,8 +268,11 @@ __global__ void __launch_bounds__(kThreads)
 sample_critic_batch_kernel(const float* __restrict__ ring, RecGeom g, const int64_t* __restrict__ idx,
                            int64_t B, const float* __restrict__ mean, const float* __restrict__ var,
                            float eps, float* __restrict__ x_cur, float* __restrict__ x_tgt, int x_ld,
-                           float* __restrict__ o_rew, float* __restrict__ o_done) {
+                           float* __restrict__ o_rew, float* __restrict__ o_done, RngArgs ra) {
   using V = typename VecT<VEC>::type;
+  // fused sampler RNG (rng.cuh): the indices are torch.randint's for this generator state, drawn here
+  unsigned long long seed = 0, off = 0, range = 1;
+  if (ra.state) { seed = ra.state[0]; off = ra.state[1] + ra.state[2] * ra.counter[0]; range = ra.range[0]; }
   const FieldMap f = field_map<VEC>(g);
   const int lane = threadIdx.x & 31;
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -277,8 +281,16 @@ sample_critic_batch_kernel(const float* __restrict__ ring, RecGeom g, const int6
   const int items = f.per_row + rd_items + pad_items;
   for (int64_t b0 = ((((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5)) * kRec; b0 < B; b0 += nwarps * kRec) {
     const float* rec[kRec];
+    long long mine = 0;
+    if (ra.state && lane < kRec && b0 + lane < B) {
+      mine = (long long)(torch_rand_u32(seed, off, ra.threads_idx, b0 + lane) % range);
+      const_cast<int64_t*>(idx)[b0 + lane] = mine;            // kept for inspection / tests
+    }
 #pragma unroll
-    for (int r = 0; r < kRec; ++r) rec[r] = b0 + r < B ? ring + __ldg(idx + b0 + r) * g.rec_ld : nullptr;
+    for (int r = 0; r < kRec; ++r) {
+      const long long ix = ra.state ? __shfl_sync(0xffffffffu, mine, r) : (b0 + r < B ? __ldg(idx + b0 + r) : 0);
+      rec[r] = b0 + r < B ? ring + ix * g.rec_ld : nullptr;
+    }
     for (int it = lane; it < items; it += 32) {
       if (it >= f.per_row + rd_items) {                       // padding columns
         const int k = g.O + g.A + (it - f.per_row - rd_items) * VEC;
@@ -327,7 +339,58 @@ sample_critic_batch_kernel(const float* __restrict__ ring, RecGeom g, const int6
       }
     }
   }
+  if (ra.state && ra.noise) {      // the update's N(0,1) draw (target-policy noise), next in the generator's stream
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < ra.noise_numel; i += stride)
+      ra.noise[i] = torch_normal_f32(seed, off + 4, ra.threads_noise, i);
+  }
 }
+
+// P-learner batch with the fused index draw: one warp per kRec rows (lanes < kRec draw the indices),
+// lanes walk the columns.  Same values as sample_obs_batch_kernel on torch.randint's indices.
+__global__ void __launch_bounds__(kThreads)
+sample_obs_batch_rng_kernel(const float* __restrict__ obsring, int O, int64_t* __restrict__ idx,
+                            int64_t B, const float* __restrict__ mean, const float* __restrict__ var,
+                            float eps, float* __restrict__ x, int x_ld, int A, RngArgs ra) {
+  const int lane = threadIdx.x & 31;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const unsigned long long seed = ra.state[0], off = ra.state[1] + ra.state[2] * ra.counter[0], range = ra.range[0];
+  for (int64_t b0 = ((((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5)) * kRec; b0 < B; b0 += nwarps * kRec) {
+    long long mine = 0;
+    if (lane < kRec && b0 + lane < B) {
+      mine = (long long)(torch_rand_u32(seed, off, ra.threads_idx, b0 + lane) % range);
+      idx[b0 + lane] = mine;
+    }
+    const float* src[kRec];
+#pragma unroll
+    for (int r = 0; r < kRec; ++r) {
+      const long long ix = __shfl_sync(0xffffffffu, mine, r);
+      src[r] = b0 + r < B ? obsring + ix * O : nullptr;
+    }
+    for (int k = lane; k < x_ld; k += 32) {
+      if (k < O) {
+        float v[kRec];
+#pragma unroll
+        for (int r = 0; r < kRec; ++r) v[r] = src[r] ? __ldcs(src[r] + k) : 0.f;
+        float m = 0.f, vr = 1.f;
+        if (mean) { m = mean[k]; vr = var[k]; }
+#pragma unroll
+        for (int r = 0; r < kRec; ++r) {
+          if (!src[r]) continue;
+          float y = v[r];
+          if (mean) y = norm_clamp(y, m, vr, eps);
+          x[(b0 + r) * x_ld + k] = rn_tf32(y);
+        }
+      } else if (k >= O + A) {
+#pragma unroll
+        for (int r = 0; r < kRec; ++r)
+          if (src[r]) x[(b0 + r) * x_ld + k] = 0.f;
+      }
+    }
+  }
+}
+
+__global__ void store_i64_kernel(long long* dst, long long v) { *dst = v; }
 
 __global__ void __launch_bounds__(kThreads)
 sample_obs_batch_kernel(const float* __restrict__ obsring, int O, const int64_t* __restrict__ idx,
@@ -498,10 +561,70 @@ extern "C" int pqlb_sample_critic_batch(const float* ring, int64_t capacity, int
                     (!mean || (aligned16(mean) && aligned16(var)));
   if (vec4)
     sample_critic_batch_kernel<4><<<grid_for(batch * 32, kThreads, kRec, kBlocksPerSM), kThreads, 0, (cudaStream_t)stream>>>(
-        ring, g, idx, batch, mean, var, eps, x_cur, x_tgt, x_ld, reward, done);
+        ring, g, idx, batch, mean, var, eps, x_cur, x_tgt, x_ld, reward, done, RngArgs{});
   else
     sample_critic_batch_kernel<1><<<grid_for(batch * 32, kThreads, kRec, kBlocksPerSM), kThreads, 0, (cudaStream_t)stream>>>(
-        ring, g, idx, batch, mean, var, eps, x_cur, x_tgt, x_ld, reward, done);
+        ring, g, idx, batch, mean, var, eps, x_cur, x_tgt, x_ld, reward, done, RngArgs{});
+  PQLB_LAUNCH_RET();
+}
+
+static int make_rng_args(RngArgs* ra, const int64_t* state, const int64_t* counter, const int64_t* range,
+                         int64_t batch, int64_t capacity, float* noise, int64_t noise_numel) {
+  PQLB_CHECK_ARG(state && counter && range && noise_numel >= 0 && (noise_numel == 0 || noise));
+  if (capacity >= (1LL << 28)) return PQLB_E_UNSUPPORTED;        // ATen switches to 64-bit draws there
+  ra->state = reinterpret_cast<const long long*>(state);
+  ra->counter = reinterpret_cast<const long long*>(counter);
+  ra->range = reinterpret_cast<const long long*>(range);
+  ra->noise = noise_numel ? noise : nullptr; ra->noise_numel = noise_numel;
+  ra->threads_idx = aten_rng_threads(batch);
+  ra->threads_noise = noise_numel ? aten_rng_threads(noise_numel) : 1;
+  if (ra->threads_idx == 0 || ra->threads_noise == 0) return PQLB_E_UNSUPPORTED;
+  return PQLB_OK;
+}
+
+extern "C" int pqlb_sample_critic_batch_rng(const float* ring, int64_t capacity, int obs_dim, int act_dim,
+                                            int64_t* idx_out, int64_t batch, const float* mean,
+                                            const float* var, float eps, float* x_cur, float* x_tgt,
+                                            int x_ld, float* reward, float* done, const int64_t* rng_state,
+                                            const int64_t* counter, const int64_t* cur_capacity,
+                                            float* noise_out, int64_t noise_numel, pqlb_stream_t stream) {
+  PQLB_CHECK_ARG(ring && capacity > 0 && obs_dim > 0 && act_dim > 0 && batch > 0 && idx_out);
+  PQLB_CHECK_ARG(x_cur && x_tgt && reward && done && ((mean == nullptr) == (var == nullptr)));
+  const RecGeom g = rec_geom(obs_dim, act_dim);
+  PQLB_CHECK_SHAPE(x_ld >= obs_dim + act_dim && x_ld % 4 == 0);
+  RngArgs ra;
+  const int rc = make_rng_args(&ra, rng_state, counter, cur_capacity, batch, capacity, noise_out, noise_numel);
+  if (rc != PQLB_OK) return rc;
+  const bool vec4 = obs_dim % 4 == 0 && act_dim % 4 == 0 && aligned16(ring) && aligned16(x_cur) && aligned16(x_tgt) &&
+                    (!mean || (aligned16(mean) && aligned16(var)));
+  if (vec4)
+    sample_critic_batch_kernel<4><<<grid_for(batch * 32, kThreads, kRec, kBlocksPerSM), kThreads, 0, (cudaStream_t)stream>>>(
+        ring, g, idx_out, batch, mean, var, eps, x_cur, x_tgt, x_ld, reward, done, ra);
+  else
+    sample_critic_batch_kernel<1><<<grid_for(batch * 32, kThreads, kRec, kBlocksPerSM), kThreads, 0, (cudaStream_t)stream>>>(
+        ring, g, idx_out, batch, mean, var, eps, x_cur, x_tgt, x_ld, reward, done, ra);
+  PQLB_LAUNCH_RET();
+}
+
+extern "C" int pqlb_sample_obs_batch_rng(const float* obsring, int64_t capacity, int obs_dim, int64_t* idx_out,
+                                         int64_t batch, const float* mean, const float* var, float eps,
+                                         float* x, int x_ld, int act_dim, const int64_t* rng_state,
+                                         const int64_t* counter, const int64_t* cur_capacity,
+                                         pqlb_stream_t stream) {
+  PQLB_CHECK_ARG(obsring && capacity > 0 && obs_dim > 0 && batch > 0 && idx_out && x && act_dim >= 0);
+  PQLB_CHECK_ARG((mean == nullptr) == (var == nullptr));
+  PQLB_CHECK_SHAPE(x_ld >= obs_dim + act_dim);
+  RngArgs ra;
+  const int rc = make_rng_args(&ra, rng_state, counter, cur_capacity, batch, capacity, nullptr, 0);
+  if (rc != PQLB_OK) return rc;
+  sample_obs_batch_rng_kernel<<<grid_for(batch * 32, kThreads, kRec, kBlocksPerSM), kThreads, 0, (cudaStream_t)stream>>>(
+      obsring, obs_dim, idx_out, batch, mean, var, eps, x, x_ld, act_dim, ra);
+  PQLB_LAUNCH_RET();
+}
+
+extern "C" int pqlb_store_i64(int64_t* dst, int64_t value, pqlb_stream_t stream) {
+  PQLB_CHECK_ARG(dst);
+  store_i64_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(reinterpret_cast<long long*>(dst), (long long)value);
   PQLB_LAUNCH_RET();
 }
 

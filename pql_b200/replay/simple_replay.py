@@ -64,6 +64,9 @@ class ReplayBuffer:
         self._O = int(self.obs_dim[0])
         self._g = _geom(self._O, self.action_dim)
         self.ring = create_buffer(self.capacity, self._O, self.action_dim, device=self.device)
+        # device-resident copy of cur_capacity: the range of the index draw when the sampler RNG is
+        # fused into the gather kernel (a CUDA-graph replay cannot take it as a launch argument)
+        self.cur_capacity_dev = torch.zeros(1, dtype=torch.int64, device=self.device)
         self.left_agent = left_agent
         self.reserve_space = reserve_space
 
@@ -118,6 +121,8 @@ class ReplayBuffer:
             p -= self.capacity
         self.next_p = p
         self.cur_capacity = self.capacity if self.if_full else self.next_p
+        with torch.cuda.device(dev):
+            _lib.call("pqlb_store_i64", _lib.ptr(self.cur_capacity_dev), self.cur_capacity)
 
     # ---- sample ----------------------------------------------------------------------------
     @torch.no_grad()

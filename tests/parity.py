@@ -117,10 +117,13 @@ def _expected_step(shadow, grads, target_before, max_grad_norm, tau):
     return shadow.params, tgt
 
 
-def make_cfg(B, distl, device_index=0, memory=None, obs_norm=True):
+def make_cfg(B, distl, device_index=0, memory=None, obs_norm=True, fused_rng=False):
+    """fused_rng is off here: these harnesses inject the oracle's draws through torch.randint /
+    Tensor.normal_ (injected_draws), which the in-kernel draw would bypass.  The fused draw has its
+    own tests (tests/test_gpu_rng.py)."""
     from pql_b200.utils import default_pql_cfg
     return default_pql_cfg(batch_size=B, memory_size=memory or B, distl=distl, v_learner_gpu=device_index,
-                           p_learner_gpu=device_index, obs_norm=obs_norm)
+                           p_learner_gpu=device_index, obs_norm=obs_norm, fused_rng=fused_rng)
 
 
 def _record(case, res):

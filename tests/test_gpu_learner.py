@@ -140,7 +140,7 @@ def test_update_launch_list_is_bit_reproducible(B, distl, which):
     assert parity.plan_divergence(B, distl, which, repeats=4, device=DEV) is None
 
 
-def _run_interleaved(streams, seed=9, B=512, steps=3):
+def _run_interleaved(streams, seed=9, B=512, steps=3, fused_rng=True, graph=True):
     """bench.py's loop in miniature: per env step one update() exchange, 4 critic + 2 actor updates."""
     from pql_b200.algo import PQLPLearner, PQLVLearner
     from pql_b200.replay import NStepReplay
@@ -149,6 +149,8 @@ def _run_interleaved(streams, seed=9, B=512, steps=3):
     torch.manual_seed(seed)
     cfg = default_pql_cfg(batch_size=B, memory_size=4096, num_envs=E)
     cfg.learner_streams = streams
+    cfg.fused_rng = fused_rng
+    cfg.use_cuda_graph = graph
     v, p = PQLVLearner(O, A, cfg), PQLPLearner(O, A, cfg)
     ns = NStepReplay(O, A, num_envs=E, nstep=3, device=DEV)
     g = torch.Generator(device=DEV).manual_seed(seed)
@@ -180,3 +182,14 @@ def test_learner_streams_match_single_stream():
     assert torch.equal(c0, c1) and torch.equal(a0, a1)
     assert l0 == l1
     assert torch.isfinite(c0).all() and torch.isfinite(a0).all()
+
+
+def test_fused_rng_update_equals_torch_draws():
+    """cfg.fused_rng moves torch.randint / normal_ into the gather kernel (csrc/rng.cuh): same
+    generator state => same indices and noise => bit-identical weights and losses, with and without
+    CUDA-graph replay (the offsets advance on the device)."""
+    c0, a0, l0 = _run_interleaved(False, fused_rng=False)
+    c1, a1, l1 = _run_interleaved(False, fused_rng=True)
+    c2, a2, l2 = _run_interleaved(True, fused_rng=True, graph=False)
+    assert torch.equal(c0, c1) and torch.equal(a0, a1) and l0 == l1
+    assert torch.equal(c0, c2) and torch.equal(a0, a2) and l0 == l2
