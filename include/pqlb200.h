@@ -143,6 +143,37 @@ int pqlb_sample_obs_batch_rng(const float* obsring, int64_t capacity, int obs_di
 /* *dst = value, stream-ordered (device-resident copies of host-side ring state). */
 int pqlb_store_i64(int64_t* dst, int64_t value, pqlb_stream_t stream);
 
+/* ---- Actor-side env-step path (pql/algo/pql_actor.py:87-127) ---------------------------
+ * RunningMeanStd.update (pql/utils/torch_util.py:77-103) on device-resident state: batch mean and
+ * unbiased variance of x[rows, cols] (column statistics accumulated in fp64, fixed order), merged
+ * into mean[cols] / var[cols] / count[0] (fp64, like the reference's Python float) with the
+ * reference's update_from_moments arithmetic in fp32.  workspace: pqlb_rms_workspace_bytes(rows,
+ * cols) bytes, 16-byte aligned, zero-filled before the FIRST call (the kernel re-arms it). */
+int64_t pqlb_rms_workspace_bytes(int64_t rows, int cols);
+int pqlb_rms_update(const float* x, int64_t rows, int cols, int64_t ldx, float* mean, float* var,
+                    double* count, void* workspace, int64_t workspace_bytes, pqlb_stream_t stream);
+/* Inputs of the policy forward for one env step.  x (optional): x[r, :obs_dim] = obs normalised with
+ * (mean, var, eps) as RunningMeanStd.normalize does ((x - mean) / sqrt(var + eps), torch_util.py:83-85;
+ * clamp5 adds pql/utils/common.py:139-145's clamp to +-5; mean == NULL: plain copy), columns up to
+ * x_ld zeroed, TF32-rounded with round_tf32 (tensor-core operand).  noise (optional):
+ * noise[r, j] = z * std_r, z the N(0,1) draw ATen makes for a [rows, act_dim] tensor from the
+ * generator state (seed, offset) - i.e. torch.normal(zeros, std) of add_normal_noise /
+ * add_mixed_normal_noise (pql/utils/noise.py:19-41); std_r = row_std[r], or std when row_std == NULL.
+ * The caller advances its generator offset by 4. */
+int pqlb_actor_inputs(const float* obs, int64_t rows, int obs_dim, int64_t ld_obs, const float* mean,
+                      const float* var, float eps, int clamp5, int round_tf32, float* x, int x_ld,
+                      float* noise, int act_dim, const float* row_std, float std, int64_t seed,
+                      int64_t offset, pqlb_stream_t stream);
+/* After env.step(): PQLActor.update_tracker (pql_actor.py:129-136: returns += reward, lengths += 1,
+ * finished episodes pushed in env order into the Tracker windows, then reset), handle_timeout
+ * (common.py:195-202: done_out = done * ~truncated; truncated may be NULL) and the reward scaling of
+ * pql_actor.py:117 (reward_out = reward_scale * reward).  ret_window / len_window: Tracker deques as
+ * rings of window_len floats; pushed[0] = episodes pushed so far (slot = pushed % window_len). */
+int pqlb_env_post(const float* reward, const float* done, const uint8_t* truncated, float reward_scale,
+                  int num_envs, float* returns, float* lengths, float* ret_window, float* len_window,
+                  int window_len, int64_t* pushed, float* reward_out, float* done_out,
+                  pqlb_stream_t stream);
+
 /* ---- K3: dense layers on tcgen05 (kind::tf32, fp32 accumulate in TMEM) ---------------------- */
 enum pqlb_epilogue {
   PQLB_EPI_STORE = 0,          /* out = acc                     (split-K partial, no rounding)  */
@@ -215,7 +246,7 @@ typedef struct {
    * in the same launch: act_w [act_n, 128] (TF32 copy), act_b [act_n], act_n a multiple of 4 <= 16.
    * act_out[row * act_ldo + j] = rn_tf32(tanh(.)) or, with act_noise (N(0,1) draws, [M, act_ldnoise]),
    * rn_tf32(clamp(tanh(.) + clamp(noise_std * noise, +-noise_bound), +-1)) (pql/utils/noise.py:19-27);
-   * act_out2 (optional) keeps the fp32 tanh.  act_w == NULL: no policy head.  Mutually exclusive with q. */
+   * act_out2 (optional) keeps the same value in fp32, before the TF32 rounding.  act_w == NULL: no policy head.  Mutually exclusive with q. */
   const float* act_w; const float* act_b; const float* act_noise;
   float* act_out; float* act_out2;
   int64_t act_ldo, act_ldo2, act_ldnoise;

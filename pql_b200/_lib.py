@@ -94,6 +94,11 @@ _PROTOS = {
                                             _f, _f, _f, _f, _f, _f, _i64, _st]),
     "pqlb_sample_obs_batch_rng": (_int, [_f, _i64, _int, _f, _i64, _f, _f, _flt, _f, _int, _int, _f, _f, _f, _st]),
     "pqlb_store_i64": (_int, [_f, _i64, _st]),
+    "pqlb_rms_workspace_bytes": (_i64, [_i64, _int]),
+    "pqlb_rms_update": (_int, [_f, _i64, _int, _i64, _f, _f, _f, _f, _i64, _st]),
+    "pqlb_actor_inputs": (_int, [_f, _i64, _int, _i64, _f, _f, _flt, _int, _int, _f, _int, _f, _int, _f, _flt,
+                                 _i64, _i64, _st]),
+    "pqlb_env_post": (_int, [_f, _f, _f, _flt, _int, _f, _f, _f, _f, _int, _f, _f, _f, _st]),
     "pqlb_gemm_tf32": (_int, [C.POINTER(GemmDesc), _st]),
     "pqlb_mlp_forward": (_int, [C.POINTER(MlpDesc), _st]),
     "pqlb_mlp_forward_cluster": (None, [_int]),

@@ -280,13 +280,13 @@ gemm_tf32_kernel(const __grid_constant__ GemmDev P) {
         else if (EPI == PQLB_EPI_BIAS_TANH_NOISE) {
           const float t = tanhf(x + s_bias[c0 + j]);
           const float z = fminf(fmaxf(a[EpiTraits<EPI>::kAux ? j : 0] * P.noise_std, -P.noise_bound), P.noise_bound);
-          x = rn_tf32(fminf(fmaxf(t + z, -1.f), 1.f));
+          x = fminf(fmaxf(t + z, -1.f), 1.f);                                   // rounded below (out2 keeps fp32)
         }
         else if (EPI == PQLB_EPI_MUL_ELUGRAD) { const float h = a[EpiTraits<EPI>::kAux ? j : 0]; x = rn_tf32(x * (h > 0.f ? 1.f : h + 1.f)); }
         else if (EPI == PQLB_EPI_MUL_TANHGRAD) { const float t = a[EpiTraits<EPI>::kAux ? j : 0]; x = rn_tf32(x * (1.f - t * t)); }
         v[j] = x;
       }
-      if (EPI == PQLB_EPI_BIAS_TANH) {
+      if (EPI == PQLB_EPI_BIAS_TANH || EPI == PQLB_EPI_BIAS_TANH_NOISE) {
         if (G.out2 && row_ok) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) { const int n = nb + j; if (j < chunkw && n < P.N) G.out2[(long long)row * G.ldo2 + n] = v[j]; }

@@ -403,6 +403,7 @@ mlp_fwd_kernel(const __grid_constant__ MlpDev P) {
                 const float z = fminf(fmaxf(G.act_noise[(long long)row * G.act_ldnoise + j] * G.noise_std, -G.noise_bound), G.noise_bound);
                 r = fminf(fmaxf(t + z, -1.f), 1.f);
               }
+              t = r;                               // act_out2: the same value before the operand rounding
               r = rn_tf32(r);
             }
             o[j] = r; o2[j] = t;

@@ -41,7 +41,7 @@ inline int aten_rng_threads(long long numel) {
   return (int)T;
 }
 
-__device__ __noinline__ unsigned torch_rand_u32(unsigned long long seed, unsigned long long offset, int T, long long li) {
+static __device__ __noinline__ unsigned torch_rand_u32(unsigned long long seed, unsigned long long offset, int T, long long li) {
   curandStatePhilox4_32_10_t st;
   curand_init(seed, (unsigned long long)(li % T), offset, &st);
   const uint4 r = curand4(&st);
@@ -49,7 +49,7 @@ __device__ __noinline__ unsigned torch_rand_u32(unsigned long long seed, unsigne
   return c == 0 ? r.x : c == 1 ? r.y : c == 2 ? r.z : r.w;
 }
 
-__device__ __noinline__ float torch_normal_f32(unsigned long long seed, unsigned long long offset, int T, long long li) {
+static __device__ __noinline__ float torch_normal_f32(unsigned long long seed, unsigned long long offset, int T, long long li) {
   curandStatePhilox4_32_10_t st;
   curand_init(seed, (unsigned long long)(li % T), offset, &st);
   const float4 r = curand_normal4(&st);

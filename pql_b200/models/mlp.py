@@ -185,12 +185,12 @@ def policy_head_call(B, it):
     n, act = it["net"], it["act"]
     A, H3 = n.dims[4], HIDDEN[2]
     g = dict(a=it["h"][2], lda=H3, b=n.W[3], ldb=H3, bias=n.b[3], out=act["out"], ldo=act["ldo"])
+    if act.get("out2"):
+        g.update(out2=act["out2"], ldo2=act["ldo2"])
     if act.get("noise"):
         g.update(aux=act["noise"], ldaux=act["ldnoise"])
         return K.Gemm(B, A, H3, [g], epilogue=K.EPI_BIAS_TANH_NOISE, tile_n=K.pick_tile_n(A),
                       noise_bound=act["noise_bound"], noise_std=act["noise_std"])
-    if act.get("out2"):
-        g.update(out2=act["out2"], ldo2=act["ldo2"])
     return K.Gemm(B, A, H3, [g], epilogue=K.EPI_BIAS_TANH, tile_n=K.pick_tile_n(A))
 
 

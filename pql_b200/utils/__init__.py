@@ -1,1 +1,3 @@
 from .common import AttrDict, DeviceTracker, Tracker, default_pql_cfg  # noqa: F401
+from .schedule_util import ExponentialSchedule, LinearSchedule  # noqa: F401
+from .torch_util import RunningMeanStd  # noqa: F401

@@ -262,8 +262,52 @@ def learner_case(tag, seed, B, O, A, distl, steps=3):
     np.savez(os.path.join(HERE, f"learner_{tag}.npz"), **rec)
 
 
+def actor_small():
+    """The unmodified PQLActor (pql/algo/pql_actor.py) on the scripted env: warm-up with random
+    actions, then policy steps with mixed exploration noise; everything it returns or tracks."""
+    import pql.algo.pql_actor as ACT
+    from pql.models.mlp import TanhMLPPolicy
+    ACT.torch = _TorchCPU()
+    for noise_type in ("mixed", "fixed"):
+        c = inputs.ACTOR_CASE
+        E, O, A = c["E"], c["O"], c["A"]
+        env = inputs.ScriptedEnv(c["seed"], E, O, A, c["warm_up"] + sum(c["calls"]))
+        cfg = make_cfg(False, 64, 1000)
+        cfg.num_envs = E
+        cfg.algo.tracker_len = c["tracker_len"]
+        cfg.algo.reward_scale = 0.01
+        cfg.algo.noise.type = noise_type
+        actor = ACT.PQLActor(env, cfg)
+        pol = TanhMLPPolicy(O, A)
+        load_mlp(pol, inputs.actor_case_params(c["seed"], O, A))
+        actor.actor = pol
+        torch.manual_seed(c["seed"])          # after the module constructors, which consume the generator
+        actor.reset_agent()
+        rec = {}
+
+        def record(tag, res):
+            p_data, v_data, steps = res
+            rec[f"{tag}_p"] = p_data.numpy()
+            for name, x in zip(("obs", "act", "rew", "next", "done"), v_data):
+                rec[f"{tag}_{name}"] = x.float().numpy()
+            rec[f"{tag}_steps"] = np.array(steps)
+            rec[f"{tag}_rms_mean"] = actor.obs_rms.mean.numpy().copy()
+            rec[f"{tag}_rms_var"] = actor.obs_rms.var.numpy().copy()
+            rec[f"{tag}_rms_count"] = np.array(actor.obs_rms.count, dtype=np.float64)
+            rec[f"{tag}_ret_window"] = np.array(list(actor.return_tracker.moving_average), dtype=np.float64)
+            rec[f"{tag}_len_window"] = np.array(list(actor.step_tracker.moving_average), dtype=np.float64)
+            rec[f"{tag}_returns"] = actor.current_returns.numpy().copy()
+            rec[f"{tag}_lengths"] = actor.current_lengths.numpy().copy()
+
+        record("warm", actor.explore_env(env, c["warm_up"], random=True))
+        for j, T in enumerate(c["calls"]):
+            record(f"call{j}", actor.explore_env(env, T, random=False))
+        np.savez(os.path.join(HERE, f"actor_small_{noise_type}.npz"), **rec)
+
+
 if __name__ == "__main__":
     torch.set_num_threads(8)
+    actor_small()
     replay_small()
     nstep_small()
     replay_allegro_stream()

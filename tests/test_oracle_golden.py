@@ -127,3 +127,43 @@ def test_learner_oracle_vs_reference(golden_dir, tag, seed, B, O, A, distl, step
         np.testing.assert_allclose(gn, g["p_grad_norms"][s], rtol=2e-4, atol=1e-9)
     for name, t in zip([f"net.{k}.{wb}" for k in (0, 2, 4, 6) for wb in ("weight", "bias")], L.flat([p.actor])):
         np.testing.assert_allclose(_digest(t), g[f"actor.{name}"], rtol=2e-5, atol=2e-6, err_msg=name)
+
+
+@pytest.mark.parametrize("noise_type", ["mixed", "fixed"])
+def test_actor_oracle_vs_reference(golden_dir, noise_type):
+    """oracle.actor (RunningMeanStd, exploration noise, trackers, timeout handling, n-step hand-off)
+    against the unmodified PQLActor run on the scripted env (tests/golden/make_golden.py::actor_small).
+    Same torch CPU seed => same draws; everything else is fp32 arithmetic in the same order."""
+    from oracle.actor import ActorOracle
+    g = np.load(os.path.join(golden_dir, f"actor_small_{noise_type}.npz"))
+    c = inputs.ACTOR_CASE
+    E, O, A = c["E"], c["O"], c["A"]
+    env = inputs.ScriptedEnv(c["seed"], E, O, A, c["warm_up"] + sum(c["calls"]))
+    torch.manual_seed(c["seed"])
+    act = ActorOracle(env, E, O, A, inputs.actor_case_params(c["seed"], O, A), nstep=c["nstep"], noise_type=noise_type,
+                      reward_scale=0.01, tracker_len=c["tracker_len"])
+    act.reset_agent()
+
+    def check(tag, res):
+        p_data, v_data, steps = res
+        assert steps == int(g[f"{tag}_steps"])
+        np.testing.assert_array_equal(p_data.numpy(), g[f"{tag}_p"])
+        for name, x in zip(("obs", "next", "done"), (v_data[0], v_data[3], v_data[4])):
+            np.testing.assert_array_equal(x.numpy(), g[f"{tag}_{name}"], err_msg=f"{tag} {name}")
+        # actions / rewards pass through the policy MLP: MKL-vs-oracle matmul association only
+        np.testing.assert_allclose(v_data[1].numpy(), g[f"{tag}_act"], rtol=0, atol=2e-6)
+        np.testing.assert_allclose(v_data[2].numpy(), g[f"{tag}_rew"], rtol=0, atol=1e-7)
+        np.testing.assert_array_equal(act.obs_rms.mean.numpy(), g[f"{tag}_rms_mean"])
+        np.testing.assert_array_equal(act.obs_rms.var.numpy(), g[f"{tag}_rms_var"])
+        assert act.obs_rms.count == float(g[f"{tag}_rms_count"])
+        np.testing.assert_allclose(np.array(list(act.return_tracker.moving_average), dtype=np.float64),
+                                   g[f"{tag}_ret_window"], rtol=0, atol=1e-5)
+        np.testing.assert_array_equal(np.array(list(act.step_tracker.moving_average), dtype=np.float64),
+                                      g[f"{tag}_len_window"])
+        np.testing.assert_allclose(act.current_returns.numpy(), g[f"{tag}_returns"], rtol=0, atol=1e-5)
+        np.testing.assert_array_equal(act.current_lengths.numpy(), g[f"{tag}_lengths"])
+
+    check("warm", act.explore_env(c["warm_up"], random=True))
+    for j, T in enumerate(c["calls"]):
+        check(f"call{j}", act.explore_env(T, random=False))
+    assert (g["call5_len_window"] > 0).sum() >= 3          # the script does finish episodes
