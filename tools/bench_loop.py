@@ -1,0 +1,92 @@
+"""BASELINE.json configs[3]: the full actor / P-learner / V-learner loop with a synthetic vectorised
+env stub - 16384 envs, ShadowHand shape (obs 211, act 20), 5M-slot replay, batch 8192, the reference's
+8 : 4 : 1 schedule - through pql_b200.train.LockStepTrainer.  Prints one JSON line:
+env steps/s (transitions/s), critic updates/s, ms per loop iteration.
+
+    python tools/bench_loop.py [--envs 16384] [--obs 211] [--act 20] [--memory 5000000] [--iters 50]
+"""
+import argparse
+import json
+import os
+import sys
+import time
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch  # noqa: E402
+
+
+class _Space:
+    def __init__(self, shape):
+        self.shape = shape
+
+
+class StubEnv:
+    """reset()/step(a) -> (obs, reward, done, info) on the GPU: next_obs = 0.9 * obs + noise block,
+    reward = -|a|^2 mean, 1 % random episode ends; a handful of launches, no physics."""
+
+    def __init__(self, E, O, A, device):
+        self.E, self.O, self.A, self.dev = E, O, A, device
+        g = torch.Generator(device=device).manual_seed(0)
+        self.noise = torch.randn(64, E, O, device=device, generator=g)
+        self.dones = (torch.rand(64, E, device=device, generator=g) < 0.01).float()
+        self.observation_space, self.action_space = _Space((O,)), _Space((A,))
+        self.t = 0
+
+    def reset(self):
+        self.obs = self.noise[0].clone()
+        return self.obs
+
+    def step(self, action):
+        self.t += 1
+        self.obs = 0.9 * self.obs + self.noise[self.t % 64]
+        return self.obs, -(action * action).mean(dim=1), self.dones[self.t % 64], {}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--envs", type=int, default=16384)
+    ap.add_argument("--obs", type=int, default=211)
+    ap.add_argument("--act", type=int, default=20)
+    ap.add_argument("--memory", type=int, default=5_000_000)
+    ap.add_argument("--batch", type=int, default=8192)
+    ap.add_argument("--iters", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--distl", action="store_true")
+    args = ap.parse_args()
+    from pql_b200.train import LockStepTrainer
+    from pql_b200.utils import default_pql_cfg
+    dev = torch.device("cuda:0")
+    torch.manual_seed(42)
+    cfg = default_pql_cfg(num_envs=args.envs, sim_device="cuda:0", batch_size=args.batch, memory_size=args.memory,
+                          distl=args.distl)
+    cfg.learner_streams = True
+    tr = LockStepTrainer(StubEnv(args.envs, args.obs, args.act, dev), cfg)
+    tr.warm_up()
+    for _ in range(args.warmup):
+        tr.step()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    e0.record()
+    for _ in range(args.iters):
+        info = tr.step()
+    for l in (tr.v_learner, tr.p_learner):
+        if l.stream is not None:
+            torch.cuda.current_stream().wait_stream(l.stream)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / args.iters
+    wall = (time.perf_counter() - t0) / args.iters * 1e3
+    print(json.dumps({"workload": f"configs[3]: full loop, {args.envs} envs, obs {args.obs}, act {args.act}, "
+                                  f"{args.memory}-slot replay, batch {args.batch}, {'C51' if args.distl else 'twin-Q'}, "
+                                  f"{tr.v_per_step} critic : {tr.v_per_step // tr.p_every} actor : 1 env step",
+                      "ms_per_iteration": ms, "host_wall_ms_per_iteration": wall,
+                      "env_transitions_per_s": args.envs / (ms * 1e-3),
+                      "critic_updates_per_s": tr.v_per_step / (ms * 1e-3),
+                      "actor_updates_per_s": tr.v_per_step / tr.p_every / (ms * 1e-3),
+                      "replay_gb": tr.v_learner.memory.ring.numel() * 4 / 1e9,
+                      "losses": {"critic": info["train/critic_loss"], "actor": info["train/actor_loss"]}}))
+
+
+if __name__ == "__main__":
+    main()
