@@ -362,6 +362,11 @@ def main():
             sys.stdout.flush(); sys.stderr.flush()
             os._exit(0)
 
+    dp_phases = None
+    if world > 1 and v._plan.dp is not None:
+        dp_phases = {name: dict(zip(("exchanges", "mean_ns"), l._plan.dp.phase_ns())) for name, l in (("critic", v), ("actor", p))}
+        dp_phases["phases"] = ["wait for every rank's gradient", "reduce own slice + deliver", "wait for the other slices",
+                               "norm + clip + AdamW + Polyak"]
     if rank != 0:
         leave()
         return
@@ -398,6 +403,8 @@ def main():
                        "bytes_per_unit": {"insert": BYTES_INSERT, "sample": BYTES_SAMPLE}},
             "host_wall_ms_per_step": 1e3 * wall / args.steps,
             "losses": {"critic": float(losses[0]), "actor": float(losses[1])}}
+    if dp_phases is not None:
+        line["dp_exchange_phases"] = dp_phases
     if not args.no_cpu_baseline and world == 1:
         r = cpu_reference_rate(seconds_budget=15.0)
         line["cpu_baseline"] = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}

@@ -397,7 +397,7 @@ int pqlb_adamw_polyak_pre(float* param, const float* grad, float* m, float* v, f
 /* ---- K4-DP: gradient all-reduce fused into the optimiser kernel (one process per GPU) ----------
  * grad_peers[r] / red_peers[r] / ctl_peers[r]: rank r's gradient arena, reduced-gradient receive
  * buffer (n floats each) and control block (32 words of flags + world * grid floats), all in
- * peer-mapped (symmetric) memory; local: two int64 in local memory, zero-initialised.  Every rank
+ * peer-mapped (symmetric) memory; local: eight int64 in local memory, zero-initialised ([0] epoch, [1] blocks done, [2..5] accumulated phase clocks in ns).  Every rank
  * launches the same grid (<= 148 blocks, all co-resident).  Replaces ncclAllReduce(grad) +
  * pqlb_grad_sumsq + pqlb_adamw_polyak_pre: slice `rank` of the gradient is summed over ranks in rank
  * order by its owner and delivered to every rank (two-shot all-reduce over NVLink), the global norm is

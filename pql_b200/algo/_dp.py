@@ -66,9 +66,15 @@ class FusedExchange:
         for t in (self.grad, self.red, self.ctl):
             t.zero_()
         self.handles = [symm_mem.rendezvous(t, name) for t in (self.grad, self.red, self.ctl)]
-        self.local = torch.zeros(2, dtype=torch.int64, device=device)
+        self.local = torch.zeros(8, dtype=torch.int64, device=device)   # [epoch, blocks done, 4 phase clocks (ns), -, -]
         torch.cuda.synchronize(device)
         dist.barrier(group)              # every rank's flags are zero before anybody can signal
+
+    def phase_ns(self):
+        """(exchanges, [wait for gradients, reduce + deliver, wait for slices, optimiser] mean ns of block 0)."""
+        v = self.local.tolist()
+        n = max(1, v[0])
+        return v[0], [x / n for x in v[2:6]]
 
     def desc(self):
         from .. import _lib

@@ -215,6 +215,7 @@ __device__ __forceinline__ void st_sys_f4(float* p, float4 v) {
 }
 __device__ __forceinline__ float ld_sys_f(const float* p) { float v; asm volatile("ld.relaxed.sys.global.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory"); return v; }
 __device__ __forceinline__ void st_sys_f(float* p, float v) { asm volatile("st.relaxed.sys.global.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory"); }
+__device__ __forceinline__ unsigned long long globaltimer_ns() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
 // bounded spin: a protocol bug or a dead peer must surface as a launch failure, not as a hung GPU
 __device__ __forceinline__ void wait_flag(const unsigned* p, unsigned epoch) {
   const long long t0 = clock64();
@@ -232,6 +233,11 @@ adamw_polyak_dp_kernel(float* __restrict__ param, float* __restrict__ m, float* 
   __shared__ AdamScalars sa;
   const unsigned G = gridDim.x;
   const unsigned epoch = (unsigned)(dp.local[0] + 1ull);
+  // phase clocks of block 0 (ns, accumulated in local[2..5]: wait-for-gradients, reduce+deliver, wait-for-slices,
+  // optimiser): how the exchange's time splits into skew between the ranks and transfer (bench.py --dp-timing)
+  const bool timed = blockIdx.x == 0 && threadIdx.x == 0;
+  unsigned long long tk0 = 0, tk1 = 0, tk2 = 0, tk3 = 0;
+  if (timed) tk0 = globaltimer_ns();
   unsigned* my_ctl = dp.ctl_peers[dp.rank];
   if (threadIdx.x == 0) sa = *scal_dev;
 
@@ -242,20 +248,37 @@ adamw_polyak_dp_kernel(float* __restrict__ param, float* __restrict__ m, float* 
   }
   if ((int)threadIdx.x < dp.world) wait_flag(my_ctl + threadIdx.x, epoch);
   __syncthreads();
+  if (timed) tk1 = globaltimer_ns();
 
   // ---- B: reduce my slice in rank order, deliver it (and its sums of squares) to every rank
   const int64_t n4 = n >> 2;
   const int64_t s4 = (n4 + dp.world - 1) / dp.world;
   const int64_t lo = (int64_t)dp.rank * s4, hi = lo + s4 < n4 ? lo + s4 : n4;
   float sq = 0.f;
-  for (int64_t i = lo + (int64_t)blockIdx.x * kOptThreads + threadIdx.x; i < hi; i += (int64_t)G * kOptThreads) {
-    float4 acc = ld_sys_f4(dp.grad_peers[0] + 4 * i);
-    for (int r = 1; r < dp.world; ++r) {
-      const float4 t = ld_sys_f4(dp.grad_peers[r] + 4 * i);
-      acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
+  // kDpIlp elements per thread and trip, all peers' loads of all of them issued before the first
+  // add: an NVLink round trip costs ~2 us, serialised loads would cost world x trips of them
+  constexpr int kDpIlp = 2;
+  const int64_t gstride = (int64_t)G * kOptThreads;
+  for (int64_t i0 = lo + (int64_t)blockIdx.x * kOptThreads + threadIdx.x; i0 < hi; i0 += gstride * kDpIlp) {
+    float4 t[kDpIlp][kDpMaxWorld];
+#pragma unroll
+    for (int u = 0; u < kDpIlp; ++u)
+#pragma unroll
+      for (int r = 0; r < kDpMaxWorld; ++r)
+        if (r < dp.world && i0 + u * gstride < hi) t[u][r] = ld_sys_f4(dp.grad_peers[r] + 4 * (i0 + u * gstride));
+#pragma unroll
+    for (int u = 0; u < kDpIlp; ++u) {
+      const int64_t i = i0 + u * gstride;
+      if (i >= hi) break;
+      float4 acc = t[u][0];                          // summed in rank order: deterministic, same on every rank
+#pragma unroll
+      for (int r = 1; r < kDpMaxWorld; ++r)
+        if (r < dp.world) { acc.x += t[u][r].x; acc.y += t[u][r].y; acc.z += t[u][r].z; acc.w += t[u][r].w; }
+      sq += acc.x * acc.x + acc.y * acc.y + acc.z * acc.z + acc.w * acc.w;
+#pragma unroll
+      for (int q = 0; q < kDpMaxWorld; ++q)
+        if (q < dp.world) st_sys_f4(dp.red_peers[q] + 4 * i, acc);
     }
-    sq += acc.x * acc.x + acc.y * acc.y + acc.z * acc.z + acc.w * acc.w;
-    for (int q = 0; q < dp.world; ++q) st_sys_f4(dp.red_peers[q] + 4 * i, acc);
   }
   const float tot = block_sum_256(sq, red);
   if (threadIdx.x == 0)
@@ -272,8 +295,10 @@ adamw_polyak_dp_kernel(float* __restrict__ param, float* __restrict__ m, float* 
   }
 
   // ---- C: every rank's slice has arrived
+  if (timed) tk2 = globaltimer_ns();
   if ((int)threadIdx.x < dp.world) wait_flag(my_ctl + 16 + threadIdx.x, epoch);
   __syncthreads();
+  if (timed) tk3 = globaltimer_ns();
 
   // ---- D: global norm (world x G partials, fixed order), clip, AdamW, Polyak
   const float* sumsq_all = reinterpret_cast<const float*>(my_ctl + kDpFlagWords);
@@ -316,6 +341,8 @@ adamw_polyak_dp_kernel(float* __restrict__ param, float* __restrict__ m, float* 
     if (grad_norm_out) grad_norm_out[0] = norm;
     if (counter_inc) counter_inc[0] += 1;
     dp.local[0] = epoch;          // every block of this rank passed phase C, i.e. has read the old value
+    const unsigned long long tk4 = globaltimer_ns();
+    dp.local[2] += tk1 - tk0; dp.local[3] += tk2 - tk1; dp.local[4] += tk3 - tk2; dp.local[5] += tk4 - tk3;
   }
 }
 
