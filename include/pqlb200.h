@@ -217,6 +217,10 @@ typedef struct {
   int n_groups;               /* 1..PQLB_MAX_GROUPS                            */
   int col_lo, col_hi;         /* only output columns [col_lo,col_hi) are stored, at out[row*ldo + n-col_lo];
                                  col_hi == 0 means [0, N).  aux/bias are indexed with the absolute n. */
+  int cluster;                /* split-K only: 0/1 = every split stores its own partial; 2, 4 or 8 = the splits of
+                                 a thread-block cluster are summed (in split order) through distributed shared
+                                 memory before they leave the SMs, and out receives splits / cluster partials
+                                 (partial p at out + p * split_stride).  splits % cluster == 0.            */
   float noise_bound;          /* BIAS_TANH_NOISE: clamp(noise_std * aux, +-noise_bound)         */
   float noise_std;            /* aux holds N(0,1) draws (out.normal_()), scaled here like
                                  torch.normal(zeros, full(std)) does (mul_(std).add_(mean))     */

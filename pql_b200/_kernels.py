@@ -75,11 +75,11 @@ class Gemm(Call):
     INTS = ("lda", "ldb", "lda2", "ldb2", "ldaux", "ldo", "ldo2", "split_stride")
 
     def __init__(self, M, N, K, groups, *, epilogue, tile_n, a_major=K_MAJOR, b_major=K_MAJOR,
-                 splits=1, K2=0, col_lo=0, col_hi=0, noise_bound=0.0, noise_std=1.0, keep=()):
+                 splits=1, K2=0, col_lo=0, col_hi=0, noise_bound=0.0, noise_std=1.0, cluster=1, keep=()):
         d = _lib.GemmDesc()
         d.M, d.N, d.K, d.K2 = int(M), int(N), int(K), int(K2)
         d.a_major, d.b_major, d.epilogue, d.tile_n = a_major, b_major, epilogue, int(tile_n)
-        d.splits, d.n_groups = int(splits), len(groups)
+        d.splits, d.n_groups, d.cluster = int(splits), len(groups), int(cluster)
         d.col_lo, d.col_hi, d.noise_bound, d.noise_std = int(col_lo), int(col_hi), float(noise_bound), float(noise_std)
         if not 1 <= len(groups) <= _lib.MAX_GROUPS:
             raise ValueError("1..%d groups per launch" % _lib.MAX_GROUPS)
@@ -169,6 +169,21 @@ def wgrad_tiling(M, N, K, n_groups, target_ctas=int(_os.environ.get("PQLB_WGRAD_
     if best is None:
         return pick_tile_n(min(N, 256)), 1
     return best[1], best[2]
+
+
+WGRAD_CLUSTER = int(_os.environ.get("PQLB_WGRAD_CLUSTER", 1))
+
+
+def wgrad_cluster(splits, tile_n):
+    """Thread-block cluster size for the in-cluster (distributed shared memory) reduction of the
+    split-K partials: the largest of 8 / 4 / 2 that divides the split count (tile_n >= 32: the
+    receive area is counted in 32-column chunks)."""
+    if tile_n < 32:
+        return 1
+    for c in (8, 4, 2):
+        if c <= WGRAD_CLUSTER and splits % c == 0:
+            return c
+    return 1
 
 
 class Workspace:

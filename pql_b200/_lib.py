@@ -42,7 +42,7 @@ class ColsumDesc(C.Structure):
 class GemmDesc(C.Structure):
     _fields_ = [("M", _int), ("N", _int), ("K", _int), ("K2", _int),
                 ("a_major", _int), ("b_major", _int), ("epilogue", _int), ("tile_n", _int),
-                ("splits", _int), ("n_groups", _int), ("col_lo", _int), ("col_hi", _int),
+                ("splits", _int), ("n_groups", _int), ("col_lo", _int), ("col_hi", _int), ("cluster", _int),
                 ("noise_bound", _flt), ("noise_std", _flt), ("g", GemmGroup * MAX_GROUPS)]
 
 

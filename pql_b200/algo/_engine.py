@@ -18,7 +18,8 @@ from .. import _lib
 from ..models.mlp import HIDDEN, NetAddrs, NetLayout, _ru, forward_calls, fwd_tile
 
 H1, H2, H3 = HIDDEN
-SEG = 256
+import os as _os
+SEG = int(_os.environ.get("PQLB_REDUCE_SEG", 256))      # elements per block of the gradient reduction
 
 
 class _Optim:
@@ -151,16 +152,18 @@ class _UpdateBase:
         in the workspace; grad_reduce sums them in a fixed order)."""
         B = self.B
         tile_n, splits = K.wgrad_tiling(n_out, n_in, B, len(net_ids))
+        cluster = K.wgrad_cluster(splits, tile_n)       # the splits of a cluster leave the SMs as one partial
+        n_part = splits // cluster
         ldw = layout.ldw[layer]
         stride = n_out * ldw
         groups = []
         for j, i in enumerate(net_ids):
-            off = self._ws_alloc(splits * stride)
+            off = self._ws_alloc(n_part * stride)
             groups.append(dict(a=K.addr(dz[j]), lda=ldz, b=K.addr(h[j]), ldb=ldh, out=K.addr(self.ws, off), ldo=ldw,
                                split_stride=stride))
-            opt.add_source(layout.w_off[i][layer], stride, off, stride, splits)
+            opt.add_source(layout.w_off[i][layer], stride, off, stride, n_part)
         return K.Gemm(n_out, n_in, B, groups, epilogue=K.EPI_STORE, tile_n=tile_n, a_major=K.MN_MAJOR,
-                      b_major=K.MN_MAJOR, splits=splits)
+                      b_major=K.MN_MAJOR, splits=splits, cluster=cluster)
 
     def _bias_grads(self, opt, layout, entries):
         """entries: (net, layer, dz tensor, ld, n_cols).  One launch for all bias gradients."""

@@ -49,6 +49,7 @@ struct alignas(64) GemmDev {
   int splits, kb1, kb_total, kb_per_split;
   int stages, stage_bytes, b_tile_bytes, tmem_cols;
   int col_lo, col_hi, ring_bytes, aux_bytes;
+  int cluster;
   float noise_bound, noise_std;
   unsigned idesc;
 };
@@ -177,6 +178,12 @@ gemm_tf32_kernel(const __grid_constant__ GemmDev P) {
     __syncwarp();
   } else {
     // ===================== epilogue (warps 2..9) =====================
+    if (EPI == PQLB_EPI_STORE && P.cluster > 1) {
+      // split-K partials reduced inside the cluster (below, with every warp at the cluster barriers):
+      // here only wait until the accumulator is complete, i.e. until this CTA's operand ring is idle
+      mbar_wait(smem_u32(&accum_bar), 0);
+      tcgen05_fence_after();
+    } else {
     const int e = warp - 2;
     const int quarter = warp & 3;                           // TMEM lanes [32q, 32q+32) belong to warp%4 == q
     const int half = e >> 2;                                // which half of the tile's column chunks
@@ -332,6 +339,78 @@ gemm_tf32_kernel(const __grid_constant__ GemmDev P) {
       if (half == 0 && row_ok) G.q[row] = (qacc + s_q[quarter * 32 + lane]) + G.head_b[0];
     }
     if (n_stores > 0) { if (elect_one()) bulk_wait_read<0>(); __syncwarp(); }   // staging memory must outlive the bulk reads
+    }
+  }
+
+  if (EPI == PQLB_EPI_STORE && P.cluster > 1) {
+    // ---- split-K reduction through distributed shared memory.  The tile's accumulator is 4 lane
+    // quarters x tile_n / 32 chunks of 32 x 32 words; chunk j belongs to the CTA of cluster rank j % C.
+    // Every CTA sends each of its chunks to the owner's receive area (the idle operand ring:
+    // slot [j / C][sender]), the owner adds the C versions in sender (= split) order and stores one
+    // partial per cluster: C times fewer bytes leave the SMs, and the reduction kernel reads C times
+    // fewer.  Fixed order => bit-reproducible.
+    const int C = P.cluster;
+    const uint32_t rank = cluster_ctarank();
+    const int NC = P.tile_n >> 5;
+    const int n_chunks = max(0, (min(P.tile_n, P.col_hi - n0) + 31) / 32);
+    const uint32_t swz = (uint32_t)(lane & 7) << 4;
+    const uint32_t row_off = (uint32_t)lane * 128u;
+    cluster_arrive_release();          // #0: my ring is idle (epilogue warps arrive after accum_bar) ...
+    cluster_wait_acquire();            //     ... and so is everybody else's
+    if (warp >= 2) {
+      const int e = warp - 2, quarter = warp & 3, half = e >> 2;
+      const int per = (n_chunks + 1) >> 1;
+      const int c_begin = half * per, c_end = min(n_chunks, c_begin + per);
+      const uint32_t taddr = tmem_d + ((uint32_t)(quarter * 32) << 16);
+      for (int c = c_begin; c < c_end; ++c) {
+        float v[32];
+        tmem_ld32(taddr + c * 32, v);
+        const int j = quarter * NC + c;
+        const uint32_t slot = tiles + (uint32_t)((j / C) * C + (int)rank) * kChunkBytes;
+        const uint32_t dst = mapa_shared(slot, (uint32_t)(j % C)) + row_off;
+#pragma unroll
+        for (int j4 = 0; j4 < 8; ++j4)
+          sts128_cluster(dst + (((uint32_t)j4 << 4) ^ swz), v[4 * j4], v[4 * j4 + 1], v[4 * j4 + 2], v[4 * j4 + 3]);
+      }
+    }
+    cluster_arrive_release();          // #1: my chunks are delivered ...
+    cluster_wait_acquire();            //     ... and all chunks I own have arrived
+    if (warp >= 2) {
+      const int e = warp - 2;
+      const int owned = (4 * NC + C - 1 - (int)rank) / C;        // chunks j = rank + C * t < 4 * NC
+      for (int t = e; t < owned; t += kEpiWarps) {
+        const int j = (int)rank + C * t;
+        const int quarter = j / NC, c = j - quarter * NC;
+        if (c >= n_chunks) continue;
+        float acc[32];
+        const uint32_t base = tiles + (uint32_t)(t * C) * kChunkBytes + row_off;
+#pragma unroll
+        for (int j4 = 0; j4 < 8; ++j4) {
+          const float4 x = lds128(base + (((uint32_t)j4 << 4) ^ swz));
+          acc[4 * j4] = x.x; acc[4 * j4 + 1] = x.y; acc[4 * j4 + 2] = x.z; acc[4 * j4 + 3] = x.w;
+        }
+        for (int s2 = 1; s2 < C; ++s2) {
+#pragma unroll
+          for (int j4 = 0; j4 < 8; ++j4) {
+            const float4 x = lds128(base + (uint32_t)s2 * kChunkBytes + (((uint32_t)j4 << 4) ^ swz));
+            acc[4 * j4] += x.x; acc[4 * j4 + 1] += x.y; acc[4 * j4 + 2] += x.z; acc[4 * j4 + 3] += x.w;
+          }
+        }
+        const int row = m0 + quarter * 32 + lane;
+        const int nb = n0 + c * 32;
+        if (row < P.M) {
+          float* dst = G.out + (long long)(split / C) * G.split_stride + (long long)row * G.ldo + nb;
+          const int hi = min(nb + 32, P.col_hi);
+          if (hi == nb + 32 && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+#pragma unroll
+            for (int q = 0; q < 32; q += 4) *reinterpret_cast<float4*>(dst + q) = make_float4(acc[q], acc[q + 1], acc[q + 2], acc[q + 3]);
+          } else {
+#pragma unroll
+            for (int q = 0; q < 32; ++q) if (nb + q < hi) dst[q] = acc[q];
+          }
+        }
+      }
+    }
   }
 
   tcgen05_fence_before();
@@ -455,6 +534,11 @@ extern "C" int pqlb_gemm_tf32(const pqlb_gemm_desc* d, pqlb_stream_t stream) {
   P.M = d->M; P.N = d->N; P.K = d->K; P.K2 = d->K2;
   P.a_mn = d->a_major == PQLB_MN_MAJOR; P.b_mn = d->b_major == PQLB_MN_MAJOR;
   P.epi = d->epilogue; P.tile_n = tn; P.splits = d->splits;
+  P.cluster = d->cluster > 1 ? d->cluster : 1;
+  if (P.cluster > 1) {
+    PQLB_CHECK_ARG(d->epilogue == PQLB_EPI_STORE && (P.cluster == 2 || P.cluster == 4 || P.cluster == 8));
+    PQLB_CHECK_SHAPE(d->splits % P.cluster == 0 && tn >= 32 && d->col_lo == 0);
+  }
   P.kb1 = (d->K + kTileK - 1) / kTileK;
   P.kb_total = P.kb1 + (d->K2 + kTileK - 1) / kTileK;
   PQLB_CHECK_SHAPE(P.kb_total % d->splits == 0);
@@ -518,6 +602,19 @@ extern "C" int pqlb_gemm_tf32(const pqlb_gemm_desc* d, pqlb_stream_t stream) {
   PQLB_CHECK_SHAPE(smem_bytes <= kSmemMax);
   { int rc = pqlb_init(); if (rc != PQLB_OK) return rc; }
   dim3 grid((unsigned)((d->M + kTileM - 1) / kTileM), (unsigned)((d->N + tn - 1) / tn), (unsigned)(d->n_groups * d->splits));
+  if (P.cluster > 1) {
+    PQLB_CHECK_SHAPE(4 * (tn / 32) * kChunkBytes <= P.ring_bytes);        // the receive area is the operand ring
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = dim3(kGemmThreads); cfg.dynamicSmemBytes = (size_t)smem_bytes; cfg.stream = (cudaStream_t)stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 1; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = (unsigned)P.cluster;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    cudaError_t le = cudaLaunchKernelEx(&cfg, kernel_for(d->epilogue), P);
+    PQLB_COUNT_LAUNCH(1);
+    if (le != cudaSuccess) { (void)cudaGetLastError(); return (int)le; }
+    return PQLB_OK;
+  }
   kernel_for(d->epilogue)<<<grid, kGemmThreads, smem_bytes, (cudaStream_t)stream>>>(P);
   PQLB_LAUNCH_RET();
 }

@@ -132,6 +132,41 @@ def test_wgrad_mn_mn_split_k(K, n_out, n_in, B, tile_n, splits):
     assert torch.count_nonzero(part[:, :, n_in:]) == 0
 
 
+@pytest.mark.parametrize("n_out,n_in,B,tile_n,splits,cluster,groups", [
+    (256, 512, 8192, 256, 32, 8, 2), (256, 512, 8192, 256, 32, 4, 2), (128, 256, 8192, 256, 64, 8, 2),
+    (512, 104, 8192, 128, 32, 8, 2), (512, 104, 8192, 128, 32, 2, 1), (16, 128, 2048, 128, 8, 4, 1),
+    (51, 128, 1024, 128, 4, 4, 2), (512, 231, 1024, 256, 8, 8, 1), (128, 256, 2048, 64, 16, 8, 1)])
+def test_wgrad_cluster_reduction_equals_split_order_sum(K, n_out, n_in, B, tile_n, splits, cluster, groups):
+    """Split-K partials summed through distributed shared memory inside a thread-block cluster
+    (pqlb_gemm_desc.cluster): partial p must equal, bit for bit, the per-split partials
+    [p * cluster, (p + 1) * cluster) of the un-clustered launch added in split order."""
+    g = torch.Generator(device=DEV).manual_seed(n_out * 7 + n_in + cluster)
+    ldz = (n_out + 3) // 4 * 4 if n_out != 51 else 64
+    ldh = (n_in + 3) // 4 * 4
+    stride = n_out * ldh
+    dz, h, part, red = [], [], [], []
+    for _ in range(groups):
+        a = torch.zeros(B, ldz, device=DEV); a[:, :n_out] = mk((B, n_out), g)
+        b = torch.zeros(B, ldh, device=DEV); b[:, :n_in] = mk((B, n_in), g)
+        dz.append(a); h.append(b)
+        part.append(torch.zeros(splits, n_out, ldh, device=DEV))
+        red.append(torch.full((splits // cluster, n_out, ldh), 3.0, device=DEV))
+    def launch(outs, c):
+        K.Gemm(n_out, n_in, B, [dict(a=K.addr(dz[i]), lda=ldz, b=K.addr(h[i]), ldb=ldh, out=K.addr(outs[i]), ldo=ldh,
+                                      split_stride=stride) for i in range(groups)],
+               epilogue=K.EPI_STORE, tile_n=tile_n, a_major=K.MN_MAJOR, b_major=K.MN_MAJOR, splits=splits, cluster=c)()
+    launch(part, 1)
+    launch(red, cluster)
+    torch.cuda.synchronize()
+    for i in range(groups):
+        exp = part[i][0::cluster].clone()
+        for s in range(1, cluster):
+            exp += part[i][s::cluster]
+        assert torch.equal(red[i][:, :, :n_in], exp[:, :, :n_in]), f"group {i}"
+        ref = dz[i][:, :n_out].double().t() @ h[i][:, :n_in].double()
+        check(red[i].sum(0)[:, :n_in], ref, 2e-5, "wgrad cluster")
+
+
 def test_actor_head_tanh_and_noise(K):
     M, Kd, A, O, x_ld = 300, 128, 16, 88, 104
     g = torch.Generator(device=DEV).manual_seed(9)
