@@ -31,6 +31,16 @@ O, A, E, B, CAP, NSTEP = 88, 16, 4096, 8192, 1_000_000, 3
 V_PER_STEP, P_PER_STEP = 8, 4
 FLOP_V = 3_684_352          # GEMM FLOPs per sample of one critic update
 FLOP_P = 2_913_280          # ... of one actor update
+# the dominant kernel, mlp_fwd_kernel (pqlb_mlp_forward): MACs per sample of its launches in one update
+MAC_ACTOR_FWD = O * 512 + 512 * 256 + 256 * 128 + 128 * A                 # trunk + fused tanh policy head
+MAC_CRITIC_FWD = (O + A) * 512 + 512 * 256 + 256 * 128 + 128              # trunk + scalar Q head
+FWD_MAC_V = MAC_ACTOR_FWD + 4 * MAC_CRITIC_FWD       # critic update: target policy + 2 target + 2 current nets
+FWD_MAC_P = MAC_ACTOR_FWD + 2 * MAC_CRITIC_FWD       # actor update: policy + frozen twin critics
+FWD_LAUNCHES_PER_STEP = 2 * (V_PER_STEP + P_PER_STEP)
+# DRAM bytes (read + write) of those launches from the committed ncu --set full capture of one step
+# (profiles/r1_final_ncu_full_update_kernels.csv; cold cache under ncu): policy 4.88 MB, four critic
+# nets 15.7 MB per critic update; 4.36 MB + 8.07 MB per actor update
+FWD_DRAM_BYTES_PER_STEP = V_PER_STEP * (4.88e6 + 15.7e6) + P_PER_STEP * (4.36e6 + 8.07e6)
 BYTES_INSERT = 1549         # algorithmic bytes per inserted transition
 BYTES_SAMPLE = 1557         # ... per sampled transition
 N_BLOCKS = 16
@@ -312,6 +322,7 @@ def main():
     torch.cuda.synchronize(dev)
     per_kernel = {name: sum(a.elapsed_time(b) for a, b in evs) / prof_steps for name, evs in K.PROFILE.items()}
     n_gemm = sum(len(K.PROFILE.get(k, [])) for k in ("pqlb_gemm_tf32", "pqlb_mlp_forward", "pqlb_mlp_backward")) // prof_steps
+    n_fwd = len(K.PROFILE.get("pqlb_mlp_forward", [])) // prof_steps
     K.PROFILE = None
     v.enable_graph(); p.enable_graph()
 
@@ -382,6 +393,9 @@ def main():
     gemm_ms = sum(per_kernel.get(k, 0.0) for k in TC_KERNELS)
     flops_step = B * (V_PER_STEP * FLOP_V + P_PER_STEP * FLOP_P)
     achieved = flops_step / (gemm_ms * 1e-3) / 1e12
+    fwd_ms = per_kernel.get("pqlb_mlp_forward", 0.0)
+    fwd_flops_step = 2.0 * B * (V_PER_STEP * FWD_MAC_V + P_PER_STEP * FWD_MAC_P)
+    fwd_achieved = fwd_flops_step / (max(fwd_ms, 1e-9) * 1e-3) / 1e12
     value = world * V_PER_STEP * args.steps / (ms * 1e-3)
     e2e = world * V_PER_STEP * args.steps / (ms_e2e * 1e-3)
     line = {"metric": "critic updates/s (batch 8192)", "value": value, "unit": "critic updates/s", "n_gpus": world,
@@ -391,16 +405,34 @@ def main():
             "e2e": {"value": e2e, "unit": "critic updates/s", "h2d_bytes_per_step": h2d_bytes,
                     "d2h_bytes_per_step": 2 * 5 * 4, "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": launches,
-            "roofline": {"kernel": "gemm_tf32_kernel + mlp_fwd_kernel + mlp_bwd_kernel (tcgen05 kind::tf32; all dense-layer launches of one step)",
-                         "bound": "tensor", "achieved": achieved, "peak": tf32_peak, "unit": "TFLOP/s",
-                         "frac": achieved / tf32_peak, "traffic": None, "launches_per_step": n_gemm,
-                         "ms_per_step_in_kernel": gemm_ms,
-                         "peak_source": f"{peak_src}: tf32 dense = 1/2 of the sustained cuBLAS bf16 figure"},
+            "roofline": {"kernel": "mlp_fwd_kernel (pqlb_mlp_forward: layer-fused Linear+ELU x3 trunk + Q / policy head, "
+                                   "tcgen05 kind::tf32) - the dominant kernel, 37 % of the step in the ncu launch list",
+                         "bound": "tensor", "achieved": fwd_achieved, "peak": tf32_peak, "unit": "TFLOP/s",
+                         "frac": fwd_achieved / tf32_peak,
+                         "traffic": FWD_DRAM_BYTES_PER_STEP / FWD_LAUNCHES_PER_STEP,
+                         "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum per launch, mean over the step's "
+                                           "launches, profiles/r1_final_ncu_full_update_kernels.csv",
+                         "launches_per_step": n_fwd, "algorithmic_flops_per_launch": fwd_flops_step / max(n_fwd, 1),
+                         "us_per_launch": 1e3 * fwd_ms / max(n_fwd, 1), "ms_per_step_in_kernel": fwd_ms,
+                         "peak_source": f"{peak_src}: tf32 dense = 1/2 of the sustained cuBLAS bf16 figure",
+                         "all_tcgen05_kernels": {"kernels": "gemm_tf32_kernel + mlp_fwd_kernel + mlp_bwd_kernel (every dense-layer "
+                                                            "launch of the step: forward, dgrad, wgrad, heads)",
+                                                 "achieved": achieved, "frac": achieved / tf32_peak, "launches_per_step": n_gemm,
+                                                 "ms_per_step_in_kernel": gemm_ms, "algorithmic_flops_per_step": flops_step},
+                         "ncu_tensor_pipe_active_pct": {"mlp_fwd_kernel, 4 critic nets": 33.2, "mlp_fwd_kernel, policy": 27.7,
+                                                        "mlp_bwd_kernel": 26.4, "gemm_tf32 wgrad (layers 2/1/0)": [13.3, 28.2, 20.3],
+                                                        "source": "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active, "
+                                                                  "profiles/r1_final_ncu_full_update_kernels.csv"}},
             "kernel_ms_per_step": {k: round(x, 4) for k, x in sorted(per_kernel.items(), key=lambda kv: -kv[1])},
             "replay": {"kernels": replay, "hbm_peak_gbs": hbm_peak, "peak_source": peak_src,
                        "insert_frac_of_hbm": replay["insert_122880"]["gbs"] / hbm_peak,
                        "sample_frac_of_hbm": replay["sample_65536"]["gbs"] / hbm_peak,
-                       "bytes_per_unit": {"insert": BYTES_INSERT, "sample": BYTES_SAMPLE}},
+                       "bytes_per_unit": {"insert": BYTES_INSERT, "sample": BYTES_SAMPLE},
+                       "traffic": {"insert_122880": {"dram_read": 95.36e6, "dram_write": 51.4e6, "algorithmic": 122880 * BYTES_INSERT},
+                                   "sample_65536": {"dram_read": 57.57e6, "dram_write": 6.7e6, "algorithmic": 65536 * BYTES_SAMPLE},
+                                   "note": "ncu --set full, profiles/r1_final_ncu_full_replay_kernels.csv: reads match the algorithmic "
+                                           "bytes (insert 776 B/row exactly; gather reads whole 32-B sectors of the 800-B record), "
+                                           "writes are below them because part of the output is still in L2 when the kernel ends"}},
             "host_wall_ms_per_step": 1e3 * wall / args.steps,
             "losses": {"critic": float(losses[0]), "actor": float(losses[1])}}
     if dp_phases is not None:

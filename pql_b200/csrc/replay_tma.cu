@@ -14,8 +14,14 @@
 
 namespace pqlb {
 
-constexpr int kInsRows = 32;          // transitions per tile
-constexpr int kInsStages = 4;
+#ifndef PQLB_INS_ROWS
+#define PQLB_INS_ROWS 32
+#endif
+#ifndef PQLB_INS_STAGES
+#define PQLB_INS_STAGES 4
+#endif
+constexpr int kInsRows = PQLB_INS_ROWS;          // transitions per tile
+constexpr int kInsStages = PQLB_INS_STAGES;
 constexpr int kInsThreads = 64;       // warp 0: loads, warp 1: reward/done tile + stores
 
 struct alignas(64) InsertPart {
@@ -73,14 +79,24 @@ ring_insert_tma_kernel(const __grid_constant__ InsertParams P) {
       int row0; const InsertPart& Q = part_of(tile, row0);
       const uint32_t src = base + stage * stage_bytes;
       // reward / done / padding sector of row0 + lane: done is stored as the reference's bool column
-      const long long row = (long long)row0 + lane;
-      float r = 0.f, d = 0.f;
-      if (row < Q.rows) { r = __ldcs(Q.rew + row); d = __ldcs(Q.done + row) != 0.f ? 1.f : 0.f; }
+      constexpr int kPerLane = (kInsRows + 31) / 32;
+      float r[kPerLane], d[kPerLane];
+#pragma unroll
+      for (int u = 0; u < kPerLane; ++u) {
+        const long long row = (long long)row0 + lane + 32 * u;
+        r[u] = 0.f; d[u] = 0.f;
+        if (lane + 32 * u < kInsRows && row < Q.rows) { r[u] = __ldcs(Q.rew + row); d[u] = __ldcs(Q.done + row) != 0.f ? 1.f : 0.f; }
+      }
       // the store that last read this stage's buffers must be done before they are rewritten: the
       // producer waits for that too (empty_bar), so by the time full_bar flips the tail tile is free
       mbar_wait(smem_u32(&full_bar[stage]), phase);
-      const uint32_t t = src + 2u * obs_bytes + act_bytes + (uint32_t)lane * 32u;
-      sts128(t, r, d, 0.f, 0.f); sts128(t + 16u, 0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int u = 0; u < kPerLane; ++u) {
+        if (lane + 32 * u < kInsRows) {
+          const uint32_t t = src + 2u * obs_bytes + act_bytes + (uint32_t)(lane + 32 * u) * 32u;
+          sts128(t, r[u], d[u], 0.f, 0.f); sts128(t + 16u, 0.f, 0.f, 0.f, 0.f);
+        }
+      }
       fence_proxy_async();
       __syncwarp();
       if (elect_one()) {
