@@ -154,14 +154,16 @@ def cpu_reference_rate(seconds_budget=20.0, threads=None):
                 ms_per_actor_update=1e3 * t_p / (n_steps * P_PER_STEP), ms_per_insert=1e3 * t_ins / n_steps)
 
 
-def config_dict(n_gpus):
+def config_dict(n_gpus, dp="fused"):
     return {"workload": "configs[1]: DoubleQ V-learner + P-learner, AllegroHand shape (obs 88, act 16), batch 8192, "
                         "1M-slot replay, n-step 3, 4096-env synthetic insert stream, Polyak target update",
             "step": f"1 n-step push + ring insert of {E} transitions, {V_PER_STEP} critic updates, {P_PER_STEP} actor updates",
             "critic_updates_per_step": V_PER_STEP, "actor_updates_per_step": P_PER_STEP, "batch_per_gpu": B,
             "num_envs_per_gpu": E, "replay_slots_per_gpu": CAP, "parallelism": f"dp{n_gpus}",
-            "gradient_exchange": "none (1 GPU)" if n_gpus == 1 else "two-shot all-reduce over symmetric memory fused into the "
-                                 "optimiser kernel (pqlb_adamw_polyak_dp); --dp nccl / nccl-graph for the NCCL paths",
+            "gradient_exchange": "none (1 GPU)" if n_gpus == 1 else
+                                 {"fused": "two-shot all-reduce over symmetric memory fused into the optimiser kernel "
+                                           "(pqlb_adamw_polyak_dp); --dp nccl / nccl-graph for the NCCL paths",
+                                  "nccl": "ncclAllReduce between two CUDA graphs", "nccl-graph": "ncclAllReduce captured in the update's CUDA graph"}[dp],
             "settle_steps": 30,
             "learner_streams": "V-learner and P-learner each enqueue on their own CUDA stream (the reference runs them as "
                                "two concurrent Ray actors); update() is the exchange/join point",
@@ -176,7 +178,7 @@ def run_reference(args, rank):
     line = {"metric": "critic updates/s (batch 8192)", "value": r["value"], "unit": "critic updates/s", "impl": "reference",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"],
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": config_dict(args.gpus), "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "config": config_dict(args.gpus, args.dp), "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": r["value"], "unit": "critic updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
@@ -401,7 +403,9 @@ def main():
     line = {"metric": "critic updates/s (batch 8192)", "value": value, "unit": "critic updates/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "tf32 (fp32 accumulate)", "data": "synthetic",
-            "config": config_dict(world), "clocks": clocks,
+            "config": dict(config_dict(world, args.dp), **({"gradient_exchange": "ncclAllReduce (fused exchange unavailable on this box)"}
+                                                  if world > 1 and args.dp == "fused" and v._plan.dp is None else {})),
+            "clocks": clocks,
             "e2e": {"value": e2e, "unit": "critic updates/s", "h2d_bytes_per_step": h2d_bytes,
                     "d2h_bytes_per_step": 2 * 5 * 4, "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": launches,

@@ -419,6 +419,14 @@ int pqlb_adamw_polyak_dp(float* param, float* m, float* v, float* target, float*
                          const float* scalars, int64_t* counter, float* grad_norm_out,
                          pqlb_stream_t stream);
 
+/* The exchange alone (phases "wait for every rank's gradient", "reduce + deliver the own slice", "wait for the
+ * other slices") as a NARROW launch of dp->grid blocks: afterwards red_peers[rank] holds the gradient summed
+ * over the ranks and the floats behind the 32 flag words of ctl_peers[rank] hold world * grid partial sums of
+ * squares, to be consumed by pqlb_adamw_polyak_pre (grad = red, sumsq_part = ctl + 32 words, n_part =
+ * world * grid, grad_scale = 1 / world) at full width.  The spinning blocks then occupy dp->grid SMs instead of
+ * sharing 64 with the optimiser pass. */
+int pqlb_grad_exchange_dp(int64_t n, const pqlb_dp_desc* dp, pqlb_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

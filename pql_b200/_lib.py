@@ -123,6 +123,7 @@ _PROTOS = {
                                        _flt, _flt, _flt, _flt, _flt, _flt, _f, _st]),
     "pqlb_adamw_polyak_pre": (_int, [_f, _f, _f, _f, _f, _f, _f, _i64, _f, _int, _flt, _flt, _f, _f, _f, _st]),
     "pqlb_adamw_polyak_dp": (_int, [_f, _f, _f, _f, _f, _f, _i64, C.POINTER(DpDesc), _flt, _f, _f, _f, _st]),
+    "pqlb_grad_exchange_dp": (_int, [_i64, C.POINTER(DpDesc), _st]),
     "pqlb_sum_partials": (_int, [_f, _int, _flt, _f, _f, _f, _int, _st]),
 }
 

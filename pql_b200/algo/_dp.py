@@ -52,9 +52,13 @@ class FusedExchange:
     kernel its peer is waiting for): 64 one-block-per-SM blocks leave 84 SMs to everything else."""
 
     GRID = 64
+    GRID_SPLIT = 32        # split mode: the exchange is a launch of its own (pqlb_grad_exchange_dp), the optimiser follows
     FLAG_WORDS = 32
 
-    def __init__(self, n, device, group=None):
+    def __init__(self, n, device, group=None, split=False):
+        self.split = bool(split)
+        if self.split:
+            self.GRID = self.GRID_SPLIT
         import torch.distributed._symmetric_memory as symm_mem
         name = (group if group is not None else dist.group.WORLD).group_name
         self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)

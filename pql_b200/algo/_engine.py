@@ -511,8 +511,14 @@ def _finish_plan(plan, opt, p_flat, t_flat, p_tf, t_tf):
         # data parallel without NCCL on the path: the gradient arena lives in symmetric memory and the
         # optimiser kernel does the two-shot all-reduce over NVLink itself (csrc/optim.cu)
         from ._dp import FusedExchange
-        plan.dp = FusedExchange(opt.layout.total, plan.device, getattr(plan, "process_group", None))
-        opt.grad = plan.dp.grad
+        try:
+            plan.dp = FusedExchange(opt.layout.total, plan.device, getattr(plan, "process_group", None),
+                                    split=bool(_os.environ.get("PQLB_DP_SPLIT")) or getattr(plan, "dp_split", False))
+            opt.grad = plan.dp.grad
+        except Exception as e:      # no peer-mapped memory on this box (every rank fails alike): NCCL all-reduce instead
+            import warnings
+            warnings.warn(f"fused gradient exchange unavailable ({type(e).__name__}: {e}); falling back to ncclAllReduce")
+            plan.dp = None
     big = plan.ws
     max_norm = -1.0 if plan.max_grad_norm is None else float(plan.max_grad_norm)
     tau = getattr(plan, "tau", 0.0)
@@ -529,7 +535,17 @@ def _finish_plan(plan, opt, p_flat, t_flat, p_tf, t_tf):
                              _lib.ptr(t_flat), _lib.ptr(p_tf), _lib.ptr(t_tf), opt.layout.total, _lib.ptr(opt.sumsq),
                              opt.n_seg, 1.0 / plan.world_size, max_norm, _lib.ptr(plan.adam_scalars),
                              _lib.ptr(opt.count), _lib.ptr(plan.grad_norm))
-    if plan.dp is not None:
+    if plan.dp is not None and plan.dp.split:
+        # narrow exchange launch, then the ordinary full-width optimiser on the received gradient
+        desc = plan.dp.desc()
+        exch = K.Call("pqlb_grad_exchange_dp", opt.layout.total, C.byref(desc), keep=(desc, plan.dp))
+        sumsq_addr = C.c_void_p(plan.dp.ctl.data_ptr() + 4 * plan.dp.FLAG_WORDS)
+        step = K.Call("pqlb_adamw_polyak_pre", _lib.ptr(p_flat), _lib.ptr(plan.dp.red), _lib.ptr(opt.m), _lib.ptr(opt.v),
+                      _lib.ptr(t_flat), _lib.ptr(p_tf), _lib.ptr(t_tf), opt.layout.total, sumsq_addr,
+                      plan.dp.world * plan.dp.GRID, 1.0 / plan.world_size, max_norm, _lib.ptr(plan.adam_scalars),
+                      _lib.ptr(opt.count), _lib.ptr(plan.grad_norm))
+        plan.adamw_call = lambda: (exch(), step())
+    elif plan.dp is not None:
         desc = plan.dp.desc()
         plan.adamw_call = K.Call("pqlb_adamw_polyak_dp", _lib.ptr(p_flat), _lib.ptr(opt.m), _lib.ptr(opt.v), _lib.ptr(t_flat),
                                  _lib.ptr(p_tf), _lib.ptr(t_tf), opt.layout.total, C.byref(desc), max_norm,

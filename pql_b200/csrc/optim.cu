@@ -224,11 +224,43 @@ __device__ __forceinline__ void wait_flag(const unsigned* p, unsigned epoch) {
   }
 }
 
+// Phase B of the exchange: sum elements [lo, hi) (float4 units) of all ranks' gradients in rank order
+// and store the result into every rank's receive buffer; returns this thread's sum of squares.  ILP
+// elements per thread and trip, all peers' loads of all of them issued before the first add: an
+// NVLink round trip costs ~2-3 us, serialised loads would cost world x trips of them.
+template <int ILP, int WMAX>
+__device__ __forceinline__ float dp_reduce_slice(const DpArgs& dp, int64_t lo, int64_t hi, unsigned G) {
+  float sq = 0.f;
+  const int64_t gstride = (int64_t)G * kOptThreads;
+  for (int64_t i0 = lo + (int64_t)blockIdx.x * kOptThreads + threadIdx.x; i0 < hi; i0 += gstride * ILP) {
+    float4 t[ILP][WMAX];
+#pragma unroll
+    for (int u = 0; u < ILP; ++u)
+#pragma unroll
+      for (int r = 0; r < WMAX; ++r)
+        if (r < dp.world && i0 + u * gstride < hi) t[u][r] = ld_sys_f4(dp.grad_peers[r] + 4 * (i0 + u * gstride));
+#pragma unroll
+    for (int u = 0; u < ILP; ++u) {
+      const int64_t i = i0 + u * gstride;
+      if (i >= hi) break;
+      float4 acc = t[u][0];                          // summed in rank order: deterministic, same on every rank
+#pragma unroll
+      for (int r = 1; r < WMAX; ++r)
+        if (r < dp.world) { acc.x += t[u][r].x; acc.y += t[u][r].y; acc.z += t[u][r].z; acc.w += t[u][r].w; }
+      sq += acc.x * acc.x + acc.y * acc.y + acc.z * acc.z + acc.w * acc.w;
+#pragma unroll
+      for (int q = 0; q < WMAX; ++q)
+        if (q < dp.world) st_sys_f4(dp.red_peers[q] + 4 * i, acc);
+    }
+  }
+  return sq;
+}
+
 __global__ void __launch_bounds__(kOptThreads, 1)
 adamw_polyak_dp_kernel(float* __restrict__ param, float* __restrict__ m, float* __restrict__ v,
                        float* __restrict__ target, float* __restrict__ p_tf32, float* __restrict__ t_tf32,
                        int64_t n, DpArgs dp, float max_norm, const AdamScalars* __restrict__ scal_dev,
-                       long long* __restrict__ counter_inc, float* __restrict__ grad_norm_out) {
+                       long long* __restrict__ counter_inc, float* __restrict__ grad_norm_out, int exchange_only) {
   __shared__ float red[8];
   __shared__ AdamScalars sa;
   const unsigned G = gridDim.x;
@@ -239,7 +271,7 @@ adamw_polyak_dp_kernel(float* __restrict__ param, float* __restrict__ m, float* 
   unsigned long long tk0 = 0, tk1 = 0, tk2 = 0, tk3 = 0;
   if (timed) tk0 = globaltimer_ns();
   unsigned* my_ctl = dp.ctl_peers[dp.rank];
-  if (threadIdx.x == 0) sa = *scal_dev;
+  if (threadIdx.x == 0 && !exchange_only) sa = *scal_dev;
 
   // ---- A: every rank's gradient is complete (the kernel boundary before this launch made ours visible)
   if (blockIdx.x == 0 && (int)threadIdx.x < dp.world) {
@@ -254,32 +286,8 @@ adamw_polyak_dp_kernel(float* __restrict__ param, float* __restrict__ m, float* 
   const int64_t n4 = n >> 2;
   const int64_t s4 = (n4 + dp.world - 1) / dp.world;
   const int64_t lo = (int64_t)dp.rank * s4, hi = lo + s4 < n4 ? lo + s4 : n4;
-  float sq = 0.f;
-  // kDpIlp elements per thread and trip, all peers' loads of all of them issued before the first
-  // add: an NVLink round trip costs ~2 us, serialised loads would cost world x trips of them
-  constexpr int kDpIlp = 2;
-  const int64_t gstride = (int64_t)G * kOptThreads;
-  for (int64_t i0 = lo + (int64_t)blockIdx.x * kOptThreads + threadIdx.x; i0 < hi; i0 += gstride * kDpIlp) {
-    float4 t[kDpIlp][kDpMaxWorld];
-#pragma unroll
-    for (int u = 0; u < kDpIlp; ++u)
-#pragma unroll
-      for (int r = 0; r < kDpMaxWorld; ++r)
-        if (r < dp.world && i0 + u * gstride < hi) t[u][r] = ld_sys_f4(dp.grad_peers[r] + 4 * (i0 + u * gstride));
-#pragma unroll
-    for (int u = 0; u < kDpIlp; ++u) {
-      const int64_t i = i0 + u * gstride;
-      if (i >= hi) break;
-      float4 acc = t[u][0];                          // summed in rank order: deterministic, same on every rank
-#pragma unroll
-      for (int r = 1; r < kDpMaxWorld; ++r)
-        if (r < dp.world) { acc.x += t[u][r].x; acc.y += t[u][r].y; acc.z += t[u][r].z; acc.w += t[u][r].w; }
-      sq += acc.x * acc.x + acc.y * acc.y + acc.z * acc.z + acc.w * acc.w;
-#pragma unroll
-      for (int q = 0; q < kDpMaxWorld; ++q)
-        if (q < dp.world) st_sys_f4(dp.red_peers[q] + 4 * i, acc);
-    }
-  }
+  // (at most 4 ranks: 4 elements per thread and trip, else 2 - the same 16 / 8 float4 in flight)
+  const float sq = dp.world <= 4 ? dp_reduce_slice<4, 4>(dp, lo, hi, G) : dp_reduce_slice<2, kDpMaxWorld>(dp, lo, hi, G);
   const float tot = block_sum_256(sq, red);
   if (threadIdx.x == 0)
     for (int q = 0; q < dp.world; ++q)
@@ -299,6 +307,15 @@ adamw_polyak_dp_kernel(float* __restrict__ param, float* __restrict__ m, float* 
   if ((int)threadIdx.x < dp.world) wait_flag(my_ctl + 16 + threadIdx.x, epoch);
   __syncthreads();
   if (timed) tk3 = globaltimer_ns();
+  if (exchange_only) {
+    // narrow launch (pqlb_grad_exchange_dp): the reduced gradient and the world x G sums of squares are
+    // in this rank's receive buffer / control block; the full-width optimiser launch follows
+    if (timed) {
+      dp.local[0] = epoch;
+      dp.local[2] += tk1 - tk0; dp.local[3] += tk2 - tk1; dp.local[4] += tk3 - tk2;
+    }
+    return;
+  }
 
   // ---- D: global norm (world x G partials, fixed order), clip, AdamW, Polyak
   const float* sumsq_all = reinterpret_cast<const float*>(my_ctl + kDpFlagWords);
@@ -527,7 +544,24 @@ extern "C" int pqlb_adamw_polyak_dp(float* param, float* m, float* v, float* tar
   a.rank = dp->rank; a.world = dp->world; a.local = reinterpret_cast<unsigned long long*>(dp->local);
   adamw_polyak_dp_kernel<<<(unsigned)dp->grid, kOptThreads, 0, (cudaStream_t)stream>>>(
       param, m, v, target, param_tf32, target_tf32, n, a, max_norm, reinterpret_cast<const AdamScalars*>(scalars),
-      reinterpret_cast<long long*>(counter), grad_norm_out);
+      reinterpret_cast<long long*>(counter), grad_norm_out, 0);
+  PQLB_LAUNCH_RET();
+}
+
+extern "C" int pqlb_grad_exchange_dp(int64_t n, const pqlb_dp_desc* dp, pqlb_stream_t stream) {
+  PQLB_CHECK_ARG(n > 0 && (n % 4) == 0 && dp);
+  PQLB_CHECK_ARG(dp->world >= 2 && dp->world <= kDpMaxWorld && dp->rank >= 0 && dp->rank < dp->world && dp->local);
+  PQLB_CHECK_ARG(dp->grid >= 1 && dp->grid <= kNumSMs);
+  DpArgs a;
+  for (int r = 0; r < kDpMaxWorld; ++r) {
+    const bool on = r < dp->world;
+    if (on) PQLB_CHECK_ARG(dp->grad_peers[r] && dp->red_peers[r] && dp->ctl_peers[r] && aligned16(dp->grad_peers[r]) && aligned16(dp->red_peers[r]));
+    a.grad_peers[r] = on ? dp->grad_peers[r] : nullptr; a.red_peers[r] = on ? dp->red_peers[r] : nullptr;
+    a.ctl_peers[r] = on ? reinterpret_cast<unsigned*>(dp->ctl_peers[r]) : nullptr;
+  }
+  a.rank = dp->rank; a.world = dp->world; a.local = reinterpret_cast<unsigned long long*>(dp->local);
+  adamw_polyak_dp_kernel<<<(unsigned)dp->grid, kOptThreads, 0, (cudaStream_t)stream>>>(
+      nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, n, a, -1.f, nullptr, nullptr, nullptr, 1);
   PQLB_LAUNCH_RET();
 }
 

@@ -52,6 +52,7 @@ def main():
     ap.add_argument("--iters", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--distl", action="store_true")
+    ap.add_argument("--profile", action="store_true", help="per-kernel device time (CUDA events around every launch, graphs off)")
     args = ap.parse_args()
     from pql_b200.train import LockStepTrainer
     from pql_b200.utils import default_pql_cfg
@@ -77,6 +78,17 @@ def main():
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / args.iters
     wall = (time.perf_counter() - t0) / args.iters * 1e3
+    per_kernel = None
+    if args.profile:
+        from pql_b200 import _kernels as K
+        tr.v_learner.disable_graph(); tr.p_learner.disable_graph()
+        K.PROFILE = {}
+        for _ in range(3):
+            tr.step()
+        torch.cuda.synchronize()
+        per_kernel = {k: [round(sum(a.elapsed_time(b) for a, b in ev) / 3, 4), len(ev) // 3]
+                      for k, ev in sorted(K.PROFILE.items(), key=lambda kv: -sum(a.elapsed_time(b) for a, b in kv[1]))}
+        K.PROFILE = None
     print(json.dumps({"workload": f"configs[3]: full loop, {args.envs} envs, obs {args.obs}, act {args.act}, "
                                   f"{args.memory}-slot replay, batch {args.batch}, {'C51' if args.distl else 'twin-Q'}, "
                                   f"{tr.v_per_step} critic : {tr.v_per_step // tr.p_every} actor : 1 env step",
@@ -85,7 +97,8 @@ def main():
                       "critic_updates_per_s": tr.v_per_step / (ms * 1e-3),
                       "actor_updates_per_s": tr.v_per_step / tr.p_every / (ms * 1e-3),
                       "replay_gb": tr.v_learner.memory.ring.numel() * 4 / 1e9,
-                      "losses": {"critic": info["train/critic_loss"], "actor": info["train/actor_loss"]}}))
+                      "losses": {"critic": info["train/critic_loss"], "actor": info["train/actor_loss"]},
+                      "kernel_ms_and_launches_per_iteration": per_kernel}))
 
 
 if __name__ == "__main__":
