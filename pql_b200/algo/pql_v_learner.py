@@ -125,6 +125,7 @@ class PQLVLearner:
         self.graph_allreduce = bool(getattr(cfg, "dp_graph_allreduce", False)) and process_group is not None
         # cfg.dp_fused: no NCCL on the path - the optimiser kernel all-reduces over symmetric memory
         self.dp_fused = bool(getattr(cfg, "dp_fused", False)) and self.world_size > 1
+        self._sync_loss = bool(getattr(cfg, "sync_loss", False))
         self._ls = LearnerStream(cfg, self.device)
         self._ls.tag(self.critic)
         self.generator, self.fused_rng = make_generator(cfg, self.device, salt=0)
@@ -210,5 +211,7 @@ class PQLVLearner:
                     self._build()
                 self._plan.set_actor(module_flat(actor, self._plan.La.total, self.device))
                 self._plan.set_norm(normalize_tuple if self.cfg.algo.obs_norm else None)
-                loss = self.loss_tracker.mean()          # the one host sync per env step (this learner's stream)
+                # cfg.sync_loss: block until this learner's stream has drained and return the current mean;
+                # default: the mean as of the previous update() (non-blocking, DeviceTracker.mean_lagged)
+                loss = self.loss_tracker.mean() if self._sync_loss else self.loss_tracker.mean_lagged()
         return self.critic, loss, self.update_count

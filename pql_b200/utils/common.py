@@ -44,9 +44,26 @@ class DeviceTracker:
     def __init__(self, max_len, device):
         self.max_len = max_len
         self.window = torch.zeros(max_len, dtype=torch.float32, device=device)
+        self._host, self._event, self._last = None, None, 0.0
 
     def mean(self):
         return float(np.mean(self.window.tolist()))
+
+    def mean_lagged(self):
+        """Non-blocking read-back: returns the window mean as of the PREVIOUS call and starts the
+        device-to-host copy (pinned memory, current stream) that the next call will read.  The caller
+        never waits for the work it has just enqueued, so it can keep one env step of launches queued
+        ahead of the GPU.  In the reference the main loop receives a learner's loss asynchronously as
+        well (``ray.wait(..., timeout=0)``, scripts/train_pql.py:101-109)."""
+        if self._host is None:
+            self._host = torch.zeros(self.max_len, dtype=torch.float32).pin_memory()
+        if self._event is not None:
+            self._event.synchronize()            # the copy of the previous call: long done
+            self._last = float(np.mean(self._host.numpy().astype(np.float64)))
+        self._host.copy_(self.window, non_blocking=True)
+        self._event = torch.cuda.Event()
+        self._event.record()
+        return self._last
 
     def std(self):
         return float(np.std(self.window.tolist()))

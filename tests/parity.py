@@ -123,7 +123,7 @@ def make_cfg(B, distl, device_index=0, memory=None, obs_norm=True, fused_rng=Fal
     own tests (tests/test_gpu_rng.py)."""
     from pql_b200.utils import default_pql_cfg
     return default_pql_cfg(batch_size=B, memory_size=memory or B, distl=distl, v_learner_gpu=device_index,
-                           p_learner_gpu=device_index, obs_norm=obs_norm, fused_rng=fused_rng)
+                           p_learner_gpu=device_index, obs_norm=obs_norm, fused_rng=fused_rng, sync_loss=True)
 
 
 def _record(case, res):

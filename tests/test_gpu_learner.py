@@ -140,7 +140,7 @@ def test_update_launch_list_is_bit_reproducible(B, distl, which):
     assert parity.plan_divergence(B, distl, which, repeats=4, device=DEV) is None
 
 
-def _run_interleaved(streams, seed=9, B=512, steps=3, fused_rng=True, graph=True):
+def _run_interleaved(streams, seed=9, B=512, steps=3, fused_rng=True, graph=True, sync_loss=True):
     """bench.py's loop in miniature: per env step one update() exchange, 4 critic + 2 actor updates."""
     from pql_b200.algo import PQLPLearner, PQLVLearner
     from pql_b200.replay import NStepReplay
@@ -151,6 +151,7 @@ def _run_interleaved(streams, seed=9, B=512, steps=3, fused_rng=True, graph=True
     cfg.learner_streams = streams
     cfg.fused_rng = fused_rng
     cfg.use_cuda_graph = graph
+    cfg.sync_loss = sync_loss
     v, p = PQLVLearner(O, A, cfg), PQLPLearner(O, A, cfg)
     ns = NStepReplay(O, A, num_envs=E, nstep=3, device=DEV)
     g = torch.Generator(device=DEV).manual_seed(seed)
@@ -193,3 +194,13 @@ def test_fused_rng_update_equals_torch_draws():
     c2, a2, l2 = _run_interleaved(True, fused_rng=True, graph=False)
     assert torch.equal(c0, c1) and torch.equal(a0, a1) and l0 == l1
     assert torch.equal(c0, c2) and torch.equal(a0, a2) and l0 == l2
+
+
+def test_lagged_loss_readback_is_the_previous_mean():
+    """Default (cfg.sync_loss off): update() returns the loss mean as of the previous update() without
+    waiting for the GPU; weights are unaffected."""
+    c0, a0, l0 = _run_interleaved(True, sync_loss=True)
+    c1, a1, l1 = _run_interleaved(True, sync_loss=False)
+    assert torch.equal(c0, c1) and torch.equal(a0, a1)
+    assert l1[0] == (0.0, 0.0)
+    assert l1[1:] == l0[:-1]
