@@ -9,8 +9,8 @@ construction: per env step one ``explore_env`` (actor-side kernels + ``env.step`
 ``update()`` exchanges (ring inserts, weight / normaliser hand-off), then ``critic_sample_ratio``
 critic updates interleaved with ``critic_sample_ratio / critic_actor_ratio`` actor updates, each a
 CUDA-graph replay on its learner's stream.  Weights move between the workers as device-to-device
-copies of flat arenas (no pickling), and the only host synchronisation per env step is the loss
-read-back inside ``update()``.
+copies of flat arenas (no pickling), and the host never waits for the step it has just enqueued: the
+loss read-back inside ``update()`` returns the previous step's value (DeviceTracker.mean_lagged).
 """
 import time
 
