@@ -14,6 +14,7 @@ shard, critic / actor gradients are all-reduced before clip + AdamW (weak scalin
 all host threads) on a bounded sample of the same workload.
 """
 import argparse
+import gc
 import json
 import os
 import subprocess
@@ -275,6 +276,16 @@ def main():
         return vloss, ploss
 
     def timed(n, host_inputs, base):
+        # no cyclic-GC pass inside a timed region: a generation-2 collection over the interpreter's heap
+        # takes 10-20 ms - a third of a 20-step region (seen as one rank stalling the others at 2 GPUs)
+        gc.collect()
+        gc.disable()
+        try:
+            return _timed(n, host_inputs, base)
+        finally:
+            gc.enable()
+
+    def _timed(n, host_inputs, base):
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize(dev)
