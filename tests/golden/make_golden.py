@@ -305,8 +305,23 @@ def actor_small():
         np.savez(os.path.join(HERE, f"actor_small_{noise_type}.npz"), **rec)
 
 
+def schedules():
+    """pql/utils/schedule_util.py: the value sequences of the two exploration-noise schedules."""
+    from pql.utils.schedule_util import ExponentialSchedule, LinearSchedule
+    out = {}
+    for name, sch in (("linear_0.8_0.05_7", LinearSchedule(0.8, 0.05, 7)), ("linear_1_0_3", LinearSchedule(1.0, 0.0, 3)),
+                      ("exp_0.8_0.9_0.05", ExponentialSchedule(0.8, 0.9, 0.05)), ("exp_0.5_0.5_none", ExponentialSchedule(0.5, 0.5))):
+        vals = [sch.val()]
+        for _ in range(40):
+            vals.append(sch.step())
+            vals.append(sch.val())
+        out[name] = vals
+    json.dump(out, open(os.path.join(HERE, "schedules.json"), "w"))
+
+
 if __name__ == "__main__":
     torch.set_num_threads(8)
+    schedules()
     actor_small()
     replay_small()
     nstep_small()

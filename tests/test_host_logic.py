@@ -1,0 +1,63 @@
+"""CPU tier: host-side logic above the C ABI that needs no GPU - parameter-arena geometry, launch
+tiling heuristics, and the arithmetic of bench.py's roofline figures."""
+import pytest
+import torch
+
+from pql_b200 import _kernels as K
+from pql_b200.models import DistributionalDoubleQ, DoubleQ, TanhMLPPolicy
+from pql_b200.models.mlp import HIDDEN, NetLayout
+
+
+@pytest.mark.parametrize("in_dim,out_dim,n_nets,n_params", [(104, 1, 2, 436_226), (88, 16, 1, 211_856),
+                                                            (231, 1, 2, 566_274), (211, 20, 1, 275_348),
+                                                            (104, 51, 2, 449_126)])
+def test_arena_layout_matches_reference_parameter_counts(in_dim, out_dim, n_nets, n_params):
+    """Parameter counts of SURVEY §8(a8-a11); every tensor starts on a 32-word (128-byte) boundary,
+    weight rows are padded to a multiple of 4 words (16-byte TMA rows), tensors do not overlap."""
+    L = NetLayout(in_dim, out_dim, n_nets)
+    assert L.n_params() == n_params
+    spans = sorted((off, off + cnt) for _, _, _, off, cnt in L.tensors())
+    assert all(off % 32 == 0 for off, _ in spans)
+    assert all(a_end <= b_off for (_, a_end), (b_off, _) in zip(spans, spans[1:]))
+    assert spans[-1][1] <= L.total and L.total % 32 == 0
+    assert all(ld % 4 == 0 and ld >= d for ld, d in zip(L.ldw, L.dims[:-1]))
+
+
+def test_module_parameters_are_views_of_the_arena():
+    for m in (DoubleQ(9, 3), TanhMLPPolicy(9, 3), DistributionalDoubleQ(9, 3, device="cpu")):
+        flat = m.arena.flat
+        lo, hi = flat.data_ptr(), flat.data_ptr() + 4 * flat.numel()
+        assert all(lo <= p.data_ptr() < hi for p in m.parameters())
+        n = sum(p.numel() for p in m.parameters())
+        assert n == m._layout.n_params()
+        with torch.no_grad():
+            next(m.parameters()).fill_(7.0)
+        assert (flat == 7.0).sum() == next(m.parameters()).numel()
+
+
+@pytest.mark.parametrize("M,N,B,groups", [(128, 256, 8192, 2), (256, 512, 8192, 2), (512, 104, 8192, 2), (51, 128, 16384, 2),
+                                          (16, 128, 8192, 1), (512, 231, 8192, 2), (128, 256, 200, 1)])
+def test_wgrad_tiling_invariants(M, N, B, groups):
+    tile_n, splits = K.wgrad_tiling(M, N, B, groups)
+    kb = (B + 31) // 32
+    assert tile_n in (16, 32, 64, 128, 256) and splits >= 1 and kb % splits == 0
+    c = K.wgrad_cluster(splits, tile_n)
+    assert c in (1, 2, 4, 8) and splits % c == 0 and c <= max(1, K.WGRAD_CLUSTER)
+
+
+def test_bench_flop_model_matches_survey():
+    """bench.py's algorithmic FLOP constants against the layer shapes (3 684 352 FLOP per
+    sample and critic update, 2 913 280 per actor update, AllegroHand)."""
+    import bench
+    O, A = bench.O, bench.A
+    h1, h2, h3 = HIDDEN
+    actor_fwd = O * h1 + h1 * h2 + h2 * h3 + h3 * A
+    critic_fwd = (O + A) * h1 + h1 * h2 + h2 * h3 + h3
+    critic_wgrad_dgrad = critic_fwd + (h1 * h2 + h2 * h3 + h3)        # wgrad of all layers + dgrad without layer 1
+    assert 2 * (actor_fwd + 4 * critic_fwd + 2 * critic_wgrad_dgrad) == bench.FLOP_V
+    assert bench.MAC_ACTOR_FWD == actor_fwd and bench.MAC_CRITIC_FWD == critic_fwd
+    critic_dgrad_all = critic_fwd                                       # dgrad through every layer of the frozen critic
+    actor_bwd = actor_fwd + (h1 * h2 + h2 * h3 + h3 * A)
+    assert 2 * (actor_fwd + 2 * critic_fwd + 2 * critic_dgrad_all + actor_bwd) == bench.FLOP_P
+    assert bench.BYTES_INSERT == 4 * (2 * O + A + 2) + 4 * (2 * O + A + 1) + 1
+    assert bench.BYTES_SAMPLE == 8 + (4 * (2 * O + A + 1) + 1) + 4 * (2 * O + A + 2)

@@ -167,3 +167,18 @@ def test_actor_oracle_vs_reference(golden_dir, noise_type):
     for j, T in enumerate(c["calls"]):
         check(f"call{j}", act.explore_env(T, random=False))
     assert (g["call5_len_window"] > 0).sum() >= 3          # the script does finish episodes
+
+
+def test_noise_schedules_match_reference(golden_dir):
+    """pql_b200.utils.{LinearSchedule, ExponentialSchedule} against value sequences recorded from
+    pql/utils/schedule_util.py (host-side scalars: exact equality)."""
+    from pql_b200.utils.schedule_util import ExponentialSchedule, LinearSchedule
+    g = json.load(open(os.path.join(golden_dir, "schedules.json")))
+    cases = {"linear_0.8_0.05_7": LinearSchedule(0.8, 0.05, 7), "linear_1_0_3": LinearSchedule(1.0, 0.0, 3),
+             "exp_0.8_0.9_0.05": ExponentialSchedule(0.8, 0.9, 0.05), "exp_0.5_0.5_none": ExponentialSchedule(0.5, 0.5)}
+    for name, sch in cases.items():
+        vals = [sch.val()]
+        for _ in range(40):
+            vals.append(sch.step())
+            vals.append(sch.val())
+        assert vals == g[name], name
