@@ -524,7 +524,7 @@ def _finish_plan(plan, opt, p_flat, t_flat, p_tf, t_tf):
     tau = getattr(plan, "tau", 0.0)
     plan.adam_scalars = torch.zeros(16, device=plan.device)
     # reduction + loss sum + AdamW bias corrections in one launch; clip + AdamW (+ Polyak) + step
-    # count in the second (pqlb_sum_partials and the per-block pow() are gone from the update)
+    # count in the second
     plan.reduce_call = K.Call("pqlb_grad_reduce_finish", _lib.ptr(opt.seg_table), opt.n_seg, _lib.ptr(big), _lib.ptr(opt.grad),
                               _lib.ptr(opt.sumsq), _lib.ptr(plan.loss_part), plan.n_loss_part, plan.loss_scale,
                               _lib.ptr(plan.loss), _lib.ptr(opt.count), _lib.ptr(plan.loss_ring), plan.loss_ring.numel(),

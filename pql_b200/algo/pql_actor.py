@@ -15,7 +15,6 @@ pqlb_actor_inputs from this actor's ``generator`` (seed, offset) - bit-identical
 with that generator (csrc/rng.cuh).  The warm-up's uniform random actions (``random=True``,
 pql_actor.py:101-103) are a ``torch.rand`` draw: once per run, not on the hot path.
 """
-import numpy as np
 import torch
 
 from .. import _kernels as K

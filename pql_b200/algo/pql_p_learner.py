@@ -1,8 +1,9 @@
 """P-learner (policy update) entry points: drop-in for pql/algo/pql_p_learner.py:16-96.
 
 Owns the actor, its AdamW state and the observation-only ring (``memory``, ``next_p``,
-``if_full``, ``cur_capacity`` as in the reference); ``learn()`` is torch.randint followed by a fixed
-list of sm_100a kernel launches (DPG through the frozen critic)."""
+``if_full``, ``cur_capacity`` as in the reference); ``learn()`` is a fixed list of sm_100a kernel
+launches (DPG through the frozen critic) whose first kernel also draws the reference's
+torch.randint indices from this learner's generator state (``cfg.fused_rng = False``: torch.randint)."""
 import os
 
 import torch

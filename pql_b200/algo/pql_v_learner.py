@@ -2,8 +2,10 @@
 
 Same constructor, ``start()``, ``learn()``, ``update(actor, trajectory, normalize_tuple, sleep_time)``
 and the same attributes (critic, critic_target weights, memory, loss_tracker, update_count).
-``learn()`` is: torch.randint (the reference's index stream), torch.normal (its noise stream),
-then a fixed list of sm_100a kernel launches (pql_b200/algo/_engine.py).  The reference's
+``learn()`` is a fixed list of sm_100a kernel launches (pql_b200/algo/_engine.py), replayed from a CUDA
+graph; the reference's two random draws per update (torch.randint for the indices, torch.normal for
+the target-policy noise) are made inside the gather kernel from this learner's generator state, bit
+for bit what torch returns for it (``cfg.fused_rng = False``: the torch calls themselves).  The reference's
 ``@ray.remote`` decoration is the caller's business: these are plain classes,
 one process per GPU.
 """

@@ -36,10 +36,10 @@ class Tracker:
 
 class DeviceTracker:
     """Tracker whose window lives on the GPU: the last kernel of every update writes its loss into
-    ``window[update_index % max_len]`` (pqlb_sum_partials) instead of the reference's
-    ``loss.item()`` host sync after every update (pql_v_learner.py:111); ``mean()`` - called once
-    per env step from ``update()`` - is the only synchronisation point.  Same
-    pre-filled-with-zeros window semantics as Tracker."""
+    ``window[update_index % max_len]`` (pqlb_grad_reduce_finish) instead of the reference's
+    ``loss.item()`` host sync after every update (pql_v_learner.py:111).  ``mean()`` reads the window
+    (a host synchronisation); ``mean_lagged()`` - what ``update()`` uses once per env step unless
+    ``cfg.sync_loss`` - does not block.  Same pre-filled-with-zeros window semantics as Tracker."""
 
     def __init__(self, max_len, device):
         self.max_len = max_len
