@@ -55,3 +55,38 @@ def test_no_cpu_path():
     with pytest.raises(RuntimeError):
         NStepReplay(4, 2, num_envs=2, device="cpu")
     assert not torch.cuda.is_available() or True
+
+
+def test_ctypes_structs_match_the_header(tmp_path):
+    """The descriptor structs of include/pqlb200.h and their ctypes mirrors in pql_b200/_lib.py must agree
+    in size and field offsets (a silent mismatch would hand the kernels garbage pointers)."""
+    import ctypes as C
+    import shutil
+    import subprocess
+    cxx = shutil.which("g++") or shutil.which("gcc")
+    if cxx is None:
+        pytest.skip("no host compiler")
+    probes = {"pqlb_gemm_desc": (_lib.GemmDesc, ["M", "tile_n", "splits", "cluster", "noise_bound", "g"]),
+              "pqlb_gemm_group": (_lib.GemmGroup, ["a", "a2", "bias", "q", "out2", "split_stride"]),
+              "pqlb_mlp_desc": (_lib.MlpDesc, ["M", "n_groups", "g"]),
+              "pqlb_mlp_group": (_lib.MlpGroup, ["x", "w2", "q", "h3", "act_w", "act_ldo", "noise_std", "act_n"]),
+              "pqlb_mlp_bwd_desc": (_lib.MlpBwdDesc, ["M", "g"]),
+              "pqlb_colsum_desc": (_lib.ColsumDesc, ["n", "rows", "dz", "ld", "n_cols", "part"]),
+              "pqlb_dp_desc": (_lib.DpDesc, ["grad_peers", "red_peers", "ctl_peers", "local", "rank", "world", "grid"])}
+    lines = ['#include "pqlb200.h"', "#include <cstdio>", "#include <cstddef>", "int main() {"]
+    for cname, (_, fields) in probes.items():
+        lines.append(f'  printf("{cname} %zu", sizeof({cname}));')
+        for f in fields:
+            lines.append(f'  printf(" %zu", offsetof({cname}, {f}));')
+        lines.append('  printf("\\n");')
+    lines.append("  return 0; }")
+    src = tmp_path / "layout.cpp"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.run([cxx, "-x", "c++", "-I", os.path.join(entry.ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.strip().splitlines()
+    for line in out:
+        name, size, *offs = line.split()
+        ctype, fields = probes[name]
+        assert C.sizeof(ctype) == int(size), name
+        assert [getattr(ctype, f).offset for f in fields] == [int(o) for o in offs], name
