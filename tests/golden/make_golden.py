@@ -268,7 +268,7 @@ def actor_small():
     import pql.algo.pql_actor as ACT
     from pql.models.mlp import TanhMLPPolicy
     ACT.torch = _TorchCPU()
-    for noise_type in ("mixed", "fixed"):
+    for noise_type, obs_norm, timeout in (("mixed", True, True), ("fixed", True, True), ("mixed", False, False)):
         c = inputs.ACTOR_CASE
         E, O, A = c["E"], c["O"], c["A"]
         env = inputs.ScriptedEnv(c["seed"], E, O, A, c["warm_up"] + sum(c["calls"]))
@@ -277,6 +277,7 @@ def actor_small():
         cfg.algo.tracker_len = c["tracker_len"]
         cfg.algo.reward_scale = 0.01
         cfg.algo.noise.type = noise_type
+        cfg.algo.obs_norm, cfg.algo.handle_timeout = obs_norm, timeout
         actor = ACT.PQLActor(env, cfg)
         pol = TanhMLPPolicy(O, A)
         load_mlp(pol, inputs.actor_case_params(c["seed"], O, A))
@@ -291,9 +292,10 @@ def actor_small():
             for name, x in zip(("obs", "act", "rew", "next", "done"), v_data):
                 rec[f"{tag}_{name}"] = x.float().numpy()
             rec[f"{tag}_steps"] = np.array(steps)
-            rec[f"{tag}_rms_mean"] = actor.obs_rms.mean.numpy().copy()
-            rec[f"{tag}_rms_var"] = actor.obs_rms.var.numpy().copy()
-            rec[f"{tag}_rms_count"] = np.array(actor.obs_rms.count, dtype=np.float64)
+            if actor.obs_rms is not None:
+                rec[f"{tag}_rms_mean"] = actor.obs_rms.mean.numpy().copy()
+                rec[f"{tag}_rms_var"] = actor.obs_rms.var.numpy().copy()
+                rec[f"{tag}_rms_count"] = np.array(actor.obs_rms.count, dtype=np.float64)
             rec[f"{tag}_ret_window"] = np.array(list(actor.return_tracker.moving_average), dtype=np.float64)
             rec[f"{tag}_len_window"] = np.array(list(actor.step_tracker.moving_average), dtype=np.float64)
             rec[f"{tag}_returns"] = actor.current_returns.numpy().copy()
@@ -302,7 +304,8 @@ def actor_small():
         record("warm", actor.explore_env(env, c["warm_up"], random=True))
         for j, T in enumerate(c["calls"]):
             record(f"call{j}", actor.explore_env(env, T, random=False))
-        np.savez(os.path.join(HERE, f"actor_small_{noise_type}.npz"), **rec)
+        tag = noise_type if obs_norm else f"{noise_type}_raw"       # _raw: no normaliser, no timeout handling
+        np.savez(os.path.join(HERE, f"actor_small_{tag}.npz"), **rec)
 
 
 def schedules():

@@ -129,19 +129,20 @@ def test_learner_oracle_vs_reference(golden_dir, tag, seed, B, O, A, distl, step
         np.testing.assert_allclose(_digest(t), g[f"actor.{name}"], rtol=2e-5, atol=2e-6, err_msg=name)
 
 
-@pytest.mark.parametrize("noise_type", ["mixed", "fixed"])
-def test_actor_oracle_vs_reference(golden_dir, noise_type):
+@pytest.mark.parametrize("noise_type,plain", [("mixed", False), ("fixed", False), ("mixed", True)])
+def test_actor_oracle_vs_reference(golden_dir, noise_type, plain):
     """oracle.actor (RunningMeanStd, exploration noise, trackers, timeout handling, n-step hand-off)
     against the unmodified PQLActor run on the scripted env (tests/golden/make_golden.py::actor_small).
     Same torch CPU seed => same draws; everything else is fp32 arithmetic in the same order."""
     from oracle.actor import ActorOracle
-    g = np.load(os.path.join(golden_dir, f"actor_small_{noise_type}.npz"))
+    # plain: cfg.algo.obs_norm = False and handle_timeout = False (fixture actor_small_mixed_raw.npz)
+    g = np.load(os.path.join(golden_dir, f"actor_small_{noise_type}{'_raw' if plain else ''}.npz"))
     c = inputs.ACTOR_CASE
     E, O, A = c["E"], c["O"], c["A"]
     env = inputs.ScriptedEnv(c["seed"], E, O, A, c["warm_up"] + sum(c["calls"]))
     torch.manual_seed(c["seed"])
     act = ActorOracle(env, E, O, A, inputs.actor_case_params(c["seed"], O, A), nstep=c["nstep"], noise_type=noise_type,
-                      reward_scale=0.01, tracker_len=c["tracker_len"])
+                      reward_scale=0.01, tracker_len=c["tracker_len"], obs_norm=not plain, do_handle_timeout=not plain)
     act.reset_agent()
 
     def check(tag, res):
@@ -153,9 +154,10 @@ def test_actor_oracle_vs_reference(golden_dir, noise_type):
         # actions / rewards pass through the policy MLP: MKL-vs-oracle matmul association only
         np.testing.assert_allclose(v_data[1].numpy(), g[f"{tag}_act"], rtol=0, atol=2e-6)
         np.testing.assert_allclose(v_data[2].numpy(), g[f"{tag}_rew"], rtol=0, atol=1e-7)
-        np.testing.assert_array_equal(act.obs_rms.mean.numpy(), g[f"{tag}_rms_mean"])
-        np.testing.assert_array_equal(act.obs_rms.var.numpy(), g[f"{tag}_rms_var"])
-        assert act.obs_rms.count == float(g[f"{tag}_rms_count"])
+        if not plain:
+            np.testing.assert_array_equal(act.obs_rms.mean.numpy(), g[f"{tag}_rms_mean"])
+            np.testing.assert_array_equal(act.obs_rms.var.numpy(), g[f"{tag}_rms_var"])
+            assert act.obs_rms.count == float(g[f"{tag}_rms_count"])
         np.testing.assert_allclose(np.array(list(act.return_tracker.moving_average), dtype=np.float64),
                                    g[f"{tag}_ret_window"], rtol=0, atol=1e-5)
         np.testing.assert_array_equal(np.array(list(act.step_tracker.moving_average), dtype=np.float64),
