@@ -24,6 +24,11 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+if "reference" in sys.argv:
+    # torch.distributed.run exports OMP_NUM_THREADS=1 to its workers: the CPU arm must use every host
+    # core regardless (round-1 VERDICT: the N > 1 reference lines ran single-threaded)
+    for _k in ("OMP_NUM_THREADS", "MKL_NUM_THREADS"):
+        os.environ[_k] = str(os.cpu_count() or 1)
 
 import numpy as np  # noqa: E402
 import torch  # noqa: E402
@@ -111,22 +116,25 @@ class ClockSampler:
 
 def cpu_reference_rate(seconds_budget=20.0, threads=None):
     """The reference's CPU torch path (oracle restatement, every host thread) on a bounded sample:
-    a few full-size updates (batch 8192, AllegroHand shape) at the 8 V : 4 P : 1 insert ratio."""
+    a few full-size updates (batch 8192, AllegroHand shape) at the 8 V : 4 P : 1 insert ratio, sampling
+    from a full 1M-slot ring like the GPU arm."""
     from oracle import learner as L
     from oracle import replay as R
-    if threads:
-        torch.set_num_threads(threads)
+    torch.set_num_threads(int(threads or os.cpu_count() or 1))
     g = torch.Generator().manual_seed(0)
     q1, q2 = L.init_mlp(O + A, 1, g), L.init_mlp(O + A, 1, g)
     actor = L.init_mlp(O, A, g)
     v, p = L.VLearnerOracle(q1, q2), L.PLearnerOracle(actor)
     rs = np.random.RandomState(0)
-    cap = 100_000
+    cap = CAP
     ring = R.RingOracle(cap, O, A)
     ns = R.NStepOracle(O, A, E, NSTEP, 0.99)
     ring.insert(*ns.push(*synth_block(rs, 8)))
     norm = (torch.zeros(O), torch.ones(O), 1e-4)
     blocks = [synth_block(rs) for _ in range(4)]
+    fill = ns.push(*synth_block(rs, 16))             # 16 * E rows per insert until every slot is live
+    while not ring.if_full:
+        ring.insert(*fill)
     t_ins = t_v = t_p = 0.0
     n_steps = 0
     t_start = time.perf_counter()
@@ -150,9 +158,61 @@ def cpu_reference_rate(seconds_budget=20.0, threads=None):
     total = t_ins + t_v + t_p
     return dict(value=V_PER_STEP * n_steps / total, unit="critic updates/s", cores=torch.get_num_threads(), kind="port",
                 sample=f"{n_steps} steps of (1 insert of {E} rows + {V_PER_STEP} critic + {P_PER_STEP} actor updates, batch {B}) "
-                       f"through oracle/ (torch-CPU fp32 restatement of the reference path, 100k-slot ring)",
+                       f"through oracle/ (torch-CPU fp32 restatement of the reference path; full {cap}-slot numpy ring, "
+                       f"numpy RandomState indices, {torch.get_num_threads()} torch threads)",
+                ring_slots=cap, index_source="numpy RandomState.randint", torch_threads=torch.get_num_threads(),
+                host_cpus=os.cpu_count(),
                 ms_per_step=1e3 * total / n_steps, ms_per_critic_update=1e3 * t_v / (n_steps * V_PER_STEP),
                 ms_per_actor_update=1e3 * t_p / (n_steps * P_PER_STEP), ms_per_insert=1e3 * t_ins / n_steps)
+
+
+def cuda_eager_rate(dev, seconds_budget=6.0):
+    """the reference's own arithmetic as eager PyTorch on the same B200 - the oracle
+    learners with every tensor on ``dev``, fp32 SGEMM (allow_tf32 off, as the reference never enables
+    it), torch.randint / torch.normal draws on the device, five index gathers per sample, five slice
+    copies per insert and the reference's one host sync per update (``loss.item()``,
+    pql_v_learner.py:111).  Baseline leg only: nothing of this is on the product path."""
+    from oracle import learner as L
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    g = torch.Generator().manual_seed(0)
+    mv = lambda ps: [(w.to(dev), b.to(dev)) for w, b in ps]          # noqa: E731
+    q1, q2, actor = mv(L.init_mlp(O + A, 1, g)), mv(L.init_mlp(O + A, 1, g)), mv(L.init_mlp(O, A, g))
+    v, p = L.VLearnerOracle(q1, q2), L.PLearnerOracle(actor)
+    gen = torch.Generator(device=dev).manual_seed(0)
+    widths = (O, A, 1, O, 1)
+    ring = [torch.randn(CAP, w, device=dev, generator=gen) * (0.01 if i == 2 else 1.0) for i, w in enumerate(widths)]
+    ring[4] = (torch.rand(CAP, 1, device=dev, generator=gen) < 0.01).float()
+    rows = [torch.randn(E, w, device=dev, generator=gen) for w in widths]
+    norm = (torch.zeros(O, device=dev), torch.ones(O, device=dev), 1e-4)
+
+    def step(k):
+        p0 = (k * E) % (CAP - E)
+        for buf, x in zip(ring, rows):                                   # simple_replay.py:40-83
+            buf[p0:p0 + E] = x
+        for j in range(V_PER_STEP):
+            idx = torch.randint(CAP, (B,), device=dev)                   # simple_replay.py:87
+            batch = tuple(buf[idx] for buf in ring)
+            noise = torch.normal(torch.zeros(B, A, device=dev), torch.full((B, A), 0.8, device=dev))
+            v.learn(batch, noise, actor, norm)                           # ends with float(loss): the reference's .item()
+            if (j + 1) % (V_PER_STEP // P_PER_STEP) == 0:
+                idx = torch.randint(CAP, (B,), device=dev)
+                p.learn(ring[0][idx], v.q1, v.q2, norm)
+    for k in range(3):
+        step(k)
+    torch.cuda.synchronize(dev)
+    n, t0 = 0, time.perf_counter()
+    while True:
+        step(3 + n)
+        n += 1
+        torch.cuda.synchronize(dev)
+        if time.perf_counter() - t0 > seconds_budget or n >= 200:
+            break
+    dt = time.perf_counter() - t0
+    return {"value": V_PER_STEP * n / dt, "unit": "critic updates/s", "ms_per_step": 1e3 * dt / n, "steps": n,
+            "kind": "oracle/ learners as eager PyTorch on the same GPU: fp32 SGEMM (allow_tf32 = False), device-side "
+                    "torch.randint / torch.normal, index gathers from five column tensors, one host sync per update",
+            "torch": torch.__version__}
 
 
 def config_dict(n_gpus, dp="fused"):
@@ -172,6 +232,19 @@ def config_dict(n_gpus, dp="fused"):
                      "step's own working set and are not flushed"}
 
 
+def reference_config(r):
+    """What the CPU arm actually runs (same workload and step definition as the B200 arm)."""
+    return {"workload": "configs[1]: DoubleQ V-learner + P-learner, AllegroHand shape (obs 88, act 16), batch 8192, "
+                        "1M-slot replay, n-step 3, 4096-env synthetic insert stream, Polyak target update",
+            "step": f"1 n-step push + ring insert of {E} transitions, {V_PER_STEP} critic updates, {P_PER_STEP} actor updates",
+            "critic_updates_per_step": V_PER_STEP, "actor_updates_per_step": P_PER_STEP, "batch": B, "num_envs": E,
+            "replay_slots": r["ring_slots"], "parallelism": "one process, all host threads (no GPU, no data parallelism)",
+            "implementation": "oracle/ : torch-CPU fp32 restatement of pql_v_learner.py:73-133 / pql_p_learner.py:47-96 / "
+                              "simple_replay.py / nstep_replay.py (the reference itself needs Ray/Hydra/gym and cannot travel)",
+            "index_source": r["index_source"], "torch_threads": r["torch_threads"], "host_cpus": r["host_cpus"],
+            "sample": r["sample"]}
+
+
 def run_reference(args, rank):
     if rank != 0:
         return
@@ -179,9 +252,10 @@ def run_reference(args, rank):
     line = {"metric": "critic updates/s (batch 8192)", "value": r["value"], "unit": "critic updates/s", "impl": "reference",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"],
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": config_dict(args.gpus, args.dp), "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "config": reference_config(r), "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": r["value"], "unit": "critic updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "gpu_launches": 0}
+            "ms_per_critic_update": r["ms_per_critic_update"], "ms_per_actor_update": r["ms_per_actor_update"],
+            "ms_per_insert": r["ms_per_insert"], "gpu_launches": 0}
     print(json.dumps(line), flush=True)
 
 
@@ -192,6 +266,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-sub", action="store_true", help="skip the configs[2] / configs[3] sub-records and the eager-CUDA leg")
+    ap.add_argument("--repeats", type=int, default=5, help="timed blocks of --steps steps each; value = the median block")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--one-stream", action="store_true", help="both learners on the caller's stream (no overlap)")
     ap.add_argument("--dp", default="fused", choices=["fused", "nccl", "nccl-graph"],
@@ -214,9 +290,8 @@ def main():
     import torch.distributed as dist
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        # keep stdout to the one JSON line: NCCL's own messages (the version banner at WARN) go to stderr
-        os.environ["NCCL_DEBUG"] = os.environ.get("PQLB_NCCL_DEBUG", "WARN")
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        # stdout carries the one JSON line; NCCL_DEBUG is whatever the launcher set (never overridden)
+        os.environ.setdefault("NCCL_DEBUG", "WARN")
         dist.init_process_group("nccl", device_id=dev)
         dist.barrier()
     from pql_b200 import _kernels as K
@@ -236,11 +311,8 @@ def main():
     # a CUDA graph must not share NCCL's per-communicator ordering with the other learner's
     pg_v = dist.new_group(list(range(world))) if world > 1 else None
     pg_p = dist.new_group(list(range(world))) if world > 1 else None
-    v = PQLVLearner(O, A, cfg, process_group=pg_v)
+    v = PQLVLearner(O, A, cfg, process_group=pg_v)      # the constructors broadcast rank 0's initial weights
     p = PQLPLearner(O, A, cfg, process_group=pg_p)
-    if world > 1:      # identical initial weights on every rank
-        dist.broadcast(v.critic.arena.flat, 0)
-        dist.broadcast(p.actor.arena.flat, 0)
     ns = NStepReplay(O, A, num_envs=E, nstep=NSTEP, device=dev, gamma=0.99)
     rs = np.random.RandomState(42 + rank)
     host_blocks = [tuple(torch.from_numpy(x).pin_memory() for x in synth_block(rs)) for _ in range(N_BLOCKS)]
@@ -248,6 +320,12 @@ def main():
     h2d_bytes = sum(x.numel() * 4 for x in host_blocks[0])
     all_obs = torch.cat([b[0].reshape(-1, O) for b in host_blocks])
     norm = (all_obs.mean(0).to(dev), all_obs.var(0).to(dev), 1e-4)      # RunningMeanStd.get_states stand-in
+    if world > 1:
+        # one normaliser for the whole job: the per-rank (mean, var, count) merged with the
+        # reference's parallel-variance formula (torch_util.py:91-103) - pql_b200.algo._dp.merge_moments
+        from pql_b200.algo._dp import merge_moments
+        m, var_, _ = merge_moments(norm[0], norm[1], float(all_obs.shape[0]))
+        norm = (m, var_, 1e-4)
 
     # warm-up block of 32 steps (train_pql.py:58) then fill the ring so that sampling spans all 800 MB
     warm = tuple(torch.from_numpy(x).to(dev) for x in synth_block(rs, 32))
@@ -318,12 +396,38 @@ def main():
     def n_launches():      # C-ABI launches + the kernels replayed from the learners' CUDA graphs
         return _lib.launch_count() + sum(getattr(l._plan, "graph_launches", 0) for l in (v, p) if l._plan is not None)
     launches0 = n_launches()
+    reps = max(1, args.repeats)
+    blocks_ms, blocks_wall = [], []
     with ClockSampler(local) as clk:
-        ms, wall, losses = timed(args.steps, False, args.warmup)
-    launches = n_launches() - launches0
+        for r in range(reps):        # each block: EXACTLY --steps steps between barrier + synchronize, max over ranks
+            ms_r, wall_r, losses = timed(args.steps, False, args.warmup + r * args.steps)
+            blocks_ms.append(ms_r); blocks_wall.append(wall_r)
+    launches = (n_launches() - launches0) // reps
     clocks = clk.summary()
+    order = sorted(range(reps), key=lambda i: blocks_ms[i])
+    ms, wall = blocks_ms[order[reps // 2]], blocks_wall[order[reps // 2]]       # the median block is the reported one
     timed(2, True, 0)
-    ms_e2e, wall_e2e, _ = timed(args.steps, True, args.warmup)
+    e2e_blocks = [timed(args.steps, True, args.warmup + r * args.steps)[0] for r in range(min(reps, 3))]
+    ms_e2e = sorted(e2e_blocks)[len(e2e_blocks) // 2]
+    # like-for-like with the reference's blocking loss read: update() waits for the learner's stream
+    # and returns the current loss mean (cfg.sync_loss = True) instead of the previous step's
+    v._sync_loss = p._sync_loss = True
+    timed(2, False, 0)
+    sync_blocks = [timed(args.steps, False, args.warmup + r * args.steps)[0] for r in range(min(reps, 3))]
+    ms_sync = sorted(sync_blocks)[len(sync_blocks) // 2]
+    v._sync_loss = p._sync_loss = False
+    # data parallel: every rank must hold bit-identical parameters after the run (checked on the device)
+    sync_check = None
+    if world > 1:
+        from pql_b200.algo import _dp
+        torch.cuda.synchronize(dev)
+        ok_c = _dp.params_in_sync(v.critic.arena.flat); ok_a = _dp.params_in_sync(p.actor.arena.flat)
+        ok_t = _dp.params_in_sync(v._plan.t_flat)
+        sync_check = {"critic": ok_c, "actor": ok_a, "critic_target": ok_t,
+                      "critic_checksum": int(v.critic.arena.flat.view(torch.int32).to(torch.int64).sum().item()),
+                      "actor_checksum": int(p.actor.arena.flat.view(torch.int32).to(torch.int64).sum().item()),
+                      "updates": int(v._plan.opt.step)}
+        assert ok_c and ok_a and ok_t, f"data-parallel replicas diverged: {sync_check}"
 
     # ---- per-kernel device time over the same super-step (CUDA events around every launch)
     K.PROFILE = {}
@@ -355,21 +459,31 @@ def main():
                 torch.randn(big_n, 1, device=dev, generator=gen), torch.randn(big_n, O, device=dev, generator=gen),
                 torch.zeros(big_n, 1, device=dev))
     mem = v.memory
-    idx1 = torch.randint(CAP, (B,), device=dev)
-    idx8 = torch.randint(CAP, (8 * B,), device=dev)
-    out1 = mem.gather(idx1); out8 = mem.gather(idx8)
+    idx1s = [torch.randint(CAP, (B,), device=dev) for _ in range(8)]         # fresh indices every call
+    idx8s = [torch.randint(CAP, (8 * B,), device=dev) for _ in range(8)]
+    out1 = mem.gather(idx1s[0]); out8 = mem.gather(idx8s[0])
+    turn = {"i": 0}
+
+    def next_idx(pool):
+        turn["i"] += 1
+        return pool[turn["i"] % len(pool)]
+
+    walk = {"p": 12345}
 
     def raw_insert(rows):
+        # consecutive calls land on consecutive slot ranges and walk the whole 1 GB ring, like the real
+        # insert stream: nothing is re-written while it is still in L2
         n = rows[0].shape[0]
-        _lib.call("pqlb_ring_insert", _lib.ptr(mem.ring), CAP, O, A, *(_lib.ptr(x) for x in rows), n, 12345)
+        _lib.call("pqlb_ring_insert", _lib.ptr(mem.ring), CAP, O, A, *(_lib.ptr(x) for x in rows), n, walk["p"])
+        walk["p"] = (walk["p"] + n) % (CAP - n)
 
     def raw_gather(idx, out):
         _lib.call("pqlb_sample_gather", _lib.ptr(mem.ring), CAP, O, A, _lib.ptr(idx), idx.numel(), *(_lib.ptr(x) for x in out))
     replay = {}
     for name, fn, units, per in (("insert_4096", lambda: raw_insert(rows1), E, BYTES_INSERT),
                                  ("insert_122880", lambda: raw_insert(rows_big), big_n, BYTES_INSERT),
-                                 ("sample_8192", lambda: raw_gather(idx1, out1), B, BYTES_SAMPLE),
-                                 ("sample_65536", lambda: raw_gather(idx8, out8), 8 * B, BYTES_SAMPLE)):
+                                 ("sample_8192", lambda: raw_gather(next_idx(idx1s), out1), B, BYTES_SAMPLE),
+                                 ("sample_65536", lambda: raw_gather(next_idx(idx8s), out8), 8 * B, BYTES_SAMPLE)):
         t_ms = ev_time(fn, 200 if units <= 8 * B else 50)
         replay[name] = {"us": round(t_ms * 1e3, 2), "gbs": round(units * per / (t_ms * 1e-3) / 1e9, 1)}
 
@@ -386,6 +500,13 @@ def main():
             sys.stdout.flush(); sys.stderr.flush()
             os._exit(0)
 
+    # ---- tcgen05 issue throughput with all SMs busy and resident operands (csrc/peak.cu): the roofline denominator
+    def mma_peak(kind, n, iters=4000):
+        t_ms = ev_time(lambda: _lib.call("pqlb_mma_peak", kind, n, iters), 5)
+        return 148 * iters * 4 * 2.0 * 128 * n * (8 if kind == 0 else 16) / (t_ms * 1e-3) / 1e12
+    mma_peaks = {"tf32_m128_n256": mma_peak(0, 256), "tf32_m128_n128": mma_peak(0, 128),
+                 "f16_m128_n256": mma_peak(1, 256), "f16_m128_n128": mma_peak(1, 128)}
+
     dp_phases = None
     if world > 1 and v._plan.dp is not None:
         dp_phases = {name: dict(zip(("exchanges", "mean_ns"), l._plan.dp.phase_ns())) for name, l in (("critic", v), ("actor", p))}
@@ -400,7 +521,9 @@ def main():
     except OSError:
         pass
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
-    tf32_peak = peaks.get("bf16_tflops_sustained", 1400.0) / 2.0
+    # TF32 dense peak: the larger of half the BURST cuBLAS bf16 figure (the bench runs at the maximum SM
+    # clock, the sustained figure was taken at 1282 MHz) and this run's own tcgen05 kind::tf32 issue rate
+    tf32_peak = max(peaks.get("bf16_tflops", 1675.7) / 2.0, mma_peaks["tf32_m128_n256"])
     peak_src = "measured (MEASURED_PEAKS.json)" if peaks else "fallback (B200_PROFILING.md)"
     TC_KERNELS = ("pqlb_gemm_tf32", "pqlb_mlp_forward", "pqlb_mlp_backward")      # every tcgen05 launch of the step
     gemm_ms = sum(per_kernel.get(k, 0.0) for k in TC_KERNELS)
@@ -420,6 +543,15 @@ def main():
             "e2e": {"value": e2e, "unit": "critic updates/s", "h2d_bytes_per_step": h2d_bytes,
                     "d2h_bytes_per_step": 2 * 5 * 4, "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": launches,
+            "timing": {"blocks": reps, "steps_per_block": args.steps, "ms_per_step_blocks": [x / args.steps for x in blocks_ms],
+                       "ms_per_step_median": ms / args.steps, "ms_per_step_min": min(blocks_ms) / args.steps,
+                       "value_best_block": world * V_PER_STEP * args.steps / (min(blocks_ms) * 1e-3),
+                       "e2e_ms_per_step_blocks": [x / args.steps for x in e2e_blocks], "reported": "median block"},
+            "sync_loss": {"value": world * V_PER_STEP * args.steps / (ms_sync * 1e-3), "unit": "critic updates/s",
+                          "ms_per_step": ms_sync / args.steps,
+                          "note": "cfg.sync_loss = True: update() blocks on the learner's stream and returns the current loss "
+                                  "mean, as the reference's update() does; the headline uses the non-blocking read-back "
+                                  "(DeviceTracker.mean_lagged: the mean as of the previous env step)"},
             "roofline": {"kernel": "mlp_fwd_kernel (pqlb_mlp_forward: layer-fused Linear+ELU x3 trunk + Q / policy head, "
                                    "tcgen05 kind::tf32) - the dominant kernel, 37 % of the step in the ncu launch list",
                          "bound": "tensor", "achieved": fwd_achieved, "peak": tf32_peak, "unit": "TFLOP/s",
@@ -429,7 +561,9 @@ def main():
                                            "launches, profiles/r1_final_ncu_full_update_kernels.csv",
                          "launches_per_step": n_fwd, "algorithmic_flops_per_launch": fwd_flops_step / max(n_fwd, 1),
                          "us_per_launch": 1e3 * fwd_ms / max(n_fwd, 1), "ms_per_step_in_kernel": fwd_ms,
-                         "peak_source": f"{peak_src}: tf32 dense = 1/2 of the sustained cuBLAS bf16 figure",
+                         "peak_source": f"{peak_src}: max(1/2 of the burst cuBLAS bf16 figure, this run's own tcgen05 "
+                                        f"kind::tf32 issue rate, pqlb_mma_peak)",
+                         "tcgen05_issue_rate_tflops": {k: round(x, 1) for k, x in mma_peaks.items()},
                          "all_tcgen05_kernels": {"kernels": "gemm_tf32_kernel + mlp_fwd_kernel + mlp_bwd_kernel (every dense-layer "
                                                             "launch of the step: forward, dgrad, wgrad, heads)",
                                                  "achieved": achieved, "frac": achieved / tf32_peak, "launches_per_step": n_gemm,
@@ -452,6 +586,28 @@ def main():
             "losses": {"critic": float(losses[0]), "actor": float(losses[1])}}
     if dp_phases is not None:
         line["dp_exchange_phases"] = dp_phases
+    if sync_check is not None:
+        line["params_in_sync"] = sync_check
+    if world == 1 and not args.no_sub:
+        # the other single-GPU configurations of BASELINE.json, measured in the same run through the full
+        # lock-step loop (pql_b200.train.LockStepTrainer on a stub env): sub-records, not the headline
+        del v, p
+        gc.collect(); torch.cuda.empty_cache()
+        from tools.bench_loop import measure_loop
+        subs = {}
+        for name, kw in (("configs[2]_c51_b16384", dict(envs=E, obs=O, act=A, memory=CAP, batch=16384, distl=True, iters=30, warmup=8)),
+                         ("configs[3]_shadowhand_loop", dict(envs=16384, obs=211, act=20, memory=5_000_000, batch=8192, iters=30, warmup=8)),
+                         ("configs[1]_allegro_loop", dict(envs=E, obs=O, act=A, memory=CAP, batch=B, iters=30, warmup=8))):
+            try:
+                subs[name] = measure_loop(**kw)
+            except Exception as e:      # a sub-record must never take the headline down
+                subs[name] = {"error": f"{type(e).__name__}: {e}"}
+            gc.collect(); torch.cuda.empty_cache()
+        line["sub_records"] = subs
+        try:
+            line["cuda_eager_baseline"] = cuda_eager_rate(dev)
+        except Exception as e:
+            line["cuda_eager_baseline"] = {"error": f"{type(e).__name__}: {e}"}
     if not args.no_cpu_baseline and world == 1:
         r = cpu_reference_rate(seconds_budget=15.0)
         line["cpu_baseline"] = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}

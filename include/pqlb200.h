@@ -50,6 +50,11 @@ const char* pqlb_error_string(int code);
 int pqlb_init(void);
 /* Number of CUDA kernels this library has launched so far in this process. */
 uint64_t pqlb_launch_count(void);
+/* Measurement aid (bench.py's tensor-pipe roofline denominator), not on the path:
+ * `iters` groups of four tcgen05.mma (M 128, N `n` = 128 | 256, 32 bytes of K each; kind 0 = tf32,
+ * 1 = f16) on every SM from resident shared-memory operands; time it with CUDA events.
+ * FLOPs per launch = 148 * iters * 4 * 2 * 128 * n * (8 | 16). */
+int pqlb_mma_peak(int kind, int n, int iters, pqlb_stream_t stream);
 /* Geometry helpers (pure host arithmetic). */
 int pqlb_obs_pad(int obs_dim);
 int pqlb_record_ld(int obs_dim, int act_dim);

@@ -78,6 +78,7 @@ _PROTOS = {
     "pqlb_error_string": (C.c_char_p, [_int]),
     "pqlb_launch_count": (C.c_uint64, []),
     "pqlb_init": (_int, []),
+    "pqlb_mma_peak": (_int, [_int, _int, _int, _st]),
     "pqlb_obs_pad": (_int, [_int]),
     "pqlb_record_ld": (_int, [_int, _int]),
     "pqlb_x_ld": (_int, [_int, _int]),

@@ -40,6 +40,31 @@ def params_in_sync(flat_params, group=None, atol=0.0):
     return bool((hi - lo).abs().max().item() <= atol)
 
 
+def merge_moments(mean, var, count, group=None):
+    """One (mean, var, count) for the whole job out of every rank's own: the ranks' statistics are
+    folded in rank order with the reference's parallel-variance update
+    (RunningMeanStd.update_from_moments, pql/utils/torch_util.py:91-103), so every rank ends with the
+    same normaliser.  For statistics that are merged once (checkpoints, static
+    normalisers); the per-env-step path is ``RunningMeanStd(process_group=...)``, which all-reduces
+    the batch sums before the update."""
+    w = world_size(group)
+    if w <= 1:
+        return mean, var, count
+    n = mean.numel()
+    mine = torch.cat([mean.reshape(-1).float(), var.reshape(-1).float(),
+                      torch.tensor([float(count)], dtype=torch.float32, device=mean.device)])
+    parts = [torch.empty_like(mine) for _ in range(w)]
+    dist.all_gather(parts, mine, group=group)
+    m, v, c = parts[0][:n].clone(), parts[0][n:2 * n].clone(), float(parts[0][2 * n])
+    for t in parts[1:]:
+        bm, bv, bc = t[:n], t[n:2 * n], float(t[2 * n])
+        delta = bm - m
+        tot = c + bc
+        m_2 = v * c + bv * bc + delta ** 2 * c * bc / tot
+        m, v, c = m + delta * bc / tot, m_2 / tot, tot
+    return m.reshape(mean.shape), v.reshape(var.shape), c
+
+
 class FusedExchange:
     """Symmetric-memory state of the fused all-reduce + optimiser kernel (pqlb_adamw_polyak_dp): this
     rank's gradient arena, the receive buffer of the reduced gradient and the control block (flags +

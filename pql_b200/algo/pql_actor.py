@@ -24,7 +24,7 @@ from ..replay.nstep_replay import NStepReplay
 from ..utils.common import DeviceTracker
 from ..utils.schedule_util import ExponentialSchedule, LinearSchedule
 from ..utils.torch_util import RunningMeanStd
-from .pql_v_learner import _PRODUCER_STREAM, module_flat
+from .pql_v_learner import _PRODUCER_STREAM, module_flat, note_read
 
 
 class EpisodeTracker(DeviceTracker):
@@ -143,6 +143,7 @@ class PQLActor:
             if src is not None:
                 torch.cuda.current_stream(self.sim_device).wait_stream(src)
             p.a_flat.copy_(module_flat(self._actor, p.La.total, self.sim_device), non_blocking=True)
+            note_read(self._actor)           # the P-learner's next in-place update waits for this copy
             _lib.call("pqlb_round_tf32", _lib.ptr(p.a_flat), _lib.ptr(p.a_tf), p.a_flat.numel())
             self._weights_stale = False
 

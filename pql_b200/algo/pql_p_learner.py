@@ -13,7 +13,7 @@ from ..models import load_class
 from ..utils.common import DeviceTracker
 from . import _dp
 from ._engine import ActorUpdate
-from .pql_v_learner import LearnerStream, make_generator, module_flat
+from .pql_v_learner import LearnerStream, carry_plan_state, make_generator, module_flat, note_read, wait_readers
 
 
 class PQLPLearner:
@@ -61,6 +61,8 @@ class PQLPLearner:
         self._ls = LearnerStream(cfg, self.device)
         self._ls.tag(self.actor)
         self.generator, self.fused_rng = make_generator(cfg, self.device, salt=1)
+        if self.world_size > 1:          # rank 0's initial actor becomes everyone's (see PQLVLearner)
+            _dp.broadcast_(self.actor.arena.flat, 0, process_group)
         self.cur_capacity_dev = torch.zeros(1, dtype=torch.int64, device=self.device)
 
     @property
@@ -77,13 +79,18 @@ class PQLPLearner:
         a = self.cfg.algo
         distl = bool(a.distl)
         eps = 1e-4 if self.normalize_tuple is None else float(self.normalize_tuple[2])
+        old = self._plan
         self._plan = ActorUpdate(self._O, self.action_dim, int(a.batch_size), self.device, self.actor.arena.flat,
                                  distl=distl, num_atoms=a.num_atoms, v_min=a.v_min, v_max=a.v_max, lr=a.actor_lr,
                                  max_grad_norm=a.max_grad_norm,
                                  obs_norm=bool(a.obs_norm) and self.normalize_tuple is not None, eps=eps,
                                  world_size=self.world_size, loss_ring=self.loss_tracker.window,
                                   process_group=self.process_group, dp_fused=self.dp_fused)
+        if old is not None:              # rebuilt launch list, same learner state (see PQLVLearner._build)
+            carry_plan_state(old, self._plan)
         if self.fused_rng and self.memory_size < (1 << 28):
+            if old is not None and old.rng_state is not None:
+                self.generator.set_offset(int(old.rng_state[1].item()) + int(old.rng_state[2].item()) * old.opt.step)
             self._plan.enable_fused_rng(self.generator, draws_per_update=1)      # randint
         self._sample = self._plan.sample_call(self.memory, self.memory_size, self.cur_capacity_dev)
 
@@ -103,6 +110,7 @@ class PQLPLearner:
                                   generator=self.generator)                                          # :49
                 elif self.cur_capacity <= 0:
                     raise RuntimeError("learn(): the observation ring is empty (random_ expects 'from' to be less than 'to')")
+                wait_readers(self.actor, torch.cuda.current_stream(self.device))      # pending copies of the live actor
                 p.run(self._sample, self._allreduce if self.world_size > 1 and p.dp is None else None, self.use_cuda_graph,
                       self.graph_allreduce)
             self.update_count += 1
@@ -136,6 +144,7 @@ class PQLPLearner:
                 if self._plan is None or rebuild:
                     self._build()
                 self._plan.set_critic(module_flat(critic, self._plan.Lc.total, self.device))
+                note_read(critic)
                 self._plan.set_norm(normalize_tuple if self.cfg.algo.obs_norm else None)
                 # cfg.sync_loss: block until this learner's stream has drained and return the current mean;
                 # default: the mean as of the previous update() (non-blocking, DeviceTracker.mean_lagged)

@@ -24,6 +24,27 @@ from ._engine import CriticUpdate
 
 
 _PRODUCER_STREAM = weakref.WeakKeyDictionary()     # module -> the learner stream that writes its weights
+_READ_EVENTS = weakref.WeakKeyDictionary()         # module -> events recorded after other streams' copies of its live arena
+
+
+def note_read(module, stream=None):
+    """A consumer has just enqueued a copy of ``module``'s live arena on ``stream`` (default: the
+    current one).  The reference hands over snapshots (Ray pickles the module at return time,
+    SURVEY App. A 18); here the weights are read in place, so the producer's next in-place write
+    (AdamW in its ``learn()``) must be ordered after this copy: ``wait_readers`` makes it so."""
+    if module is None or _PRODUCER_STREAM.get(module) is None:
+        return
+    ev = torch.cuda.Event()
+    ev.record(stream if stream is not None else torch.cuda.current_stream())
+    _READ_EVENTS.setdefault(module, []).append(ev)
+
+
+def wait_readers(module, stream):
+    """Order ``stream``'s next writes to ``module``'s arena after every pending copy of it."""
+    evs = _READ_EVENTS.pop(module, None) if module is not None else None
+    if evs:
+        for ev in evs:
+            stream.wait_event(ev)
 
 
 class LearnerStream:
@@ -84,7 +105,46 @@ def module_flat(module, layout_total, device):
         if flat.numel() != layout_total:
             raise ValueError("module shape does not match this learner")
         return flat.to(device, non_blocking=True)
-    raise TypeError("expected a pql_b200.models module (load a reference checkpoint with load_state_dict first)")
+    return repack_reference_module(module, layout_total, device)
+
+
+def repack_reference_module(module, layout_total, device):
+    """Flat kernel-layout arena of a *reference* module (pql/models/mlp.py: ``TanhMLPPolicy`` /
+    ``MLPNet`` with ``net.{0,2,4,6}.{weight,bias}``, ``DoubleQ`` / ``DistributionalDoubleQ`` with
+    ``net_q1.net.*`` / ``net_q2.net.*``), read through its ``state_dict`` - what ``update()`` is handed
+    when the caller still constructs the reference's own classes (pql_v_learner.py:117-122)."""
+    from ..models.mlp import HIDDEN, NetLayout, ParamArena
+    if not hasattr(module, "state_dict"):
+        raise TypeError("expected an actor / critic nn.Module")
+    sd = module.state_dict()
+    prefixes = ["net_q1.net.", "net_q2.net."] if any(k.startswith("net_q1.") for k in sd) else ["net."]
+    try:
+        w0 = sd[prefixes[0] + "0.weight"]
+        w_last = sd[prefixes[0] + "6.weight"]
+        hidden = tuple(sd[prefixes[0] + f"{k}.weight"].shape[0] for k in (0, 2, 4))
+    except KeyError as e:
+        raise TypeError(f"module has no reference MLP state_dict keys ({e})") from None
+    if hidden != tuple(HIDDEN):
+        raise NotImplementedError(f"the kernels are specialised to hidden_layers={list(HIDDEN)}, module has {list(hidden)}")
+    layout = NetLayout(w0.shape[1], w_last.shape[0], len(prefixes))
+    if layout.total != layout_total:
+        raise ValueError("module shape does not match this learner")
+    arena = ParamArena(layout, "cpu")
+    for i, pre in enumerate(prefixes):
+        for l, k in enumerate((0, 2, 4, 6)):
+            arena.weight(i, l).copy_(sd[f"{pre}{k}.weight"].detach().float().cpu())
+            arena.bias(i, l).copy_(sd[f"{pre}{k}.bias"].detach().float().cpu())
+    return arena.flat.to(device)
+
+
+def carry_plan_state(old, new):
+    """Optimiser moments, step count and Polyak target of ``old`` into the rebuilt plan ``new``."""
+    new.opt.m.copy_(old.opt.m)
+    new.opt.v.copy_(old.opt.v)
+    new.opt.count.copy_(old.opt.count)
+    if getattr(old, "t_flat", None) is not None and getattr(new, "t_flat", None) is not None and hasattr(new, "tau"):
+        new.t_flat.copy_(old.t_flat)
+        new.round_weights()
 
 
 class PQLVLearner:
@@ -131,6 +191,11 @@ class PQLVLearner:
         self._ls = LearnerStream(cfg, self.device)
         self._ls.tag(self.critic)
         self.generator, self.fused_rng = make_generator(cfg, self.device, salt=0)
+        if self.world_size > 1:
+            # ranks are seeded differently (distinct envs / replay shards), so their default-initialised
+            # critics differ: rank 0's weights become everyone's BEFORE the Polyak target is cloned and the
+            # tensor-core twins are rounded (_build), or the replicas would share gradients but never agree
+            _dp.broadcast_(self.critic.arena.flat, 0, process_group)
 
     @property
     def stream(self):
@@ -149,6 +214,7 @@ class PQLVLearner:
     def _build(self):
         a = self.cfg.algo
         eps = 1e-4 if self.normalize_tuple is None else float(self.normalize_tuple[2])
+        old = self._plan
         self._plan = CriticUpdate(self._obs_dim_int(), self.action_dim, int(a.batch_size), self.device,
                                   self.critic.arena.flat, distl=bool(a.distl), num_atoms=a.num_atoms, v_min=a.v_min,
                                   v_max=a.v_max, gamma_n=a.gamma ** a.nstep, lr=a.critic_lr, tau=a.tau,
@@ -157,7 +223,14 @@ class PQLVLearner:
                                   obs_norm=bool(a.obs_norm) and self.normalize_tuple is not None, eps=eps,
                                   world_size=self.world_size, loss_ring=self.loss_tracker.window,
                                   process_group=self.process_group, dp_fused=self.dp_fused)
+        if old is not None:
+            # normalize_tuple switched between None and a tuple: the launch list is rebuilt, the learner's
+            # state is not - AdamW moments, step count and the Polyak target carry over, and the fused
+            # sampler's stream continues where it was (enable_fused_rng rebases on the restored count)
+            carry_plan_state(old, self._plan)
         if self.fused_rng and self.memory.capacity < (1 << 28):
+            if old is not None and old.rng_state is not None:
+                self.generator.set_offset(int(old.rng_state[1].item()) + int(old.rng_state[2].item()) * old.opt.step)
             self._plan.enable_fused_rng(self.generator, draws_per_update=2)      # randint, then normal
         self._sample = self._plan.sample_call(self.memory.ring, self.memory.capacity, self.memory.cur_capacity_dev)
 
@@ -194,6 +267,7 @@ class PQLVLearner:
                     p.noise.normal_(generator=self.generator)
                 elif self.memory.cur_capacity <= 0:       # what torch.randint(0, ...) raises in the reference
                     raise RuntimeError("learn(): the replay buffer is empty (random_ expects 'from' to be less than 'to')")
+                wait_readers(self.critic, torch.cuda.current_stream(self.device))     # pending copies of the live critic
                 p.run(self._sample, self._allreduce if self.world_size > 1 and p.dp is None else None, self.use_cuda_graph,
                       self.graph_allreduce)
             self.update_count += 1
@@ -212,6 +286,7 @@ class PQLVLearner:
                 if self._plan is None or rebuild:
                     self._build()
                 self._plan.set_actor(module_flat(actor, self._plan.La.total, self.device))
+                note_read(actor)
                 self._plan.set_norm(normalize_tuple if self.cfg.algo.obs_norm else None)
                 # cfg.sync_loss: block until this learner's stream has drained and return the current mean;
                 # default: the mean as of the previous update() (non-blocking, DeviceTracker.mean_lagged)

@@ -43,10 +43,10 @@ class LockStepTrainer:
         """train_pql.py:60-68 / 112-119: hand the new transitions, the other worker's weights and the
         normaliser statistics to both learners; take their current weights and losses back."""
         a = self.actor_worker
-        self.critic, self.critic_loss, self.critic_updates = self.v_learner.update(
-            self.actor, v_data, self._rms(a.v_learner_device), 0)
-        self.actor, self.actor_loss, self.actor_updates = self.p_learner.update(
-            self.critic, p_data, self._rms(a.p_learner_device), 0)
+        rms_v = self._rms(a.v_learner_device)             # one snapshot per env step (get_states clones)
+        rms_p = rms_v if a.p_learner_device == a.v_learner_device else self._rms(a.p_learner_device)
+        self.critic, self.critic_loss, self.critic_updates = self.v_learner.update(self.actor, v_data, rms_v, 0)
+        self.actor, self.actor_loss, self.actor_updates = self.p_learner.update(self.critic, p_data, rms_p, 0)
         a.actor = self.actor
 
     def warm_up(self):

@@ -1,37 +1,6 @@
 """Host-side helpers mirroring pql/utils/common.py for the learner path."""
-from collections import deque
-from collections.abc import Sequence
-
 import numpy as np
 import torch
-
-
-class Tracker:
-    """pql/utils/common.py:103-126 - fixed-length window pre-filled with zeros."""
-
-    def __init__(self, max_len):
-        self.moving_average = deque([0 for _ in range(max_len)], maxlen=max_len)
-        self.max_len = max_len
-
-    def __repr__(self):
-        return self.moving_average.__repr__()
-
-    def update(self, value):
-        if isinstance(value, (np.ndarray, torch.Tensor)):
-            self.moving_average.extend(value.tolist())
-        elif isinstance(value, Sequence):
-            self.moving_average.extend(value)
-        else:
-            self.moving_average.append(value)
-
-    def mean(self):
-        return np.mean(self.moving_average)
-
-    def std(self):
-        return np.std(self.moving_average)
-
-    def max(self):
-        return np.max(self.moving_average)
 
 
 class DeviceTracker:
@@ -39,7 +8,8 @@ class DeviceTracker:
     ``window[update_index % max_len]`` (pqlb_grad_reduce_finish) instead of the reference's
     ``loss.item()`` host sync after every update (pql_v_learner.py:111).  ``mean()`` reads the window
     (a host synchronisation); ``mean_lagged()`` - what ``update()`` uses once per env step unless
-    ``cfg.sync_loss`` - does not block.  Same pre-filled-with-zeros window semantics as Tracker."""
+    ``cfg.sync_loss`` - does not block.  Same pre-filled-with-zeros window semantics as the reference's
+    Tracker (pql/utils/common.py:103-126)."""
 
     def __init__(self, max_len, device):
         self.max_len = max_len

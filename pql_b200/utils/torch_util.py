@@ -68,9 +68,12 @@ class RunningMeanStd:
         raise NotImplementedError("moments are merged inside pqlb_rms_update: call update(x)")
 
     def get_states(self, device=None):
-        if device is not None:
+        """Snapshot of (mean, var, epsilon).  ``update`` writes mean / var in place, so - unlike the
+        reference, which rebinds fresh tensors every update (torch_util.py:91-103) - the live tensors
+        must not be handed to a consumer that reads them later on another stream: clones are."""
+        if device is not None and torch.device(device) != self.device:
             return self.mean.to(device), self.var.to(device), self.epsilon
-        return self.mean, self.var, self.epsilon
+        return self.mean.clone(), self.var.clone(), self.epsilon
 
     def load_state_dict(self, info):
         """(mean, var, count) as stored in the reference's checkpoints ('obs_rms', model_util.py:24-41;

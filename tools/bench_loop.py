@@ -42,6 +42,55 @@ class StubEnv:
         return self.obs, -(action * action).mean(dim=1), self.dones[self.t % 64], {}
 
 
+def measure_loop(envs=16384, obs=211, act=20, memory=5_000_000, batch=8192, iters=50, warmup=10, distl=False,
+                 profile=False, device="cuda:0"):
+    """Time ``iters`` iterations of LockStepTrainer.step() on the stub env; returns the result dict."""
+    from pql_b200.train import LockStepTrainer
+    from pql_b200.utils import default_pql_cfg
+    dev = torch.device(device)
+    torch.manual_seed(42)
+    cfg = default_pql_cfg(num_envs=envs, sim_device=str(dev), batch_size=batch, memory_size=memory, distl=distl,
+                          v_learner_gpu=dev.index or 0, p_learner_gpu=dev.index or 0)
+    cfg.learner_streams = True
+    tr = LockStepTrainer(StubEnv(envs, obs, act, dev), cfg)
+    tr.warm_up()
+    for _ in range(warmup):
+        tr.step()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    e0.record()
+    for _ in range(iters):
+        info = tr.step()
+    for l in (tr.v_learner, tr.p_learner):
+        if l.stream is not None:
+            torch.cuda.current_stream().wait_stream(l.stream)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / iters
+    wall = (time.perf_counter() - t0) / iters * 1e3
+    per_kernel = None
+    if profile:
+        from pql_b200 import _kernels as K
+        tr.v_learner.disable_graph(); tr.p_learner.disable_graph()
+        K.PROFILE = {}
+        for _ in range(3):
+            tr.step()
+        torch.cuda.synchronize()
+        per_kernel = {k: [round(sum(a.elapsed_time(b) for a, b in ev) / 3, 4), len(ev) // 3]
+                      for k, ev in sorted(K.PROFILE.items(), key=lambda kv: -sum(a.elapsed_time(b) for a, b in kv[1]))}
+        K.PROFILE = None
+    return {"workload": f"full loop, {envs} envs, obs {obs}, act {act}, {memory}-slot replay, batch {batch}, "
+                        f"{'C51' if distl else 'twin-Q'}, {tr.v_per_step} critic : {tr.v_per_step // tr.p_every} actor : 1 env step",
+            "ms_per_iteration": ms, "host_wall_ms_per_iteration": wall, "iterations": iters,
+            "env_transitions_per_s": envs / (ms * 1e-3),
+            "critic_updates_per_s": tr.v_per_step / (ms * 1e-3),
+            "actor_updates_per_s": tr.v_per_step / tr.p_every / (ms * 1e-3),
+            "replay_gb": tr.v_learner.memory.ring.numel() * 4 / 1e9,
+            "losses": {"critic": info["train/critic_loss"], "actor": info["train/actor_loss"]},
+            "kernel_ms_and_launches_per_iteration": per_kernel}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--envs", type=int, default=16384)
@@ -54,51 +103,8 @@ def main():
     ap.add_argument("--distl", action="store_true")
     ap.add_argument("--profile", action="store_true", help="per-kernel device time (CUDA events around every launch, graphs off)")
     args = ap.parse_args()
-    from pql_b200.train import LockStepTrainer
-    from pql_b200.utils import default_pql_cfg
-    dev = torch.device("cuda:0")
-    torch.manual_seed(42)
-    cfg = default_pql_cfg(num_envs=args.envs, sim_device="cuda:0", batch_size=args.batch, memory_size=args.memory,
-                          distl=args.distl)
-    cfg.learner_streams = True
-    tr = LockStepTrainer(StubEnv(args.envs, args.obs, args.act, dev), cfg)
-    tr.warm_up()
-    for _ in range(args.warmup):
-        tr.step()
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    t0 = time.perf_counter()
-    e0.record()
-    for _ in range(args.iters):
-        info = tr.step()
-    for l in (tr.v_learner, tr.p_learner):
-        if l.stream is not None:
-            torch.cuda.current_stream().wait_stream(l.stream)
-    e1.record()
-    torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / args.iters
-    wall = (time.perf_counter() - t0) / args.iters * 1e3
-    per_kernel = None
-    if args.profile:
-        from pql_b200 import _kernels as K
-        tr.v_learner.disable_graph(); tr.p_learner.disable_graph()
-        K.PROFILE = {}
-        for _ in range(3):
-            tr.step()
-        torch.cuda.synchronize()
-        per_kernel = {k: [round(sum(a.elapsed_time(b) for a, b in ev) / 3, 4), len(ev) // 3]
-                      for k, ev in sorted(K.PROFILE.items(), key=lambda kv: -sum(a.elapsed_time(b) for a, b in kv[1]))}
-        K.PROFILE = None
-    print(json.dumps({"workload": f"configs[3]: full loop, {args.envs} envs, obs {args.obs}, act {args.act}, "
-                                  f"{args.memory}-slot replay, batch {args.batch}, {'C51' if args.distl else 'twin-Q'}, "
-                                  f"{tr.v_per_step} critic : {tr.v_per_step // tr.p_every} actor : 1 env step",
-                      "ms_per_iteration": ms, "host_wall_ms_per_iteration": wall,
-                      "env_transitions_per_s": args.envs / (ms * 1e-3),
-                      "critic_updates_per_s": tr.v_per_step / (ms * 1e-3),
-                      "actor_updates_per_s": tr.v_per_step / tr.p_every / (ms * 1e-3),
-                      "replay_gb": tr.v_learner.memory.ring.numel() * 4 / 1e9,
-                      "losses": {"critic": info["train/critic_loss"], "actor": info["train/actor_loss"]},
-                      "kernel_ms_and_launches_per_iteration": per_kernel}))
+    print(json.dumps(measure_loop(args.envs, args.obs, args.act, args.memory, args.batch, args.iters, args.warmup,
+                                  args.distl, args.profile)))
 
 
 if __name__ == "__main__":
