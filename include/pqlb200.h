@@ -111,14 +111,16 @@ int pqlb_sample_critic_batch(const float* ring, int64_t capacity, int obs_dim, i
                              const int64_t* idx, int64_t batch,
                              const float* mean, const float* var, float eps,
                              float* x_cur, float* x_tgt, int x_ld,
-                             float* reward, float* done, pqlb_stream_t stream);
+                             float* reward, float* done, float* xf_cur, float* xf_tgt, pqlb_stream_t stream);
+/* xf_cur / xf_tgt (optional, same shape as x_cur / x_tgt): the same rows WITHOUT the TF32 rounding -
+ * the input of the split-fp16 forward (pqlb_mlp_forward_h), which splits fp32 values itself. */
 
 /* Fused gather for the P-learner: memory[indices] + normalize, pql/algo/pql_p_learner.py:49-52.
  * Writes x[:, :O] (TF32-rounded) and zeroes the padding columns [O+A, x_ld). */
 int pqlb_sample_obs_batch(const float* obsring, int64_t capacity, int obs_dim,
                           const int64_t* idx, int64_t batch,
                           const float* mean, const float* var, float eps,
-                          float* x, int x_ld, int act_dim, pqlb_stream_t stream);
+                          float* x, int x_ld, int act_dim, float* xf, pqlb_stream_t stream);
 
 /* ---- Fused sampler RNG ---------------------------------------------------------------
  * The same two fused gathers with the random draws of the update made INSIDE the kernel instead of
@@ -138,13 +140,13 @@ int pqlb_sample_critic_batch_rng(const float* ring, int64_t capacity, int obs_di
                                  float* x_cur, float* x_tgt, int x_ld, float* reward, float* done,
                                  const int64_t* rng_state, const int64_t* counter,
                                  const int64_t* cur_capacity, float* noise_out, int64_t noise_numel,
-                                 pqlb_stream_t stream);
+                                 float* xf_cur, float* xf_tgt, pqlb_stream_t stream);
 int pqlb_sample_obs_batch_rng(const float* obsring, int64_t capacity, int obs_dim,
                               int64_t* idx_out, int64_t batch,
                               const float* mean, const float* var, float eps,
                               float* x, int x_ld, int act_dim,
                               const int64_t* rng_state, const int64_t* counter,
-                              const int64_t* cur_capacity, pqlb_stream_t stream);
+                              const int64_t* cur_capacity, float* xf, pqlb_stream_t stream);
 /* *dst = value, stream-ordered (device-resident copies of host-side ring state). */
 int pqlb_store_i64(int64_t* dst, int64_t value, pqlb_stream_t stream);
 
@@ -268,6 +270,46 @@ int pqlb_mlp_forward(const pqlb_mlp_desc* desc, pqlb_stream_t stream);
  * streams half of every weight tile), 0 = the library default. */
 void pqlb_mlp_forward_cluster(int cluster);
 
+/* ---- K3f': the same trunk with split-fp16 operands ----------------------------------------------
+ * Every GEMM operand is hi + lo (two fp16 values, 22 significand bits) and a product is evaluated as
+ * a_hi.w_hi + a_lo.w_hi + a_hi.w_lo by three tcgen05 kind::f16 MMAs into one fp32 accumulator
+ * (terms = 3), or as a_hi.w_hi alone (terms = 1: the accuracy of one TF32 MMA at twice its rate).
+ * terms = 3 is what keeps critic losses and gradients within BASELINE.json's 1e-3 of the reference's
+ * fp32 SGEMM path (pql/algo/pql_v_learner.py:81-108, pql_p_learner.py:55-57); see DESIGN.md section 4.
+ * x is plain fp32 (NOT rounded; the kernel splits it), w?h / w?l are the fp16 hi / lo copies of the
+ * nn.Linear weights, scaled by pqlb_f16_weight_scale(), row stride ldw halves as produced by
+ * pqlb_split_f16 from a parameter arena (half i of a copy <-> element i of the arena; ldw1 % 8 == 0).
+ * h1 / h2 / h3 receive TF32-rounded fp32 activations (the backward kernels' operands) where non-NULL.
+ * Policy head as in pqlb_mlp_group; act_out (TF32-rounded) and act_out2 (unrounded) are both optional.
+ * wait_flag / done_flag / epoch (optional): tile dependencies inside one launch - a policy group
+ * publishes done_flag[tile] = 1 + (uint32)*epoch once its action rows are written, and a LATER group
+ * with wait_flag loads its input tile only after wait_flag[tile] holds that value (target policy ->
+ * target critics in one launch); epoch is a device counter that changes between launches. */
+#define PQLB_MAX_FWD_GROUPS 5
+typedef struct {
+  const float* x; int64_t ldx;
+  const void* w1h; const void* w1l; int64_t ldw1;
+  const void* w2h; const void* w2l; const void* w3h; const void* w3l;
+  const float* b1; const float* b2; const float* b3;
+  const float* head_w; const float* head_b; float* q;
+  float* h1; float* h2; float* h3;
+  const void* act_wh; const void* act_wl; const float* act_b; const float* act_noise;
+  float* act_out; float* act_out2;
+  int64_t act_ldo, act_ldo2, act_ldnoise;
+  float noise_std, noise_bound;
+  int act_n;
+  int terms;
+  int k_in;                   /* this group's input width (0: the descriptor's k_in); groups may differ */
+  const uint32_t* wait_flag; uint32_t* done_flag; const int64_t* epoch;
+} pqlb_mlp_h_group;
+typedef struct { int M, k_in, n_groups; pqlb_mlp_h_group g[PQLB_MAX_FWD_GROUPS]; } pqlb_mlp_h_desc;
+int pqlb_mlp_forward_h(const pqlb_mlp_h_desc* desc, pqlb_stream_t stream);
+/* fp16 operand copies of a parameter arena: hi[i] = fp16(s * src[i]), lo[i] = fp16(s * src[i] - hi[i])
+ * with s = pqlb_f16_weight_scale() (lo may be NULL).  The optimiser entry points below keep such
+ * copies up to date themselves (param_h / target_h). */
+int pqlb_split_f16(const float* src, void* hi, void* lo, int64_t n, pqlb_stream_t stream);
+float pqlb_f16_weight_scale(void);
+
 /* ---- K3b: layer-fused dgrad chain of the trunk ---------------------------------------------------
  * dz2[M,256] = (dz3[M,128] . W3) * elu'(h2);  dz1[M,512] = (dz2 . W2) * elu'(h1), both TF32-rounded,
  * for up to PQLB_MAX_GROUPS network instances in one launch; dz2 stays in tensor memory between the
@@ -368,12 +410,14 @@ int pqlb_grad_sumsq(const int64_t* seg_table, int n_seg, const float* grad, floa
  * pql/utils/torch_util.py:9-12; torch/optim/adam.py order):
  * coef = min(1, max_norm/(sqrt(sum sumsq_part)+1e-6)) (max_norm < 0: no clipping);
  * p,m,v updated in place; target <- p*tau + target*(1-tau) when target != NULL;
- * p_tf32 / target_tf32 = rn_tf32 copies (NULL to skip).  The 1-based AdamW step count is `step`,
+ * p_tf32 / target_tf32 = rn_tf32 copies (NULL to skip); param_h / target_h = fp16 hi | lo operand copies
+ * for pqlb_mlp_forward_h (2 n halves each: hi at [0, n), lo at [n, 2n), as pqlb_split_f16 writes them;
+ * NULL to skip; need n % 4 == 0).  The 1-based AdamW step count is `step`,
  * or step_dev[0] + 1 when step_dev != NULL (a device-resident count of completed updates, advanced
  * by pqlb_sum_partials, so that a whole update can be replayed from a CUDA graph).
  * grad_scale multiplies the gradient first (1/world for data parallel). */
 int pqlb_adamw_polyak(float* param, const float* grad, float* m, float* v, float* target,
-                      float* param_tf32, float* target_tf32, int64_t n,
+                      float* param_tf32, float* target_tf32, void* param_h, void* target_h, int64_t n,
                       const float* sumsq_part, int n_part, float grad_scale, float max_norm,
                       float lr, float beta1, float beta2, float eps, float weight_decay,
                       int64_t step, const int64_t* step_dev, float tau, float* grad_norm_out,
@@ -398,7 +442,7 @@ int pqlb_grad_reduce_finish(const int64_t* seg_table, int n_seg, const float* ws
                             float lr, float beta1, float beta2, float eps, float weight_decay,
                             float tau, float* scalars_out, pqlb_stream_t stream);
 int pqlb_adamw_polyak_pre(float* param, const float* grad, float* m, float* v, float* target,
-                          float* param_tf32, float* target_tf32, int64_t n,
+                          float* param_tf32, float* target_tf32, void* param_h, void* target_h, int64_t n,
                           const float* sumsq_part, int n_part, float grad_scale, float max_norm,
                           const float* scalars, int64_t* counter, float* grad_norm_out,
                           pqlb_stream_t stream);
@@ -420,7 +464,8 @@ typedef struct {
   int rank, world, grid;
 } pqlb_dp_desc;
 int pqlb_adamw_polyak_dp(float* param, float* m, float* v, float* target, float* param_tf32,
-                         float* target_tf32, int64_t n, const pqlb_dp_desc* dp, float max_norm,
+                         float* target_tf32, void* param_h, void* target_h, int64_t n,
+                         const pqlb_dp_desc* dp, float max_norm,
                          const float* scalars, int64_t* counter, float* grad_norm_out,
                          pqlb_stream_t stream);
 

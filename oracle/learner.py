@@ -68,17 +68,22 @@ def flat(params_list):
 #   * products are exact and accumulated in fp32 or better; biases, ELU, tanh, softmax, losses,
 #     the scalar Q head (a dot product with the un-rounded h3 and fp32 w4) stay fp32;
 #   * elu'(h) is evaluated on the rounded h (that is what the forward pass stored).
+#   * ``precise_critic`` (default): the critics' TRUNK FORWARD is computed by the split-fp16 kernel
+#     (csrc/mlp_fwd_h.cu: every operand as hi + lo halves, three MMAs per product = 22 significand
+#     bits), modelled here as un-rounded operands; what the forward STORES for the backward pass
+#     (h1..h3) is still TF32-rounded, and dgrad / wgrad / the C51 head keep TF32 operands.
 _TF32 = False
+_PRECISE_CRITIC = True
 
 
 @contextlib.contextmanager
-def tf32_operands(on=True):
-    global _TF32
-    prev, _TF32 = _TF32, on
+def tf32_operands(on=True, precise_critic=True):
+    global _TF32, _PRECISE_CRITIC
+    prev, _TF32, _PRECISE_CRITIC = (_TF32, _PRECISE_CRITIC), on, precise_critic
     try:
         yield
     finally:
-        _TF32 = prev
+        _TF32, _PRECISE_CRITIC = prev
 
 
 def rn_tf32(x):
@@ -92,12 +97,15 @@ def _mm(a, b):
 
 
 class _LinELU(torch.autograd.Function):
-    """hr, h = rn(elu(z)), elu(z) with z = rn(x) rn(W)^T + b (one hidden layer of mlp.py:15-24)."""
+    """hr, h = rn(elu(z)), elu(z) (one hidden layer of mlp.py:15-24) with z = rn(x) rn(W)^T + b, or
+    z = x W^T + b on un-rounded operands when ``precise`` (split-fp16 forward).  Either way the backward
+    pass sees the TF32-rounded x, W and h."""
 
     @staticmethod
-    def forward(ctx, x, w, b):
+    def forward(ctx, x, w, b, precise):
         xr, wr = rn_tf32(x), rn_tf32(w)
-        h = F.elu(_mm(xr, wr.t()) + b.detach())
+        z = _mm(x.detach(), w.detach().t()) if precise else _mm(xr, wr.t())
+        h = F.elu(z + b.detach())
         hr = rn_tf32(h)
         ctx.save_for_backward(xr, wr, hr)
         return hr, h
@@ -107,7 +115,7 @@ class _LinELU(torch.autograd.Function):
         xr, wr, hr = ctx.saved_tensors
         g = g_hr + g_h
         dz = rn_tf32(g * torch.where(hr > 0, torch.ones_like(hr), hr + 1))
-        return _mm(dz, wr), _mm(dz.t(), xr), dz.sum(0)
+        return _mm(dz, wr), _mm(dz.t(), xr), dz.sum(0), None
 
 
 class _LinOut(torch.autograd.Function):
@@ -142,10 +150,11 @@ class _ScalarHead(torch.autograd.Function):
         return g * w, None, _mm(g.t(), hr), g.sum(0)
 
 
-def _mlp_tf32(x, params):
+def _mlp_tf32(x, params, precise=False):
     hr, h = x, x
     for w, b in params[:-1]:
-        hr, h = _LinELU.apply(hr, w, b)
+        # precise: the next layer consumes the un-rounded activation (hi + lo halves in tensor memory)
+        hr, h = _LinELU.apply(h if precise else hr, w, b, precise)
     w, b = params[-1]
     if w.shape[0] == 1:
         return _ScalarHead.apply(h, hr, w, b)
@@ -161,10 +170,10 @@ def normalize(x, norm):
     return torch.clamp((x - mean.float()) / torch.sqrt(var.float() + eps), min=-5.0, max=5.0)
 
 
-def mlp(x, params):
+def mlp(x, params, critic=False):
     """mlp.py:15-24: ELU after every layer but the last."""
     if _TF32:
-        return _mlp_tf32(x, params)
+        return _mlp_tf32(x, params, precise=critic and _PRECISE_CRITIC)
     h = x
     last = len(params) - 1
     for i, (w, b) in enumerate(params):
@@ -188,7 +197,7 @@ def target_policy_action(next_obs, actor, noise, noise_bound=0.2):
 def q1_q2(obs, act, q1, q2, distl=False):
     """mlp.py:197-199 / 261-263."""
     x = torch.cat((obs, act), dim=1)
-    o1, o2 = mlp(x, q1), mlp(x, q2)
+    o1, o2 = mlp(x, q1, critic=True), mlp(x, q2, critic=True)
     if distl:
         return torch.softmax(o1, dim=1), torch.softmax(o2, dim=1)
     return o1, o2

@@ -122,6 +122,36 @@ class MlpForward(Call):
         super().__init__("pqlb_mlp_forward", C.byref(d))
 
 
+class MlpForwardH(Call):
+    """Layer-fused trunk forward with split-fp16 operands (pqlb_mlp_forward_h) for up to five network
+    instances.  ``groups``: dicts with x (fp32, un-rounded), ldx, w1h/w1l, ldw1 (halves), w2h/w2l, w3h/w3l,
+    b1..b3, terms (1 | 3), [head_w, head_b, q], [h1, h2, h3], [act_wh, act_wl, act_b, ...],
+    [wait_flag, done_flag, epoch]."""
+
+    FIELDS = ("x", "w1h", "w1l", "w2h", "w2l", "w3h", "w3l", "b1", "b2", "b3", "head_w", "head_b", "q", "h1", "h2", "h3",
+              "act_wh", "act_wl", "act_b", "act_noise", "act_out", "act_out2", "wait_flag", "done_flag", "epoch")
+    INTS = ("ldx", "ldw1", "act_ldo", "act_ldo2", "act_ldnoise", "act_n", "terms", "k_in")
+    FLOATS = ("noise_std", "noise_bound")
+
+    def __init__(self, M, k_in, groups):
+        d = _lib.MlpHDesc()
+        d.M, d.k_in, d.n_groups = int(M), int(k_in), len(groups)
+        if not 1 <= len(groups) <= _lib.MAX_FWD_GROUPS:
+            raise ValueError("1..%d groups per launch" % _lib.MAX_FWD_GROUPS)
+        for i, g in enumerate(groups):
+            unknown = set(g) - set(self.FIELDS) - set(self.INTS) - set(self.FLOATS)
+            if unknown:
+                raise KeyError(f"unknown mlp group fields {sorted(unknown)}")
+            for k in self.FIELDS:
+                setattr(d.g[i], k, g.get(k, 0) or None)
+            for k in self.INTS:
+                setattr(d.g[i], k, int(g.get(k, 0)))
+            for k in self.FLOATS:
+                setattr(d.g[i], k, float(g.get(k, 0.0)))
+        self.desc = d
+        super().__init__("pqlb_mlp_forward_h", C.byref(d))
+
+
 class MlpBackward(Call):
     """Layer-fused dgrad chain (pqlb_mlp_backward) for up to four network instances.
     ``groups``: dicts with dz3, w3, w2, h2, h1, dz2, dz1, [bias_part2, bias_part1] device addresses."""

@@ -55,6 +55,24 @@ class MlpGroup(C.Structure):
                 ("noise_std", _flt), ("noise_bound", _flt), ("act_n", _int)]
 
 
+MAX_FWD_GROUPS = 5
+
+
+class MlpHGroup(C.Structure):
+    _fields_ = [("x", _f), ("ldx", _i64), ("w1h", _f), ("w1l", _f), ("ldw1", _i64),
+                ("w2h", _f), ("w2l", _f), ("w3h", _f), ("w3l", _f),
+                ("b1", _f), ("b2", _f), ("b3", _f), ("head_w", _f), ("head_b", _f), ("q", _f),
+                ("h1", _f), ("h2", _f), ("h3", _f),
+                ("act_wh", _f), ("act_wl", _f), ("act_b", _f), ("act_noise", _f), ("act_out", _f), ("act_out2", _f),
+                ("act_ldo", _i64), ("act_ldo2", _i64), ("act_ldnoise", _i64),
+                ("noise_std", _flt), ("noise_bound", _flt), ("act_n", _int), ("terms", _int), ("k_in", _int),
+                ("wait_flag", _f), ("done_flag", _f), ("epoch", _f)]
+
+
+class MlpHDesc(C.Structure):
+    _fields_ = [("M", _int), ("k_in", _int), ("n_groups", _int), ("g", MlpHGroup * MAX_FWD_GROUPS)]
+
+
 class DpDesc(C.Structure):
     _fields_ = [("grad_peers", _f * 8), ("red_peers", _f * 8), ("ctl_peers", _f * 8), ("local", _f),
                 ("rank", _int), ("world", _int), ("grid", _int)]
@@ -89,11 +107,11 @@ _PROTOS = {
                                C.POINTER(_flt), _f, _f, _f, _f, _f, _st]),
     "pqlb_sample_gather": (_int, [_f, _i64, _int, _int, _f, _i64, _f, _f, _f, _f, _f, _st]),
     "pqlb_sample_critic_batch": (_int, [_f, _i64, _int, _int, _f, _i64, _f, _f, _flt, _f, _f, _int,
-                                        _f, _f, _st]),
-    "pqlb_sample_obs_batch": (_int, [_f, _i64, _int, _f, _i64, _f, _f, _flt, _f, _int, _int, _st]),
+                                        _f, _f, _f, _f, _st]),
+    "pqlb_sample_obs_batch": (_int, [_f, _i64, _int, _f, _i64, _f, _f, _flt, _f, _int, _int, _f, _st]),
     "pqlb_sample_critic_batch_rng": (_int, [_f, _i64, _int, _int, _f, _i64, _f, _f, _flt, _f, _f, _int,
-                                            _f, _f, _f, _f, _f, _f, _i64, _st]),
-    "pqlb_sample_obs_batch_rng": (_int, [_f, _i64, _int, _f, _i64, _f, _f, _flt, _f, _int, _int, _f, _f, _f, _st]),
+                                            _f, _f, _f, _f, _f, _f, _i64, _f, _f, _st]),
+    "pqlb_sample_obs_batch_rng": (_int, [_f, _i64, _int, _f, _i64, _f, _f, _flt, _f, _int, _int, _f, _f, _f, _f, _st]),
     "pqlb_store_i64": (_int, [_f, _i64, _st]),
     "pqlb_rms_workspace_bytes": (_i64, [_i64, _int]),
     "pqlb_rms_update": (_int, [_f, _i64, _int, _i64, _f, _f, _f, _f, _i64, _st]),
@@ -103,6 +121,9 @@ _PROTOS = {
     "pqlb_gemm_tf32": (_int, [C.POINTER(GemmDesc), _st]),
     "pqlb_mlp_forward": (_int, [C.POINTER(MlpDesc), _st]),
     "pqlb_mlp_forward_cluster": (None, [_int]),
+    "pqlb_mlp_forward_h": (_int, [C.POINTER(MlpHDesc), _st]),
+    "pqlb_split_f16": (_int, [_f, _f, _f, _i64, _st]),
+    "pqlb_f16_weight_scale": (_flt, []),
     "pqlb_mlp_backward": (_int, [C.POINTER(MlpBwdDesc), _st]),
     "pqlb_round_tf32": (_int, [_f, _f, _i64, _st]),
     "pqlb_doubleq_td_loss": (_int, [_f, _f, _f, _f, _f, _f, _flt, _i64, _f, _f, _f, _f, _f, _f, _f,
@@ -118,12 +139,12 @@ _PROTOS = {
     "pqlb_pack_x": (_int, [_f, _i64, _int, _f, _i64, _int, _f, _int, _i64, _st]),
     "pqlb_grad_reduce": (_int, [_f, _int, _f, _f, _f, _st]),
     "pqlb_grad_sumsq": (_int, [_f, _int, _f, _f, _st]),
-    "pqlb_adamw_polyak": (_int, [_f, _f, _f, _f, _f, _f, _f, _i64, _f, _int, _flt, _flt, _flt, _flt,
+    "pqlb_adamw_polyak": (_int, [_f, _f, _f, _f, _f, _f, _f, _f, _f, _i64, _f, _int, _flt, _flt, _flt, _flt,
                                  _flt, _flt, _flt, _i64, _f, _flt, _f, _st]),
     "pqlb_grad_reduce_finish": (_int, [_f, _int, _f, _f, _f, _f, _int, _flt, _f, _f, _f, _int,
                                        _flt, _flt, _flt, _flt, _flt, _flt, _f, _st]),
-    "pqlb_adamw_polyak_pre": (_int, [_f, _f, _f, _f, _f, _f, _f, _i64, _f, _int, _flt, _flt, _f, _f, _f, _st]),
-    "pqlb_adamw_polyak_dp": (_int, [_f, _f, _f, _f, _f, _f, _i64, C.POINTER(DpDesc), _flt, _f, _f, _f, _st]),
+    "pqlb_adamw_polyak_pre": (_int, [_f, _f, _f, _f, _f, _f, _f, _f, _f, _i64, _f, _int, _flt, _flt, _f, _f, _f, _st]),
+    "pqlb_adamw_polyak_dp": (_int, [_f, _f, _f, _f, _f, _f, _f, _f, _i64, C.POINTER(DpDesc), _flt, _f, _f, _f, _st]),
     "pqlb_grad_exchange_dp": (_int, [_i64, C.POINTER(DpDesc), _st]),
     "pqlb_sum_partials": (_int, [_f, _int, _flt, _f, _f, _f, _int, _st]),
 }

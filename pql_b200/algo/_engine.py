@@ -15,11 +15,26 @@ import torch
 
 from .. import _kernels as K
 from .. import _lib
-from ..models.mlp import HIDDEN, NetAddrs, NetLayout, _ru, forward_calls, fwd_tile
+from ..models.mlp import FUSED_MAX_IN, HIDDEN, NetAddrs, NetLayout, _ru, forward_calls, fwd_tile, half_arena
 
 H1, H2, H3 = HIDDEN
 import os as _os
 SEG = int(_os.environ.get("PQLB_REDUCE_SEG", 256))      # elements per block of the gradient reduction
+
+
+def forward_mode(requested, obs_dim, action_dim):
+    """Number format of the fused forward launches: 'f16x3' (default) - critics with split-fp16
+    operands and three MMAs per product, policy nets with one fp16 MMA (pqlb_mlp_forward_h; keeps every
+    gradient tensor within 1e-3 of the fp32 reference) - or 'tf32' (the round-1
+    kernels: one TF32 MMA per product everywhere).  Shapes the split-fp16 kernel does not take (inputs
+    wider than 128, weight rows that are not 16-byte aligned as halves, action widths the fused policy
+    head does not take) run as 'tf32'."""
+    mode = _os.environ.get("PQLB_FWD_MODE") or requested or "f16x3"
+    if mode not in ("f16x3", "tf32"):
+        raise ValueError(f"forward mode {mode!r}: expected 'f16x3' or 'tf32'")
+    O, A = int(obs_dim), int(action_dim)
+    ok = O + A <= FUSED_MAX_IN and _ru(O + A, 4) % 8 == 0 and _ru(O, 4) % 8 == 0 and O % 4 == 0 and A % 4 == 0 and A <= 16
+    return mode if ok else "tf32"
 
 
 class _Optim:
@@ -181,10 +196,12 @@ class CriticUpdate(_UpdateBase):
     def __init__(self, obs_dim, action_dim, batch, device, critic_flat, *, distl=False, num_atoms=51,
                  v_min=-10.0, v_max=10.0, gamma_n=0.99 ** 3, lr=5e-4, tau=0.05, max_grad_norm=0.5,
                  noise_bound=0.2, noise_std=0.8, obs_norm=True, eps=1e-4, world_size=1, loss_ring=None,
-                 process_group=None, dp_fused=False):
+                 process_group=None, dp_fused=False, fwd_mode=None):
         super().__init__(obs_dim, action_dim, batch, device, distl, num_atoms, v_min, v_max, loss_ring)
         self.process_group, self.dp_fused = process_group, bool(dp_fused)
         O, A, B, N, x_ld = self.O, self.A, self.B, self.N, self.x_ld
+        self.fwd_mode = forward_mode(fwd_mode, O, A)
+        split = self.fwd_mode == "f16x3"
         dev = self.device
         self.lr, self.tau, self.max_grad_norm = float(lr), float(tau), max_grad_norm
         self.gamma_n = float(np.float32(gamma_n))
@@ -198,6 +215,10 @@ class CriticUpdate(_UpdateBase):
         self.t_flat = critic_flat.clone()                       # deepcopy(critic), :47
         self.c_tf, self.t_tf = self._buf(self.Lc.total), self._buf(self.Lc.total)
         self.a_flat, self.a_tf = self._buf(self.La.total), self._buf(self.La.total)
+        # split-fp16 operand copies (hi | lo) of the three arenas, kept current by the optimiser kernel / set_actor
+        self.c_h = half_arena(self.Lc, dev) if split else None
+        self.t_h = half_arena(self.Lc, dev) if split else None
+        self.a_h = half_arena(self.La, dev) if split else None
         self.round_weights()
         self.opt = _Optim(self.Lc, dev)
 
@@ -205,6 +226,9 @@ class CriticUpdate(_UpdateBase):
         self.idx = torch.zeros(B, dtype=torch.int64, device=dev)
         self.noise = self._buf(B, A)
         self.x_cur, self.x_tgt = self._buf(B, x_ld), self._buf(B, x_ld)
+        # the same rows without the TF32 operand rounding: inputs of the split-fp16 forward
+        self.xf_cur = self._buf(B, x_ld) if split else None
+        self.xf_tgt = self._buf(B, x_ld) if split else None
         self.reward, self.done = self._buf(B), self._buf(B)
         self.mean, self.var = self._buf(O), torch.ones(O, device=dev)
         ha = [self._buf(B, d) for d in HIDDEN]
@@ -226,23 +250,27 @@ class CriticUpdate(_UpdateBase):
         else:
             self.loss_part = self._buf(2 * self.nblk_head)
 
-        actor = NetAddrs(self.La, 0, self.a_tf, self.a_flat)
-        cnet = [NetAddrs(self.Lc, i, self.c_tf, self.c_flat) for i in range(2)]
-        tnet = [NetAddrs(self.Lc, i, self.t_tf, self.t_flat) for i in range(2)]
+        actor = NetAddrs(self.La, 0, self.a_tf, self.a_flat, self.a_h)
+        cnet = [NetAddrs(self.Lc, i, self.c_tf, self.c_flat, self.c_h) for i in range(2)]
+        tnet = [NetAddrs(self.Lc, i, self.t_tf, self.t_flat, self.t_h) for i in range(2)]
         self._ring_args = None
         calls = self.calls
 
         # -- target policy: a' = clamp(tanh(actor(next_obs)) + clamp(noise), +-1)   :62-71, noise.py:19-27
-        a_inst = dict(net=actor, x=K.addr(self.x_tgt), x_ld=x_ld, k_in=O, h=[K.addr(t) for t in ha],
-                      store=(False, False, False),
+        a_inst = dict(net=actor, x=K.addr(self.x_tgt), xf=K.addr(self.xf_tgt), x_ld=x_ld, k_in=O, h=[K.addr(t) for t in ha],
+                      store=(False, False, False), terms=1,
                       act=dict(out=K.addr(self.x_tgt, O), ldo=x_ld, noise=K.addr(self.noise), ldnoise=A,
                                noise_std=self.noise_std, noise_bound=self.noise_bound))
+        if split:       # the un-rounded action goes next to the un-rounded next_obs
+            a_inst["act"].update(out2=K.addr(self.xf_tgt, O), ldo2=x_ld)
         calls += forward_calls(B, [a_inst], False)
         # -- both target nets on (next_obs, a') and both current nets on (obs, action), one launch per layer
-        insts = [dict(net=tnet[i], x=K.addr(self.x_tgt), x_ld=x_ld, k_in=O + A, h=[K.addr(t) for t in h_t[i]],
-                      store=(False, False, distl), q=K.addr(self.tq[i])) for i in range(2)]
-        insts += [dict(net=cnet[i], x=K.addr(self.x_cur), x_ld=x_ld, k_in=O + A, h=[K.addr(t) for t in h_c[i]],
-                       store=(True, True, True), q=K.addr(self.q[i])) for i in range(2)]
+        insts = [dict(net=tnet[i], x=K.addr(self.x_tgt), xf=K.addr(self.xf_tgt), x_ld=x_ld, k_in=O + A,
+                      h=[K.addr(t) for t in h_t[i]], store=(False, False, distl), q=K.addr(self.tq[i]), terms=3)
+                 for i in range(2)]
+        insts += [dict(net=cnet[i], x=K.addr(self.x_cur), xf=K.addr(self.xf_cur), x_ld=x_ld, k_in=O + A,
+                       h=[K.addr(t) for t in h_c[i]], store=(True, True, True), q=K.addr(self.q[i]), terms=3)
+                  for i in range(2)]
         wg = [(H3, H2, H2), (H2, H1, H1), (H1, O + A, x_ld)] + ([(N, H3, H3)] if distl else [])
         self._ws_init(wg, 2, [d for d in HIDDEN] * 2 + ([N, N] if distl else []),
                       extra=2 * _ru(self.nblk_head * (H3 + 1), 32) + 2 * _ru(self.nblk_head * H3, 32))
@@ -288,18 +316,19 @@ class CriticUpdate(_UpdateBase):
         if distl:
             entries = [(i, 2, self.dz[i][2], H3, H3) for i in range(2)] + [(i, 3, self.dl[i], self.pd, N) for i in range(2)]
             calls.append(self._bias_grads(self.opt, self.Lc, entries))
-        _finish_plan(self, self.opt, self.c_flat, self.t_flat, self.c_tf, self.t_tf)
+        _finish_plan(self, self.opt, self.c_flat, self.t_flat, self.c_tf, self.t_tf, self.c_h, self.t_h)
 
     def round_weights(self):
         with torch.cuda.device(self.device):
-            for src, dst in ((self.c_flat, self.c_tf), (self.t_flat, self.t_tf), (self.a_flat, self.a_tf)):
-                _lib.call("pqlb_round_tf32", _lib.ptr(src), _lib.ptr(dst), src.numel())
+            for src, dst, half in ((self.c_flat, self.c_tf, self.c_h), (self.t_flat, self.t_tf, self.t_h),
+                                   (self.a_flat, self.a_tf, self.a_h)):
+                _operand_copies(src, dst, half)
 
     def set_actor(self, flat):
         """Weights of the target policy (the actor module the driver sends with every update())."""
         self.a_flat.copy_(flat, non_blocking=True)
         with torch.cuda.device(self.device):
-            _lib.call("pqlb_round_tf32", _lib.ptr(self.a_flat), _lib.ptr(self.a_tf), self.a_flat.numel())
+            _operand_copies(self.a_flat, self.a_tf, self.a_h)
 
     def set_norm(self, normalize_tuple):
         if normalize_tuple is None:
@@ -319,10 +348,11 @@ class CriticUpdate(_UpdateBase):
         args = (_lib.ptr(ring), int(capacity), self.O, self.A, _lib.ptr(self.idx),
                 self.B, _lib.ptr(self.mean) if on else None, _lib.ptr(self.var) if on else None, self.eps,
                 _lib.ptr(self.x_cur), _lib.ptr(self.x_tgt), self.x_ld, _lib.ptr(self.reward), _lib.ptr(self.done))
+        xf = (_lib.ptr(self.xf_cur), _lib.ptr(self.xf_tgt))
         if self.rng_state is None:
-            return K.Call("pqlb_sample_critic_batch", *args, keep=(ring,))
+            return K.Call("pqlb_sample_critic_batch", *args, *xf, keep=(ring,))
         return K.Call("pqlb_sample_critic_batch_rng", *args, _lib.ptr(self.rng_state), _lib.ptr(self.opt.count),
-                      _lib.ptr(cur_capacity_dev), _lib.ptr(self.noise), self.noise.numel(), keep=(ring, cur_capacity_dev))
+                      _lib.ptr(cur_capacity_dev), _lib.ptr(self.noise), self.noise.numel(), *xf, keep=(ring, cur_capacity_dev))
 
     def run(self, sample=None, allreduce=None, use_graph=False, graph_allreduce=False):
         """One update: [sample] + forward/backward launches + gradient reduction, the gradient
@@ -390,10 +420,12 @@ class ActorUpdate(_UpdateBase):
 
     def __init__(self, obs_dim, action_dim, batch, device, actor_flat, *, distl=False, num_atoms=51,
                  v_min=-10.0, v_max=10.0, lr=5e-4, max_grad_norm=0.5, obs_norm=True, eps=1e-4, world_size=1,
-                 loss_ring=None, process_group=None, dp_fused=False):
+                 loss_ring=None, process_group=None, dp_fused=False, fwd_mode=None):
         super().__init__(obs_dim, action_dim, batch, device, distl, num_atoms, v_min, v_max, loss_ring)
         self.process_group, self.dp_fused = process_group, bool(dp_fused)
         O, A, B, N, x_ld, a_ld = self.O, self.A, self.B, self.N, self.x_ld, self.a_ld
+        self.fwd_mode = forward_mode(fwd_mode, O, A)
+        split = self.fwd_mode == "f16x3"
         dev = self.device
         self.lr, self.max_grad_norm = float(lr), max_grad_norm
         self.eps, self.obs_norm = float(eps), bool(obs_norm)
@@ -401,13 +433,18 @@ class ActorUpdate(_UpdateBase):
         assert actor_flat.numel() == self.La.total and actor_flat.is_cuda
         self.a_flat, self.a_tf = actor_flat, self._buf(self.La.total)
         self.c_flat, self.c_tf = self._buf(self.Lc.total), self._buf(self.Lc.total)
+        self.a_h = half_arena(self.La, dev) if split else None
+        self.c_h = half_arena(self.Lc, dev) if split else None
         self.round_weights()
         self.opt = _Optim(self.La, dev)
 
         self.idx = torch.zeros(B, dtype=torch.int64, device=dev)
         self.x = self._buf(B, x_ld)
+        self.xf = self._buf(B, x_ld) if split else None      # un-rounded [norm(obs) | action] rows (split-fp16 forward)
         self.mean, self.var = self._buf(O), torch.ones(O, device=dev)
-        self.act = self._buf(B, a_ld)
+        # the action tanh(actor(obs)) before any operand rounding: its own buffer, or the action columns of xf
+        self.act = self.xf[:, O:O + a_ld] if split else self._buf(B, a_ld)
+        act_addr, act_ld = (K.addr(self.xf, O), x_ld) if split else (K.addr(self.act), a_ld)
         ha = [self._buf(B, d) for d in HIDDEN]
         h_c = [[self._buf(B, d) for d in HIDDEN] for _ in range(2)]
         self.dzc = [[self._buf(B, d) for d in HIDDEN] for _ in range(2)]
@@ -421,18 +458,18 @@ class ActorUpdate(_UpdateBase):
             self.loss_part = self._buf((B + 7) // 8)
         else:
             self.loss_part = self._buf(2 * self.nblk_head)
-        actor = NetAddrs(self.La, 0, self.a_tf, self.a_flat)
-        cnet = [NetAddrs(self.Lc, i, self.c_tf, self.c_flat) for i in range(2)]
+        actor = NetAddrs(self.La, 0, self.a_tf, self.a_flat, self.a_h)
+        cnet = [NetAddrs(self.Lc, i, self.c_tf, self.c_flat, self.c_h) for i in range(2)]
         calls = self.calls
 
         self._ws_init([(A, H3, H3), (H3, H2, H2), (H2, H1, H1), (H1, O, self.La.ldw[0])], 1, [*HIDDEN, A])
         # -- action = tanh(actor(obs)) written straight into the critic input rows      :55
-        a_inst = dict(net=actor, x=K.addr(self.x), x_ld=x_ld, k_in=O, h=[K.addr(t) for t in ha],
-                      act=dict(out=K.addr(self.x, O), ldo=x_ld, out2=K.addr(self.act), ldo2=a_ld))
+        a_inst = dict(net=actor, x=K.addr(self.x), xf=K.addr(self.xf), x_ld=x_ld, k_in=O, h=[K.addr(t) for t in ha], terms=1,
+                      act=dict(out=K.addr(self.x, O), ldo=x_ld, out2=act_addr, ldo2=act_ld))
         calls += forward_calls(B, [a_inst], False)
         # -- frozen critic forward                                                     :56
-        insts = [dict(net=cnet[i], x=K.addr(self.x), x_ld=x_ld, k_in=O + A, h=[K.addr(t) for t in h_c[i]],
-                      q=K.addr(self.q[i])) for i in range(2)]
+        insts = [dict(net=cnet[i], x=K.addr(self.x), xf=K.addr(self.xf), x_ld=x_ld, k_in=O + A,
+                      h=[K.addr(t) for t in h_c[i]], q=K.addr(self.q[i]), terms=3) for i in range(2)]
         dz3 = [self.dzc[i][2] for i in range(2)]
         calls += forward_calls(B, insts, not distl)
         if not distl:
@@ -456,11 +493,11 @@ class ActorUpdate(_UpdateBase):
         g = dict(a=K.addr(dz1[0]), lda=H1, a2=K.addr(dz1[1]), lda2=H1, ldb=x_ld, ldb2=x_ld, out=K.addr(self.dz_act),
                  ldo=a_ld)
         if O % 4 == 0:
-            g.update(b=cnet[0].W[0] + 4 * O, b2=cnet[1].W[0] + 4 * O, aux=K.addr(self.act), ldaux=a_ld)
+            g.update(b=cnet[0].W[0] + 4 * O, b2=cnet[1].W[0] + 4 * O, aux=act_addr, ldaux=act_ld)
             calls.append(K.Gemm(B, A, H1, [g], epilogue=K.EPI_MUL_TANHGRAD, tile_n=K.pick_tile_n(A),
                                 b_major=K.MN_MAJOR, K2=H1))
         else:   # action columns are not 16-byte aligned inside W1: contract all columns, store the window
-            g.update(b=cnet[0].W[0], b2=cnet[1].W[0], aux=K.addr(self.act, -O), ldaux=a_ld)
+            g.update(b=cnet[0].W[0], b2=cnet[1].W[0], aux=act_addr - 4 * O, ldaux=act_ld)
             calls.append(K.Gemm(B, O + A, H1, [g], epilogue=K.EPI_MUL_TANHGRAD, tile_n=256, b_major=K.MN_MAJOR,
                                 K2=H1, col_lo=O, col_hi=O + A))
         # -- actor backward
@@ -475,17 +512,17 @@ class ActorUpdate(_UpdateBase):
         calls.append(self._wgrad(self.opt, self.La, [0], 0, [self.dza[0]], H1, H1, [self.x], x_ld, O))
         entries = [(0, 2, self.dza[2], H3, H3), (0, 3, self.dz_act, a_ld, A)]     # layers 0 / 1: fused into the dgrad chain
         calls.append(self._bias_grads(self.opt, self.La, entries))
-        _finish_plan(self, self.opt, self.a_flat, None, self.a_tf, None)
+        _finish_plan(self, self.opt, self.a_flat, None, self.a_tf, None, self.a_h, None)
 
     def round_weights(self):
         with torch.cuda.device(self.device):
-            for src, dst in ((self.a_flat, self.a_tf), (self.c_flat, self.c_tf)):
-                _lib.call("pqlb_round_tf32", _lib.ptr(src), _lib.ptr(dst), src.numel())
+            for src, dst, half in ((self.a_flat, self.a_tf, self.a_h), (self.c_flat, self.c_tf, self.c_h)):
+                _operand_copies(src, dst, half)
 
     def set_critic(self, flat):
         self.c_flat.copy_(flat, non_blocking=True)
         with torch.cuda.device(self.device):
-            _lib.call("pqlb_round_tf32", _lib.ptr(self.c_flat), _lib.ptr(self.c_tf), self.c_flat.numel())
+            _operand_copies(self.c_flat, self.c_tf, self.c_h)
 
     set_norm = CriticUpdate.set_norm
 
@@ -495,15 +532,24 @@ class ActorUpdate(_UpdateBase):
                 _lib.ptr(self.mean) if on else None, _lib.ptr(self.var) if on else None, self.eps,
                 _lib.ptr(self.x), self.x_ld, self.A)
         if self.rng_state is None:
-            return K.Call("pqlb_sample_obs_batch", *args, keep=(obsring,))
+            return K.Call("pqlb_sample_obs_batch", *args, _lib.ptr(self.xf), keep=(obsring,))
         return K.Call("pqlb_sample_obs_batch_rng", *args, _lib.ptr(self.rng_state), _lib.ptr(self.opt.count),
-                      _lib.ptr(cur_capacity_dev), keep=(obsring, cur_capacity_dev))
+                      _lib.ptr(cur_capacity_dev), _lib.ptr(self.xf), keep=(obsring, cur_capacity_dev))
 
     run, _segment_a, _segment_b, _capture = (CriticUpdate.run, CriticUpdate._segment_a, CriticUpdate._segment_b,
                                              CriticUpdate._capture)
 
 
-def _finish_plan(plan, opt, p_flat, t_flat, p_tf, t_tf):
+def _operand_copies(src, tf32, half):
+    """Tensor-core operand copies of a parameter arena: the TF32-rounded twin and, when kept, the
+    split-fp16 hi | lo copy (what the optimiser kernel maintains after every step)."""
+    _lib.call("pqlb_round_tf32", _lib.ptr(src), _lib.ptr(tf32), src.numel())
+    if half is not None:
+        n = src.numel()
+        _lib.call("pqlb_split_f16", _lib.ptr(src), C.c_void_p(half.data_ptr()), C.c_void_p(half.data_ptr() + 2 * n), n)
+
+
+def _finish_plan(plan, opt, p_flat, t_flat, p_tf, t_tf, p_h=None, t_h=None):
     """Prepare the reduce / clip+AdamW(+Polyak) / loss launches that close an update."""
     opt.finish(plan.device)
     plan.dp = None
@@ -532,7 +578,8 @@ def _finish_plan(plan, opt, p_flat, t_flat, p_tf, t_tf):
     plan.sumsq_call = K.Call("pqlb_grad_sumsq", _lib.ptr(opt.seg_table), opt.n_seg, _lib.ptr(opt.grad),
                              _lib.ptr(opt.sumsq))
     plan.adamw_call = K.Call("pqlb_adamw_polyak_pre", _lib.ptr(p_flat), _lib.ptr(opt.grad), _lib.ptr(opt.m), _lib.ptr(opt.v),
-                             _lib.ptr(t_flat), _lib.ptr(p_tf), _lib.ptr(t_tf), opt.layout.total, _lib.ptr(opt.sumsq),
+                             _lib.ptr(t_flat), _lib.ptr(p_tf), _lib.ptr(t_tf), _lib.ptr(p_h), _lib.ptr(t_h),
+                             opt.layout.total, _lib.ptr(opt.sumsq),
                              opt.n_seg, 1.0 / plan.world_size, max_norm, _lib.ptr(plan.adam_scalars),
                              _lib.ptr(opt.count), _lib.ptr(plan.grad_norm))
     if plan.dp is not None and plan.dp.split:
@@ -541,14 +588,14 @@ def _finish_plan(plan, opt, p_flat, t_flat, p_tf, t_tf):
         exch = K.Call("pqlb_grad_exchange_dp", opt.layout.total, C.byref(desc), keep=(desc, plan.dp))
         sumsq_addr = C.c_void_p(plan.dp.ctl.data_ptr() + 4 * plan.dp.FLAG_WORDS)
         step = K.Call("pqlb_adamw_polyak_pre", _lib.ptr(p_flat), _lib.ptr(plan.dp.red), _lib.ptr(opt.m), _lib.ptr(opt.v),
-                      _lib.ptr(t_flat), _lib.ptr(p_tf), _lib.ptr(t_tf), opt.layout.total, sumsq_addr,
+                      _lib.ptr(t_flat), _lib.ptr(p_tf), _lib.ptr(t_tf), _lib.ptr(p_h), _lib.ptr(t_h), opt.layout.total, sumsq_addr,
                       plan.dp.world * plan.dp.GRID, 1.0 / plan.world_size, max_norm, _lib.ptr(plan.adam_scalars),
                       _lib.ptr(opt.count), _lib.ptr(plan.grad_norm))
         plan.adamw_call = lambda: (exch(), step())
     elif plan.dp is not None:
         desc = plan.dp.desc()
         plan.adamw_call = K.Call("pqlb_adamw_polyak_dp", _lib.ptr(p_flat), _lib.ptr(opt.m), _lib.ptr(opt.v), _lib.ptr(t_flat),
-                                 _lib.ptr(p_tf), _lib.ptr(t_tf), opt.layout.total, C.byref(desc), max_norm,
+                                 _lib.ptr(p_tf), _lib.ptr(t_tf), _lib.ptr(p_h), _lib.ptr(t_h), opt.layout.total, C.byref(desc), max_norm,
                                  _lib.ptr(plan.adam_scalars), _lib.ptr(opt.count), _lib.ptr(plan.grad_norm),
                                  keep=(desc, plan.dp))
     plan.loss_call = lambda: None

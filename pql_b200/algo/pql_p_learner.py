@@ -85,7 +85,8 @@ class PQLPLearner:
                                  max_grad_norm=a.max_grad_norm,
                                  obs_norm=bool(a.obs_norm) and self.normalize_tuple is not None, eps=eps,
                                  world_size=self.world_size, loss_ring=self.loss_tracker.window,
-                                  process_group=self.process_group, dp_fused=self.dp_fused)
+                                  process_group=self.process_group, dp_fused=self.dp_fused,
+                                  fwd_mode=getattr(self.cfg, "forward_mode", None))
         if old is not None:              # rebuilt launch list, same learner state (see PQLVLearner._build)
             carry_plan_state(old, self._plan)
         if self.fused_rng and self.memory_size < (1 << 28):

@@ -222,7 +222,8 @@ class PQLVLearner:
                                   noise_std=a.noise.tgt_pol_std,
                                   obs_norm=bool(a.obs_norm) and self.normalize_tuple is not None, eps=eps,
                                   world_size=self.world_size, loss_ring=self.loss_tracker.window,
-                                  process_group=self.process_group, dp_fused=self.dp_fused)
+                                  process_group=self.process_group, dp_fused=self.dp_fused,
+                                  fwd_mode=getattr(self.cfg, "forward_mode", None))
         if old is not None:
             # normalize_tuple switched between None and a tuple: the launch list is rebuilt, the learner's
             # state is not - AdamW moments, step count and the Polyak target carry over, and the fused

@@ -497,6 +497,7 @@ static int make_operand_map(CUtensorMap* map, const float* base, int64_t ld, int
 using namespace pqlb;
 
 extern "C" int pqlb_mlp_forward_init(void);
+extern "C" int pqlb_mlp_forward_h_init(void);
 extern "C" int pqlb_mlp_backward_init(void);
 
 // One-time, non-stream setup (opt-in shared memory size, driver entry point) so that nothing but
@@ -514,6 +515,7 @@ extern "C" int pqlb_init(void) {
   }
   if (!get_encode_fn()) return PQLB_E_DRIVER;
   { int rc = pqlb_mlp_forward_init(); if (rc != PQLB_OK) return rc; }
+  { int rc = pqlb_mlp_forward_h_init(); if (rc != PQLB_OK) return rc; }
   { int rc = pqlb_mlp_backward_init(); if (rc != PQLB_OK) return rc; }
   if (dev < 64) done[dev] = true;
   return PQLB_OK;

@@ -6,6 +6,7 @@
 #include <math.h>
 
 #include "common.cuh"
+#include "f16split.cuh"
 
 namespace pqlb {
 
@@ -114,7 +115,8 @@ struct AdamHyper {     // as passed by the caller; derived scalars are computed 
 __global__ void __launch_bounds__(kOptThreads)
 adamw_polyak_kernel(float* __restrict__ param, const float* __restrict__ grad, float* __restrict__ m,
                     float* __restrict__ v, float* __restrict__ target, float* __restrict__ p_tf32,
-                    float* __restrict__ t_tf32, int64_t n, const float* __restrict__ sumsq_part,
+                    float* __restrict__ t_tf32, __half* __restrict__ p_h, __half* __restrict__ t_h,
+                    int64_t n, const float* __restrict__ sumsq_part,
                     int n_part, AdamHyper h, int64_t step_host, const int64_t* __restrict__ step_dev,
                     float* __restrict__ grad_norm_out, const AdamScalars* __restrict__ scal_dev,
                     long long* __restrict__ counter_inc) {
@@ -172,6 +174,8 @@ adamw_polyak_kernel(float* __restrict__ param, const float* __restrict__ grad, f
     if (target) *reinterpret_cast<float4*>(target + i4) = *reinterpret_cast<float4*>(tt);
     if (p_tf32) *reinterpret_cast<float4*>(p_tf32 + i4) = make_float4(rn_tf32(p[0]), rn_tf32(p[1]), rn_tf32(p[2]), rn_tf32(p[3]));
     if (target && t_tf32) *reinterpret_cast<float4*>(t_tf32 + i4) = make_float4(rn_tf32(tt[0]), rn_tf32(tt[1]), rn_tf32(tt[2]), rn_tf32(tt[3]));
+    if (p_h) store_split4(p_h, n, i4, p);                 // fp16 hi / lo operand copies (n % 4 == 0 when they are kept)
+    if (target && t_h) store_split4(t_h, n, i4, tt);
   } else {
     for (int k = 0; k < cnt; ++k) {
       param[i4 + k] = p[k]; m[i4 + k] = mm[k]; v[i4 + k] = vv[k];
@@ -259,7 +263,7 @@ __device__ __forceinline__ float dp_reduce_slice(const DpArgs& dp, int64_t lo, i
 __global__ void __launch_bounds__(kOptThreads, 1)
 adamw_polyak_dp_kernel(float* __restrict__ param, float* __restrict__ m, float* __restrict__ v,
                        float* __restrict__ target, float* __restrict__ p_tf32, float* __restrict__ t_tf32,
-                       int64_t n, DpArgs dp, float max_norm, const AdamScalars* __restrict__ scal_dev,
+                       __half* __restrict__ p_h, __half* __restrict__ t_h, int64_t n, DpArgs dp, float max_norm, const AdamScalars* __restrict__ scal_dev,
                        long long* __restrict__ counter_inc, float* __restrict__ grad_norm_out, int exchange_only) {
   __shared__ float red[8];
   __shared__ AdamScalars sa;
@@ -353,6 +357,8 @@ adamw_polyak_dp_kernel(float* __restrict__ param, float* __restrict__ m, float* 
     if (target) *reinterpret_cast<float4*>(target + i4) = *reinterpret_cast<float4*>(tt);
     if (p_tf32) *reinterpret_cast<float4*>(p_tf32 + i4) = make_float4(rn_tf32(p[0]), rn_tf32(p[1]), rn_tf32(p[2]), rn_tf32(p[3]));
     if (target && t_tf32) *reinterpret_cast<float4*>(t_tf32 + i4) = make_float4(rn_tf32(tt[0]), rn_tf32(tt[1]), rn_tf32(tt[2]), rn_tf32(tt[3]));
+    if (p_h) store_split4(p_h, n, i4, p);
+    if (target && t_h) store_split4(t_h, n, i4, tt);
   }
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     if (grad_norm_out) grad_norm_out[0] = norm;
@@ -488,7 +494,7 @@ extern "C" int pqlb_grad_sumsq(const int64_t* seg_table, int n_seg, const float*
 }
 
 extern "C" int pqlb_adamw_polyak(float* param, const float* grad, float* m, float* v, float* target,
-                                 float* param_tf32, float* target_tf32, int64_t n,
+                                 float* param_tf32, float* target_tf32, void* param_h, void* target_h, int64_t n,
                                  const float* sumsq_part, int n_part, float grad_scale,
                                  float max_norm, float lr, float beta1, float beta2, float eps,
                                  float weight_decay, int64_t step, const int64_t* step_dev, float tau,
@@ -497,18 +503,20 @@ extern "C" int pqlb_adamw_polyak(float* param, const float* grad, float* m, floa
   PQLB_CHECK_ALIGN(aligned16(param) && aligned16(grad) && aligned16(m) && aligned16(v));
   PQLB_CHECK_ALIGN((!target || aligned16(target)) && (!param_tf32 || aligned16(param_tf32)) &&
                    (!target_tf32 || aligned16(target_tf32)));
+  PQLB_CHECK_ALIGN((!param_h && !target_h) || ((n % 4) == 0 && (reinterpret_cast<uintptr_t>(param_h) & 7) == 0 && (reinterpret_cast<uintptr_t>(target_h) & 7) == 0));
   AdamHyper h;
   h.grad_scale = grad_scale; h.max_norm = max_norm; h.lr = lr; h.beta1 = beta1; h.beta2 = beta2;
   h.eps = eps; h.weight_decay = weight_decay; h.tau = tau;
   const int64_t blocks = (n + kOptThreads * 4 - 1) / (kOptThreads * 4);
   adamw_polyak_kernel<<<(unsigned)blocks, kOptThreads, 0, (cudaStream_t)stream>>>(
-      param, grad, m, v, target, param_tf32, target_tf32, n, sumsq_part, n_part, h, step, step_dev,
+      param, grad, m, v, target, param_tf32, target_tf32, reinterpret_cast<__half*>(param_h), reinterpret_cast<__half*>(target_h),
+      n, sumsq_part, n_part, h, step, step_dev,
       grad_norm_out, nullptr, nullptr);
   PQLB_LAUNCH_RET();
 }
 
 extern "C" int pqlb_adamw_polyak_pre(float* param, const float* grad, float* m, float* v, float* target,
-                                     float* param_tf32, float* target_tf32, int64_t n,
+                                     float* param_tf32, float* target_tf32, void* param_h, void* target_h, int64_t n,
                                      const float* sumsq_part, int n_part, float grad_scale, float max_norm,
                                      const float* scalars, int64_t* counter, float* grad_norm_out,
                                      pqlb_stream_t stream) {
@@ -516,17 +524,20 @@ extern "C" int pqlb_adamw_polyak_pre(float* param, const float* grad, float* m, 
   PQLB_CHECK_ALIGN(aligned16(param) && aligned16(grad) && aligned16(m) && aligned16(v));
   PQLB_CHECK_ALIGN((!target || aligned16(target)) && (!param_tf32 || aligned16(param_tf32)) &&
                    (!target_tf32 || aligned16(target_tf32)));
+  PQLB_CHECK_ALIGN((!param_h && !target_h) || ((n % 4) == 0 && (reinterpret_cast<uintptr_t>(param_h) & 7) == 0 && (reinterpret_cast<uintptr_t>(target_h) & 7) == 0));
   AdamHyper h = {};
   h.grad_scale = grad_scale; h.max_norm = max_norm;
   const int64_t blocks = (n + kOptThreads * 4 - 1) / (kOptThreads * 4);
   adamw_polyak_kernel<<<(unsigned)blocks, kOptThreads, 0, (cudaStream_t)stream>>>(
-      param, grad, m, v, target, param_tf32, target_tf32, n, sumsq_part, n_part, h, 0, nullptr,
+      param, grad, m, v, target, param_tf32, target_tf32, reinterpret_cast<__half*>(param_h), reinterpret_cast<__half*>(target_h),
+      n, sumsq_part, n_part, h, 0, nullptr,
       grad_norm_out, reinterpret_cast<const AdamScalars*>(scalars), reinterpret_cast<long long*>(counter));
   PQLB_LAUNCH_RET();
 }
 
 extern "C" int pqlb_adamw_polyak_dp(float* param, float* m, float* v, float* target, float* param_tf32,
-                                    float* target_tf32, int64_t n, const pqlb_dp_desc* dp, float max_norm,
+                                    float* target_tf32, void* param_h, void* target_h, int64_t n,
+                                    const pqlb_dp_desc* dp, float max_norm,
                                     const float* scalars, int64_t* counter, float* grad_norm_out,
                                     pqlb_stream_t stream) {
   PQLB_CHECK_ARG(param && m && v && n > 0 && (n % 4) == 0 && dp && scalars && counter);
@@ -534,6 +545,7 @@ extern "C" int pqlb_adamw_polyak_dp(float* param, float* m, float* v, float* tar
   PQLB_CHECK_ARG(dp->grid >= 1 && dp->grid <= kNumSMs);
   PQLB_CHECK_ALIGN(aligned16(param) && aligned16(m) && aligned16(v) && (!target || aligned16(target)) &&
                    (!param_tf32 || aligned16(param_tf32)) && (!target_tf32 || aligned16(target_tf32)));
+  PQLB_CHECK_ALIGN((reinterpret_cast<uintptr_t>(param_h) & 7) == 0 && (reinterpret_cast<uintptr_t>(target_h) & 7) == 0);
   DpArgs a;
   for (int r = 0; r < kDpMaxWorld; ++r) {
     const bool on = r < dp->world;
@@ -543,7 +555,8 @@ extern "C" int pqlb_adamw_polyak_dp(float* param, float* m, float* v, float* tar
   }
   a.rank = dp->rank; a.world = dp->world; a.local = reinterpret_cast<unsigned long long*>(dp->local);
   adamw_polyak_dp_kernel<<<(unsigned)dp->grid, kOptThreads, 0, (cudaStream_t)stream>>>(
-      param, m, v, target, param_tf32, target_tf32, n, a, max_norm, reinterpret_cast<const AdamScalars*>(scalars),
+      param, m, v, target, param_tf32, target_tf32, reinterpret_cast<__half*>(param_h), reinterpret_cast<__half*>(target_h),
+      n, a, max_norm, reinterpret_cast<const AdamScalars*>(scalars),
       reinterpret_cast<long long*>(counter), grad_norm_out, 0);
   PQLB_LAUNCH_RET();
 }
@@ -561,7 +574,7 @@ extern "C" int pqlb_grad_exchange_dp(int64_t n, const pqlb_dp_desc* dp, pqlb_str
   }
   a.rank = dp->rank; a.world = dp->world; a.local = reinterpret_cast<unsigned long long*>(dp->local);
   adamw_polyak_dp_kernel<<<(unsigned)dp->grid, kOptThreads, 0, (cudaStream_t)stream>>>(
-      nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, n, a, -1.f, nullptr, nullptr, nullptr, 1);
+      nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, n, a, -1.f, nullptr, nullptr, nullptr, 1);
   PQLB_LAUNCH_RET();
 }
 

@@ -268,7 +268,8 @@ __global__ void __launch_bounds__(kThreads)
 sample_critic_batch_kernel(const float* __restrict__ ring, RecGeom g, const int64_t* __restrict__ idx,
                            int64_t B, const float* __restrict__ mean, const float* __restrict__ var,
                            float eps, float* __restrict__ x_cur, float* __restrict__ x_tgt, int x_ld,
-                           float* __restrict__ o_rew, float* __restrict__ o_done, RngArgs ra) {
+                           float* __restrict__ o_rew, float* __restrict__ o_done, RngArgs ra,
+                           float* __restrict__ xf_cur, float* __restrict__ xf_tgt) {
   using V = typename VecT<VEC>::type;
   // fused sampler RNG (rng.cuh): the indices are torch.randint's for this generator state, drawn here
   unsigned long long seed = 0, off = 0, range = 1;
@@ -300,6 +301,8 @@ sample_critic_batch_kernel(const float* __restrict__ ring, RecGeom g, const int6
           if (rec[r]) {
             *reinterpret_cast<V*>(x_cur + (b0 + r) * x_ld + k) = *reinterpret_cast<V*>(z);
             *reinterpret_cast<V*>(x_tgt + (b0 + r) * x_ld + k) = *reinterpret_cast<V*>(z);
+            if (xf_cur) *reinterpret_cast<V*>(xf_cur + (b0 + r) * x_ld + k) = *reinterpret_cast<V*>(z);
+            if (xf_tgt) *reinterpret_cast<V*>(xf_tgt + (b0 + r) * x_ld + k) = *reinterpret_cast<V*>(z);
           }
         continue;
       }
@@ -324,10 +327,17 @@ sample_critic_batch_kernel(const float* __restrict__ ring, RecGeom g, const int6
           for (int q = 0; q < VEC; ++q) {
             float y = t[q];
             if (mean) y = fminf(fmaxf(__fdiv_rn(__fsub_rn(y, m[q]), sd[q]), -5.f), 5.f);
-            t[q] = rn_tf32(y);
+            t[q] = y;
           }
+          // the un-rounded row feeds the split-fp16 forward (pqlb_mlp_forward_h), the TF32-rounded one the
+          // weight-gradient contraction of the first layer
+          float* xf = d.field == 0 ? xf_cur : xf_tgt;
+          if (xf) *reinterpret_cast<V*>(xf + b * x_ld + d.fo) = val[r];
+#pragma unroll
+          for (int q = 0; q < VEC; ++q) t[q] = rn_tf32(t[q]);
           *reinterpret_cast<V*>((d.field == 0 ? x_cur : x_tgt) + b * x_ld + d.fo) = val[r];
         } else if (d.field == 2) {
+          if (xf_cur) *reinterpret_cast<V*>(xf_cur + b * x_ld + g.O + d.fo) = val[r];
 #pragma unroll
           for (int q = 0; q < VEC; ++q) t[q] = rn_tf32(t[q]);
           *reinterpret_cast<V*>(x_cur + b * x_ld + g.O + d.fo) = val[r];
@@ -351,7 +361,7 @@ sample_critic_batch_kernel(const float* __restrict__ ring, RecGeom g, const int6
 __global__ void __launch_bounds__(kThreads)
 sample_obs_batch_rng_kernel(const float* __restrict__ obsring, int O, int64_t* __restrict__ idx,
                             int64_t B, const float* __restrict__ mean, const float* __restrict__ var,
-                            float eps, float* __restrict__ x, int x_ld, int A, RngArgs ra) {
+                            float eps, float* __restrict__ x, int x_ld, int A, RngArgs ra, float* __restrict__ xf) {
   const int lane = threadIdx.x & 31;
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
   const unsigned long long seed = ra.state[0], off = ra.state[1] + ra.state[2] * ra.counter[0], range = ra.range[0];
@@ -380,11 +390,12 @@ sample_obs_batch_rng_kernel(const float* __restrict__ obsring, int O, int64_t* _
           float y = v[r];
           if (mean) y = norm_clamp(y, m, vr, eps);
           x[(b0 + r) * x_ld + k] = rn_tf32(y);
+          if (xf) xf[(b0 + r) * x_ld + k] = y;
         }
       } else if (k >= O + A) {
 #pragma unroll
         for (int r = 0; r < kRec; ++r)
-          if (src[r]) x[(b0 + r) * x_ld + k] = 0.f;
+          if (src[r]) { x[(b0 + r) * x_ld + k] = 0.f; if (xf) xf[(b0 + r) * x_ld + k] = 0.f; }
       }
     }
   }
@@ -395,7 +406,7 @@ __global__ void store_i64_kernel(long long* dst, long long v) { *dst = v; }
 __global__ void __launch_bounds__(kThreads)
 sample_obs_batch_kernel(const float* __restrict__ obsring, int O, const int64_t* __restrict__ idx,
                         int64_t B, const float* __restrict__ mean, const float* __restrict__ var,
-                        float eps, float* __restrict__ x, int x_ld, int A) {
+                        float eps, float* __restrict__ x, int x_ld, int A, float* __restrict__ xf) {
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (ItemWalk w((int64_t)blockIdx.x * blockDim.x + threadIdx.x, stride, x_ld); w.row < B; w.next()) {
     const int64_t b = w.row;
@@ -404,8 +415,10 @@ sample_obs_batch_kernel(const float* __restrict__ obsring, int O, const int64_t*
       float v = obsring[__ldg(idx + b) * O + k];
       if (mean) v = norm_clamp(v, mean[k], var[k], eps);
       x[b * x_ld + k] = rn_tf32(v);
+      if (xf) xf[b * x_ld + k] = v;
     } else if (k >= O + A) {
       x[b * x_ld + k] = 0.f;               // action columns [O, O+A) belong to the actor head
+      if (xf) xf[b * x_ld + k] = 0.f;
     }
   }
 }
@@ -551,7 +564,8 @@ extern "C" int pqlb_sample_gather(const float* ring, int64_t capacity, int obs_d
 extern "C" int pqlb_sample_critic_batch(const float* ring, int64_t capacity, int obs_dim, int act_dim,
                                         const int64_t* idx, int64_t batch, const float* mean,
                                         const float* var, float eps, float* x_cur, float* x_tgt,
-                                        int x_ld, float* reward, float* done, pqlb_stream_t stream) {
+                                        int x_ld, float* reward, float* done, float* xf_cur, float* xf_tgt,
+                                        pqlb_stream_t stream) {
   PQLB_CHECK_ARG(ring && capacity > 0 && obs_dim > 0 && act_dim > 0 && batch > 0 && idx);
   PQLB_CHECK_ARG(x_cur && x_tgt && reward && done && ((mean == nullptr) == (var == nullptr)));
   const RecGeom g = rec_geom(obs_dim, act_dim);
@@ -561,10 +575,10 @@ extern "C" int pqlb_sample_critic_batch(const float* ring, int64_t capacity, int
                     (!mean || (aligned16(mean) && aligned16(var)));
   if (vec4)
     sample_critic_batch_kernel<4><<<grid_for(batch * 32, kThreads, kRec, kBlocksPerSM), kThreads, 0, (cudaStream_t)stream>>>(
-        ring, g, idx, batch, mean, var, eps, x_cur, x_tgt, x_ld, reward, done, RngArgs{});
+        ring, g, idx, batch, mean, var, eps, x_cur, x_tgt, x_ld, reward, done, RngArgs{}, xf_cur, xf_tgt);
   else
     sample_critic_batch_kernel<1><<<grid_for(batch * 32, kThreads, kRec, kBlocksPerSM), kThreads, 0, (cudaStream_t)stream>>>(
-        ring, g, idx, batch, mean, var, eps, x_cur, x_tgt, x_ld, reward, done, RngArgs{});
+        ring, g, idx, batch, mean, var, eps, x_cur, x_tgt, x_ld, reward, done, RngArgs{}, xf_cur, xf_tgt);
   PQLB_LAUNCH_RET();
 }
 
@@ -587,7 +601,8 @@ extern "C" int pqlb_sample_critic_batch_rng(const float* ring, int64_t capacity,
                                             const float* var, float eps, float* x_cur, float* x_tgt,
                                             int x_ld, float* reward, float* done, const int64_t* rng_state,
                                             const int64_t* counter, const int64_t* cur_capacity,
-                                            float* noise_out, int64_t noise_numel, pqlb_stream_t stream) {
+                                            float* noise_out, int64_t noise_numel, float* xf_cur, float* xf_tgt,
+                                            pqlb_stream_t stream) {
   PQLB_CHECK_ARG(ring && capacity > 0 && obs_dim > 0 && act_dim > 0 && batch > 0 && idx_out);
   PQLB_CHECK_ARG(x_cur && x_tgt && reward && done && ((mean == nullptr) == (var == nullptr)));
   const RecGeom g = rec_geom(obs_dim, act_dim);
@@ -599,10 +614,10 @@ extern "C" int pqlb_sample_critic_batch_rng(const float* ring, int64_t capacity,
                     (!mean || (aligned16(mean) && aligned16(var)));
   if (vec4)
     sample_critic_batch_kernel<4><<<grid_for(batch * 32, kThreads, kRec, kBlocksPerSM), kThreads, 0, (cudaStream_t)stream>>>(
-        ring, g, idx_out, batch, mean, var, eps, x_cur, x_tgt, x_ld, reward, done, ra);
+        ring, g, idx_out, batch, mean, var, eps, x_cur, x_tgt, x_ld, reward, done, ra, xf_cur, xf_tgt);
   else
     sample_critic_batch_kernel<1><<<grid_for(batch * 32, kThreads, kRec, kBlocksPerSM), kThreads, 0, (cudaStream_t)stream>>>(
-        ring, g, idx_out, batch, mean, var, eps, x_cur, x_tgt, x_ld, reward, done, ra);
+        ring, g, idx_out, batch, mean, var, eps, x_cur, x_tgt, x_ld, reward, done, ra, xf_cur, xf_tgt);
   PQLB_LAUNCH_RET();
 }
 
@@ -610,7 +625,7 @@ extern "C" int pqlb_sample_obs_batch_rng(const float* obsring, int64_t capacity,
                                          int64_t batch, const float* mean, const float* var, float eps,
                                          float* x, int x_ld, int act_dim, const int64_t* rng_state,
                                          const int64_t* counter, const int64_t* cur_capacity,
-                                         pqlb_stream_t stream) {
+                                         float* xf, pqlb_stream_t stream) {
   PQLB_CHECK_ARG(obsring && capacity > 0 && obs_dim > 0 && batch > 0 && idx_out && x && act_dim >= 0);
   PQLB_CHECK_ARG((mean == nullptr) == (var == nullptr));
   PQLB_CHECK_SHAPE(x_ld >= obs_dim + act_dim);
@@ -618,7 +633,7 @@ extern "C" int pqlb_sample_obs_batch_rng(const float* obsring, int64_t capacity,
   const int rc = make_rng_args(&ra, rng_state, counter, cur_capacity, batch, capacity, nullptr, 0);
   if (rc != PQLB_OK) return rc;
   sample_obs_batch_rng_kernel<<<grid_for(batch * 32, kThreads, kRec, kBlocksPerSM), kThreads, 0, (cudaStream_t)stream>>>(
-      obsring, obs_dim, idx_out, batch, mean, var, eps, x, x_ld, act_dim, ra);
+      obsring, obs_dim, idx_out, batch, mean, var, eps, x, x_ld, act_dim, ra, xf);
   PQLB_LAUNCH_RET();
 }
 
@@ -631,12 +646,12 @@ extern "C" int pqlb_store_i64(int64_t* dst, int64_t value, pqlb_stream_t stream)
 extern "C" int pqlb_sample_obs_batch(const float* obsring, int64_t capacity, int obs_dim,
                                      const int64_t* idx, int64_t batch, const float* mean,
                                      const float* var, float eps, float* x, int x_ld,
-                                     int act_dim, pqlb_stream_t stream) {
+                                     int act_dim, float* xf, pqlb_stream_t stream) {
   PQLB_CHECK_ARG(obsring && capacity > 0 && obs_dim > 0 && batch > 0 && idx && x && act_dim >= 0);
   PQLB_CHECK_ARG((mean == nullptr) == (var == nullptr));
   PQLB_CHECK_SHAPE(x_ld >= obs_dim + act_dim);
   sample_obs_batch_kernel<<<grid_for(batch * x_ld, kThreads, 2), kThreads, 0, (cudaStream_t)stream>>>(
-      obsring, obs_dim, idx, batch, mean, var, eps, x, x_ld, act_dim);
+      obsring, obs_dim, idx, batch, mean, var, eps, x, x_ld, act_dim, xf);
   PQLB_LAUNCH_RET();
 }
 

@@ -78,15 +78,27 @@ class ParamArena:
         return self.flat[o:o + L.dims[l + 1]]
 
 
+def half_arena(layout, device):
+    """fp16 operand copies of a parameter arena for the split-fp16 forward: 2 * total halves, hi copy
+    at [0, total), lo copy at [total, 2 total); half i of a copy <-> element i of the arena
+    (pqlb_split_f16 / the optimiser kernel's param_h output)."""
+    return torch.zeros(2 * layout.total, dtype=torch.float16, device=device)
+
+
 class NetAddrs:
     """Device addresses of one net's tensors: ``W`` = TF32-rounded tensor-core operands,
-    ``Wf`` / ``b`` = fp32 weights / biases."""
+    ``Wf`` / ``b`` = fp32 weights / biases, ``Wh`` / ``Wl`` = fp16 hi / lo operand copies (or None)."""
 
-    def __init__(self, layout, i, flat_tf32, flat_fp32):
+    def __init__(self, layout, i, flat_tf32, flat_fp32, half=None):
         self.dims, self.ldw = layout.dims, layout.ldw
-        self.W = [K.addr(flat_tf32, layout.w_off[i][l]) for l in range(layout.n_layers)]
+        self.W = [K.addr(flat_tf32, layout.w_off[i][l]) if flat_tf32 is not None else 0 for l in range(layout.n_layers)]
         self.Wf = [K.addr(flat_fp32, layout.w_off[i][l]) for l in range(layout.n_layers)]
         self.b = [K.addr(flat_fp32, layout.b_off[i][l]) for l in range(layout.n_layers)]
+        self.Wh = self.Wl = None
+        if half is not None:
+            assert half.dtype == torch.float16 and half.numel() == 2 * layout.total
+            self.Wh = [half.data_ptr() + 2 * layout.w_off[i][l] for l in range(layout.n_layers)]
+            self.Wl = [half.data_ptr() + 2 * (layout.total + layout.w_off[i][l]) for l in range(layout.n_layers)]
 
 
 import os as _os
@@ -127,15 +139,65 @@ def trunk_calls(B, insts, n_hidden_out=3):
 FUSED_MAX_IN = 128        # pqlb_mlp_forward keeps a 128-row input tile of at most 128 columns in shared memory
 
 
+def split_f16_ok(inst):
+    """Can this instance run on the split-fp16 fused forward (pqlb_mlp_forward_h)?  Needs fp16 weight
+    copies, an input at most 128 wide whose weight rows are 16-byte aligned as halves, and - for a
+    policy net - a head the kernel fuses (A <= 16, A % 4 == 0, aligned output rows)."""
+    n = inst["net"]
+    if n.Wh is None or inst["k_in"] > FUSED_MAX_IN or n.ldw[0] % 8:
+        return False
+    act = inst.get("act")
+    if act is not None:
+        A = n.dims[4]
+        if A > 16 or A % 4 or act.get("ldo", 0) % 4 or act.get("ldo2", 0) % 4:
+            return False
+    return True
+
+
+def forward_calls_h(B, insts, scalar_head):
+    """ONE split-fp16 fused launch for up to five network instances (input widths may differ).  inst as
+    in ``forward_calls`` plus ``terms`` (3 = hi/lo split of both operands, 1 = hi only), ``xf`` (the
+    un-rounded input rows; falls back to ``x``) and optional ``wait_flag`` / ``done_flag`` / ``epoch``."""
+    k_in = insts[0]["k_in"]
+    groups = []
+    for it in insts:
+        n = it["net"]
+        st = it.get("store", (True, True, True))
+        terms = int(it.get("terms", 3))
+        g = dict(x=it.get("xf") or it["x"], ldx=it["x_ld"], w1h=n.Wh[0], ldw1=n.ldw[0], w2h=n.Wh[1], w3h=n.Wh[2],
+                 b1=n.b[0], b2=n.b[1], b3=n.b[2], terms=terms, k_in=it["k_in"],
+                 h1=it["h"][0] if st[0] else 0, h2=it["h"][1] if st[1] else 0, h3=it["h"][2] if st[2] else 0)
+        if terms == 3:
+            g.update(w1l=n.Wl[0], w2l=n.Wl[1], w3l=n.Wl[2])
+        if scalar_head and it.get("q"):
+            g.update(head_w=n.Wf[3], head_b=n.b[3], q=it["q"])
+        act = it.get("act")
+        if act is not None:
+            g.update(act_wh=n.Wh[3], act_b=n.b[3], act_n=n.dims[4], act_out=act.get("out", 0), act_ldo=act.get("ldo", 0),
+                     act_out2=act.get("out2", 0), act_ldo2=act.get("ldo2", 0), act_noise=act.get("noise", 0),
+                     act_ldnoise=act.get("ldnoise", 0), noise_std=act.get("noise_std", 0.0),
+                     noise_bound=act.get("noise_bound", 0.0))
+            if terms == 3:
+                g["act_wl"] = n.Wl[3]
+        for k in ("wait_flag", "done_flag", "epoch"):
+            if it.get(k):
+                g[k] = it[k]
+        groups.append(g)
+    return [K.MlpForwardH(B, max(it["k_in"] for it in insts), groups)]
+
+
 def forward_calls(B, insts, scalar_head):
     """Prepared launches of the trunk (three Linear+ELU layers) for up to four network instances.
     inst = dict(net, x, x_ld, k_in, h=[h1, h2, h3 addresses], store=(s1, s2, s3), q=addr or 0,
     act=dict(out, ldo, [out2, ldo2], [noise, ldnoise, noise_std, noise_bound]) for a policy net).
     Inputs up to 128 wide take ONE layer-fused launch (activations stay in tensor memory, only the
     flagged ones are written; the scalar twin-Q head or the tanh policy head ride in the same
-    launch); wider inputs (ShadowHand) run layer by layer."""
+    launch) - the split-fp16 kernel when the instances carry fp16 weight copies, the TF32 kernel
+    otherwise; wider inputs (ShadowHand) run layer by layer."""
     k_in = insts[0]["k_in"]
     calls = []
+    if all(split_f16_ok(it) for it in insts):
+        return forward_calls_h(B, insts, scalar_head)
     if k_in <= FUSED_MAX_IN:
         groups, heads_left = [], []
         for it in insts:

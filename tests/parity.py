@@ -2,9 +2,10 @@
 oracle (oracle/learner.py, itself pinned to reference-generated fixtures) on identical weights,
 batches, indices and noise, and returns the relative errors.  Two oracles are used per step:
 
-(1) ``tf32`` - the reference arithmetic with GEMM operands rounded to TF32 exactly where the
-    kernels round them (oracle.learner.tf32_operands): products exact, fp32 accumulation,
-    everything else fp32.  The CUDA path must match it to 3e-4 on EVERY quantity (loss,
+(1) ``tf32`` - the reference arithmetic with GEMM operands rounded exactly where the kernels round
+    them (oracle.learner.tf32_operands: TF32 operands in the policy forward, dgrad, wgrad and the C51
+    head; un-rounded operands in the critics' split-fp16 trunk forward): products exact, fp32
+    accumulation, everything else fp32.  The CUDA path must match it to 3e-4 on EVERY quantity (loss,
     Q-values / distributions, TD target / projected distribution, every gradient tensor).  What
     remains is not the operand format but its chaos: a ~3e-6 difference in a GEMM output
     (accumulation order inside the tensor core, ex2.approx in ELU) flips the TF32 rounding of
@@ -15,13 +16,13 @@ batches, indices and noise, and returns the relative errors.  Two oracles are us
 (2) ``fp32`` - the reference arithmetic as the reference runs it (fp32 SGEMM).  BASELINE.json
     north_star: 1e-3 relative.  All norm-wise per tensor, ||x - ref||_2 / ||ref||_2:
         loss, Q-values, TD target / projected distribution, actions   <= 1e-3, asserted
-        gradient tensors                                                <= 1e-3, asserted, unless
-            the TF32 number format itself (oracle tf32 vs oracle fp32, no CUDA involved) already
-            exceeds 7e-4 on that tensor - then <= 1.5 x that.  This happens for sums that cancel:
-            bias gradients sum_b dz_b of a critic whose mean TD error is near zero, and the
-            P-learner's gradients on untrained random networks at large batch (the mean of
-            nearly uncorrelated per-sample gradients shrinks like 1/sqrt(B); the effect of
-            rounding the forward operands does not).  Measured values are returned and printed.
+        gradient tensors, every one of them                            <= 1e-3, asserted.
+            Round 1 needed an exception here for sums that cancel (bias gradients of a critic whose mean
+            TD error is near zero: 6.7e-3; the P-learner's weight gradients on untrained networks at
+            full batch: 1.8e-3) because one TF32 MMA per product leaves ~5e-4 on every Q value.  The
+            critics' forward now runs with split-fp16 operands (three MMAs per product,
+            csrc/mlp_fwd_h.cu; which sites need it: tools/precision_study.py) and the exception is gone.
+            Measured values are returned and printed.
 (3) the fused clip+AdamW+Polyak is judged on identical inputs: against the oracle's
     clip_grad_norm + AdamW + polyak applied to the SAME (CUDA-computed) gradients, <= 1e-6 of the
     tensor.  (Adam's normalised step m/sqrt(v) turns a 1e-3 gradient difference into sign flips
@@ -155,8 +156,7 @@ def _grad_report(got_list, fp32_grads, tf32_grads, tag, out, per_tensor, check, 
         out[f"{tag}_grad_vs_fp32"] = max(out.get(f"{tag}_grad_vs_fp32", 0.0), e_f)
         if check:
             assert e_t <= max(3e-4, 0.5 * fmt), f"{tag} grad tensor {gi}: {e_t:.3e} vs the TF32-operand oracle"
-            assert e_f <= max(1e-3, 1.5 * fmt if fmt > 7e-4 else 0.0), \
-                f"{tag} grad tensor {gi}: {e_f:.3e} vs fp32 oracle (TF32 format alone: {fmt:.3e})"
+            assert e_f <= 1e-3, f"{tag} grad tensor {gi}: {e_f:.3e} vs fp32 oracle (operand-format model alone: {fmt:.3e})"
 
 
 def run_learner_parity(seed=1234, B=512, obs_dim=88, act_dim=16, distl=False, steps=2, device="cuda:0",
@@ -199,8 +199,8 @@ def run_learner_parity(seed=1234, B=512, obs_dim=88, act_dim=16, distl=False, st
         before = [t.detach().clone() for t in L.flat([ov.q1, ov.q2])]
         tbefore = [t.detach().clone() for t in L.flat([ov.tq1, ov.tq2])]
         shadow = _clone_opt(ov.opt, before)
-        ot = copy.deepcopy(ov)                                   # TF32-operand oracle on the same state
-        with L.tf32_operands():
+        ot = copy.deepcopy(ov)                                   # operand-format oracle on the same state
+        with L.tf32_operands(precise_critic=plan.fwd_mode == "f16x3"):
             tf_loss = ot.learn(batch, case["noises"][s], case["actor"], norm)
         ref_loss = ov.learn(batch, case["noises"][s], case["actor"], norm)
         with injected_draws(idx, case["noises"][s]):
@@ -250,7 +250,7 @@ def run_learner_parity(seed=1234, B=512, obs_dim=88, act_dim=16, distl=False, st
         before = [t.detach().clone() for t in L.flat([op.actor])]
         shadow = _clone_opt(op.opt, before)
         ot = copy.deepcopy(op)
-        with L.tf32_operands():
+        with L.tf32_operands(precise_critic=plan.fwd_mode == "f16x3"):
             tf_loss = ot.learn(batch[0], case["q1"], case["q2"], norm)
         ref_loss = op.learn(batch[0], case["q1"], case["q2"], norm)
         with injected_draws(idx):

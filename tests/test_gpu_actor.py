@@ -35,7 +35,9 @@ def test_running_mean_std_matches_oracle(rows, cols):
     x = torch.randn(7, cols, generator=g)
     np.testing.assert_allclose(rms.normalize(x.to(DEV)).cpu().numpy(), ref.normalize(x).numpy(), rtol=1e-5, atol=1e-6)
     m, v, eps = rms.get_states()
-    assert m is rms.mean and v is rms.var and eps == 1e-4
+    # snapshots (update() writes mean / var in place; the reference rebinds fresh tensors): same values, other storage
+    assert torch.equal(m, rms.mean) and torch.equal(v, rms.var) and eps == 1e-4
+    assert m.data_ptr() != rms.mean.data_ptr() and v.data_ptr() != rms.var.data_ptr()
 
 
 @pytest.mark.parametrize("E,A,kind", [(4096, 16, "mixed"), (16384, 20, "mixed"), (300, 3, "fixed")])

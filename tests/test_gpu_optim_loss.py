@@ -45,7 +45,7 @@ def test_adamw_polyak_matches_torch_order(n, max_norm, with_target):
         _lib.call("pqlb_grad_sumsq", _lib.ptr(segs), segs.shape[0], _lib.ptr(gd), _lib.ptr(sumsq))
         _lib.call("pqlb_adamw_polyak", _lib.ptr(p), _lib.ptr(gd), _lib.ptr(m), _lib.ptr(v),
                   _lib.ptr(tgt) if with_target else None, _lib.ptr(p_tf), _lib.ptr(t_tf) if with_target else None,
-                  n, _lib.ptr(sumsq), segs.shape[0], 1.0, max_norm, 5e-4, 0.9, 0.999, 1e-8, 0.01,
+                  None, None, n, _lib.ptr(sumsq), segs.shape[0], 1.0, max_norm, 5e-4, 0.9, 0.999, 1e-8, 0.01,
                   step if n != 4099 else 0, _lib.ptr(count) if n == 4099 else None, 0.05, _lib.ptr(norm_out))
         count += 1
         grads = [grad]

@@ -40,9 +40,10 @@ def test_critic_batch_draws_equal_torch(B, O, A, cap, fill, seed, offset, count)
     mean, var = torch.randn(O, device=DEV, generator=g), torch.rand(O, device=DEV, generator=g) + 0.5
     outs = [[torch.zeros(B, x_ld, device=DEV), torch.zeros(B, x_ld, device=DEV), torch.zeros(B, device=DEV),
              torch.zeros(B, device=DEV)] for _ in range(2)]
+    xf = [[torch.zeros(B, x_ld, device=DEV), torch.zeros(B, x_ld, device=DEV)] for _ in range(2)]     # un-rounded twins
     _lib.call("pqlb_sample_critic_batch_rng", _lib.ptr(mem.ring), cap, O, A, _lib.ptr(idx), B, _lib.ptr(mean), _lib.ptr(var),
               1e-4, *(_lib.ptr(t) for t in outs[0][:2]), x_ld, *(_lib.ptr(t) for t in outs[0][2:]), _lib.ptr(state),
-              _lib.ptr(counter), _lib.ptr(cur), _lib.ptr(noise), noise.numel())
+              _lib.ptr(counter), _lib.ptr(cur), _lib.ptr(noise), noise.numel(), _lib.ptr(xf[0][0]), _lib.ptr(xf[0][1]))
     ref = torch.Generator(device=DEV).manual_seed(seed)
     ref.set_offset(offset)
     idx_ref = torch.randint(fill, size=(B,), device=DEV, generator=ref)
@@ -52,10 +53,15 @@ def test_critic_batch_draws_equal_torch(B, O, A, cap, fill, seed, offset, count)
     assert ref.get_offset() == offset + inc
     # and the gather itself equals the unfused entry point on those indices
     _lib.call("pqlb_sample_critic_batch", _lib.ptr(mem.ring), cap, O, A, _lib.ptr(idx_ref), B, _lib.ptr(mean), _lib.ptr(var),
-              1e-4, *(_lib.ptr(t) for t in outs[1][:2]), x_ld, *(_lib.ptr(t) for t in outs[1][2:]))
+              1e-4, *(_lib.ptr(t) for t in outs[1][:2]), x_ld, *(_lib.ptr(t) for t in outs[1][2:]),
+              _lib.ptr(xf[1][0]), _lib.ptr(xf[1][1]))
     for a, b in zip(*outs):
         assert torch.equal(a[:, :O + A] if a.dim() == 2 else a, b[:, :O + A] if b.dim() == 2 else b)
     assert torch.equal(outs[0][0], outs[1][0])
+    # the un-rounded rows: identical between the two entry points, and their TF32 rounding is the rounded row
+    assert torch.equal(xf[0][0], xf[1][0]) and torch.equal(xf[0][1][:, :O], xf[1][1][:, :O])
+    rn = lambda t: ((t.view(torch.int32) + 0x1000) & ~0x1FFF).view(torch.float32)      # noqa: E731
+    assert torch.equal(rn(xf[0][0]), outs[0][0]) and torch.equal(rn(xf[0][1][:, :O]), outs[0][1][:, :O])
 
 
 @pytest.mark.parametrize("B,O,A,cap,fill,seed,offset", [(8192, 88, 16, 60_000, 60_000, 42, 0),
@@ -71,13 +77,13 @@ def test_obs_batch_draws_equal_torch(B, O, A, cap, fill, seed, offset):
     mean, var = torch.randn(O, device=DEV, generator=g), torch.rand(O, device=DEV, generator=g) + 0.5
     x0, x1 = torch.full((B, x_ld), 7.0, device=DEV), torch.full((B, x_ld), 7.0, device=DEV)
     _lib.call("pqlb_sample_obs_batch_rng", _lib.ptr(ring), cap, O, _lib.ptr(idx), B, _lib.ptr(mean), _lib.ptr(var), 1e-4,
-              _lib.ptr(x0), x_ld, A, _lib.ptr(state), _lib.ptr(counter), _lib.ptr(cur))
+              _lib.ptr(x0), x_ld, A, _lib.ptr(state), _lib.ptr(counter), _lib.ptr(cur), None)
     ref = torch.Generator(device=DEV).manual_seed(seed)
     ref.set_offset(offset)
     idx_ref = torch.randint(fill, size=(B,), device=DEV, generator=ref)
     assert torch.equal(idx, idx_ref)
     _lib.call("pqlb_sample_obs_batch", _lib.ptr(ring), cap, O, _lib.ptr(idx_ref), B, _lib.ptr(mean), _lib.ptr(var), 1e-4,
-              _lib.ptr(x1), x_ld, A)
+              _lib.ptr(x1), x_ld, A, None)
     assert torch.equal(x0, x1)          # action columns untouched (7.0), padding zeroed, obs normalised + TF32-rounded
 
 
