@@ -280,11 +280,13 @@ void pqlb_mlp_forward_cluster(int cluster);
  * nn.Linear weights, scaled by pqlb_f16_weight_scale(), row stride ldw halves as produced by
  * pqlb_split_f16 from a parameter arena (half i of a copy <-> element i of the arena; ldw1 % 8 == 0).
  * h1 / h2 / h3 receive TF32-rounded fp32 activations (the backward kernels' operands) where non-NULL.
- * Policy head as in pqlb_mlp_group; act_out (TF32-rounded) and act_out2 (unrounded) are both optional.
- * wait_flag / done_flag / epoch (optional): tile dependencies inside one launch - a policy group
- * publishes done_flag[tile] = 1 + (uint32)*epoch once its action rows are written, and a LATER group
- * with wait_flag loads its input tile only after wait_flag[tile] holds that value (target policy ->
- * target critics in one launch); epoch is a device counter that changes between launches. */
+ * Policy head as in pqlb_mlp_group; act_out (TF32-rounded) and act_out2 (unrounded) are both optional;
+ * alternatively a C51 softmax head (sm_*).
+ * Tile dependencies inside one launch (optional): a policy group with `publish` marks a 128-row tile
+ * in desc.tile_sync once its action rows are written, and a LATER group with `wait` loads its input
+ * tile only after that mark (target policy -> target critics in ONE launch: the SMs the 64 policy tiles
+ * leave idle start on the critics).  tile_sync: 2 + ceil(M / 128) uint32, zero-initialised once by the
+ * caller; the kernel maintains it across launches (no reset needed). */
 #define PQLB_MAX_FWD_GROUPS 5
 typedef struct {
   const float* x; int64_t ldx;
@@ -300,10 +302,21 @@ typedef struct {
   int act_n;
   int terms;
   int k_in;                   /* this group's input width (0: the descriptor's k_in); groups may differ */
-  const uint32_t* wait_flag; uint32_t* done_flag; const int64_t* epoch;
+  /* Optional C51 head (pql/models/mlp.py:261-263, softmax(Linear(128, sm_n)), sm_n <= 64) as a fourth
+   * contraction in the same launch: sm_wh / sm_wl [sm_n, 128] fp16 hi / lo, sm_b [sm_n];
+   * sm_out[row * sm_ldp + j] = probability of atom j, columns [sm_n, 64) zeroed (sm_ldp >= 64).
+   * Mutually exclusive with q and the policy head. */
+  const void* sm_wh; const void* sm_wl; const float* sm_b; float* sm_out; int64_t sm_ldp; int sm_n;
+  int publish, wait;
 } pqlb_mlp_h_group;
-typedef struct { int M, k_in, n_groups; pqlb_mlp_h_group g[PQLB_MAX_FWD_GROUPS]; } pqlb_mlp_h_desc;
+typedef struct { int M, k_in, n_groups; uint32_t* tile_sync; pqlb_mlp_h_group g[PQLB_MAX_FWD_GROUPS]; } pqlb_mlp_h_desc;
 int pqlb_mlp_forward_h(const pqlb_mlp_h_desc* desc, pqlb_stream_t stream);
+/* Tuning / tests: 1 = one CTA per (network, 128-row tile), 2 = persistent CTAs (one per SM) that
+ * software-pipeline consecutive tiles, 0 = the library default (1).  Same results bit for bit. */
+void pqlb_mlp_forward_h_mode(int mode);
+/* Debug: 64 uint64 of device memory receiving clock64 stamps of CTA (0,0) of the CTA-per-tile schedule
+ * ([0,32) MMA issuer, [32,64) first conversion warp; tools/fwd_timeline.py); NULL switches it off. */
+void pqlb_mlp_forward_h_debug(unsigned long long* buf);
 /* fp16 operand copies of a parameter arena: hi[i] = fp16(s * src[i]), lo[i] = fp16(s * src[i] - hi[i])
  * with s = pqlb_f16_weight_scale() (lo may be NULL).  The optimiser entry points below keep such
  * copies up to date themselves (param_h / target_h). */

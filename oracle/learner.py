@@ -119,20 +119,23 @@ class _LinELU(torch.autograd.Function):
 
 
 class _LinOut(torch.autograd.Function):
-    """Last layer with more than one output (actor / C51 logits): z = rn(x) rn(W)^T + b in fp32;
-    the incoming gradient is rounded (the loss / tanh' kernels emit TF32 operands)."""
+    """Last layer with more than one output (actor / C51 logits): z = rn(x) rn(W)^T + b in fp32 (or
+    on un-rounded operands for the C51 head of a precise critic); the incoming gradient is rounded
+    (the loss / tanh' kernels emit TF32 operands), the backward contractions use the rounded x and W."""
 
     @staticmethod
-    def forward(ctx, x, w, b):
+    def forward(ctx, x, w, b, x_exact):
         xr, wr = rn_tf32(x), rn_tf32(w)
         ctx.save_for_backward(xr, wr)
+        if x_exact is not None:          # split-fp16 head (C51 logits fused behind the precise trunk)
+            return _mm(x_exact.detach(), w.detach().t()) + b.detach()
         return _mm(xr, wr.t()) + b.detach()
 
     @staticmethod
     def backward(ctx, g):
         xr, wr = ctx.saved_tensors
         dz = rn_tf32(g)
-        return _mm(dz, wr), _mm(dz.t(), xr), dz.sum(0)
+        return _mm(dz, wr), _mm(dz.t(), xr), dz.sum(0), None
 
 
 class _ScalarHead(torch.autograd.Function):
@@ -158,7 +161,7 @@ def _mlp_tf32(x, params, precise=False):
     w, b = params[-1]
     if w.shape[0] == 1:
         return _ScalarHead.apply(h, hr, w, b)
-    return _LinOut.apply(hr, w, b)
+    return _LinOut.apply(hr, w, b, h if precise else None)
 
 
 # ----------------------------------------------------------------------------- forward pieces

@@ -125,17 +125,19 @@ class MlpForward(Call):
 class MlpForwardH(Call):
     """Layer-fused trunk forward with split-fp16 operands (pqlb_mlp_forward_h) for up to five network
     instances.  ``groups``: dicts with x (fp32, un-rounded), ldx, w1h/w1l, ldw1 (halves), w2h/w2l, w3h/w3l,
-    b1..b3, terms (1 | 3), [head_w, head_b, q], [h1, h2, h3], [act_wh, act_wl, act_b, ...],
-    [wait_flag, done_flag, epoch]."""
+    b1..b3, terms (1 | 3), [head_w, head_b, q], [h1, h2, h3], [act_wh, act_wl, act_b, ...], [sm_*],
+    [publish | wait] (tile dependencies through ``tile_sync``: int32 [2 + row tiles], zero-initialised)."""
 
     FIELDS = ("x", "w1h", "w1l", "w2h", "w2l", "w3h", "w3l", "b1", "b2", "b3", "head_w", "head_b", "q", "h1", "h2", "h3",
-              "act_wh", "act_wl", "act_b", "act_noise", "act_out", "act_out2", "wait_flag", "done_flag", "epoch")
-    INTS = ("ldx", "ldw1", "act_ldo", "act_ldo2", "act_ldnoise", "act_n", "terms", "k_in")
+              "act_wh", "act_wl", "act_b", "act_noise", "act_out", "act_out2", "sm_wh", "sm_wl", "sm_b", "sm_out")
+    INTS = ("ldx", "ldw1", "act_ldo", "act_ldo2", "act_ldnoise", "act_n", "terms", "k_in", "sm_ldp", "sm_n", "publish", "wait")
     FLOATS = ("noise_std", "noise_bound")
 
-    def __init__(self, M, k_in, groups):
+    def __init__(self, M, k_in, groups, tile_sync=None):
         d = _lib.MlpHDesc()
         d.M, d.k_in, d.n_groups = int(M), int(k_in), len(groups)
+        d.tile_sync = tile_sync.data_ptr() if tile_sync is not None else None
+        self._tile_sync = tile_sync
         if not 1 <= len(groups) <= _lib.MAX_FWD_GROUPS:
             raise ValueError("1..%d groups per launch" % _lib.MAX_FWD_GROUPS)
         for i, g in enumerate(groups):

@@ -66,11 +66,12 @@ class MlpHGroup(C.Structure):
                 ("act_wh", _f), ("act_wl", _f), ("act_b", _f), ("act_noise", _f), ("act_out", _f), ("act_out2", _f),
                 ("act_ldo", _i64), ("act_ldo2", _i64), ("act_ldnoise", _i64),
                 ("noise_std", _flt), ("noise_bound", _flt), ("act_n", _int), ("terms", _int), ("k_in", _int),
-                ("wait_flag", _f), ("done_flag", _f), ("epoch", _f)]
+                ("sm_wh", _f), ("sm_wl", _f), ("sm_b", _f), ("sm_out", _f), ("sm_ldp", _i64), ("sm_n", _int),
+                ("publish", _int), ("wait", _int)]
 
 
 class MlpHDesc(C.Structure):
-    _fields_ = [("M", _int), ("k_in", _int), ("n_groups", _int), ("g", MlpHGroup * MAX_FWD_GROUPS)]
+    _fields_ = [("M", _int), ("k_in", _int), ("n_groups", _int), ("tile_sync", _f), ("g", MlpHGroup * MAX_FWD_GROUPS)]
 
 
 class DpDesc(C.Structure):
@@ -122,6 +123,8 @@ _PROTOS = {
     "pqlb_mlp_forward": (_int, [C.POINTER(MlpDesc), _st]),
     "pqlb_mlp_forward_cluster": (None, [_int]),
     "pqlb_mlp_forward_h": (_int, [C.POINTER(MlpHDesc), _st]),
+    "pqlb_mlp_forward_h_mode": (None, [_int]),
+    "pqlb_mlp_forward_h_debug": (None, [_f]),
     "pqlb_split_f16": (_int, [_f, _f, _f, _i64, _st]),
     "pqlb_f16_weight_scale": (_flt, []),
     "pqlb_mlp_backward": (_int, [C.POINTER(MlpBwdDesc), _st]),
@@ -173,6 +176,8 @@ def load():
         for name, (res, args) in _PROTOS.items():
             fn = getattr(lib, name)
             fn.restype, fn.argtypes = res, args
+        if os.environ.get("PQLB_FWD_H_MODE"):       # kernel-schedule experiments: 1 = CTA per tile, 2 = persistent
+            lib.pqlb_mlp_forward_h_mode(int(os.environ["PQLB_FWD_H_MODE"]))
         _lib = lib
     return _lib
 

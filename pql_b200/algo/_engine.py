@@ -15,7 +15,8 @@ import torch
 
 from .. import _kernels as K
 from .. import _lib
-from ..models.mlp import FUSED_MAX_IN, HIDDEN, NetAddrs, NetLayout, _ru, forward_calls, fwd_tile, half_arena
+from ..models.mlp import (FUSED_MAX_IN, HIDDEN, NetAddrs, NetLayout, _ru, forward_calls, forward_calls_h, fwd_tile,
+                          half_arena)
 
 H1, H2, H3 = HIDDEN
 import os as _os
@@ -263,18 +264,35 @@ class CriticUpdate(_UpdateBase):
                                noise_std=self.noise_std, noise_bound=self.noise_bound))
         if split:       # the un-rounded action goes next to the un-rounded next_obs
             a_inst["act"].update(out2=K.addr(self.xf_tgt, O), ldo2=x_ld)
-        calls += forward_calls(B, [a_inst], False)
+        else:
+            calls += forward_calls(B, [a_inst], False)
         # -- both target nets on (next_obs, a') and both current nets on (obs, action), one launch per layer
+        # C51 + split-fp16 forward: the 51-atom softmax head rides in the fused launch (three MMAs per product
+        # like the trunk: tools/precision_study.py - the head's forward is the site the actor gradient needs)
+        fused_sm = distl and split
         insts = [dict(net=tnet[i], x=K.addr(self.x_tgt), xf=K.addr(self.xf_tgt), x_ld=x_ld, k_in=O + A,
-                      h=[K.addr(t) for t in h_t[i]], store=(False, False, distl), q=K.addr(self.tq[i]), terms=3)
+                      h=[K.addr(t) for t in h_t[i]], store=(False, False, distl and not fused_sm), q=K.addr(self.tq[i]), terms=3)
                  for i in range(2)]
         insts += [dict(net=cnet[i], x=K.addr(self.x_cur), xf=K.addr(self.xf_cur), x_ld=x_ld, k_in=O + A,
                        h=[K.addr(t) for t in h_c[i]], store=(True, True, True), q=K.addr(self.q[i]), terms=3)
                   for i in range(2)]
+        if fused_sm:
+            for j, it in enumerate(insts):
+                it["softmax"] = dict(out=K.addr(self.tp[j] if j < 2 else self.p[j - 2]), ldp=self.pd)
         wg = [(H3, H2, H2), (H2, H1, H1), (H1, O + A, x_ld)] + ([(N, H3, H3)] if distl else [])
         self._ws_init(wg, 2, [d for d in HIDDEN] * 2 + ([N, N] if distl else []),
                       extra=2 * _ru(self.nblk_head * (H3 + 1), 32) + 2 * _ru(self.nblk_head * H3, 32))
-        calls += forward_calls(B, insts, not distl)
+        if split:
+            # ONE launch for all five networks: the 64 policy tiles publish their action rows tile by tile,
+            # the target critics (dispatched last) wait for the tile they read, and the SMs the policy
+            # leaves idle start on the current critics, which do not depend on it
+            self.tile_sync = torch.zeros(2 + self.nblk, dtype=torch.int32, device=dev)
+            a_inst["publish"] = 1
+            for it in insts[:2]:
+                it["wait"] = 1
+            calls += forward_calls_h(B, [a_inst] + insts[2:] + insts[:2], not distl, tile_sync=self.tile_sync)
+        else:
+            calls += forward_calls(B, insts, not distl)
         if not distl:
             ws_head = [self._ws_alloc(self.nblk_head * (H3 + 1)) for _ in range(2)]
             for i in range(2):
@@ -292,10 +310,11 @@ class CriticUpdate(_UpdateBase):
                                 C.c_void_p(K.addr(self.ws, b3[0])), C.c_void_p(K.addr(self.ws, b3[1]))))
             self.loss_scale, self.n_loss_part = 1.0 / B, 2 * self.nblk_head
         else:
-            groups = [dict(a=it["h"][2], lda=H3, b=it["net"].W[3], ldb=H3, bias=it["net"].b[3],
-                           out=K.addr(self.tp[j] if j < 2 else self.p[j - 2]), ldo=self.pd)
-                      for j, it in enumerate(insts)]
-            calls.append(K.Gemm(B, N, H3, groups, epilogue=K.EPI_BIAS_SOFTMAX, tile_n=64))
+            if not fused_sm:
+                groups = [dict(a=it["h"][2], lda=H3, b=it["net"].W[3], ldb=H3, bias=it["net"].b[3],
+                               out=K.addr(self.tp[j] if j < 2 else self.p[j - 2]), ldo=self.pd)
+                          for j, it in enumerate(insts)]
+                calls.append(K.Gemm(B, N, H3, groups, epilogue=K.EPI_BIAS_SOFTMAX, tile_n=64))
             calls.append(K.Call("pqlb_c51_td_loss", _lib.ptr(self.p[0]), _lib.ptr(self.p[1]), _lib.ptr(self.tp[0]),
                                 _lib.ptr(self.tp[1]), self.pd, _lib.ptr(self.reward), _lib.ptr(self.done),
                                 _lib.ptr(self.z), self.gamma_n, self.v_min, self.v_max, N, B, _lib.ptr(self.target),
@@ -471,6 +490,10 @@ class ActorUpdate(_UpdateBase):
         insts = [dict(net=cnet[i], x=K.addr(self.x), xf=K.addr(self.xf), x_ld=x_ld, k_in=O + A,
                       h=[K.addr(t) for t in h_c[i]], q=K.addr(self.q[i]), terms=3) for i in range(2)]
         dz3 = [self.dzc[i][2] for i in range(2)]
+        fused_sm = distl and split
+        if fused_sm:
+            for j, it in enumerate(insts):
+                it["softmax"] = dict(out=K.addr(self.p[j]), ldp=self.pd)
         calls += forward_calls(B, insts, not distl)
         if not distl:
             calls.append(K.Call("pqlb_dpg_loss", _lib.ptr(self.q[0]), _lib.ptr(self.q[1]), B, _lib.ptr(h_c[0][2]),
@@ -478,9 +501,10 @@ class ActorUpdate(_UpdateBase):
                                 _lib.ptr(dz3[0]), _lib.ptr(dz3[1]), _lib.ptr(self.loss_part)))
             self.n_loss_part = 2 * self.nblk_head
         else:
-            groups = [dict(a=it["h"][2], lda=H3, b=it["net"].W[3], ldb=H3, bias=it["net"].b[3],
-                           out=K.addr(self.p[j]), ldo=self.pd) for j, it in enumerate(insts)]
-            calls.append(K.Gemm(B, N, H3, groups, epilogue=K.EPI_BIAS_SOFTMAX, tile_n=64))
+            if not fused_sm:
+                groups = [dict(a=it["h"][2], lda=H3, b=it["net"].W[3], ldb=H3, bias=it["net"].b[3],
+                               out=K.addr(self.p[j]), ldo=self.pd) for j, it in enumerate(insts)]
+                calls.append(K.Gemm(B, N, H3, groups, epilogue=K.EPI_BIAS_SOFTMAX, tile_n=64))
             calls.append(K.Call("pqlb_c51_dpg_loss", _lib.ptr(self.p[0]), _lib.ptr(self.p[1]), self.pd, _lib.ptr(self.z),
                                 N, B, _lib.ptr(self.dl[0]), _lib.ptr(self.dl[1]), self.pd, _lib.ptr(self.q[0]),
                                 _lib.ptr(self.loss_part)))

@@ -25,68 +25,10 @@
 // TMEM columns: P0 [0,128) P1 [128,256) Y [256,512); Z = P0; policy head output in P1.
 // Replaces: the nn.Linear + nn.ELU launches of pql/models/mlp.py:15-24 for actor and critics
 // (pql/algo/pql_v_learner.py:81-107, pql/algo/pql_p_learner.py:55-56).
-#include "f16split.cuh"
-#include "tcgen05_utils.cuh"
+#include "mlp_fwd_h.cuh"
 
 namespace pqlb {
 
-constexpr int kHH1 = 512, kHH2 = 256, kHH3 = 128;
-constexpr int kHEpiWarps = 16;
-constexpr int kHThreads = 64 + 32 * kHEpiWarps;
-constexpr int kHStages = 5;
-constexpr int kHTileBytes = 128 * 128;        // every weight tile: 128 rows x 64 halves
-constexpr int kHXKb = 4;                      // input width <= 128 floats: four 32-float blocks
-constexpr int kHXBytes = kHXKb * 128 * 128;
-constexpr int kHChunk = 32 * 128;
-constexpr int kHSmem = 1024 + kHXBytes + kHStages * kHTileBytes + kHEpiWarps * kHChunk + (kHH1 + kHH2 + 2 * kHH3) * 4;
-
-struct alignas(64) MlpHGroupDev {
-  CUtensorMap tmX, tmW1[2], tmW2[2], tmW3[2], tmW4[2], tmH1, tmH2, tmH3;      // [0] hi, [1] lo
-  const float* b1; const float* b2; const float* b3; const float* head_w; const float* head_b;
-  float* q;
-  const float* act_b; const float* act_noise; float* act_out; float* act_out2;
-  long long act_ldo, act_ldo2, act_ldnoise;
-  float noise_std, noise_bound;
-  int act_n;
-  int st1, st2, st3;
-  int terms;
-  int kb1, kw1, ksteps1;            // this group's input width in 32-float blocks / 64-half weight blocks / 16-wide k steps
-  const unsigned* wait_flag; unsigned* done_flag;      // optional per-row-tile dependency between groups of one launch
-  const long long* epoch_ptr;                          // flag value of this launch = 1 + (unsigned)*epoch_ptr (a per-update device counter)
-};
-struct alignas(64) MlpHDev {
-  MlpHGroupDev g[PQLB_MAX_FWD_GROUPS];
-  int M;
-};
-
-__host__ __device__ constexpr uint32_t idesc_f16(int n) {
-  // D fp32 (bits 4-5 = 1), A / B fp16 (format 0), both K-major, N >> 3 at bit 17, M >> 4 at bit 24
-  return (1u << 4) | ((unsigned)(n >> 3) << 17) | ((unsigned)(128 >> 4) << 24);
-}
-__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
-}
-// A operand in tensor memory: lane = row, one 32-bit column = two consecutive k (low half first)
-__device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, {%5, %5, %5, %5}, p;\n\t}"
-      ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(0u) : "memory");
-}
-__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* r) {
-  asm volatile(
-      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
-      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
-      ::"r"(taddr),
-        "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
-        "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
-      : "memory");
-}
 template <int T>
 __device__ __forceinline__ void mlp_fwd_h_body(const MlpHDev& P, const MlpHGroupDev& G, uint8_t* smem_raw) {
   __shared__ __align__(8) uint64_t x_full, x_conv, full_bar[kHStages], empty_bar[kHStages];
@@ -127,6 +69,9 @@ __device__ __forceinline__ void mlp_fwd_h_body(const MlpHDev& P, const MlpHGroup
   const uint32_t tmem = uniform_u32(tmem_slot);
   const uint32_t tY = tmem + 256u;
   const uint32_t tZ = tmem;
+  unsigned long long* dbg = (blockIdx.x == 0 && blockIdx.y == 0) ? P.dbg : nullptr;
+  int dbg_i = 0;
+#define PQLB_HSTAMP(base) do { if (dbg && lane == 0) dbg[(base) + dbg_i] = clock64(); ++dbg_i; } while (0)
 
   // Weight-tile schedule shared by producer and MMA issuer, one hex digit per phase (phase 0 is the
   // lowest digit): kind 0 = layer-1 quarter q, 1 = layer-2 K-chunk c, 2 = layer 3.
@@ -136,13 +81,13 @@ __device__ __forceinline__ void mlp_fwd_h_body(const MlpHDev& P, const MlpHGroup
 
   if (warp == 0) {
     // ===================== TMA producer =====================
-    if (G.wait_flag) {
+    if (G.wait) {
       // this tile's input is produced by another group of the same launch (target policy -> target
       // critics): its CTAs have lower block indices, are therefore resident or finished, and never
       // wait themselves, so spinning here cannot deadlock
       if (lane == 0) {
-        const volatile unsigned* f = G.wait_flag + blockIdx.x;
-        const unsigned epoch = 1u + (unsigned)*G.epoch_ptr;
+        const volatile unsigned* f = P.tile_sync + 2 + blockIdx.x;
+        const unsigned epoch = 1u + *reinterpret_cast<const volatile unsigned*>(P.tile_sync + 1);
         const long long t0 = clock64();
         while (*f != epoch) { if (clock64() - t0 > 4000000000LL) __trap(); }
         __threadfence();
@@ -185,22 +130,28 @@ __device__ __forceinline__ void mlp_fwd_h_body(const MlpHDev& P, const MlpHGroup
           for (int part = 0; part < NP; ++part) load_tile(&G.tmW3[part], t * 32, 0);
       }
     }
-    if (G.act_n > 0) {                          // policy head weights: 16 rows x 128 k as two 2 KB boxes per part in one stage
-      mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1u);
-      const uint32_t bar = smem_u32(&full_bar[stage]);
-      const uint32_t dst = ring + stage * kHTileBytes;
-      if (elect_one()) {
-        mbar_expect_tx(bar, (uint32_t)NP * 2u * 2048u);
+    if (G.head_rows > 0) {
+      // head weights (policy: 16 rows, softmax: 64 rows) x 128 k: two boxes of head_rows x 64 halves, one stage per part
+      const uint32_t box_bytes = (uint32_t)G.head_rows * 128u;
 #pragma unroll
-        for (int part = 0; part < NP; ++part)
-          for (int kb = 0; kb < 2; ++kb) tma_load_2d(dst + (part * 2 + kb) * 2048, &G.tmW4[part], kb * 32, 0, bar);
+      for (int part = 0; part < NP; ++part) {
+        mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1u);
+        const uint32_t bar = smem_u32(&full_bar[stage]);
+        const uint32_t dst = ring + stage * kHTileBytes;
+        if (elect_one()) {
+          mbar_expect_tx(bar, 2u * box_bytes);
+          for (int kb = 0; kb < 2; ++kb) tma_load_2d(dst + kb * box_bytes, &G.tmW4[part], kb * 32, 0, bar);
+        }
+        __syncwarp();
+        if (++stage == kHStages) { stage = 0; phase ^= 1u; }
       }
-      __syncwarp();
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
+    PQLB_HSTAMP(0);
     mbar_wait(smem_u32(&x_conv), 0);             // the input tile has been split into fp16 hi | lo in place
     tcgen05_fence_after();
+    PQLB_HSTAMP(0);
     int stage = 0; uint32_t phase = 0;
     auto wait_tile = [&]() -> uint64_t {
       mbar_wait(smem_u32(&full_bar[stage]), phase);
@@ -243,11 +194,13 @@ __device__ __forceinline__ void mlp_fwd_h_body(const MlpHDev& P, const MlpHGroup
         }
         if (elect_one()) umma_commit(smem_u32(&p_full[arg & 1]));
         __syncwarp();
+        PQLB_HSTAMP(0);
       } else if (kind == 1) {
         const int c = arg, b = c & 1;
         const uint32_t tP = tmem + (uint32_t)(b * 128);
         mbar_wait(smem_u32(&p_conv[b]), (uint32_t)(c >> 1) & 1u);      // quarter c converted in place
         tcgen05_fence_after();
+        PQLB_HSTAMP(0);
 #pragma unroll
         for (int t = 0; t < 4; ++t) {
 #pragma unroll
@@ -271,6 +224,7 @@ __device__ __forceinline__ void mlp_fwd_h_body(const MlpHDev& P, const MlpHGroup
           }
         }
         if (c == 3) { if (elect_one()) umma_commit(smem_u32(&y_full)); __syncwarp(); }
+        PQLB_HSTAMP(0);
       } else {
 #pragma unroll
         for (int t = 0; t < 4; ++t) {            // k block t of layer 3: Y half t >> 1, 64-k half t & 1
@@ -296,33 +250,38 @@ __device__ __forceinline__ void mlp_fwd_h_body(const MlpHDev& P, const MlpHGroup
         }
         if (elect_one()) umma_commit(smem_u32(&z_full));
         __syncwarp();
+        PQLB_HSTAMP(0);
       }
     }
-    if (G.act_n > 0) {
-      // policy head: h3 (split in place in Z) . W4^T into 16 columns of P1, N = 16
+    if (G.head_rows > 0) {
+      // head: h3 (split in place in Z) . W4^T into head_rows columns of P1 (policy N = 16, softmax N = 64)
       mbar_wait(smem_u32(&z_conv), 0);
       tcgen05_fence_after();
-      mbar_wait(smem_u32(&full_bar[stage]), phase);
-      tcgen05_fence_after();
-      if (elect_one()) {
+      const uint32_t idesc_head = G.head_rows == 16 ? idesc_f16(16) : idesc_f16(64);
+      const uint32_t box_bytes = (uint32_t)G.head_rows * 128u;
 #pragma unroll
-        for (int part = 0; part < NP; ++part)
+      for (int part = 0; part < NP; ++part) {
+        const uint64_t bdesc0 = wait_tile();
+        if (elect_one()) {
 #pragma unroll
           for (int kb = 0; kb < 2; ++kb) {
-            const uint64_t bdesc = desc0 | (uint64_t)(((ring + stage * kHTileBytes + (part * 2 + kb) * 2048) >> 4) & 0x3FFF);
+            const uint64_t bdesc = bdesc0 + (uint64_t)((kb * box_bytes) >> 4);
 #pragma unroll
             for (int s = 0; s < 4; ++s) {
               const uint32_t a_hi = tZ + (uint32_t)(kb * 32 + s * 8);
               if (part == 0) {
-                umma_f16_ts(tmem + 128u, a_hi, bdesc + 2u * s, idesc_f16(16), (uint32_t)((kb | s) != 0));
-                if (T == 3) umma_f16_ts(tmem + 128u, a_hi + 64u, bdesc + 2u * s, idesc_f16(16), 1u);
+                umma_f16_ts(tmem + 128u, a_hi, bdesc + 2u * s, idesc_head, (uint32_t)((kb | s) != 0));
+                if (T == 3) umma_f16_ts(tmem + 128u, a_hi + 64u, bdesc + 2u * s, idesc_head, 1u);
               } else {
-                umma_f16_ts(tmem + 128u, a_hi, bdesc + 2u * s, idesc_f16(16), 1u);
+                umma_f16_ts(tmem + 128u, a_hi, bdesc + 2u * s, idesc_head, 1u);
               }
             }
           }
-        umma_commit(smem_u32(&a_full));
+          release_tile();
+        }
+        next_stage();
       }
+      if (elect_one()) umma_commit(smem_u32(&a_full));
       __syncwarp();
     }
   } else {
@@ -342,7 +301,10 @@ __device__ __forceinline__ void mlp_fwd_h_body(const MlpHDev& P, const MlpHGroup
     bool pending = false;
 
     // ---- input tile: fp32 -> [hi | lo] fp16, in place (thread = one 128-byte row of one 32-float block)
+    if (e != 0) dbg = nullptr;
+    PQLB_HSTAMP(32);
     mbar_wait(smem_u32(&x_full), 0);
+    PQLB_HSTAMP(32);
     {
       const int t = (int)threadIdx.x - 64;
       const int r = t & 127, kb = t >> 7;
@@ -373,6 +335,7 @@ __device__ __forceinline__ void mlp_fwd_h_body(const MlpHDev& P, const MlpHGroup
       __syncwarp();
       if (lane == 0) mbar_arrive(smem_u32(&x_conv));
     }
+    PQLB_HSTAMP(32);
 
     // hands this warp's 32x32 chunk (already TF32-rounded) to a TMA store through its staging buffer
     auto store_chunk = [&](const float* v, const CUtensorMap* omap, int n_col) {
@@ -418,14 +381,20 @@ __device__ __forceinline__ void mlp_fwd_h_body(const MlpHDev& P, const MlpHGroup
       const int b = q & 1;
       mbar_wait(smem_u32(&p_full[b]), (uint32_t)(q >> 1) & 1u);
       tcgen05_fence_after();
+      PQLB_HSTAMP(32);
       convert(tmem + (uint32_t)(b * 128), s_b1, q * 128, &G.tmH1, G.st1 != 0, smem_u32(&p_conv[b]));
+      PQLB_HSTAMP(32);
     }
     mbar_wait(smem_u32(&y_full), 0);
     tcgen05_fence_after();
-    for (int hh = 0; hh < 2; ++hh)
+    PQLB_HSTAMP(32);
+    for (int hh = 0; hh < 2; ++hh) {
       convert(tY + (uint32_t)(hh * 128), s_b2, hh * 128, &G.tmH2, G.st2 != 0, smem_u32(&y_conv[hh]));
+      PQLB_HSTAMP(32);
+    }
     mbar_wait(smem_u32(&z_full), 0);
     tcgen05_fence_after();
+    PQLB_HSTAMP(32);
     {
       float qacc = 0.f;
       float v[32];
@@ -435,7 +404,7 @@ __device__ __forceinline__ void mlp_fwd_h_body(const MlpHDev& P, const MlpHGroup
         v[j] = elu_fast(fmaf(v[j], kWInv, s_b3[col + j]));
         qacc = fmaf(v[j], s_w4[col + j], qacc);
       }
-      if (G.act_n > 0) {                         // h3 back into Z as packed halves: the A operand of the policy head
+      if (G.head_rows > 0) {                     // h3 back into Z as packed halves: the A operand of the head contraction
         uint32_t hp[16], lp[16];
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
@@ -492,14 +461,41 @@ __device__ __forceinline__ void mlp_fwd_h_body(const MlpHDev& P, const MlpHGroup
               if (j < G.act_n) *reinterpret_cast<float4*>(dst2 + j) = make_float4(o2[j], o2[j + 1], o2[j + 2], o2[j + 3]);
           }
         }
-        if (G.done_flag) {
+        if (G.publish) {
           // the four head warps of this tile have written their rows: publish the tile to the CTAs
-          // that wait for it (wait_flag of another group)
+          // that wait for it (a later group of this launch)
           __threadfence();
           named_bar_sync(5, 128);
           if (quarter == 0 && lane == 0) {
             __threadfence();
-            *reinterpret_cast<volatile unsigned*>(G.done_flag + blockIdx.x) = 1u + (unsigned)*G.epoch_ptr;
+            *reinterpret_cast<volatile unsigned*>(P.tile_sync + 2 + blockIdx.x) =
+                1u + *reinterpret_cast<const volatile unsigned*>(P.tile_sync + 1);
+          }
+        }
+      }
+      if (G.sm_n > 0 && chunk == 0) {
+        // C51 head (pql/models/mlp.py:261-263): all sm_n <= 64 logits of a row live in this thread: softmax
+        // in registers, same arithmetic as the EPI_BIAS_SOFTMAX epilogue of gemm_tf32.cu
+        mbar_wait(smem_u32(&a_full), 0);
+        tcgen05_fence_after();
+        float l[64];
+        tmem_ld32(tmem + 128u + lane_sel, l);
+        tmem_ld32(tmem + 128u + lane_sel + 32u, l + 32);
+        float mx = -INFINITY;
+#pragma unroll
+        for (int j = 0; j < 64; ++j) if (j < G.sm_n) { l[j] = fmaf(l[j], kWInv, G.sm_b[j]); mx = fmaxf(mx, l[j]); }
+        float sum = 0.f;
+#pragma unroll
+        for (int j = 0; j < 64; ++j) if (j < G.sm_n) { l[j] = __expf(l[j] - mx); sum += l[j]; }
+        const float inv = 1.f / sum;
+        if (row < P.M) {
+          float* dst = G.sm_out + (long long)row * G.sm_ldp;
+#pragma unroll
+          for (int j = 0; j < 64; j += 4) {
+            float4 o;
+            o.x = j < G.sm_n ? l[j] * inv : 0.f; o.y = j + 1 < G.sm_n ? l[j + 1] * inv : 0.f;
+            o.z = j + 2 < G.sm_n ? l[j + 2] * inv : 0.f; o.w = j + 3 < G.sm_n ? l[j + 3] * inv : 0.f;
+            *reinterpret_cast<float4*>(dst + j) = o;
           }
         }
       }
@@ -515,6 +511,7 @@ __device__ __forceinline__ void mlp_fwd_h_body(const MlpHDev& P, const MlpHGroup
       }
     }
     if (pending) { if (elect_one()) bulk_wait_read<0>(); __syncwarp(); }
+    PQLB_HSTAMP(32);
   }
 
   tcgen05_fence_before();
@@ -522,6 +519,17 @@ __device__ __forceinline__ void mlp_fwd_h_body(const MlpHDev& P, const MlpHGroup
   if (warp == 1) {
     tcgen05_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
+  }
+  if (P.tile_sync && threadIdx.x == 0) {
+    // exit ticket: the last CTA of the launch closes the epoch (every CTA has read [1] long before)
+    const unsigned total = gridDim.x * gridDim.y;
+    const unsigned epoch = *reinterpret_cast<const volatile unsigned*>(P.tile_sync + 1);
+    __threadfence();
+    if (atomicAdd(P.tile_sync, 1u) == total - 1u) {
+      *reinterpret_cast<volatile unsigned*>(P.tile_sync) = 0u;
+      __threadfence();
+      *reinterpret_cast<volatile unsigned*>(P.tile_sync + 1) = epoch + 1u;
+    }
   }
 }
 
@@ -556,8 +564,17 @@ split_f16_kernel(const float* __restrict__ src, __half* __restrict__ hi, __half*
 
 using namespace pqlb;
 
+static unsigned long long* g_fwd_h_debug = nullptr;
+/* Debug: device buffer of 64 uint64 receiving a clock64 timeline of CTA (0,0) of the CTA-per-tile kernel (NULL = off). */
+extern "C" void pqlb_mlp_forward_h_debug(unsigned long long* buf) { g_fwd_h_debug = buf; }
+static int g_fwd_h_mode = 0;
+/* Tuning / tests: 1 = one CTA per (network, tile), 2 = persistent CTAs pipelining consecutive tiles, 0 = default (1:
+ * measured 3718 vs 3653 critic updates/s on the bench, profiles/r2_fwd_schedules.txt). */
+extern "C" void pqlb_mlp_forward_h_mode(int mode) { g_fwd_h_mode = (mode == 1 || mode == 2) ? mode : 0; }
+
 extern "C" int pqlb_mlp_forward_h_init(void) {
   cudaError_t e = cudaFuncSetAttribute(mlp_fwd_h_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kHSmem);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(mlp_fwd_hp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kHPSmem);
   return e == cudaSuccess ? PQLB_OK : (int)e;
 }
 
@@ -584,6 +601,9 @@ extern "C" int pqlb_mlp_forward_h(const pqlb_mlp_h_desc* d, pqlb_stream_t stream
   { int rc = pqlb_init(); if (rc != PQLB_OK) return rc; }
   static MlpHDev P;
   P.M = d->M;
+  P.tile_sync = d->tile_sync;
+  P.tiles_m = (d->M + 127) / 128; P.n_groups = d->n_groups;
+  P.dbg = g_fwd_h_debug;
   const int tiles_m = (d->M + 127) / 128;
   for (int i = 0; i < d->n_groups; ++i) {
     const pqlb_mlp_h_group& s = d->g[i];
@@ -616,6 +636,18 @@ extern "C" int pqlb_mlp_forward_h(const pqlb_mlp_h_desc* d, pqlb_stream_t stream
     G.terms = s.terms;
     G.act_n = 0; G.tmW4[0] = G.tmW4[1] = G.tmX;
     G.act_b = nullptr; G.act_noise = nullptr; G.act_out = nullptr; G.act_out2 = nullptr;
+    G.sm_n = 0; G.sm_b = nullptr; G.sm_out = nullptr; G.sm_ldp = 0; G.head_rows = 0;
+    if (s.sm_wh) {
+      // C51 softmax head: sm_n atoms <= 64, probability rows of 64 floats (16-byte aligned)
+      PQLB_CHECK_ARG(!s.q && !s.act_wh && s.sm_b && s.sm_out && s.sm_n > 0 && (s.terms == 1 || s.sm_wl));
+      if (s.sm_n > 64 || s.sm_ldp < 64 || s.sm_ldp % 4 || !aligned16(s.sm_out)) return PQLB_E_UNSUPPORTED;
+      const void* w5[2] = {s.sm_wh, s.sm_wl};
+      for (int p = 0; p < 2; ++p) {
+        const bool have = p == 0 || s.terms == 3;
+        if ((rc = make_half_map(&G.tmW4[p], have ? w5[p] : w5[0], kHH3, s.sm_n, kHH3, 64)) != PQLB_OK) return rc;
+      }
+      G.sm_n = s.sm_n; G.sm_b = s.sm_b; G.sm_out = s.sm_out; G.sm_ldp = s.sm_ldp; G.head_rows = 64;
+    }
     if (s.act_wh) {
       // policy head: act_n a multiple of 4 up to 16, 16-byte aligned output rows
       PQLB_CHECK_ARG(!s.q && s.act_b && (s.act_out || s.act_out2) && s.act_n > 0 && (s.terms == 1 || s.act_wl));
@@ -625,23 +657,25 @@ extern "C" int pqlb_mlp_forward_h(const pqlb_mlp_h_desc* d, pqlb_stream_t stream
         const bool have = p == 0 || s.terms == 3;
         if ((rc = make_half_map(&G.tmW4[p], have ? w4[p] : w4[0], kHH3, s.act_n, kHH3, 16)) != PQLB_OK) return rc;
       }
+      G.head_rows = 16;
       G.act_n = s.act_n; G.act_b = s.act_b; G.act_noise = s.act_noise; G.act_out = s.act_out; G.act_out2 = s.act_out2;
       G.act_ldo = s.act_ldo; G.act_ldo2 = s.act_ldo2; G.act_ldnoise = s.act_ldnoise;
       G.noise_std = s.noise_std; G.noise_bound = s.noise_bound;
     }
     // tile dependencies inside one launch: a group may only wait for a group with a LOWER index (its
     // CTAs are dispatched first), and only a policy group publishes
-    PQLB_CHECK_ARG(!s.done_flag || s.act_wh);
-    PQLB_CHECK_ARG(!s.wait_flag || i > 0);
-    PQLB_CHECK_ARG((!s.wait_flag && !s.done_flag) || s.epoch);
-    G.wait_flag = s.wait_flag; G.done_flag = s.done_flag; G.epoch_ptr = reinterpret_cast<const long long*>(s.epoch);
+    PQLB_CHECK_ARG(!s.publish || (s.act_wh && d->tile_sync));
+    PQLB_CHECK_ARG(!s.wait || (i > 0 && d->tile_sync));
+    G.publish = s.publish != 0; G.wait = s.wait != 0;
   }
+  const bool persistent = g_fwd_h_mode == 2;
+  const int n_items = tiles_m * d->n_groups;
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3((unsigned)tiles_m, (unsigned)d->n_groups, 1);
+  cfg.gridDim = persistent ? dim3((unsigned)(n_items < kNumSMs ? n_items : kNumSMs), 1, 1) : dim3((unsigned)tiles_m, (unsigned)d->n_groups, 1);
   cfg.blockDim = dim3(kHThreads, 1, 1);
-  cfg.dynamicSmemBytes = kHSmem;
+  cfg.dynamicSmemBytes = persistent ? kHPSmem : kHSmem;
   cfg.stream = (cudaStream_t)stream;
-  cudaError_t le = cudaLaunchKernelEx(&cfg, mlp_fwd_h_kernel, P);
+  cudaError_t le = persistent ? cudaLaunchKernelEx(&cfg, mlp_fwd_hp_kernel, P) : cudaLaunchKernelEx(&cfg, mlp_fwd_h_kernel, P);
   PQLB_COUNT_LAUNCH(1);
   return le == cudaSuccess ? PQLB_OK : (int)le;
 }

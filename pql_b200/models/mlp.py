@@ -154,7 +154,7 @@ def split_f16_ok(inst):
     return True
 
 
-def forward_calls_h(B, insts, scalar_head):
+def forward_calls_h(B, insts, scalar_head, tile_sync=None):
     """ONE split-fp16 fused launch for up to five network instances (input widths may differ).  inst as
     in ``forward_calls`` plus ``terms`` (3 = hi/lo split of both operands, 1 = hi only), ``xf`` (the
     un-rounded input rows; falls back to ``x``) and optional ``wait_flag`` / ``done_flag`` / ``epoch``."""
@@ -179,11 +179,16 @@ def forward_calls_h(B, insts, scalar_head):
                      noise_bound=act.get("noise_bound", 0.0))
             if terms == 3:
                 g["act_wl"] = n.Wl[3]
-        for k in ("wait_flag", "done_flag", "epoch"):
+        sm = it.get("softmax")          # C51 head fused behind the trunk: dict(out, ldp)
+        if sm is not None:
+            g.update(sm_wh=n.Wh[3], sm_b=n.b[3], sm_out=sm["out"], sm_ldp=sm["ldp"], sm_n=n.dims[4])
+            if terms == 3:
+                g["sm_wl"] = n.Wl[3]
+        for k in ("publish", "wait"):
             if it.get(k):
-                g[k] = it[k]
+                g[k] = 1
         groups.append(g)
-    return [K.MlpForwardH(B, max(it["k_in"] for it in insts), groups)]
+    return [K.MlpForwardH(B, max(it["k_in"] for it in insts), groups, tile_sync=tile_sync)]
 
 
 def forward_calls(B, insts, scalar_head):

@@ -18,6 +18,15 @@ def K():
     return _kernels
 
 
+@pytest.fixture(params=[1, 2], ids=["cta-per-tile", "persistent"])
+def mode(request):
+    """Both schedules of the kernel: one CTA per (network, tile) and persistent CTAs pipelining tiles."""
+    from pql_b200 import _lib
+    _lib.load().pqlb_mlp_forward_h_mode(request.param)
+    yield request.param
+    _lib.load().pqlb_mlp_forward_h_mode(0)
+
+
 def rn_tf32(x):
     return ((x.contiguous().view(torch.int32) + 0x1000) & ~0x1FFF).view(torch.float32)
 
@@ -69,8 +78,8 @@ def test_split_copies_reconstruct_the_weights():
 
 
 @pytest.mark.parametrize("M,k_in,n_groups,terms", [(128, 104, 1, 3), (200, 88, 1, 1), (8192, 104, 4, 3), (300, 104, 2, 3),
-                                                   (8192, 104, 5, 3), (1000, 16, 1, 3), (8192, 88, 2, 1)])
-def test_split_f16_trunk_and_q_head(K, M, k_in, n_groups, terms):
+                                                   (8192, 104, 5, 3), (1000, 16, 1, 3), (8192, 88, 2, 1), (40000, 104, 2, 3)])
+def test_split_f16_trunk_and_q_head(K, mode, M, k_in, n_groups, terms):
     g = torch.Generator(device=DEV).manual_seed(11 * M + k_in + terms)
     ld = (k_in + 3) // 4 * 4
     groups, keep = [], []
@@ -121,7 +130,7 @@ def test_split_f16_trunk_and_q_head(K, M, k_in, n_groups, terms):
 
 
 @pytest.mark.parametrize("M,A,noisy,terms", [(8192, 16, True, 1), (300, 16, False, 3), (1000, 8, True, 1), (128, 4, False, 1)])
-def test_split_f16_policy_head(K, M, A, noisy, terms):
+def test_split_f16_policy_head(K, mode, M, A, noisy, terms):
     """tanh(Linear(128, A)) (+ clipped N(0, std^2) noise, clamp) fused behind the trunk: act_out2 holds the
     value, act_out its TF32 rounding (mlp.py:177-179, noise.py:19-27)."""
     g = torch.Generator(device=DEV).manual_seed(M + A)
@@ -151,3 +160,52 @@ def test_split_f16_policy_head(K, M, A, noisy, terms):
     assert torch.equal(got, rn_tf32(got2))
     assert float((out[:, :88] - 7.0).abs().max()) == 0.0
     assert 88 + A == 104 or float((out[:, 88 + A:] - 7.0).abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("M", [8192, 1000])
+def test_policy_to_critic_dependency_in_one_launch(K, mode, M):
+    """One launch: a policy net (terms 1) publishes its action rows tile by tile, a critic that does not depend
+    on it runs meanwhile, two critics wait for the tile they read.  Must equal the two-launch sequence bit for
+    bit, on every repetition (tile_sync carries over between launches without a reset)."""
+    g = torch.Generator(device=DEV).manual_seed(M)
+    O, A, ld = 88, 16, 104
+    xa = torch.zeros(M, ld, device=DEV)
+    xa[:, :O] = torch.randn(M, O, device=DEV, generator=g)
+    xc = torch.randn(M, ld, device=DEV, generator=g)
+    actor = make_net(O, A, g)
+    crit = [make_net(O + A, 1, g, ld) for _ in range(3)]
+    noise = torch.randn(M, A, device=DEV, generator=g)
+
+    def groups(x_wait, q, with_flags):
+        ws, bs, hs, ls = actor
+        ga = dict(x=K.addr(x_wait), ldx=ld, k_in=O, w1h=hs[0].data_ptr(), ldw1=88, w2h=hs[1].data_ptr(), w3h=hs[2].data_ptr(),
+                  b1=K.addr(bs[0]), b2=K.addr(bs[1]), b3=K.addr(bs[2]), terms=1, act_wh=hs[3].data_ptr(), act_b=K.addr(bs[3]),
+                  act_n=A, act_out2=K.addr(x_wait, O), act_ldo2=ld, act_noise=K.addr(noise), act_ldnoise=A, noise_std=0.8,
+                  noise_bound=0.2, publish=int(with_flags))
+        gc = []
+        for i, (ws, bs, hs, ls) in enumerate(crit):
+            gc.append(dict(x=K.addr(xc if i == 0 else x_wait), ldx=ld, k_in=O + A, w1h=hs[0].data_ptr(), w1l=ls[0].data_ptr(), ldw1=ld,
+                           w2h=hs[1].data_ptr(), w2l=ls[1].data_ptr(), w3h=hs[2].data_ptr(), w3l=ls[2].data_ptr(),
+                           b1=K.addr(bs[0]), b2=K.addr(bs[1]), b3=K.addr(bs[2]), head_w=K.addr(ws[3]), head_b=K.addr(bs[3]),
+                           q=K.addr(q[i]), terms=3, wait=int(with_flags and i > 0)))
+        return ga, gc
+
+    x_ref, x_one = xa.clone(), xa.clone()
+    q_ref = [torch.zeros(M, device=DEV) for _ in range(3)]
+    q_one = [torch.zeros(M, device=DEV) for _ in range(3)]
+    ga, gc = groups(x_ref, q_ref, False)
+    K.MlpForwardH(M, O, [ga])()
+    K.MlpForwardH(M, O + A, gc)()
+    sync = torch.zeros(2 + (M + 127) // 128, dtype=torch.int32, device=DEV)
+    ga, gc = groups(x_one, q_one, True)
+    fused = K.MlpForwardH(M, O + A, [ga] + gc, tile_sync=sync)
+    for rep in range(4):
+        x_one[:, O:].zero_()
+        for t in q_one:
+            t.zero_()
+        fused()
+        torch.cuda.synchronize()
+        assert torch.equal(x_one, x_ref), f"rep {rep}: action rows differ"
+        for i in range(3):
+            assert torch.equal(q_one[i], q_ref[i]), f"rep {rep}: critic {i} differs"
+        assert int(sync[1]) == rep + 1 and int(sync[0]) == 0
