@@ -159,6 +159,15 @@ int pqlb_store_i64(int64_t* dst, int64_t value, pqlb_stream_t stream);
 int64_t pqlb_rms_workspace_bytes(int64_t rows, int cols);
 int pqlb_rms_update(const float* x, int64_t rows, int cols, int64_t ldx, float* mean, float* var,
                     double* count, void* workspace, int64_t workspace_bytes, pqlb_stream_t stream);
+/* The same update for data-parallel actors: pqlb_rms_moments writes this rank's column sums
+ * and sums of squares (2 * cols doubles, slab order) instead of applying them; the caller all-reduces
+ * them over the ranks (one 2 * cols fp64 sum per env step) and pqlb_rms_apply merges the moments of all
+ * total_rows rows into mean / var / count - every rank takes the reference's update on the concatenated
+ * batch and the normalisers stay bit-identical. */
+int pqlb_rms_moments(const float* x, int64_t rows, int cols, int64_t ldx, double* sums, void* workspace,
+                     int64_t workspace_bytes, pqlb_stream_t stream);
+int pqlb_rms_apply(const double* sums, int64_t total_rows, int cols, float* mean, float* var, double* count,
+                   pqlb_stream_t stream);
 /* Inputs of the policy forward for one env step.  x (optional): x[r, :obs_dim] = obs normalised with
  * (mean, var, eps) as RunningMeanStd.normalize does ((x - mean) / sqrt(var + eps), torch_util.py:83-85;
  * clamp5 adds pql/utils/common.py:139-145's clamp to +-5; mean == NULL: plain copy), columns up to

@@ -116,6 +116,8 @@ _PROTOS = {
     "pqlb_store_i64": (_int, [_f, _i64, _st]),
     "pqlb_rms_workspace_bytes": (_i64, [_i64, _int]),
     "pqlb_rms_update": (_int, [_f, _i64, _int, _i64, _f, _f, _f, _f, _i64, _st]),
+    "pqlb_rms_moments": (_int, [_f, _i64, _int, _i64, _f, _f, _i64, _st]),
+    "pqlb_rms_apply": (_int, [_f, _i64, _int, _f, _f, _f, _st]),
     "pqlb_actor_inputs": (_int, [_f, _i64, _int, _i64, _f, _f, _flt, _int, _int, _f, _int, _f, _int, _f, _flt,
                                  _i64, _i64, _st]),
     "pqlb_env_post": (_int, [_f, _f, _f, _flt, _int, _f, _f, _f, _f, _int, _f, _f, _f, _st]),

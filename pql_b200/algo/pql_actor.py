@@ -70,7 +70,9 @@ class PQLActor:
             raise NotImplementedError("info_track_keys (env-specific logging, pql_actor.py:28-32) is not on the path")
 
         if self.cfg.algo.obs_norm:
-            self.obs_rms = RunningMeanStd(shape=self.obs_dim, device=dev)
+            # data parallel (cfg.data_parallel): one normaliser for the whole job - the batch moments are summed over
+            # the ranks before every update (the reference has ONE actor)
+            self.obs_rms = RunningMeanStd(shape=self.obs_dim, device=dev, data_parallel=bool(getattr(cfg, "data_parallel", False)))
             if self.cfg.artifact is not None:
                 raise NotImplementedError("W&B artifact loading is out of scope: use obs_rms.load_state_dict()")
         else:

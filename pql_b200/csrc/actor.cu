@@ -24,7 +24,7 @@ constexpr int kRmsRows = 128;        // rows per block of the column-statistics 
 __global__ void __launch_bounds__(kActThreads)
 rms_update_kernel(const float* __restrict__ x, long long rows, int cols, long long ldx,
                   float* __restrict__ mean, float* __restrict__ var, double* __restrict__ count,
-                  double* __restrict__ part, unsigned* __restrict__ ticket) {
+                  double* __restrict__ part, unsigned* __restrict__ ticket, double* __restrict__ sums_out) {
   __shared__ double s_sum[kActThreads / 32][32], s_sq[kActThreads / 32][32];
   __shared__ bool s_last;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -55,6 +55,22 @@ rms_update_kernel(const float* __restrict__ x, long long rows, int cols, long lo
   __syncthreads();
   if (!s_last) return;
   __threadfence();
+  if (sums_out) {
+    // data parallel: this rank's column sums / sums of squares only (slab order); they are all-reduced
+    // over the ranks and applied by rms_apply_kernel, so that every rank takes the update of the
+    // concatenated batch (pqlb_rms_moments / pqlb_rms_apply)
+    for (int c = threadIdx.x; c < cols; c += kActThreads) {
+      double s = 0.0, q = 0.0;
+      for (unsigned b = 0; b < gridDim.x; ++b) {
+        s += __ldcg(part + ((long long)b * 2 + 0) * cols + c);
+        q += __ldcg(part + ((long long)b * 2 + 1) * cols + c);
+      }
+      sums_out[c] = s; sums_out[cols + c] = q;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) *ticket = 0u;
+    return;
+  }
   const double n = (double)rows, cnt = count[0], tot = cnt + n;
   const float f_n = (float)n, f_cnt = (float)cnt, f_tot = (float)tot;
   for (int c = threadIdx.x; c < cols; c += kActThreads) {
@@ -76,6 +92,28 @@ rms_update_kernel(const float* __restrict__ x, long long rows, int cols, long lo
   }
   __syncthreads();
   if (threadIdx.x == 0) { count[0] = tot; *ticket = 0u; }
+}
+
+// update_from_moments (torch_util.py:91-103) from column sums / sums of squares of n rows in total.
+__global__ void __launch_bounds__(kActThreads)
+rms_apply_kernel(const double* __restrict__ sums, double n, int cols, float* __restrict__ mean, float* __restrict__ var,
+                 double* __restrict__ count) {
+  const double cnt = count[0], tot = cnt + n;
+  const float f_n = (float)n, f_cnt = (float)cnt, f_tot = (float)tot;
+  for (int c = threadIdx.x; c < cols; c += kActThreads) {
+    const double s = sums[c], q = sums[cols + c];
+    const float b_mean = (float)(s / n);
+    const float b_var = (float)((q - s * s / n) / (n - 1.0));
+    const float m = mean[c], v = var[c];
+    const float delta = __fsub_rn(b_mean, m);
+    const float new_mean = __fadd_rn(m, __fdiv_rn(__fmul_rn(delta, f_n), f_tot));
+    const float m_a = __fmul_rn(v, f_cnt), m_b = __fmul_rn(b_var, f_n);
+    const float cross = __fdiv_rn(__fmul_rn(__fmul_rn(__fmul_rn(delta, delta), f_cnt), f_n), f_tot);
+    mean[c] = new_mean;
+    var[c] = __fdiv_rn(__fadd_rn(__fadd_rn(m_a, m_b), cross), f_tot);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) count[0] = tot;
 }
 
 // out[r, k] = (x[r, k] - mean[k]) / sqrt(var[k] + eps)  (RunningMeanStd.normalize: no clamp), or
@@ -187,7 +225,27 @@ extern "C" int pqlb_rms_update(const float* x, int64_t rows, int cols, int64_t l
   // layout: [ticket (16 bytes, zero before the first call; the kernel re-arms it)] [partials]
   unsigned* ticket = reinterpret_cast<unsigned*>(workspace);
   double* part = reinterpret_cast<double*>(reinterpret_cast<char*>(workspace) + 16);
-  rms_update_kernel<<<(unsigned)blocks, kActThreads, 0, (cudaStream_t)stream>>>(x, rows, cols, ldx, mean, var, count, part, ticket);
+  rms_update_kernel<<<(unsigned)blocks, kActThreads, 0, (cudaStream_t)stream>>>(x, rows, cols, ldx, mean, var, count, part, ticket, nullptr);
+  PQLB_LAUNCH_RET();
+}
+
+extern "C" int pqlb_rms_moments(const float* x, int64_t rows, int cols, int64_t ldx, double* sums, void* workspace,
+                                int64_t workspace_bytes, pqlb_stream_t stream) {
+  PQLB_CHECK_ARG(x && rows > 0 && cols > 0 && ldx >= cols && sums && workspace);
+  PQLB_CHECK_SHAPE(workspace_bytes >= pqlb_rms_workspace_bytes(rows, cols));
+  PQLB_CHECK_ALIGN((reinterpret_cast<uintptr_t>(workspace) & 15) == 0 && (reinterpret_cast<uintptr_t>(sums) & 7) == 0);
+  const int64_t blocks = (rows + kRmsRows - 1) / kRmsRows;
+  PQLB_CHECK_SHAPE(blocks <= 0x7fffffff);
+  unsigned* ticket = reinterpret_cast<unsigned*>(workspace);
+  double* part = reinterpret_cast<double*>(reinterpret_cast<char*>(workspace) + 16);
+  rms_update_kernel<<<(unsigned)blocks, kActThreads, 0, (cudaStream_t)stream>>>(x, rows, cols, ldx, nullptr, nullptr, nullptr, part, ticket, sums);
+  PQLB_LAUNCH_RET();
+}
+
+extern "C" int pqlb_rms_apply(const double* sums, int64_t total_rows, int cols, float* mean, float* var, double* count,
+                              pqlb_stream_t stream) {
+  PQLB_CHECK_ARG(sums && total_rows > 1 && cols > 0 && mean && var && count);
+  rms_apply_kernel<<<1, kActThreads, 0, (cudaStream_t)stream>>>(sums, (double)total_rows, cols, mean, var, count);
   PQLB_LAUNCH_RET();
 }
 

@@ -154,11 +154,29 @@ c51_td_loss_kernel(const float* __restrict__ p1, const float* __restrict__ p2,
       }
     }
     __syncwarp();
-    if (lane < 2) {
-      // index_add_ order on the CPU: every lower-atom term (source ascending), then every upper-atom term
-      float* pr = s_proj[warp][lane];
-      for (int j = 0; j < N; ++j) pr[s_l[warp][j]] += s_wl[warp][lane][j];
-      for (int j = 0; j < N; ++j) pr[s_u[warp][j]] += s_wu[warp][lane][j];
+    {
+      // index_add_ order on the CPU: for every output atom, all lower-atom terms (source ascending), then
+      // all upper-atom terms (source ascending).  Segmented form over ALL lanes: lane k owns output atoms k and
+      // k + 32 of both networks and walks the sources in that order, adding the ones that land on its atoms -
+      // the same additions in the same order as the serial scatter (l and u are monotone in the source atom,
+      // so each output atom takes a contiguous run of sources), with register accumulators instead of a
+      // dependent chain of shared-memory read-modify-writes on two lanes.
+      float acc[2][2] = {{0.f, 0.f}, {0.f, 0.f}};          // [net][atom half]
+      const int k0 = lane, k1 = lane + 32;
+      for (int j = 0; j < N; ++j) {
+        const int l = s_l[warp][j];
+        const float w0 = s_wl[warp][0][j], w1 = s_wl[warp][1][j];
+        if (l == k0) { acc[0][0] += w0; acc[1][0] += w1; }
+        if (l == k1) { acc[0][1] += w0; acc[1][1] += w1; }
+      }
+      for (int j = 0; j < N; ++j) {
+        const int u = s_u[warp][j];
+        const float w0 = s_wu[warp][0][j], w1 = s_wu[warp][1][j];
+        if (u == k0) { acc[0][0] += w0; acc[1][0] += w1; }
+        if (u == k1) { acc[0][1] += w0; acc[1][1] += w1; }
+      }
+      s_proj[warp][0][k0] = acc[0][0]; s_proj[warp][1][k0] = acc[1][0];
+      s_proj[warp][0][k1] = acc[0][1]; s_proj[warp][1][k1] = acc[1][1];
     }
     __syncwarp();
     const float gscale = 1.f / ((float)B * (float)N);

@@ -34,6 +34,7 @@ class LockStepTrainer:
         self.global_steps = 0
         self.sim_count = 0
         self._t0 = None
+        self.observer = None          # optional callable(kind) after every learn() ("v" / "p"): tests read the plans' draws
 
     def _rms(self, device):
         rms = self.actor_worker.obs_rms
@@ -67,8 +68,12 @@ class LockStepTrainer:
         self._exchange(p_data, v_data)
         for j in range(self.v_per_step):
             self.v_learner.learn()
+            if self.observer is not None:
+                self.observer("v")
             if (j + 1) % self.p_every == 0:
                 self.p_learner.learn()
+                if self.observer is not None:
+                    self.observer("p")
         self.actor_worker.update_noise()
         return {"train/critic_loss": self.critic_loss, "train/actor_loss": self.actor_loss,
                 "train/critic_update_times": self.critic_updates, "train/actor_update_times": self.actor_updates,

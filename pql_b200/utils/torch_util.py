@@ -10,8 +10,14 @@ from .. import _lib
 
 
 class RunningMeanStd:
-    def __init__(self, epsilon=1e-4, shape=(), device='cuda'):
+    def __init__(self, epsilon=1e-4, shape=(), device='cuda', process_group=None, data_parallel=False):
+        """``process_group`` / ``data_parallel`` (B200 extension): with more than one rank, every
+        ``update`` all-reduces the batch's column sums (2 * cols doubles) before merging, so all ranks apply
+        the reference's update on the CONCATENATED batch and hold bit-identical statistics."""
         self.device = torch.device(device)
+        self._group, self._world = process_group, 1
+        if process_group is not None or (data_parallel and torch.distributed.is_available() and torch.distributed.is_initialized()):
+            self._world = torch.distributed.get_world_size(process_group)
         if self.device.type != "cuda":
             raise RuntimeError("pql_b200.RunningMeanStd lives in GPU memory; there is no CPU path")
         _lib.load()
@@ -42,6 +48,16 @@ class RunningMeanStd:
             x = x.contiguous()
         ws = self._workspace(x.shape[0], cols)
         with torch.cuda.device(self.device):
+            if self._world > 1:
+                if getattr(self, "_sums", None) is None:
+                    self._sums = torch.zeros(2 * cols, dtype=torch.float64, device=self.device)
+                _lib.call("pqlb_rms_moments", _lib.ptr(x), x.shape[0], cols, x.stride(0), _lib.ptr(self._sums), _lib.ptr(ws), ws.numel())
+                torch.distributed.all_reduce(self._sums, group=self._group)      # every rank contributes the same row count
+                rows = x.shape[0] * self._world
+                _lib.call("pqlb_rms_apply", _lib.ptr(self._sums), rows, cols, _lib.ptr(self.mean), _lib.ptr(self.var),
+                          _lib.ptr(self._count_dev))
+                self.count = self.count + rows
+                return
             _lib.call("pqlb_rms_update", _lib.ptr(x), x.shape[0], cols, x.stride(0), _lib.ptr(self.mean), _lib.ptr(self.var),
                       _lib.ptr(self._count_dev), _lib.ptr(ws), ws.numel())
         self.count = self.count + x.shape[0]

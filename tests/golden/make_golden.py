@@ -322,8 +322,40 @@ def schedules():
     json.dump(out, open(os.path.join(HERE, "schedules.json"), "w"))
 
 
+def reference_checkpoint():
+    """A checkpoint as the reference writes it (pql/utils/model_util.py:24-41 from evaluator.py:112-119):
+    {'obs_rms': (mean, var, eps), 'actor': state_dict, 'critic': state_dict} of the reference's OWN modules,
+    default-initialised under a fixed seed, plus what those modules compute on a small input.  The weights
+    themselves are not stored (2 MB): torch's seeded nn.Linear initialisation is reproducible, so the fixture
+    keeps a sha256 of every tensor - the test rebuilds the state_dict from the seed, proves it is the
+    reference's bit for bit, writes the checkpoint file and loads it into the pql_b200 modules."""
+    from pql.models.mlp import DistributionalDoubleQ, DoubleQ, TanhMLPPolicy
+    O, A, n, seed = 24, 4, 96, 2024
+    torch.manual_seed(seed)
+    actor, critic = TanhMLPPolicy(O, A), DoubleQ(O, A)
+    critic_d = DistributionalDoubleQ(O, A, v_min=-10, v_max=10, num_atoms=51, device="cpu")
+    g = torch.Generator().manual_seed(seed + 1)
+    obs, act = torch.randn(n, O, generator=g), torch.rand(n, A, generator=g) * 2 - 1
+    rms = (torch.randn(O, generator=g) * 0.3, torch.rand(O, generator=g) + 0.5, 1e-4)
+    with torch.no_grad():
+        q1, q2 = critic.get_q1_q2(obs, act)
+        p1, p2 = critic_d.get_q1_q2(obs, act)
+        out = dict(action=actor(obs), q1=q1, q2=q2, q_min=critic.get_q_min(obs, act), p1=p1, p2=p2,
+                   qd_min=critic_d.get_q_min(obs, act))
+    digests = {name: {k: hashlib.sha256(v.detach().numpy().tobytes()).hexdigest() for k, v in m.state_dict().items()}
+               for name, m in (("actor", actor), ("critic", critic), ("critic_c51", critic_d))}
+    np.savez(os.path.join(HERE, "ref_checkpoint.npz"), obs=obs.numpy(), act=act.numpy(), rms_mean=rms[0].numpy(),
+             rms_var=rms[1].numpy(), **{k: v.numpy() for k, v in out.items()})
+    json.dump(dict(seed=seed, obs_dim=O, act_dim=A, order=["actor", "critic", "critic_c51"], digests=digests),
+              open(os.path.join(HERE, "ref_checkpoint.json"), "w"), indent=1)
+
+
 if __name__ == "__main__":
     torch.set_num_threads(8)
+    if "--checkpoint-only" in sys.argv:
+        reference_checkpoint()
+        sys.exit(0)
+    reference_checkpoint()
     schedules()
     actor_small()
     replay_small()
