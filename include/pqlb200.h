@@ -484,6 +484,9 @@ typedef struct {
   void* ctl_peers[8];
   int64_t* local;
   int rank, world, grid;
+  /* Optional NVLS multicast addresses of the same gradient arenas / receive buffers (both or neither): the
+   * slice reduction then runs inside the NVSwitch (multimem.ld_reduce / multimem.st), one NVLink round trip. */
+  const float* grad_mc; float* red_mc;
 } pqlb_dp_desc;
 int pqlb_adamw_polyak_dp(float* param, float* m, float* v, float* target, float* param_tf32,
                          float* target_tf32, void* param_h, void* target_h, int64_t n,

@@ -76,7 +76,7 @@ class MlpHDesc(C.Structure):
 
 class DpDesc(C.Structure):
     _fields_ = [("grad_peers", _f * 8), ("red_peers", _f * 8), ("ctl_peers", _f * 8), ("local", _f),
-                ("rank", _int), ("world", _int), ("grid", _int)]
+                ("rank", _int), ("world", _int), ("grid", _int), ("grad_mc", _f), ("red_mc", _f)]
 
 
 class MlpBwdGroup(C.Structure):

@@ -114,4 +114,10 @@ class FusedExchange:
             d.ctl_peers[r] = self.handles[2].buffer_ptrs[r]
         d.local = self.local.data_ptr()
         d.rank, d.world, d.grid = self.rank, self.world, self.GRID
+        # NVLS (in-switch reduction) when the symmetric-memory handles carry multicast mappings; PQLB_DP_NVLS=0: per-peer loads
+        import os
+        mc = [int(getattr(h, "multicast_ptr", 0) or 0) for h in self.handles[:2]]
+        mc = [p + int(getattr(h, "offset", 0) or 0) if p else 0 for p, h in zip(mc, self.handles[:2])]
+        self.nvls = all(mc) and os.environ.get("PQLB_DP_NVLS", "1") != "0"
+        d.grad_mc, d.red_mc = (mc[0], mc[1]) if self.nvls else (None, None)
         return d

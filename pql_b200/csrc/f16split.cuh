@@ -14,6 +14,11 @@ __device__ __forceinline__ uint32_t pack_hi(float a, float b) {
   const __half2 h = __floats2half2_rn(fminf(fmaxf(a, -65504.f), 65504.f), fminf(fmaxf(b, -65504.f), 65504.f));
   return *reinterpret_cast<const uint32_t*>(&h);
 }
+// the same for values bounded below (ELU outputs are > -1): only the upper clamp
+__device__ __forceinline__ uint32_t pack_hi_pos(float a, float b) {
+  const __half2 h = __floats2half2_rn(fminf(a, 65504.f), fminf(b, 65504.f));
+  return *reinterpret_cast<const uint32_t*>(&h);
+}
 __device__ __forceinline__ uint32_t pack_lo(float a, float b, uint32_t hi) {
   const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&hi));
   const __half2 l = __floats2half2_rn(a - f.x, b - f.y);

@@ -55,18 +55,24 @@ __device__ __forceinline__ void mlp_fwd_h_body(const MlpHDev& P, const MlpHGroup
     mbar_init(smem_u32(&z_conv), kHEpiWarps); mbar_init(smem_u32(&a_full), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  for (int j = threadIdx.x; j < kHH1; j += kHThreads) s_b1[j] = G.b1[j];
-  for (int j = threadIdx.x; j < kHH2; j += kHThreads) s_b2[j] = G.b2[j];
-  for (int j = threadIdx.x; j < kHH3; j += kHThreads) { s_b3[j] = G.b3[j]; s_w4[j] = G.q ? G.head_w[j] : 0.f; }
-  __syncthreads();
-  if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(512u) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  __syncthreads();                               // barriers initialised
+  // The TMA producer needs neither the bias vectors nor the tensor-memory address: it starts streaming the
+  // input tile and the first weight tiles right away, while the other warps load the biases (global-memory
+  // latency) and allocate tensor memory, and meets nobody until the final __syncthreads.
+  if (warp != 0) {
+    const int t = (int)threadIdx.x - 32;
+    for (int j = t; j < kHH1; j += kHThreads - 32) s_b1[j] = G.b1[j];
+    for (int j = t; j < kHH2; j += kHThreads - 32) s_b2[j] = G.b2[j];
+    for (int j = t; j < kHH3; j += kHThreads - 32) { s_b3[j] = G.b3[j]; s_w4[j] = G.q ? G.head_w[j] : 0.f; }
+    if (warp == 1) {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(512u) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tcgen05_fence_before();
+    named_bar_sync(7, kHThreads - 32);
+    tcgen05_fence_after();
   }
-  tcgen05_fence_before();
-  __syncthreads();
-  tcgen05_fence_after();
-  const uint32_t tmem = uniform_u32(tmem_slot);
+  const uint32_t tmem = warp != 0 ? uniform_u32(tmem_slot) : 0u;
   const uint32_t tY = tmem + 256u;
   const uint32_t tZ = tmem;
   unsigned long long* dbg = (blockIdx.x == 0 && blockIdx.y == 0) ? P.dbg : nullptr;
@@ -360,7 +366,7 @@ __device__ __forceinline__ void mlp_fwd_h_body(const MlpHDev& P, const MlpHGroup
       for (int j = 0; j < 32; ++j) v[j] = elu_fast(fmaf(v[j], kWInv, bias[n_base + col + j]));
 #pragma unroll
       for (int j = 0; j < 16; ++j) {
-        hp[j] = pack_hi(v[2 * j], v[2 * j + 1]);
+        hp[j] = pack_hi_pos(v[2 * j], v[2 * j + 1]);
         if (T == 3) lp[j] = pack_lo(v[2 * j], v[2 * j + 1], hp[j]);
       }
       named_bar_sync(1 + quarter, 128);
@@ -408,7 +414,7 @@ __device__ __forceinline__ void mlp_fwd_h_body(const MlpHDev& P, const MlpHGroup
         uint32_t hp[16], lp[16];
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
-          hp[j] = pack_hi(v[2 * j], v[2 * j + 1]);
+          hp[j] = pack_hi_pos(v[2 * j], v[2 * j + 1]);
           if (T == 3) lp[j] = pack_lo(v[2 * j], v[2 * j + 1], hp[j]);
         }
         named_bar_sync(1 + quarter, 128);

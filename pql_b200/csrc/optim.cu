@@ -207,6 +207,7 @@ struct DpArgs {
   unsigned* ctl_peers[kDpMaxWorld];      // kDpFlagWords flags, then float sumsq[world][grid]
   int rank, world;
   unsigned long long* local;             // [0] epoch of the last completed exchange, [1] blocks done (monotonic)
+  const float* grad_mc; float* red_mc;   // NVLS multicast addresses of the gradient arenas / receive buffers (or NULL)
 };
 
 __device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) { asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
@@ -232,6 +233,39 @@ __device__ __forceinline__ void wait_flag(const unsigned* p, unsigned epoch) {
 // and store the result into every rank's receive buffer; returns this thread's sum of squares.  ILP
 // elements per thread and trip, all peers' loads of all of them issued before the first add: an
 // NVLink round trip costs ~2-3 us, serialised loads would cost world x trips of them.
+// The same phase through the NVSwitch's in-fabric reduction (NVLS): ONE multimem.ld_reduce returns the sum of all
+// ranks' copies of four gradient words, ONE multimem.st delivers the result to every rank's receive buffer -
+// one NVLink round trip and 1/world of the transactions of the per-peer version.  The switch's summation order
+// is not specified, but each word is reduced once, by its owner, and broadcast: all ranks still apply the same values.
+__device__ __forceinline__ float4 multimem_ld_reduce_f4(const float* mc) {
+  float4 v;
+  asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(mc) : "memory");
+  return v;
+}
+__device__ __forceinline__ void multimem_st_f4(float* mc, float4 v) {
+  asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(mc), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+template <int ILP>
+__device__ __forceinline__ float dp_reduce_slice_nvls(const DpArgs& dp, int64_t lo, int64_t hi, unsigned G) {
+  float sq = 0.f;
+  const int64_t gstride = (int64_t)G * kOptThreads;
+  for (int64_t i0 = lo + (int64_t)blockIdx.x * kOptThreads + threadIdx.x; i0 < hi; i0 += gstride * ILP) {
+    float4 t[ILP];
+#pragma unroll
+    for (int u = 0; u < ILP; ++u)
+      if (i0 + u * gstride < hi) t[u] = multimem_ld_reduce_f4(dp.grad_mc + 4 * (i0 + u * gstride));
+#pragma unroll
+    for (int u = 0; u < ILP; ++u) {
+      const int64_t i = i0 + u * gstride;
+      if (i >= hi) break;
+      sq += t[u].x * t[u].x + t[u].y * t[u].y + t[u].z * t[u].z + t[u].w * t[u].w;
+      multimem_st_f4(dp.red_mc + 4 * i, t[u]);
+    }
+  }
+  return sq;
+}
+
 template <int ILP, int WMAX>
 __device__ __forceinline__ float dp_reduce_slice(const DpArgs& dp, int64_t lo, int64_t hi, unsigned G) {
   float sq = 0.f;
@@ -291,7 +325,8 @@ adamw_polyak_dp_kernel(float* __restrict__ param, float* __restrict__ m, float* 
   const int64_t s4 = (n4 + dp.world - 1) / dp.world;
   const int64_t lo = (int64_t)dp.rank * s4, hi = lo + s4 < n4 ? lo + s4 : n4;
   // (at most 4 ranks: 4 elements per thread and trip, else 2 - the same 16 / 8 float4 in flight)
-  const float sq = dp.world <= 4 ? dp_reduce_slice<4, 4>(dp, lo, hi, G) : dp_reduce_slice<2, kDpMaxWorld>(dp, lo, hi, G);
+  const float sq = dp.grad_mc ? dp_reduce_slice_nvls<4>(dp, lo, hi, G)
+                   : dp.world <= 4 ? dp_reduce_slice<4, 4>(dp, lo, hi, G) : dp_reduce_slice<2, kDpMaxWorld>(dp, lo, hi, G);
   const float tot = block_sum_256(sq, red);
   if (threadIdx.x == 0)
     for (int q = 0; q < dp.world; ++q)
@@ -554,6 +589,7 @@ extern "C" int pqlb_adamw_polyak_dp(float* param, float* m, float* v, float* tar
     a.ctl_peers[r] = on ? reinterpret_cast<unsigned*>(dp->ctl_peers[r]) : nullptr;
   }
   a.rank = dp->rank; a.world = dp->world; a.local = reinterpret_cast<unsigned long long*>(dp->local);
+  a.grad_mc = dp->grad_mc && dp->red_mc ? dp->grad_mc : nullptr; a.red_mc = a.grad_mc ? dp->red_mc : nullptr;
   adamw_polyak_dp_kernel<<<(unsigned)dp->grid, kOptThreads, 0, (cudaStream_t)stream>>>(
       param, m, v, target, param_tf32, target_tf32, reinterpret_cast<__half*>(param_h), reinterpret_cast<__half*>(target_h),
       n, a, max_norm, reinterpret_cast<const AdamScalars*>(scalars),
@@ -573,6 +609,7 @@ extern "C" int pqlb_grad_exchange_dp(int64_t n, const pqlb_dp_desc* dp, pqlb_str
     a.ctl_peers[r] = on ? reinterpret_cast<unsigned*>(dp->ctl_peers[r]) : nullptr;
   }
   a.rank = dp->rank; a.world = dp->world; a.local = reinterpret_cast<unsigned long long*>(dp->local);
+  a.grad_mc = dp->grad_mc && dp->red_mc ? dp->grad_mc : nullptr; a.red_mc = a.grad_mc ? dp->red_mc : nullptr;
   adamw_polyak_dp_kernel<<<(unsigned)dp->grid, kOptThreads, 0, (cudaStream_t)stream>>>(
       nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, n, a, -1.f, nullptr, nullptr, nullptr, 1);
   PQLB_LAUNCH_RET();

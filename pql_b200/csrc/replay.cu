@@ -263,7 +263,7 @@ __device__ __forceinline__ float norm_clamp(float x, float m, float v, float eps
 // Fused V-learner batch: x_cur = [norm(obs)|action|0], x_tgt = [norm(next_obs)| (actor head) |0];
 // TF32-rounded because both are tensor-core operands.  VEC = 4: one item = one float4 of one
 // output row (requires O % 4 == 0 and A % 4 == 0, so a float4 never straddles two fields).
-template <int VEC>
+template <int VEC, int REC>
 __global__ void __launch_bounds__(kThreads)
 sample_critic_batch_kernel(const float* __restrict__ ring, RecGeom g, const int64_t* __restrict__ idx,
                            int64_t B, const float* __restrict__ mean, const float* __restrict__ var,
@@ -280,15 +280,15 @@ sample_critic_batch_kernel(const float* __restrict__ ring, RecGeom g, const int6
   const int rd_items = VEC == 4 ? 1 : 2;
   const int pad_items = (x_ld - g.O - g.A) / VEC;           // zero padding columns of both input rows
   const int items = f.per_row + rd_items + pad_items;
-  for (int64_t b0 = ((((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5)) * kRec; b0 < B; b0 += nwarps * kRec) {
-    const float* rec[kRec];
+  for (int64_t b0 = ((((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5)) * REC; b0 < B; b0 += nwarps * REC) {
+    const float* rec[REC];
     long long mine = 0;
-    if (ra.state && lane < kRec && b0 + lane < B) {
+    if (ra.state && lane < REC && b0 + lane < B) {
       mine = (long long)(torch_rand_u32(seed, off, ra.threads_idx, b0 + lane) % range);
       const_cast<int64_t*>(idx)[b0 + lane] = mine;            // kept for inspection / tests
     }
 #pragma unroll
-    for (int r = 0; r < kRec; ++r) {
+    for (int r = 0; r < REC; ++r) {
       const long long ix = ra.state ? __shfl_sync(0xffffffffu, mine, r) : (b0 + r < B ? __ldg(idx + b0 + r) : 0);
       rec[r] = b0 + r < B ? ring + ix * g.rec_ld : nullptr;
     }
@@ -297,7 +297,7 @@ sample_critic_batch_kernel(const float* __restrict__ ring, RecGeom g, const int6
         const int k = g.O + g.A + (it - f.per_row - rd_items) * VEC;
         float z[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-        for (int r = 0; r < kRec; ++r)
+        for (int r = 0; r < REC; ++r)
           if (rec[r]) {
             *reinterpret_cast<V*>(x_cur + (b0 + r) * x_ld + k) = *reinterpret_cast<V*>(z);
             *reinterpret_cast<V*>(x_tgt + (b0 + r) * x_ld + k) = *reinterpret_cast<V*>(z);
@@ -307,9 +307,9 @@ sample_critic_batch_kernel(const float* __restrict__ ring, RecGeom g, const int6
         continue;
       }
       const ItemDecode<VEC> d(it, g, f);
-      V val[kRec];
+      V val[REC];
 #pragma unroll
-      for (int r = 0; r < kRec; ++r)
+      for (int r = 0; r < REC; ++r)
         if (rec[r]) val[r] = __ldcs(reinterpret_cast<const V*>(rec[r] + d.ro));
       float m[4] = {0.f, 0.f, 0.f, 0.f}, sd[4] = {1.f, 1.f, 1.f, 1.f};
       if (mean && d.field <= 1) {
@@ -317,7 +317,7 @@ sample_critic_batch_kernel(const float* __restrict__ ring, RecGeom g, const int6
         for (int q = 0; q < VEC; ++q) { m[q] = mean[d.fo + q]; sd[q] = __fsqrt_rn(__fadd_rn(var[d.fo + q], eps)); }
       }
 #pragma unroll
-      for (int r = 0; r < kRec; ++r) {
+      for (int r = 0; r < REC; ++r) {
         if (!rec[r]) continue;
         const int64_t b = b0 + r;
         float* t = reinterpret_cast<float*>(&val[r]);
@@ -358,6 +358,7 @@ sample_critic_batch_kernel(const float* __restrict__ ring, RecGeom g, const int6
 
 // P-learner batch with the fused index draw: one warp per kRec rows (lanes < kRec draw the indices),
 // lanes walk the columns.  Same values as sample_obs_batch_kernel on torch.randint's indices.
+template <int REC>
 __global__ void __launch_bounds__(kThreads)
 sample_obs_batch_rng_kernel(const float* __restrict__ obsring, int O, int64_t* __restrict__ idx,
                             int64_t B, const float* __restrict__ mean, const float* __restrict__ var,
@@ -365,27 +366,27 @@ sample_obs_batch_rng_kernel(const float* __restrict__ obsring, int O, int64_t* _
   const int lane = threadIdx.x & 31;
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
   const unsigned long long seed = ra.state[0], off = ra.state[1] + ra.state[2] * ra.counter[0], range = ra.range[0];
-  for (int64_t b0 = ((((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5)) * kRec; b0 < B; b0 += nwarps * kRec) {
+  for (int64_t b0 = ((((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5)) * REC; b0 < B; b0 += nwarps * REC) {
     long long mine = 0;
-    if (lane < kRec && b0 + lane < B) {
+    if (lane < REC && b0 + lane < B) {
       mine = (long long)(torch_rand_u32(seed, off, ra.threads_idx, b0 + lane) % range);
       idx[b0 + lane] = mine;
     }
-    const float* src[kRec];
+    const float* src[REC];
 #pragma unroll
-    for (int r = 0; r < kRec; ++r) {
+    for (int r = 0; r < REC; ++r) {
       const long long ix = __shfl_sync(0xffffffffu, mine, r);
       src[r] = b0 + r < B ? obsring + ix * O : nullptr;
     }
     for (int k = lane; k < x_ld; k += 32) {
       if (k < O) {
-        float v[kRec];
+        float v[REC];
 #pragma unroll
-        for (int r = 0; r < kRec; ++r) v[r] = src[r] ? __ldcs(src[r] + k) : 0.f;
+        for (int r = 0; r < REC; ++r) v[r] = src[r] ? __ldcs(src[r] + k) : 0.f;
         float m = 0.f, vr = 1.f;
         if (mean) { m = mean[k]; vr = var[k]; }
 #pragma unroll
-        for (int r = 0; r < kRec; ++r) {
+        for (int r = 0; r < REC; ++r) {
           if (!src[r]) continue;
           float y = v[r];
           if (mean) y = norm_clamp(y, m, vr, eps);
@@ -394,7 +395,7 @@ sample_obs_batch_rng_kernel(const float* __restrict__ obsring, int O, int64_t* _
         }
       } else if (k >= O + A) {
 #pragma unroll
-        for (int r = 0; r < kRec; ++r)
+        for (int r = 0; r < REC; ++r)
           if (src[r]) { x[(b0 + r) * x_ld + k] = 0.f; if (xf) xf[(b0 + r) * x_ld + k] = 0.f; }
       }
     }
@@ -437,6 +438,19 @@ pack_x_kernel(const float* __restrict__ a, int64_t lda, int na, const float* __r
     else if (k < na + nb) v = b[r * ldb + (k - na)];
     x[r * x_ld + k] = rn_tf32(v);
   }
+}
+
+// Records per warp: four for batches that fill the machine anyway (fewer index / field decodes per byte), ONE for
+// the batches the learners actually issue (8192-16384 rows): with four, a batch of 8192 is 2048 warps = 14 per SM,
+// each walking its records' items in seven dependent rounds of memory latency (11.7 us, 0.2 of the HBM roofline);
+// with one record per warp there are four times as many warps in flight and two rounds.
+constexpr int64_t kSmallBatch = 32768;
+template <int VEC, typename... Args>
+static inline void launch_critic_batch(int64_t batch, cudaStream_t st, Args... args) {
+  if (batch <= kSmallBatch)
+    sample_critic_batch_kernel<VEC, 1><<<grid_for(batch * 32, kThreads, 1, kBlocksPerSM), kThreads, 0, st>>>(args...);
+  else
+    sample_critic_batch_kernel<VEC, kRec><<<grid_for(batch * 32, kThreads, kRec, kBlocksPerSM), kThreads, 0, st>>>(args...);
 }
 
 static inline void split_insert(int64_t n, int64_t next_p, int64_t capacity, int64_t* head, int64_t* tail) {
@@ -574,11 +588,9 @@ extern "C" int pqlb_sample_critic_batch(const float* ring, int64_t capacity, int
   const bool vec4 = obs_dim % 4 == 0 && act_dim % 4 == 0 && aligned16(ring) && aligned16(x_cur) && aligned16(x_tgt) &&
                     (!mean || (aligned16(mean) && aligned16(var)));
   if (vec4)
-    sample_critic_batch_kernel<4><<<grid_for(batch * 32, kThreads, kRec, kBlocksPerSM), kThreads, 0, (cudaStream_t)stream>>>(
-        ring, g, idx, batch, mean, var, eps, x_cur, x_tgt, x_ld, reward, done, RngArgs{}, xf_cur, xf_tgt);
+    launch_critic_batch<4>(batch, (cudaStream_t)stream, ring, g, idx, batch, mean, var, eps, x_cur, x_tgt, x_ld, reward, done, RngArgs{}, xf_cur, xf_tgt);
   else
-    sample_critic_batch_kernel<1><<<grid_for(batch * 32, kThreads, kRec, kBlocksPerSM), kThreads, 0, (cudaStream_t)stream>>>(
-        ring, g, idx, batch, mean, var, eps, x_cur, x_tgt, x_ld, reward, done, RngArgs{}, xf_cur, xf_tgt);
+    launch_critic_batch<1>(batch, (cudaStream_t)stream, ring, g, idx, batch, mean, var, eps, x_cur, x_tgt, x_ld, reward, done, RngArgs{}, xf_cur, xf_tgt);
   PQLB_LAUNCH_RET();
 }
 
@@ -613,11 +625,9 @@ extern "C" int pqlb_sample_critic_batch_rng(const float* ring, int64_t capacity,
   const bool vec4 = obs_dim % 4 == 0 && act_dim % 4 == 0 && aligned16(ring) && aligned16(x_cur) && aligned16(x_tgt) &&
                     (!mean || (aligned16(mean) && aligned16(var)));
   if (vec4)
-    sample_critic_batch_kernel<4><<<grid_for(batch * 32, kThreads, kRec, kBlocksPerSM), kThreads, 0, (cudaStream_t)stream>>>(
-        ring, g, idx_out, batch, mean, var, eps, x_cur, x_tgt, x_ld, reward, done, ra, xf_cur, xf_tgt);
+    launch_critic_batch<4>(batch, (cudaStream_t)stream, ring, g, idx_out, batch, mean, var, eps, x_cur, x_tgt, x_ld, reward, done, ra, xf_cur, xf_tgt);
   else
-    sample_critic_batch_kernel<1><<<grid_for(batch * 32, kThreads, kRec, kBlocksPerSM), kThreads, 0, (cudaStream_t)stream>>>(
-        ring, g, idx_out, batch, mean, var, eps, x_cur, x_tgt, x_ld, reward, done, ra, xf_cur, xf_tgt);
+    launch_critic_batch<1>(batch, (cudaStream_t)stream, ring, g, idx_out, batch, mean, var, eps, x_cur, x_tgt, x_ld, reward, done, ra, xf_cur, xf_tgt);
   PQLB_LAUNCH_RET();
 }
 
@@ -632,8 +642,12 @@ extern "C" int pqlb_sample_obs_batch_rng(const float* obsring, int64_t capacity,
   RngArgs ra;
   const int rc = make_rng_args(&ra, rng_state, counter, cur_capacity, batch, capacity, nullptr, 0);
   if (rc != PQLB_OK) return rc;
-  sample_obs_batch_rng_kernel<<<grid_for(batch * 32, kThreads, kRec, kBlocksPerSM), kThreads, 0, (cudaStream_t)stream>>>(
-      obsring, obs_dim, idx_out, batch, mean, var, eps, x, x_ld, act_dim, ra, xf);
+  if (batch <= kSmallBatch)
+    sample_obs_batch_rng_kernel<1><<<grid_for(batch * 32, kThreads, 1, kBlocksPerSM), kThreads, 0, (cudaStream_t)stream>>>(
+        obsring, obs_dim, idx_out, batch, mean, var, eps, x, x_ld, act_dim, ra, xf);
+  else
+    sample_obs_batch_rng_kernel<kRec><<<grid_for(batch * 32, kThreads, kRec, kBlocksPerSM), kThreads, 0, (cudaStream_t)stream>>>(
+        obsring, obs_dim, idx_out, batch, mean, var, eps, x, x_ld, act_dim, ra, xf);
   PQLB_LAUNCH_RET();
 }
 
