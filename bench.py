@@ -42,11 +42,6 @@ MAC_ACTOR_FWD = O * 512 + 512 * 256 + 256 * 128 + 128 * A                 # trun
 MAC_CRITIC_FWD = (O + A) * 512 + 512 * 256 + 256 * 128 + 128              # trunk + scalar Q head
 FWD_MAC_V = MAC_ACTOR_FWD + 4 * MAC_CRITIC_FWD       # critic update: target policy + 2 target + 2 current nets
 FWD_MAC_P = MAC_ACTOR_FWD + 2 * MAC_CRITIC_FWD       # actor update: policy + frozen twin critics
-FWD_LAUNCHES_PER_STEP = 2 * (V_PER_STEP + P_PER_STEP)
-# DRAM bytes (read + write) of those launches from the committed ncu --set full capture of one step
-# (profiles/r1_final_ncu_full_update_kernels.csv; cold cache under ncu): policy 4.88 MB, four critic
-# nets 15.7 MB per critic update; 4.36 MB + 8.07 MB per actor update
-FWD_DRAM_BYTES_PER_STEP = V_PER_STEP * (4.88e6 + 15.7e6) + P_PER_STEP * (4.36e6 + 8.07e6)
 BYTES_INSERT = 1549         # algorithmic bytes per inserted transition
 BYTES_SAMPLE = 1557         # ... per sampled transition
 N_BLOCKS = 16
@@ -438,8 +433,8 @@ def main():
         super_step(k, False)
     torch.cuda.synchronize(dev)
     per_kernel = {name: sum(a.elapsed_time(b) for a, b in evs) / prof_steps for name, evs in K.PROFILE.items()}
-    n_gemm = sum(len(K.PROFILE.get(k, [])) for k in ("pqlb_gemm_tf32", "pqlb_mlp_forward", "pqlb_mlp_backward")) // prof_steps
-    n_fwd = len(K.PROFILE.get("pqlb_mlp_forward", [])) // prof_steps
+    n_gemm = sum(len(K.PROFILE.get(k, [])) for k in ("pqlb_gemm_tf32", "pqlb_mlp_forward", "pqlb_mlp_forward_h", "pqlb_mlp_backward")) // prof_steps
+    len_fwd = {k: len(x) // prof_steps for k, x in K.PROFILE.items()}
     K.PROFILE = None
     v.enable_graph(); p.enable_graph()
 
@@ -521,22 +516,38 @@ def main():
     except OSError:
         pass
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    # figures that only a profiler gives (DRAM bytes, tensor-pipe activity), from the committed capture
+    ncu = {}
+    try:
+        ncu = json.load(open(os.path.join(ROOT, "profiles", "ncu_summary.json")))
+    except OSError:
+        pass
     # TF32 dense peak: the larger of half the BURST cuBLAS bf16 figure (the bench runs at the maximum SM
     # clock, the sustained figure was taken at 1282 MHz) and this run's own tcgen05 kind::tf32 issue rate
     tf32_peak = max(peaks.get("bf16_tflops", 1675.7) / 2.0, mma_peaks["tf32_m128_n256"])
     peak_src = "measured (MEASURED_PEAKS.json)" if peaks else "fallback (B200_PROFILING.md)"
-    TC_KERNELS = ("pqlb_gemm_tf32", "pqlb_mlp_forward", "pqlb_mlp_backward")      # every tcgen05 launch of the step
+    TC_KERNELS = ("pqlb_gemm_tf32", "pqlb_mlp_forward", "pqlb_mlp_forward_h", "pqlb_mlp_backward")   # every tcgen05 launch of the step
     gemm_ms = sum(per_kernel.get(k, 0.0) for k in TC_KERNELS)
     flops_step = B * (V_PER_STEP * FLOP_V + P_PER_STEP * FLOP_P)
     achieved = flops_step / (gemm_ms * 1e-3) / 1e12
-    fwd_ms = per_kernel.get("pqlb_mlp_forward", 0.0)
+    fwd_mode = v._plan.fwd_mode
+    fwd_name = "pqlb_mlp_forward_h" if fwd_mode == "f16x3" else "pqlb_mlp_forward"
+    fwd_ms = per_kernel.get(fwd_name, 0.0)
     fwd_flops_step = 2.0 * B * (V_PER_STEP * FWD_MAC_V + P_PER_STEP * FWD_MAC_P)
+    # split-fp16: the critic nets issue three kind::f16 MMAs per product, the policy nets one
+    fwd_issued_step = 2.0 * B * (V_PER_STEP * (MAC_ACTOR_FWD + 12 * MAC_CRITIC_FWD) + P_PER_STEP * (MAC_ACTOR_FWD + 6 * MAC_CRITIC_FWD)) \
+        if fwd_mode == "f16x3" else fwd_flops_step
     fwd_achieved = fwd_flops_step / (max(fwd_ms, 1e-9) * 1e-3) / 1e12
+    fwd_issued = fwd_issued_step / (max(fwd_ms, 1e-9) * 1e-3) / 1e12
+    # dense peak of the forward's MMA kind: kind::f16 -> the burst cuBLAS bf16 figure (the bench runs at the maximum
+    # SM clock with no power cap active; the sustained figure was taken at 1282 MHz), kind::tf32 -> half of it
+    dense_peak = peaks.get("bf16_tflops", 1590.0) / (1.0 if fwd_mode == "f16x3" else 2.0)
+    n_fwd = len_fwd.get(fwd_name, 0)
     value = world * V_PER_STEP * args.steps / (ms * 1e-3)
     e2e = world * V_PER_STEP * args.steps / (ms_e2e * 1e-3)
     line = {"metric": "critic updates/s (batch 8192)", "value": value, "unit": "critic updates/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "tf32 (fp32 accumulate)", "data": "synthetic",
+            "scaling": "weak", "vs_baseline": None, "dtype": "split-fp16 x3 forward (22 significand bits) + tf32 backward, fp32 accumulate" if fwd_mode == "f16x3" else "tf32 (fp32 accumulate)", "data": "synthetic",
             "config": dict(config_dict(world, args.dp), **({"gradient_exchange": "ncclAllReduce (fused exchange unavailable on this box)"}
                                                   if world > 1 and args.dp == "fused" and v._plan.dp is None else {})),
             "clocks": clocks,
@@ -552,36 +563,33 @@ def main():
                           "note": "cfg.sync_loss = True: update() blocks on the learner's stream and returns the current loss "
                                   "mean, as the reference's update() does; the headline uses the non-blocking read-back "
                                   "(DeviceTracker.mean_lagged: the mean as of the previous env step)"},
-            "roofline": {"kernel": "mlp_fwd_kernel (pqlb_mlp_forward: layer-fused Linear+ELU x3 trunk + Q / policy head, "
-                                   "tcgen05 kind::tf32) - the dominant kernel, 37 % of the step in the ncu launch list",
-                         "bound": "tensor", "achieved": fwd_achieved, "peak": tf32_peak, "unit": "TFLOP/s",
-                         "frac": fwd_achieved / tf32_peak,
-                         "traffic": FWD_DRAM_BYTES_PER_STEP / FWD_LAUNCHES_PER_STEP,
-                         "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum per launch, mean over the step's "
-                                           "launches, profiles/r1_final_ncu_full_update_kernels.csv",
+            "roofline": {"kernel": f"{'mlp_fwd_h_kernel' if fwd_mode == 'f16x3' else 'mlp_fwd_kernel'} ({fwd_name}: layer-fused Linear+ELU x3 "
+                                   f"trunk + Q / policy head, tcgen05 {'kind::f16 on split-fp16 operands, three MMAs per product in the critics' if fwd_mode == 'f16x3' else 'kind::tf32'}) "
+                                   "- the dominant kernel of the step",
+                         "bound": "tensor", "achieved": fwd_achieved, "peak": dense_peak, "unit": "TFLOP/s",
+                         "frac": fwd_achieved / dense_peak,
+                         "traffic": ncu.get("fwd_dram_bytes_per_launch"),
+                         "traffic_source": ncu.get("source"),
                          "launches_per_step": n_fwd, "algorithmic_flops_per_launch": fwd_flops_step / max(n_fwd, 1),
                          "us_per_launch": 1e3 * fwd_ms / max(n_fwd, 1), "ms_per_step_in_kernel": fwd_ms,
-                         "peak_source": f"{peak_src}: max(1/2 of the burst cuBLAS bf16 figure, this run's own tcgen05 "
-                                        f"kind::tf32 issue rate, pqlb_mma_peak)",
+                         "peak_source": f"{peak_src}: burst cuBLAS bf16 figure for kind::f16 (half of it for kind::tf32); the run's own "
+                                        "tcgen05 issue rates are listed beside it",
+                         "issued_mma": {"tflops": fwd_issued, "frac_of_peak": fwd_issued / dense_peak,
+                                        "note": "FLOPs the tensor pipe executes: a critic product is a_hi.w_hi + a_lo.w_hi + a_hi.w_lo "
+                                                "(three fp16 MMAs, 22 significand bits; DESIGN.md section 4), a policy product one; "
+                                                "'achieved' counts every product once (SURVEY 8d's algorithmic FLOPs)"},
                          "tcgen05_issue_rate_tflops": {k: round(x, 1) for k, x in mma_peaks.items()},
-                         "all_tcgen05_kernels": {"kernels": "gemm_tf32_kernel + mlp_fwd_kernel + mlp_bwd_kernel (every dense-layer "
+                         "all_tcgen05_kernels": {"kernels": "gemm_tf32_kernel + mlp_fwd(_h)_kernel + mlp_bwd_kernel (every dense-layer "
                                                             "launch of the step: forward, dgrad, wgrad, heads)",
-                                                 "achieved": achieved, "frac": achieved / tf32_peak, "launches_per_step": n_gemm,
+                                                 "achieved": achieved, "frac_of_tf32_peak": achieved / tf32_peak, "launches_per_step": n_gemm,
                                                  "ms_per_step_in_kernel": gemm_ms, "algorithmic_flops_per_step": flops_step},
-                         "ncu_tensor_pipe_active_pct": {"mlp_fwd_kernel, 4 critic nets": 33.2, "mlp_fwd_kernel, policy": 27.7,
-                                                        "mlp_bwd_kernel": 26.4, "gemm_tf32 wgrad (layers 2/1/0)": [13.3, 28.2, 20.3],
-                                                        "source": "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active, "
-                                                                  "profiles/r1_final_ncu_full_update_kernels.csv"}},
+                         "ncu_tensor_pipe_active_pct": ncu.get("tensor_pipe_active_pct")},
             "kernel_ms_per_step": {k: round(x, 4) for k, x in sorted(per_kernel.items(), key=lambda kv: -kv[1])},
             "replay": {"kernels": replay, "hbm_peak_gbs": hbm_peak, "peak_source": peak_src,
                        "insert_frac_of_hbm": replay["insert_122880"]["gbs"] / hbm_peak,
                        "sample_frac_of_hbm": replay["sample_65536"]["gbs"] / hbm_peak,
                        "bytes_per_unit": {"insert": BYTES_INSERT, "sample": BYTES_SAMPLE},
-                       "traffic": {"insert_122880": {"dram_read": 95.36e6, "dram_write": 51.4e6, "algorithmic": 122880 * BYTES_INSERT},
-                                   "sample_65536": {"dram_read": 57.57e6, "dram_write": 6.7e6, "algorithmic": 65536 * BYTES_SAMPLE},
-                                   "note": "ncu --set full, profiles/r1_final_ncu_full_replay_kernels.csv: reads match the algorithmic "
-                                           "bytes (insert 776 B/row exactly; gather reads whole 32-B sectors of the 800-B record), "
-                                           "writes are below them because part of the output is still in L2 when the kernel ends"}},
+                       "traffic": ncu.get("replay_traffic")},
             "host_wall_ms_per_step": 1e3 * wall / args.steps,
             "losses": {"critic": float(losses[0]), "actor": float(losses[1])}}
     if dp_phases is not None:

@@ -350,6 +350,27 @@ typedef struct {
 typedef struct { int M, n_groups; pqlb_mlp_bwd_group g[PQLB_MAX_GROUPS]; } pqlb_mlp_bwd_desc;
 int pqlb_mlp_backward(const pqlb_mlp_bwd_desc* desc, pqlb_stream_t stream);
 
+/* ---- K3w: all weight gradients of an update in one launch ------------------------------------------
+ * Problem i: part_i[s][m][n] = sum over the k-blocks of split s of dz_i[k][m] * h_i[k][n], m < M (the
+ * layer's output features), n < N (its input features), k < K (the batch); dz and h are the row-major
+ * [K][ld] buffers the backward / forward kernels wrote (TF32-rounded values).  The CTAs of the launch are
+ * the (128 x tile_n tile, split) pairs of all problems; split s of S owns k-blocks [s kb / S, (s + 1) kb / S)
+ * (kb = ceil(K / 32)), so S need not divide kb; pqlb_grad_reduce sums the S partials in split order.
+ * Replaces the weight-gradient GEMMs of loss.backward() (pql/algo/pql_v_learner.py:125,
+ * pql/algo/pql_p_learner.py:60) for every nn.Linear of pql/models/mlp.py:15-24 at once. */
+#define PQLB_MAX_WGRAD 8
+typedef struct {
+  const float* dz; int64_t lddz;
+  const float* h;  int64_t ldh;
+  float* part; int64_t ldo;       /* partial s at part + s * split_stride, row stride ldo words */
+  int64_t split_stride;
+  int M, N;
+  int tile_n;                     /* 32, 64, 128 or 256 */
+  int splits;
+} pqlb_wgrad_problem;
+typedef struct { int K, n_problems; pqlb_wgrad_problem p[PQLB_MAX_WGRAD]; } pqlb_wgrad_desc;
+int pqlb_wgrad_multi(const pqlb_wgrad_desc* desc, pqlb_stream_t stream);
+
 /* dst = rn_tf32(src) elementwise (tensor-core operand copies of weights). */
 int pqlb_round_tf32(const float* src, float* dst, int64_t n, pqlb_stream_t stream);
 

@@ -203,6 +203,60 @@ def wgrad_tiling(M, N, K, n_groups, target_ctas=int(_os.environ.get("PQLB_WGRAD_
     return best[1], best[2]
 
 
+def wgrad_tile_n(N):
+    return 256 if N > 128 else 128 if N > 64 else 64 if N > 32 else 32
+
+
+def wgrad_plan(problems, K, target_ctas=None):
+    """Split-K factors of the weight-gradient problems of ONE launch (pqlb_wgrad_multi).
+
+    ``problems``: [(M, N)] = (output features, input features) of every dW = dz^T . h of the update.
+    The launch is one wave of at most ``target_ctas`` CTAs (one per SM); these GEMMs are bound by the
+    operand bytes a CTA streams in from L2, so the splits are handed out greedily to the problem whose
+    CTAs currently stream the most bytes.  Returns [(tile_n, splits)]."""
+    target = int(target_ctas or _os.environ.get("PQLB_WGRAD_CTAS", 148))
+    kb = (K + 31) // 32
+    max_split = max(1, kb // 2)
+    info = []
+    for M, N in problems:
+        tn = wgrad_tile_n(N)
+        tiles, cost = 0, 0.0
+        for m0 in range(0, M, 128):
+            for n0 in range(0, N, tn):
+                tiles += 1
+                cost = max(cost, 4096.0 * (-(-min(M - m0, 128) // 32) + -(-min(N - n0, tn) // 32)))
+        info.append([tn, tiles, cost, 1])
+    total = sum(t for _, t, _, _ in info)
+    while True:
+        order = sorted(range(len(info)), key=lambda i: -info[i][2] / info[i][3])
+        for i in order:
+            if info[i][3] < max_split and total + info[i][1] <= target:
+                info[i][3] += 1
+                total += info[i][1]
+                break
+        else:
+            break
+    return [(tn, s) for tn, _, _, s in info]
+
+
+class WgradMulti(Call):
+    """All weight gradients of an update in one launch (pqlb_wgrad_multi).  ``problems``: dicts with
+    dz, lddz, h, ldh, part, ldo, split_stride, M, N, tile_n, splits (addresses from ``addr``)."""
+
+    def __init__(self, K, problems):
+        d = _lib.WgradDesc()
+        d.K, d.n_problems = int(K), len(problems)
+        if not 1 <= len(problems) <= _lib.MAX_WGRAD:
+            raise ValueError("1..%d problems per launch" % _lib.MAX_WGRAD)
+        for i, g in enumerate(problems):
+            for k in ("dz", "h", "part"):
+                setattr(d.p[i], k, g[k])
+            for k in ("lddz", "ldh", "ldo", "split_stride", "M", "N", "tile_n", "splits"):
+                setattr(d.p[i], k, int(g[k]))
+        self.desc = d
+        super().__init__("pqlb_wgrad_multi", C.byref(d))
+
+
 WGRAD_CLUSTER = int(_os.environ.get("PQLB_WGRAD_CLUSTER", 1))
 
 

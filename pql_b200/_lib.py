@@ -88,6 +88,18 @@ class MlpBwdDesc(C.Structure):
     _fields_ = [("M", _int), ("n_groups", _int), ("g", MlpBwdGroup * MAX_GROUPS)]
 
 
+MAX_WGRAD = 8
+
+
+class WgradProblem(C.Structure):
+    _fields_ = [("dz", _f), ("lddz", _i64), ("h", _f), ("ldh", _i64), ("part", _f), ("ldo", _i64),
+                ("split_stride", _i64), ("M", _int), ("N", _int), ("tile_n", _int), ("splits", _int)]
+
+
+class WgradDesc(C.Structure):
+    _fields_ = [("K", _int), ("n_problems", _int), ("p", WgradProblem * MAX_WGRAD)]
+
+
 class MlpDesc(C.Structure):
     _fields_ = [("M", _int), ("k_in", _int), ("n_groups", _int), ("g", MlpGroup * MAX_GROUPS)]
 
@@ -130,6 +142,7 @@ _PROTOS = {
     "pqlb_split_f16": (_int, [_f, _f, _f, _i64, _st]),
     "pqlb_f16_weight_scale": (_flt, []),
     "pqlb_mlp_backward": (_int, [C.POINTER(MlpBwdDesc), _st]),
+    "pqlb_wgrad_multi": (_int, [C.POINTER(WgradDesc), _st]),
     "pqlb_round_tf32": (_int, [_f, _f, _i64, _st]),
     "pqlb_doubleq_td_loss": (_int, [_f, _f, _f, _f, _f, _f, _flt, _i64, _f, _f, _f, _f, _f, _f, _f,
                                     _f, _f, _f, _st]),

@@ -21,6 +21,8 @@ from ..models.mlp import (FUSED_MAX_IN, HIDDEN, NetAddrs, NetLayout, _ru, forwar
 H1, H2, H3 = HIDDEN
 import os as _os
 SEG = int(_os.environ.get("PQLB_REDUCE_SEG", 256))      # elements per block of the gradient reduction
+# every weight gradient of an update in one launch (pqlb_wgrad_multi); "0" = one grouped GEMM per layer (round 1)
+WGRAD_MULTI = _os.environ.get("PQLB_WGRAD_MULTI", "1") != "0"
 
 
 def forward_mode(requested, obs_dim, action_dim):
@@ -68,6 +70,10 @@ class _Optim:
         self.seg_table = torch.tensor(self._segs, dtype=torch.int64, device=device)
         self.n_seg = len(self._segs)
         self.sumsq = torch.zeros(self.n_seg, device=device)
+
+
+def _some(call):
+    return [] if call is None else [call]
 
 
 def _colsum_call(B, entries, keep):
@@ -126,9 +132,19 @@ class _UpdateBase:
         """One workspace for every split-K / per-block partial sum of the update, sized up front
         so that all addresses are fixed while the launch list is being prepared."""
         total = extra + 64
-        for n_out, n_in, ldw in wgrads:
-            _, splits = K.wgrad_tiling(n_out, n_in, self.B, n_nets)
-            total += n_nets * _ru(splits * n_out * ldw, 32)
+        self._wg_multi = WGRAD_MULTI and len(wgrads) * n_nets <= _lib.MAX_WGRAD
+        self._wg_pending = []
+        if self._wg_multi:
+            # one launch for every weight gradient of the update: split counts balanced over one wave of CTAs
+            plan = K.wgrad_plan([(n_out, n_in) for n_out, n_in, _ in wgrads for _ in range(n_nets)], self.B)
+            self._wg_plan = {}
+            for j, (n_out, n_in, ldw) in enumerate(wgrads):
+                self._wg_plan[(n_out, n_in)] = plan[j * n_nets: (j + 1) * n_nets]
+                total += sum(_ru(s * n_out * ldw, 32) for _, s in plan[j * n_nets: (j + 1) * n_nets])
+        else:
+            for n_out, n_in, ldw in wgrads:
+                _, splits = K.wgrad_tiling(n_out, n_in, self.B, n_nets)
+                total += n_nets * _ru(splits * n_out * ldw, 32)
         total += sum(_ru(self.nblk * c, 32) for c in bias_cols)
         self.ws = self._buf(total)
         self._ws_used = 0
@@ -167,6 +183,17 @@ class _UpdateBase:
         """dW[layer] of len(net_ids) nets = dz^T . h (contraction over the batch, split-K partials
         in the workspace; grad_reduce sums them in a fixed order)."""
         B = self.B
+        if self._wg_multi:
+            # recorded now, launched by _wgrad_flush() once every dz of the update exists
+            ldw = layout.ldw[layer]
+            stride = n_out * ldw
+            for j, i in enumerate(net_ids):
+                tile_n, splits = self._wg_plan[(n_out, n_in)][j]
+                off = self._ws_alloc(splits * stride)
+                self._wg_pending.append(dict(dz=K.addr(dz[j]), lddz=ldz, h=K.addr(h[j]), ldh=ldh, part=K.addr(self.ws, off),
+                                             ldo=ldw, split_stride=stride, M=n_out, N=n_in, tile_n=tile_n, splits=splits))
+                opt.add_source(layout.w_off[i][layer], stride, off, stride, splits)
+            return None
         tile_n, splits = K.wgrad_tiling(n_out, n_in, B, len(net_ids))
         cluster = K.wgrad_cluster(splits, tile_n)       # the splits of a cluster leave the SMs as one partial
         n_part = splits // cluster
@@ -180,6 +207,16 @@ class _UpdateBase:
             opt.add_source(layout.w_off[i][layer], stride, off, stride, n_part)
         return K.Gemm(n_out, n_in, B, groups, epilogue=K.EPI_STORE, tile_n=tile_n, a_major=K.MN_MAJOR,
                       b_major=K.MN_MAJOR, splits=splits, cluster=cluster)
+
+    def _wgrad_flush(self):
+        """The one pqlb_wgrad_multi launch for the problems recorded by _wgrad (or nothing)."""
+        if not self._wg_pending:
+            return []
+        call = K.WgradMulti(self.B, self._wg_pending)
+        self.wgrad_ctas = sum(-(-g["M"] // 128) * -(-g["N"] // g["tile_n"]) * g["splits"] for g in self._wg_pending)
+        self.wgrad_partial_bytes = 4 * sum(g["splits"] * g["split_stride"] for g in self._wg_pending)
+        self._wg_pending = []
+        return [call]
 
     def _bias_grads(self, opt, layout, entries):
         """entries: (net, layer, dz tensor, ld, n_cols).  One launch for all bias gradients."""
@@ -321,16 +358,17 @@ class CriticUpdate(_UpdateBase):
                                 _lib.ptr(self.dl[0]), _lib.ptr(self.dl[1]), self.pd, _lib.ptr(self.loss_part)))
             calls.append(self._head_backward_c51(cnet, self.dl, [h_c[i][2] for i in range(2)],
                                                  [self.dz[i][2] for i in range(2)]))
-            calls.append(self._wgrad(self.opt, self.Lc, [0, 1], 3, self.dl, self.pd, N,
-                                     [h_c[i][2] for i in range(2)], H3, H3))
+            calls += _some(self._wgrad(self.opt, self.Lc, [0, 1], 3, self.dl, self.pd, N,
+                                       [h_c[i][2] for i in range(2)], H3, H3))
             self.loss_scale, self.n_loss_part = 1.0 / (B * N), (B + 7) // 8
         # -- backward of the current nets
         dz3, dz2, dz1 = ([self.dz[i][l] for i in range(2)] for l in (2, 1, 0))
         calls += self._dgrad_chain(cnet, dz3, dz2, dz1, [h_c[i][0] for i in range(2)], [h_c[i][1] for i in range(2)],
                                    bias=(self.opt, self.Lc, [0, 1]))
-        calls.append(self._wgrad(self.opt, self.Lc, [0, 1], 2, dz3, H3, H3, [h_c[i][1] for i in range(2)], H2, H2))
-        calls.append(self._wgrad(self.opt, self.Lc, [0, 1], 1, dz2, H2, H2, [h_c[i][0] for i in range(2)], H1, H1))
-        calls.append(self._wgrad(self.opt, self.Lc, [0, 1], 0, dz1, H1, H1, [self.x_cur, self.x_cur], x_ld, O + A))
+        calls += _some(self._wgrad(self.opt, self.Lc, [0, 1], 2, dz3, H3, H3, [h_c[i][1] for i in range(2)], H2, H2))
+        calls += _some(self._wgrad(self.opt, self.Lc, [0, 1], 1, dz2, H2, H2, [h_c[i][0] for i in range(2)], H1, H1))
+        calls += _some(self._wgrad(self.opt, self.Lc, [0, 1], 0, dz1, H1, H1, [self.x_cur, self.x_cur], x_ld, O + A))
+        calls += self._wgrad_flush()
         # bias gradients: layers 0 / 1 come out of the dgrad chain, layer 2 out of the twin-Q loss kernel
         if distl:
             entries = [(i, 2, self.dz[i][2], H3, H3) for i in range(2)] + [(i, 3, self.dl[i], self.pd, N) for i in range(2)]
@@ -530,10 +568,11 @@ class ActorUpdate(_UpdateBase):
                             epilogue=K.EPI_MUL_ELUGRAD, tile_n=fwd_tile(B, H3, 1), b_major=K.MN_MAJOR))
         calls += self._dgrad_chain([actor], [self.dza[2]], [self.dza[1]], [self.dza[0]], [ha[0]], [ha[1]],
                                    bias=(self.opt, self.La, [0]))
-        calls.append(self._wgrad(self.opt, self.La, [0], 3, [self.dz_act], a_ld, A, [ha[2]], H3, H3))
-        calls.append(self._wgrad(self.opt, self.La, [0], 2, [self.dza[2]], H3, H3, [ha[1]], H2, H2))
-        calls.append(self._wgrad(self.opt, self.La, [0], 1, [self.dza[1]], H2, H2, [ha[0]], H1, H1))
-        calls.append(self._wgrad(self.opt, self.La, [0], 0, [self.dza[0]], H1, H1, [self.x], x_ld, O))
+        calls += _some(self._wgrad(self.opt, self.La, [0], 3, [self.dz_act], a_ld, A, [ha[2]], H3, H3))
+        calls += _some(self._wgrad(self.opt, self.La, [0], 2, [self.dza[2]], H3, H3, [ha[1]], H2, H2))
+        calls += _some(self._wgrad(self.opt, self.La, [0], 1, [self.dza[1]], H2, H2, [ha[0]], H1, H1))
+        calls += _some(self._wgrad(self.opt, self.La, [0], 0, [self.dza[0]], H1, H1, [self.x], x_ld, O))
+        calls += self._wgrad_flush()
         entries = [(0, 2, self.dza[2], H3, H3), (0, 3, self.dz_act, a_ld, A)]     # layers 0 / 1: fused into the dgrad chain
         calls.append(self._bias_grads(self.opt, self.La, entries))
         _finish_plan(self, self.opt, self.a_flat, None, self.a_tf, None, self.a_h, None)

@@ -499,6 +499,7 @@ using namespace pqlb;
 extern "C" int pqlb_mlp_forward_init(void);
 extern "C" int pqlb_mlp_forward_h_init(void);
 extern "C" int pqlb_mlp_backward_init(void);
+extern "C" int pqlb_wgrad_init(void);
 
 // One-time, non-stream setup (opt-in shared memory size, driver entry point) so that nothing but
 // kernel launches happens while a caller is capturing a CUDA graph.  Per device.
@@ -517,6 +518,7 @@ extern "C" int pqlb_init(void) {
   { int rc = pqlb_mlp_forward_init(); if (rc != PQLB_OK) return rc; }
   { int rc = pqlb_mlp_forward_h_init(); if (rc != PQLB_OK) return rc; }
   { int rc = pqlb_mlp_backward_init(); if (rc != PQLB_OK) return rc; }
+  { int rc = pqlb_wgrad_init(); if (rc != PQLB_OK) return rc; }
   if (dev < 64) done[dev] = true;
   return PQLB_OK;
 }

@@ -71,6 +71,8 @@ def test_ctypes_structs_match_the_header(tmp_path):
               "pqlb_mlp_desc": (_lib.MlpDesc, ["M", "n_groups", "g"]),
               "pqlb_mlp_group": (_lib.MlpGroup, ["x", "w2", "q", "h3", "act_w", "act_ldo", "noise_std", "act_n"]),
               "pqlb_mlp_bwd_desc": (_lib.MlpBwdDesc, ["M", "g"]),
+              "pqlb_wgrad_desc": (_lib.WgradDesc, ["K", "n_problems", "p"]),
+              "pqlb_wgrad_problem": (_lib.WgradProblem, ["dz", "h", "part", "split_stride", "M", "tile_n", "splits"]),
               "pqlb_colsum_desc": (_lib.ColsumDesc, ["n", "rows", "dz", "ld", "n_cols", "part"]),
               "pqlb_dp_desc": (_lib.DpDesc, ["grad_peers", "red_peers", "ctl_peers", "local", "rank", "world", "grid"])}
     lines = ['#include "pqlb200.h"', "#include <cstdio>", "#include <cstddef>", "int main() {"]

@@ -132,6 +132,36 @@ def test_wgrad_mn_mn_split_k(K, n_out, n_in, B, tile_n, splits):
     assert torch.count_nonzero(part[:, :, n_in:]) == 0
 
 
+@pytest.mark.parametrize("shapes,B", [([(128, 256), (256, 512), (512, 104)] * 2, 8192),
+                                      ([(16, 128), (128, 256), (256, 512), (512, 88)], 8192),
+                                      ([(51, 128), (128, 256), (256, 512), (512, 104)] * 2, 1024),
+                                      ([(128, 256), (256, 512), (512, 231)], 416),
+                                      ([(20, 128), (512, 211)], 64)])
+def test_wgrad_multi_one_launch(K, shapes, B):
+    """pqlb_wgrad_multi: every dW = dz^T . h of an update in one launch, uneven split-K ranges
+    (wgrad_plan), partial tiles summed in split order."""
+    g = torch.Generator(device=DEV).manual_seed(B + len(shapes))
+    plan = K.wgrad_plan(shapes, B)
+    problems, checks = [], []
+    for (n_out, n_in), (tile_n, splits) in zip(shapes, plan):
+        ldz = 64 if n_out == 51 else (n_out + 3) // 4 * 4
+        ldh = (n_in + 3) // 4 * 4
+        dz = torch.zeros(B, ldz, device=DEV); dz[:, :n_out] = mk((B, n_out), g)
+        h = torch.zeros(B, ldh, device=DEV); h[:, :n_in] = mk((B, n_in), g)
+        part = torch.full((splits, n_out, ldh), 3.0, device=DEV)
+        part[:, :, n_in:] = 0
+        problems.append(dict(dz=K.addr(dz), lddz=ldz, h=K.addr(h), ldh=ldh, part=K.addr(part), ldo=ldh,
+                             split_stride=n_out * ldh, M=n_out, N=n_in, tile_n=tile_n, splits=splits))
+        checks.append((dz, h, part, n_out, n_in))
+    assert sum(-(-m // 128) * -(-n // t) * s for (m, n), (t, s) in zip(shapes, plan)) <= 148
+    K.WgradMulti(B, problems)()
+    torch.cuda.synchronize()
+    for dz, h, part, n_out, n_in in checks:
+        ref = dz[:, :n_out].double().t() @ h[:, :n_in].double()
+        check(part.sum(0)[:, :n_in], ref, 2e-5, f"wgrad_multi {n_out}x{n_in}")
+        assert torch.count_nonzero(part[:, :, n_in:]) == 0
+
+
 @pytest.mark.parametrize("n_out,n_in,B,tile_n,splits,cluster,groups", [
     (256, 512, 8192, 256, 32, 8, 2), (256, 512, 8192, 256, 32, 4, 2), (128, 256, 8192, 256, 64, 8, 2),
     (512, 104, 8192, 128, 32, 8, 2), (512, 104, 8192, 128, 32, 2, 1), (16, 128, 2048, 128, 8, 4, 1),
