@@ -285,8 +285,7 @@ def main():
     import torch.distributed as dist
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        # stdout carries the one JSON line; NCCL_DEBUG is whatever the launcher set (never overridden)
-        os.environ.setdefault("NCCL_DEBUG", "WARN")
+        # stdout carries the one JSON line; NCCL_DEBUG is whatever the launcher set (never touched here)
         dist.init_process_group("nccl", device_id=dev)
         dist.barrier()
     from pql_b200 import _kernels as K

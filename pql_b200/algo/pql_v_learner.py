@@ -57,9 +57,11 @@ class LearnerStream:
     current stream (which produced the trajectory) and after the stream that produced the module it
     is handed.  Off by default: then everything runs on the caller's current stream."""
 
-    def __init__(self, cfg, device):
+    def __init__(self, cfg, device, priority=0):
         self.device = device
-        self.stream = torch.cuda.Stream(device) if getattr(cfg, "learner_streams", False) else None
+        # priority < 0: this learner's kernels are dispatched ahead of the other learner's whenever SMs free up
+        # (the V-learner is the longer chain of a step, 8 updates against 4: see DESIGN.md section 7)
+        self.stream = torch.cuda.Stream(device, priority=int(priority)) if getattr(cfg, "learner_streams", False) else None
 
     def ctx(self):
         return torch.cuda.stream(self.stream) if self.stream is not None else contextlib.nullcontext()
@@ -188,7 +190,7 @@ class PQLVLearner:
         # cfg.dp_fused: no NCCL on the path - the optimiser kernel all-reduces over symmetric memory
         self.dp_fused = bool(getattr(cfg, "dp_fused", False)) and self.world_size > 1
         self._sync_loss = bool(getattr(cfg, "sync_loss", False))
-        self._ls = LearnerStream(cfg, self.device)
+        self._ls = LearnerStream(cfg, self.device, priority=int(os.environ.get("PQLB_V_PRIORITY", getattr(cfg, "v_stream_priority", 0))))
         self._ls.tag(self.critic)
         self.generator, self.fused_rng = make_generator(cfg, self.device, salt=0)
         if self.world_size > 1:

@@ -254,6 +254,8 @@ sample_gather_kernel(const float* __restrict__ ring, RecGeom g, const int64_t* _
   }
 }
 
+constexpr int kNormCols = 512;      // widest observation whose (mean, sd) table is kept in shared memory
+
 __device__ __forceinline__ float norm_clamp(float x, float m, float v, float eps) {
   // common.py:139-145: clamp((x - mean) / sqrt(var + eps), -5, 5)
   float y = __fdiv_rn(__fsub_rn(x, m), __fsqrt_rn(__fadd_rn(v, eps)));
@@ -276,6 +278,14 @@ sample_critic_batch_kernel(const float* __restrict__ ring, RecGeom g, const int6
   if (ra.state) { seed = ra.state[0]; off = ra.state[1] + ra.state[2] * ra.counter[0]; range = ra.range[0]; }
   const FieldMap f = field_map<VEC>(g);
   const int lane = threadIdx.x & 31;
+  // sqrt(var + eps) once per block instead of once per element (an IEEE square root is ~15 instructions, and
+  // the kernel is issue-bound at learner batch sizes): same values, same rounding
+  __shared__ float s_mean[kNormCols], s_sd[kNormCols];
+  const bool tab = mean != nullptr && g.O <= kNormCols;
+  if (tab) {
+    for (int k = threadIdx.x; k < g.O; k += blockDim.x) { s_mean[k] = mean[k]; s_sd[k] = __fsqrt_rn(__fadd_rn(var[k], eps)); }
+    __syncthreads();
+  }
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
   const int rd_items = VEC == 4 ? 1 : 2;
   const int pad_items = (x_ld - g.O - g.A) / VEC;           // zero padding columns of both input rows
@@ -284,7 +294,7 @@ sample_critic_batch_kernel(const float* __restrict__ ring, RecGeom g, const int6
     const float* rec[REC];
     long long mine = 0;
     if (ra.state && lane < REC && b0 + lane < B) {
-      mine = (long long)(torch_rand_u32(seed, off, ra.threads_idx, b0 + lane) % range);
+      mine = mod_range(torch_rand_u32(seed, off, ra.threads_idx, b0 + lane), range);
       const_cast<int64_t*>(idx)[b0 + lane] = mine;            // kept for inspection / tests
     }
 #pragma unroll
@@ -314,7 +324,10 @@ sample_critic_batch_kernel(const float* __restrict__ ring, RecGeom g, const int6
       float m[4] = {0.f, 0.f, 0.f, 0.f}, sd[4] = {1.f, 1.f, 1.f, 1.f};
       if (mean && d.field <= 1) {
 #pragma unroll
-        for (int q = 0; q < VEC; ++q) { m[q] = mean[d.fo + q]; sd[q] = __fsqrt_rn(__fadd_rn(var[d.fo + q], eps)); }
+        for (int q = 0; q < VEC; ++q) {
+          if (tab) { m[q] = s_mean[d.fo + q]; sd[q] = s_sd[d.fo + q]; }
+          else { m[q] = mean[d.fo + q]; sd[q] = __fsqrt_rn(__fadd_rn(var[d.fo + q], eps)); }
+        }
       }
 #pragma unroll
       for (int r = 0; r < REC; ++r) {
@@ -364,12 +377,18 @@ sample_obs_batch_rng_kernel(const float* __restrict__ obsring, int O, int64_t* _
                             int64_t B, const float* __restrict__ mean, const float* __restrict__ var,
                             float eps, float* __restrict__ x, int x_ld, int A, RngArgs ra, float* __restrict__ xf) {
   const int lane = threadIdx.x & 31;
+  __shared__ float s_mean[kNormCols], s_sd[kNormCols];
+  const bool tab = mean != nullptr && O <= kNormCols;
+  if (tab) {
+    for (int k = threadIdx.x; k < O; k += blockDim.x) { s_mean[k] = mean[k]; s_sd[k] = __fsqrt_rn(__fadd_rn(var[k], eps)); }
+    __syncthreads();
+  }
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
   const unsigned long long seed = ra.state[0], off = ra.state[1] + ra.state[2] * ra.counter[0], range = ra.range[0];
   for (int64_t b0 = ((((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5)) * REC; b0 < B; b0 += nwarps * REC) {
     long long mine = 0;
     if (lane < REC && b0 + lane < B) {
-      mine = (long long)(torch_rand_u32(seed, off, ra.threads_idx, b0 + lane) % range);
+      mine = mod_range(torch_rand_u32(seed, off, ra.threads_idx, b0 + lane), range);
       idx[b0 + lane] = mine;
     }
     const float* src[REC];
@@ -383,13 +402,14 @@ sample_obs_batch_rng_kernel(const float* __restrict__ obsring, int O, int64_t* _
         float v[REC];
 #pragma unroll
         for (int r = 0; r < REC; ++r) v[r] = src[r] ? __ldcs(src[r] + k) : 0.f;
-        float m = 0.f, vr = 1.f;
-        if (mean) { m = mean[k]; vr = var[k]; }
+        float m = 0.f, sd = 1.f;
+        if (tab) { m = s_mean[k]; sd = s_sd[k]; }
+        else if (mean) { m = mean[k]; sd = __fsqrt_rn(__fadd_rn(var[k], eps)); }
 #pragma unroll
         for (int r = 0; r < REC; ++r) {
           if (!src[r]) continue;
           float y = v[r];
-          if (mean) y = norm_clamp(y, m, vr, eps);
+          if (mean) y = fminf(fmaxf(__fdiv_rn(__fsub_rn(y, m), sd), -5.f), 5.f);     // common.py:139-145
           x[(b0 + r) * x_ld + k] = rn_tf32(y);
           if (xf) xf[(b0 + r) * x_ld + k] = y;
         }

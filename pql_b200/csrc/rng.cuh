@@ -41,19 +41,34 @@ inline int aten_rng_threads(long long numel) {
   return (int)T;
 }
 
+// thread / component of element li under ATen's policy: (li % T, li / T).  The fused draws have numel <= 4T < 2^32:
+// 32-bit division (the 64-bit one is a ~90-instruction subroutine, and there were three of them per index drawn)
+__device__ __forceinline__ void aten_thread_of(long long li, int T, unsigned* t, int* c) {
+  if (li < (long long)T) { *t = (unsigned)li; *c = 0; }
+  else if ((li >> 32) == 0) { const unsigned q = (unsigned)li / (unsigned)T; *c = (int)q; *t = (unsigned)li - q * (unsigned)T; }
+  else { *c = (int)(li / T); *t = (unsigned)(li % T); }
+}
+
 static __device__ __noinline__ unsigned torch_rand_u32(unsigned long long seed, unsigned long long offset, int T, long long li) {
+  unsigned t; int c;
+  aten_thread_of(li, T, &t, &c);
   curandStatePhilox4_32_10_t st;
-  curand_init(seed, (unsigned long long)(li % T), offset, &st);
+  curand_init(seed, (unsigned long long)t, offset, &st);
   const uint4 r = curand4(&st);
-  const int c = (int)(li / T);
   return c == 0 ? r.x : c == 1 ? r.y : c == 2 ? r.z : r.w;
 }
 
+// u32 % range as ATen computes it (uint64 arithmetic), through a 32-bit remainder when range fits
+__device__ __forceinline__ long long mod_range(unsigned v, unsigned long long range) {
+  return (range >> 32) == 0 ? (long long)(v % (unsigned)range) : (long long)((unsigned long long)v % range);
+}
+
 static __device__ __noinline__ float torch_normal_f32(unsigned long long seed, unsigned long long offset, int T, long long li) {
+  unsigned t; int c;
+  aten_thread_of(li, T, &t, &c);
   curandStatePhilox4_32_10_t st;
-  curand_init(seed, (unsigned long long)(li % T), offset, &st);
+  curand_init(seed, (unsigned long long)t, offset, &st);
   const float4 r = curand_normal4(&st);
-  const int c = (int)(li / T);
   return c == 0 ? r.x : c == 1 ? r.y : c == 2 ? r.z : r.w;
 }
 
