@@ -149,6 +149,9 @@ int pqlb_sample_obs_batch_rng(const float* obsring, int64_t capacity, int obs_di
                               const int64_t* cur_capacity, float* xf, pqlb_stream_t stream);
 /* *dst = value, stream-ordered (device-resident copies of host-side ring state). */
 int pqlb_store_i64(int64_t* dst, int64_t value, pqlb_stream_t stream);
+/* *dst = *src + delta, stream-ordered (the prefetching sampler's own update index: the index of the batch
+ * it draws next, kept apart from the optimiser's counter, which advances concurrently). */
+int pqlb_add_i64(int64_t* dst, const int64_t* src, int64_t delta, pqlb_stream_t stream);
 
 /* ---- Actor-side env-step path (pql/algo/pql_actor.py:87-127) ---------------------------
  * RunningMeanStd.update (pql/utils/torch_util.py:77-103) on device-resident state: batch mean and

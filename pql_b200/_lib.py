@@ -126,6 +126,7 @@ _PROTOS = {
                                             _f, _f, _f, _f, _f, _f, _i64, _f, _f, _st]),
     "pqlb_sample_obs_batch_rng": (_int, [_f, _i64, _int, _f, _i64, _f, _f, _flt, _f, _int, _int, _f, _f, _f, _f, _st]),
     "pqlb_store_i64": (_int, [_f, _i64, _st]),
+    "pqlb_add_i64": (_int, [_f, _f, _i64, _st]),
     "pqlb_rms_workspace_bytes": (_i64, [_i64, _int]),
     "pqlb_rms_update": (_int, [_f, _i64, _int, _i64, _f, _f, _f, _f, _i64, _st]),
     "pqlb_rms_moments": (_int, [_f, _i64, _int, _i64, _f, _f, _i64, _st]),

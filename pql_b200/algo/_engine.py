@@ -23,6 +23,9 @@ import os as _os
 SEG = int(_os.environ.get("PQLB_REDUCE_SEG", 256))      # elements per block of the gradient reduction
 # every weight gradient of an update in one launch (pqlb_wgrad_multi); "0" = one grouped GEMM per layer (round 1)
 WGRAD_MULTI = _os.environ.get("PQLB_WGRAD_MULTI", "1") != "0"
+# the V-learner's sampler runs one update ahead, as a side branch of the update's CUDA graph ("0": every update draws its own batch first)
+PREFETCH = _os.environ.get("PQLB_PREFETCH", "1") != "0"
+PF_FORK = int(_os.environ.get("PQLB_PF_FORK", 1))      # the side branch forks before main launch PF_FORK (0 = the critics' forward)
 
 
 def forward_mode(requested, obs_dim, action_dim):
@@ -51,6 +54,7 @@ class _Optim:
         self.v = torch.zeros(n, device=device)
         self.count = torch.zeros(1, dtype=torch.int64, device=device)   # completed updates (device-resident)
         self._segs = []            # rows of the segment table
+        self.frozen = False        # second build pass of the same launches (other input set): sources already registered
 
     @property
     def step(self):
@@ -63,6 +67,8 @@ class _Optim:
 
     def add_source(self, arena_off, count, ws_off, ws_stride, n_part):
         """grad[arena_off + i] = sum_{s < n_part} ws[ws_off + s * ws_stride + i], i < count."""
+        if self.frozen:
+            return
         for o in range(0, count, SEG):
             self._segs.append([arena_off + o, min(SEG, count - o), ws_off + o, ws_stride, n_part])
 
@@ -85,6 +91,12 @@ def _colsum_call(B, entries, keep):
 
 
 class _UpdateBase:
+    _pf_samples = None         # prefetching sampler (CriticUpdate only)
+    _pf_valid = False
+
+    def _bind_set(self, si):
+        pass
+
     def __init__(self, obs_dim, action_dim, batch, device, distl, num_atoms, v_min, v_max, loss_ring=None):
         self.O, self.A, self.B = int(obs_dim), int(action_dim), int(batch)
         self.device = torch.device(device)
@@ -148,11 +160,17 @@ class _UpdateBase:
         total += sum(_ru(self.nblk * c, 32) for c in bias_cols)
         self.ws = self._buf(total)
         self._ws_used = 0
+        self._ws_log, self._ws_replay = [], None
 
     def _ws_alloc(self, n):
+        if self._ws_replay is not None:       # second build pass: the same launches on the other input set share every buffer
+            off, n0 = self._ws_replay.pop(0)
+            assert n0 == n, "build passes diverged"
+            return off
         off = self._ws_used
         self._ws_used = _ru(off + n, 32)
         assert self._ws_used <= self.ws.numel(), "workspace under-sized"
+        self._ws_log.append((off, n))
         return off
 
     # ---- pieces shared by both updates -----------------------------------------------------
@@ -260,14 +278,24 @@ class CriticUpdate(_UpdateBase):
         self.round_weights()
         self.opt = _Optim(self.Lc, dev)
 
-        # batch buffers
-        self.idx = torch.zeros(B, dtype=torch.int64, device=dev)
-        self.noise = self._buf(B, A)
-        self.x_cur, self.x_tgt = self._buf(B, x_ld), self._buf(B, x_ld)
-        # the same rows without the TF32 operand rounding: inputs of the split-fp16 forward
-        self.xf_cur = self._buf(B, x_ld) if split else None
-        self.xf_tgt = self._buf(B, x_ld) if split else None
-        self.reward, self.done = self._buf(B), self._buf(B)
+        # batch buffers: TWO input sets when the sampler prefetches (set k % 2 feeds update k while a side branch of the
+        # same CUDA graph draws batch k + 1 and runs its target-policy forward into the other set), else one
+        self.n_sets = 2 if PREFETCH else 1
+        self.sets = []
+        for _ in range(self.n_sets):
+            st = dict(idx=torch.zeros(B, dtype=torch.int64, device=dev), noise=self._buf(B, A),
+                      x_cur=self._buf(B, x_ld), x_tgt=self._buf(B, x_ld),
+                      # the same rows without the TF32 operand rounding: inputs of the split-fp16 forward
+                      xf_cur=self._buf(B, x_ld) if split else None, xf_tgt=self._buf(B, x_ld) if split else None,
+                      reward=self._buf(B), done=self._buf(B))
+            self.sets.append(st)
+        self._bind_set(0)
+        self.cur_set = 0                  # input set of the next update on the prefetching path
+        self._pf_valid = False            # set cur_set already holds the next update's batch and target action
+        self._pf_graphs = {}
+        self._pf_samples = None
+        self._side = None
+        self.pre_k = torch.zeros(1, dtype=torch.int64, device=dev)     # update index of the batch the side branch draws next
         self.mean, self.var = self._buf(O), torch.ones(O, device=dev)
         ha = [self._buf(B, d) for d in HIDDEN]
         h_t = [[self._buf(B, d) for d in HIDDEN] for _ in range(2)]
@@ -291,45 +319,55 @@ class CriticUpdate(_UpdateBase):
         actor = NetAddrs(self.La, 0, self.a_tf, self.a_flat, self.a_h)
         cnet = [NetAddrs(self.Lc, i, self.c_tf, self.c_flat, self.c_h) for i in range(2)]
         tnet = [NetAddrs(self.Lc, i, self.t_tf, self.t_flat, self.t_h) for i in range(2)]
-        self._ring_args = None
-        calls = self.calls
+        wg = [(H3, H2, H2), (H2, H1, H1), (H1, O + A, x_ld)] + ([(N, H3, H3)] if distl else [])
+        self._ws_init(wg, 2, [d for d in HIDDEN] * 2 + ([N, N] if distl else []),
+                      extra=2 * _ru(self.nblk_head * (H3 + 1), 32) + 2 * _ru(self.nblk_head * H3, 32))
+        # the launch list once per input set: identical launches, every buffer but the inputs shared
+        self.policy_calls, self.main_calls = [], []
+        for si, st in enumerate(self.sets):
+            self.opt.frozen = si > 0
+            self._ws_replay = list(self._ws_log) if si > 0 else None
+            pol, main = self._build_calls(st, actor, cnet, tnet, ha, h_t, h_c, split)
+            self.policy_calls.append(pol)
+            self.main_calls.append(main)
+        self.opt.frozen, self._ws_replay = False, None
+        self.calls = self.policy_calls[0] + self.main_calls[0]       # one update, serially, on input set 0
+        _finish_plan(self, self.opt, self.c_flat, self.t_flat, self.c_tf, self.t_tf, self.c_h, self.t_h)
 
+    def _bind_set(self, si):
+        """``idx`` / ``noise`` / ``x_cur`` ... name the input set of the update that ran last (tests and the loop
+        observer read the draws there)."""
+        for k, v in self.sets[si].items():
+            setattr(self, k, v)
+
+    def _build_calls(self, st, actor, cnet, tnet, ha, h_t, h_c, split):
+        """(target-policy launches, everything from the critics' forward to the last weight gradient) on input set ``st``."""
+        O, A, B, N, x_ld, distl = self.O, self.A, self.B, self.N, self.x_ld, self.distl
+        x_cur, x_tgt, xf_cur, xf_tgt = st["x_cur"], st["x_tgt"], st["xf_cur"], st["xf_tgt"]
+        calls = []
         # -- target policy: a' = clamp(tanh(actor(next_obs)) + clamp(noise), +-1)   :62-71, noise.py:19-27
-        a_inst = dict(net=actor, x=K.addr(self.x_tgt), xf=K.addr(self.xf_tgt), x_ld=x_ld, k_in=O, h=[K.addr(t) for t in ha],
+        a_inst = dict(net=actor, x=K.addr(x_tgt), xf=K.addr(xf_tgt), x_ld=x_ld, k_in=O, h=[K.addr(t) for t in ha],
                       store=(False, False, False), terms=1,
-                      act=dict(out=K.addr(self.x_tgt, O), ldo=x_ld, noise=K.addr(self.noise), ldnoise=A,
+                      act=dict(out=K.addr(x_tgt, O), ldo=x_ld, noise=K.addr(st["noise"]), ldnoise=A,
                                noise_std=self.noise_std, noise_bound=self.noise_bound))
         if split:       # the un-rounded action goes next to the un-rounded next_obs
-            a_inst["act"].update(out2=K.addr(self.xf_tgt, O), ldo2=x_ld)
-        else:
-            calls += forward_calls(B, [a_inst], False)
-        # -- both target nets on (next_obs, a') and both current nets on (obs, action), one launch per layer
+            a_inst["act"].update(out2=K.addr(xf_tgt, O), ldo2=x_ld)
+        policy = forward_calls(B, [a_inst], False)
+        # -- both target nets on (next_obs, a') and both current nets on (obs, action), one launch
         # C51 + split-fp16 forward: the 51-atom softmax head rides in the fused launch (three MMAs per product
         # like the trunk: tools/precision_study.py - the head's forward is the site the actor gradient needs)
         fused_sm = distl and split
-        insts = [dict(net=tnet[i], x=K.addr(self.x_tgt), xf=K.addr(self.xf_tgt), x_ld=x_ld, k_in=O + A,
+        insts = [dict(net=tnet[i], x=K.addr(x_tgt), xf=K.addr(xf_tgt), x_ld=x_ld, k_in=O + A,
                       h=[K.addr(t) for t in h_t[i]], store=(False, False, distl and not fused_sm), q=K.addr(self.tq[i]), terms=3)
                  for i in range(2)]
-        insts += [dict(net=cnet[i], x=K.addr(self.x_cur), xf=K.addr(self.xf_cur), x_ld=x_ld, k_in=O + A,
+        insts += [dict(net=cnet[i], x=K.addr(x_cur), xf=K.addr(xf_cur), x_ld=x_ld, k_in=O + A,
                        h=[K.addr(t) for t in h_c[i]], store=(True, True, True), q=K.addr(self.q[i]), terms=3)
                   for i in range(2)]
         if fused_sm:
             for j, it in enumerate(insts):
                 it["softmax"] = dict(out=K.addr(self.tp[j] if j < 2 else self.p[j - 2]), ldp=self.pd)
-        wg = [(H3, H2, H2), (H2, H1, H1), (H1, O + A, x_ld)] + ([(N, H3, H3)] if distl else [])
-        self._ws_init(wg, 2, [d for d in HIDDEN] * 2 + ([N, N] if distl else []),
-                      extra=2 * _ru(self.nblk_head * (H3 + 1), 32) + 2 * _ru(self.nblk_head * H3, 32))
-        if split:
-            # ONE launch for all five networks: the 64 policy tiles publish their action rows tile by tile,
-            # the target critics (dispatched last) wait for the tile they read, and the SMs the policy
-            # leaves idle start on the current critics, which do not depend on it
-            self.tile_sync = torch.zeros(2 + self.nblk, dtype=torch.int32, device=dev)
-            a_inst["publish"] = 1
-            for it in insts[:2]:
-                it["wait"] = 1
-            calls += forward_calls_h(B, [a_inst] + insts[2:] + insts[:2], not distl, tile_sync=self.tile_sync)
-        else:
-            calls += forward_calls(B, insts, not distl)
+        # the current critics (which store their activations: the longer tiles) are dispatched first
+        calls += forward_calls(B, insts[2:] + insts[:2], not distl)
         if not distl:
             ws_head = [self._ws_alloc(self.nblk_head * (H3 + 1)) for _ in range(2)]
             for i in range(2):
@@ -339,7 +377,7 @@ class CriticUpdate(_UpdateBase):
             for i in range(2):
                 self.opt.add_source(self.Lc.b_off[i][2], H3, b3[i], H3, self.nblk_head)
             calls.append(K.Call("pqlb_doubleq_td_loss_b3", _lib.ptr(self.q[0]), _lib.ptr(self.q[1]), _lib.ptr(self.tq[0]),
-                                _lib.ptr(self.tq[1]), _lib.ptr(self.reward), _lib.ptr(self.done), self.gamma_n, B,
+                                _lib.ptr(self.tq[1]), _lib.ptr(st["reward"]), _lib.ptr(st["done"]), self.gamma_n, B,
                                 _lib.ptr(h_c[0][2]), _lib.ptr(h_c[1][2]), C.c_void_p(cnet[0].Wf[3]),
                                 C.c_void_p(cnet[1].Wf[3]), _lib.ptr(self.dz[0][2]), _lib.ptr(self.dz[1][2]),
                                 _lib.ptr(self.y), C.c_void_p(K.addr(self.ws, ws_head[0])),
@@ -353,7 +391,7 @@ class CriticUpdate(_UpdateBase):
                           for j, it in enumerate(insts)]
                 calls.append(K.Gemm(B, N, H3, groups, epilogue=K.EPI_BIAS_SOFTMAX, tile_n=64))
             calls.append(K.Call("pqlb_c51_td_loss", _lib.ptr(self.p[0]), _lib.ptr(self.p[1]), _lib.ptr(self.tp[0]),
-                                _lib.ptr(self.tp[1]), self.pd, _lib.ptr(self.reward), _lib.ptr(self.done),
+                                _lib.ptr(self.tp[1]), self.pd, _lib.ptr(st["reward"]), _lib.ptr(st["done"]),
                                 _lib.ptr(self.z), self.gamma_n, self.v_min, self.v_max, N, B, _lib.ptr(self.target),
                                 _lib.ptr(self.dl[0]), _lib.ptr(self.dl[1]), self.pd, _lib.ptr(self.loss_part)))
             calls.append(self._head_backward_c51(cnet, self.dl, [h_c[i][2] for i in range(2)],
@@ -367,13 +405,13 @@ class CriticUpdate(_UpdateBase):
                                    bias=(self.opt, self.Lc, [0, 1]))
         calls += _some(self._wgrad(self.opt, self.Lc, [0, 1], 2, dz3, H3, H3, [h_c[i][1] for i in range(2)], H2, H2))
         calls += _some(self._wgrad(self.opt, self.Lc, [0, 1], 1, dz2, H2, H2, [h_c[i][0] for i in range(2)], H1, H1))
-        calls += _some(self._wgrad(self.opt, self.Lc, [0, 1], 0, dz1, H1, H1, [self.x_cur, self.x_cur], x_ld, O + A))
+        calls += _some(self._wgrad(self.opt, self.Lc, [0, 1], 0, dz1, H1, H1, [x_cur, x_cur], x_ld, O + A))
         calls += self._wgrad_flush()
         # bias gradients: layers 0 / 1 come out of the dgrad chain, layer 2 out of the twin-Q loss kernel
         if distl:
             entries = [(i, 2, self.dz[i][2], H3, H3) for i in range(2)] + [(i, 3, self.dl[i], self.pd, N) for i in range(2)]
             calls.append(self._bias_grads(self.opt, self.Lc, entries))
-        _finish_plan(self, self.opt, self.c_flat, self.t_flat, self.c_tf, self.t_tf, self.c_h, self.t_h)
+        return policy, calls
 
     def round_weights(self):
         with torch.cuda.device(self.device):
@@ -398,18 +436,41 @@ class CriticUpdate(_UpdateBase):
         self.mean.copy_(mean.reshape(-1).float(), non_blocking=True)
         self.var.copy_(var.reshape(-1).float(), non_blocking=True)
 
-    def sample_call(self, ring, capacity, cur_capacity_dev=None):
-        """The fused gather + normalise + cat launch for a given replay ring; with the fused sampler
-        RNG enabled the same launch also draws the indices and the target-policy noise."""
+    def sample_call(self, ring, capacity, cur_capacity_dev=None, si=0, counter=None):
+        """The fused gather + normalise + cat launch for a given replay ring into input set ``si``; with the fused
+        sampler RNG enabled the same launch also draws the indices and the target-policy noise (``counter``: the
+        device word holding the update index the draw belongs to; default: the optimiser's completed-update count)."""
         on = self.obs_norm
-        args = (_lib.ptr(ring), int(capacity), self.O, self.A, _lib.ptr(self.idx),
+        st = self.sets[si]
+        args = (_lib.ptr(ring), int(capacity), self.O, self.A, _lib.ptr(st["idx"]),
                 self.B, _lib.ptr(self.mean) if on else None, _lib.ptr(self.var) if on else None, self.eps,
-                _lib.ptr(self.x_cur), _lib.ptr(self.x_tgt), self.x_ld, _lib.ptr(self.reward), _lib.ptr(self.done))
-        xf = (_lib.ptr(self.xf_cur), _lib.ptr(self.xf_tgt))
+                _lib.ptr(st["x_cur"]), _lib.ptr(st["x_tgt"]), self.x_ld, _lib.ptr(st["reward"]), _lib.ptr(st["done"]))
+        xf = (_lib.ptr(st["xf_cur"]), _lib.ptr(st["xf_tgt"]))
         if self.rng_state is None:
             return K.Call("pqlb_sample_critic_batch", *args, *xf, keep=(ring,))
-        return K.Call("pqlb_sample_critic_batch_rng", *args, _lib.ptr(self.rng_state), _lib.ptr(self.opt.count),
-                      _lib.ptr(cur_capacity_dev), _lib.ptr(self.noise), self.noise.numel(), *xf, keep=(ring, cur_capacity_dev))
+        cnt = self.opt.count if counter is None else counter
+        return K.Call("pqlb_sample_critic_batch_rng", *args, _lib.ptr(self.rng_state), _lib.ptr(cnt),
+                      _lib.ptr(cur_capacity_dev), _lib.ptr(st["noise"]), st["noise"].numel(), *xf, keep=(ring, cur_capacity_dev, cnt))
+
+    def bind_replay(self, ring, capacity, cur_capacity_dev):
+        """Prepare the sampler launches of the prefetching path: per input set one that draws the CURRENT update's
+        batch (first update after an exchange) and one that draws the NEXT update's batch from the side branch."""
+        self._pf_samples = None
+        self._pf_graphs = {}
+        self._pf_valid = False
+        if self.n_sets == 2 and self.rng_state is not None:
+            self._pf_samples = [(self.sample_call(ring, capacity, cur_capacity_dev, si),
+                                 self.sample_call(ring, capacity, cur_capacity_dev, si, counter=self.pre_k)) for si in range(2)]
+            self._prek_init = K.Call("pqlb_add_i64", _lib.ptr(self.pre_k), _lib.ptr(self.opt.count), 1)
+            self._prek_bump = K.Call("pqlb_add_i64", _lib.ptr(self.pre_k), _lib.ptr(self.pre_k), 1)
+        call = self.sample_call(ring, capacity, cur_capacity_dev, 0)
+        call.prefetchable = True
+        return call
+
+    def invalidate_prefetch(self):
+        """The ring, the actor or the normaliser changed (update()): the batch drawn ahead is stale; the next
+        update draws its own, with the same generator offsets, so the random stream is the reference's."""
+        self._pf_valid = False
 
     def run(self, sample=None, allreduce=None, use_graph=False, graph_allreduce=False):
         """One update: [sample] + forward/backward launches + gradient reduction, the gradient
@@ -418,7 +479,16 @@ class CriticUpdate(_UpdateBase):
         fixed; the step count and the loss window live on the device): one graph per update, or two
         with the all-reduce issued eagerly between them; ``graph_allreduce`` captures the NCCL
         all-reduce as well (one graph per update also when data parallel - the learner must then own
-        its communicator, because two learners replaying on two streams give NCCL no common order)."""
+        its communicator, because two learners replaying on two streams give NCCL no common order).
+
+        Prefetching path (CUDA graphs + fused sampler RNG + one graph per update): the graph of update k
+        has a side branch that draws batch k + 1 and runs its target-policy forward into the other input
+        set, concurrently with update k's own launches; update k + 1 then starts at the critics' forward."""
+        if (use_graph and sample is not None and self._pf_samples is not None and getattr(sample, "prefetchable", False)
+                and (allreduce is None or graph_allreduce)):
+            return self._run_prefetching(allreduce)
+        self._pf_valid = False
+        self._bind_set(0)
         if not use_graph:
             self._segment_a(sample)
             if allreduce is not None:
@@ -434,6 +504,49 @@ class CriticUpdate(_UpdateBase):
         if allreduce is not None and not self.graphs[3]:
             allreduce(self.opt.grad)
         self.graphs[1].replay()
+
+    def _run_prefetching(self, allreduce):
+        si, fresh = self.cur_set, not self._pf_valid
+        key = (fresh, si)
+        g = self._pf_graphs.get(key)
+        if g is None:
+            g = self._pf_graphs[key] = self._capture_prefetching(fresh, si, allreduce)
+        n_pol = len(self.policy_calls[si])
+        self.graph_launches += ((2 + n_pol) if fresh else 0) + (2 + n_pol) + len(self.main_calls[si]) + 2 + (1 if allreduce is not None else 0)
+        g.replay()
+        self._bind_set(si)
+        self.cur_set, self._pf_valid = 1 - si, True
+
+    def _capture_prefetching(self, fresh, si, allreduce):
+        torch.cuda.synchronize(self.device)
+        if self._side is None:
+            self._side = torch.cuda.Stream(self.device)
+        g = torch.cuda.CUDAGraph()
+        main_s, side_s = self._pf_samples[si][0], self._pf_samples[1 - si][1]
+        with torch.cuda.graph(g):
+            cur = torch.cuda.current_stream(self.device)
+            if fresh:
+                self._prek_init()                     # pre_k = completed updates + 1: the side branch draws the NEXT batch
+                main_s()
+                for c in self.policy_calls[si]:
+                    c()
+            for j, c in enumerate(self.main_calls[si]):
+                if j == PF_FORK:
+                    # the side branch: batch k + 1 and its target action, concurrent with the rest of update k
+                    self._side.wait_stream(cur)
+                    with torch.cuda.stream(self._side):
+                        side_s()
+                        for c2 in self.policy_calls[1 - si]:
+                            c2()
+                        self._prek_bump()
+                c()
+            self.reduce_call()
+            if allreduce is not None:
+                allreduce(self.opt.grad)
+                self.sumsq_call()
+            self._segment_b()
+            cur.wait_stream(self._side)
+        return g
 
     def _segment_a(self, sample):
         if sample is not None:

@@ -235,7 +235,7 @@ class PQLVLearner:
             if old is not None and old.rng_state is not None:
                 self.generator.set_offset(int(old.rng_state[1].item()) + int(old.rng_state[2].item()) * old.opt.step)
             self._plan.enable_fused_rng(self.generator, draws_per_update=2)      # randint, then normal
-        self._sample = self._plan.sample_call(self.memory.ring, self.memory.capacity, self.memory.cur_capacity_dev)
+        self._sample = self._plan.bind_replay(self.memory.ring, self.memory.capacity, self.memory.cur_capacity_dev)
 
     @property
     def critic_target(self):
@@ -291,6 +291,7 @@ class PQLVLearner:
                 self._plan.set_actor(module_flat(actor, self._plan.La.total, self.device))
                 note_read(actor)
                 self._plan.set_norm(normalize_tuple if self.cfg.algo.obs_norm else None)
+                self._plan.invalidate_prefetch()      # new transitions / actor / statistics: the batch drawn ahead is stale
                 # cfg.sync_loss: block until this learner's stream has drained and return the current mean;
                 # default: the mean as of the previous update() (non-blocking, DeviceTracker.mean_lagged)
                 loss = self.loss_tracker.mean() if self._sync_loss else self.loss_tracker.mean_lagged()

@@ -423,6 +423,7 @@ sample_obs_batch_rng_kernel(const float* __restrict__ obsring, int O, int64_t* _
 }
 
 __global__ void store_i64_kernel(long long* dst, long long v) { *dst = v; }
+__global__ void add_i64_kernel(long long* dst, const long long* src, long long delta) { *dst = *src + delta; }
 
 __global__ void __launch_bounds__(kThreads)
 sample_obs_batch_kernel(const float* __restrict__ obsring, int O, const int64_t* __restrict__ idx,
@@ -674,6 +675,12 @@ extern "C" int pqlb_sample_obs_batch_rng(const float* obsring, int64_t capacity,
 extern "C" int pqlb_store_i64(int64_t* dst, int64_t value, pqlb_stream_t stream) {
   PQLB_CHECK_ARG(dst);
   store_i64_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(reinterpret_cast<long long*>(dst), (long long)value);
+  PQLB_LAUNCH_RET();
+}
+
+extern "C" int pqlb_add_i64(int64_t* dst, const int64_t* src, int64_t delta, pqlb_stream_t stream) {
+  PQLB_CHECK_ARG(dst && src);
+  add_i64_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(reinterpret_cast<long long*>(dst), reinterpret_cast<const long long*>(src), (long long)delta);
   PQLB_LAUNCH_RET();
 }
 
