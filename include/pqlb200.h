@@ -58,6 +58,9 @@ int pqlb_mma_peak(int kind, int n, int iters, pqlb_stream_t stream);
 /* Geometry helpers (pure host arithmetic). */
 int pqlb_obs_pad(int obs_dim);
 int pqlb_record_ld(int obs_dim, int act_dim);
+/* Measurement switch (call before any ring exists): 0 = the default power-of-two stride, 1 = the next multiple of
+ * 32 words (128 bytes): denser records (896 B instead of 1 KB for AllegroHand), slower random gathers. */
+void pqlb_record_stride_mode(int mode);
 int pqlb_x_ld(int obs_dim, int act_dim);
 
 /* ---- K1: ring scatter-insert -------------------------------------------------------------

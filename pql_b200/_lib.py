@@ -112,6 +112,7 @@ _PROTOS = {
     "pqlb_mma_peak": (_int, [_int, _int, _int, _st]),
     "pqlb_obs_pad": (_int, [_int]),
     "pqlb_record_ld": (_int, [_int, _int]),
+    "pqlb_record_stride_mode": (None, [_int]),
     "pqlb_x_ld": (_int, [_int, _int]),
     "pqlb_ring_insert": (_int, [_f, _i64, _int, _int, _f, _f, _f, _f, _f, _i64, _i64, _st]),
     "pqlb_ring_insert_force_ldg": (None, [_int]),
@@ -192,6 +193,8 @@ def load():
         for name, (res, args) in _PROTOS.items():
             fn = getattr(lib, name)
             fn.restype, fn.argtypes = res, args
+        if os.environ.get("PQLB_REC_STRIDE"):        # record-stride experiment: "128" = 128-byte aligned instead of a power of two
+            lib.pqlb_record_stride_mode(1 if os.environ["PQLB_REC_STRIDE"] == "128" else 0)
         if os.environ.get("PQLB_FWD_H_MODE"):       # kernel-schedule experiments: 1 = CTA per tile, 2 = persistent
             lib.pqlb_mlp_forward_h_mode(int(os.environ["PQLB_FWD_H_MODE"]))
         _lib = lib

@@ -332,7 +332,8 @@ class CriticUpdate(_UpdateBase):
             self.main_calls.append(main)
         self.opt.frozen, self._ws_replay = False, None
         self.calls = self.policy_calls[0] + self.main_calls[0]       # one update, serially, on input set 0
-        _finish_plan(self, self.opt, self.c_flat, self.t_flat, self.c_tf, self.t_tf, self.c_h, self.t_h)
+        # the target nets only run forward: in split-fp16 mode nobody reads their TF32 twin, so the optimiser does not write it
+        _finish_plan(self, self.opt, self.c_flat, self.t_flat, self.c_tf, None if split else self.t_tf, self.c_h, self.t_h)
 
     def _bind_set(self, si):
         """``idx`` / ``noise`` / ``x_cur`` ... name the input set of the update that ran last (tests and the loop

@@ -16,6 +16,7 @@ namespace pqlb {
 
 constexpr int kNumSMs = 148;  // B200
 extern unsigned long long g_launches;
+extern int g_rec_stride_mode;       // 0: record stride = next power of two (default); 1: next multiple of 32 words (128 B)
 
 __host__ __device__ inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
 
@@ -24,7 +25,7 @@ struct RecGeom {
   int O, A, obs_pad, act_pad, rec_ld;
   int off_obs, off_next, off_act, off_rew, off_done;
 };
-__host__ __device__ inline RecGeom rec_geom(int O, int A) {
+inline RecGeom rec_geom(int O, int A) {
   RecGeom g;
   g.O = O; g.A = A;
   g.obs_pad = round_up(O, 4);
@@ -41,6 +42,8 @@ __host__ __device__ inline RecGeom rec_geom(int O, int A) {
   // ring trades 28 % more memory (1.02 GB for 1 M AllegroHand slots) for ~1.4x sample bandwidth.
   int ld = 8;
   while (ld < g.off_done + 1) ld <<= 1;
+  // measurement switch (pqlb_record_stride_mode): the densest 128-byte-aligned stride instead - 896 B for AllegroHand
+  if (g_rec_stride_mode == 1) ld = round_up(g.off_done + 1, 32);
   g.rec_ld = ld;
   return g;
 }

@@ -99,6 +99,18 @@ mlp_bwd_kernel(const __grid_constant__ BwdDev P) {
       for (int kb = 0; kb < 4; ++kb) tma_load_2d(as + kb * 16384, &G.tmDz3, kb * 32, m0, ab);
     }
     __syncwarp();
+    if (blockIdx.x < 2) {
+      // L2 prefetch of this network's W3 / W2 (640 KB, cold after the forward's activation traffic): see tma_prefetch_2d
+      if (elect_one()) {
+        for (int t = 0; t < 40; ++t) {
+          const CUtensorMap* map; int n0, k0;
+          if (t < 8) { map = &G.tmW3; k0 = (t >> 1) * 32; n0 = (t & 1) * 128; }
+          else { map = &G.tmW2; const int u = t - 8; k0 = (u & 7) * 32; n0 = (u >> 3) * 128; }
+          for (int cb = 0; cb < 4; ++cb) tma_prefetch_2d(map, n0 + cb * 32, k0);
+        }
+      }
+      __syncwarp();
+    }
     int stage = 0; uint32_t phase = 0;
 #pragma unroll 1
     for (int t = 0; t < 40; ++t) {

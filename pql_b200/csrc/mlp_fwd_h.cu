@@ -106,6 +106,24 @@ __device__ __forceinline__ void mlp_fwd_h_body(const MlpHDev& P, const MlpHGroup
       for (int kb = 0; kb < G.kb1; ++kb) tma_load_2d(xs + kb * 16384, &G.tmX, kb * 32, m0, smem_u32(&x_full));
     }
     __syncwarp();
+    if (blockIdx.x < kHPrefetchCtas) {
+      // a few CTAs of every group pull the group's whole weight stream into L2 right away (see tma_prefetch_2d):
+      // the ring then streams from L2 instead of paying HBM latency tile by tile
+      if (elect_one()) {
+        for (int q = 0; q < 4; ++q)
+          for (int kw = 0; kw < G.kw1; ++kw)
+            for (int part = 0; part < NP; ++part) tma_prefetch_2d(&G.tmW1[part], kw * 32, q * 128);
+        for (int c = 0; c < 4; ++c)
+          for (int t = 0; t < 4; ++t)
+            for (int part = 0; part < NP; ++part) tma_prefetch_2d(&G.tmW2[part], c * 64 + (t >> 1) * 32, (t & 1) * 128);
+        for (int t = 0; t < 4; ++t)
+          for (int part = 0; part < NP; ++part) tma_prefetch_2d(&G.tmW3[part], t * 32, 0);
+        if (G.head_rows > 0)
+          for (int part = 0; part < NP; ++part)
+            for (int kb = 0; kb < 2; ++kb) tma_prefetch_2d(&G.tmW4[part], kb * 32, 0);
+      }
+      __syncwarp();
+    }
     int stage = 0; uint32_t phase = 0;
     auto load_tile = [&](const CUtensorMap* map, int c0, int c1) {
       mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1u);
@@ -207,7 +225,9 @@ __device__ __forceinline__ void mlp_fwd_h_body(const MlpHDev& P, const MlpHGroup
         mbar_wait(smem_u32(&p_conv[b]), (uint32_t)(c >> 1) & 1u);      // quarter c converted in place
         tcgen05_fence_after();
         PQLB_HSTAMP(0);
-#pragma unroll
+        // (t not unrolled: the issuer walks its code once per tile, and in a training step that code is never in the
+        // instruction cache - 64 unrolled MMAs per phase were 9 KB of straight-line SASS fetched from L2 each time)
+#pragma unroll 1
         for (int t = 0; t < 4; ++t) {
 #pragma unroll
           for (int part = 0; part < NP; ++part) {
@@ -232,7 +252,7 @@ __device__ __forceinline__ void mlp_fwd_h_body(const MlpHDev& P, const MlpHGroup
         if (c == 3) { if (elect_one()) umma_commit(smem_u32(&y_full)); __syncwarp(); }
         PQLB_HSTAMP(0);
       } else {
-#pragma unroll
+#pragma unroll 1
         for (int t = 0; t < 4; ++t) {            // k block t of layer 3: Y half t >> 1, 64-k half t & 1
           if ((t & 1) == 0) { mbar_wait(smem_u32(&y_conv[t >> 1]), 0); tcgen05_fence_after(); }
 #pragma unroll
@@ -383,6 +403,9 @@ __device__ __forceinline__ void mlp_fwd_h_body(const MlpHDev& P, const MlpHGroup
       }
     };
 
+    // (not unrolled: the kernel's code is far larger than the instruction cache, and a tile walks it once - every copy
+    // of the conversion body is another ~7 KB fetched from L2 behind the epilogue warps; ncu: no_instruction stalls)
+#pragma unroll 1
     for (int q = 0; q < 4; ++q) {
       const int b = q & 1;
       mbar_wait(smem_u32(&p_full[b]), (uint32_t)(q >> 1) & 1u);
@@ -394,6 +417,7 @@ __device__ __forceinline__ void mlp_fwd_h_body(const MlpHDev& P, const MlpHGroup
     mbar_wait(smem_u32(&y_full), 0);
     tcgen05_fence_after();
     PQLB_HSTAMP(32);
+#pragma unroll 1
     for (int hh = 0; hh < 2; ++hh) {
       convert(tY + (uint32_t)(hh * 128), s_b2, hh * 128, &G.tmH2, G.st2 != 0, smem_u32(&y_conv[hh]));
       PQLB_HSTAMP(32);

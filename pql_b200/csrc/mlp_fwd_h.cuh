@@ -15,6 +15,7 @@ constexpr int kHTileBytes = 128 * 128;        // every weight tile: 128 rows x 6
 constexpr int kHXKb = 4;                      // input width <= 128 floats: four 32-float blocks
 constexpr int kHXBytes = kHXKb * 128 * 128;
 constexpr int kHChunk = 32 * 128;
+constexpr int kHPrefetchCtas = 2;             // row tiles per group that issue the L2 prefetch of the group's weights
 constexpr int kHSmem = 1024 + kHXBytes + kHStages * kHTileBytes + kHEpiWarps * kHChunk + (kHH1 + kHH2 + 2 * kHH3) * 4;
 
 struct alignas(64) MlpHGroupDev {

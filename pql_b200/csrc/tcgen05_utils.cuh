@@ -53,6 +53,12 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
       ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(bar) : "memory");
 }
+// L2 prefetch of one tensor-map box (no shared memory, no barrier: issue and forget).  The weight streams of the
+// fused kernels are small (0.4-1.7 MB per network) but cold - every update pushes ~250 MB of activations through the
+// 126 MB L2 - and a CTA can only keep a few 16 KB tiles in flight, so without this every tile pays HBM latency.
+__device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* map, int c0, int c1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(map), "r"(c0), "r"(c1) : "memory");
+}
 // ---- thread-block clusters: weight tiles are fetched from L2 once per cluster and multicast into
 // every CTA's shared memory; the "slot free" barrier of each CTA collects one tcgen05.commit from
 // every CTA of the cluster (a multicast load overwrites the slot everywhere).

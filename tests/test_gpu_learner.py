@@ -196,6 +196,44 @@ def test_fused_rng_update_equals_torch_draws():
     assert torch.equal(c0, c2) and torch.equal(a0, a2) and l0 == l2
 
 
+def test_prefetching_sampler_is_the_path_that_runs_and_changes_nothing():
+    """With CUDA graphs and the fused sampler RNG (the defaults) the V-learner draws batch k + 1 and runs its
+    target-policy forward in a side branch of update k's graph (_engine.CriticUpdate._run_prefetching).  The graphs
+    of both kinds (first update after an exchange / update fed by the look-ahead) must have been built for both input
+    sets, the last update's draws must be readable under the usual names, and weights and losses must equal the
+    run in which every update draws its own batch first (graphs off)."""
+    from pql_b200.algo import PQLVLearner
+    from pql_b200.utils import default_pql_cfg
+    c0, a0, l0 = _run_interleaved(False, fused_rng=True, graph=False)
+    c1, a1, l1 = _run_interleaved(True, fused_rng=True, graph=True)
+    assert torch.equal(c0, c1) and torch.equal(a0, a1) and l0 == l1
+    cfg = default_pql_cfg(batch_size=256, memory_size=2048, num_envs=64)
+    v = PQLVLearner(24, 4, cfg)
+    from pql_b200.models import TanhMLPPolicy
+    actor = TanhMLPPolicy(24, 4).to(DEV)
+    g = torch.Generator(device=DEV).manual_seed(0)
+    tr = (torch.randn(512, 24, device=DEV, generator=g), torch.rand(512, 4, device=DEV, generator=g), torch.randn(512, 1, device=DEV, generator=g),
+          torch.randn(512, 24, device=DEV, generator=g), torch.zeros(512, 1, device=DEV))
+    norm = (torch.zeros(24, device=DEV), torch.ones(24, device=DEV), 1e-4)
+    seen = []
+    for _ in range(2):
+        v.update(actor, tr, norm, 0)
+        for _ in range(3):
+            v.learn()
+            seen.append((v._plan.idx.clone(), v.memory.cur_capacity))
+    torch.cuda.synchronize()
+    plan = v._plan
+    assert plan.n_sets == 2 and sorted(plan._pf_graphs) == [(False, 0), (False, 1), (True, 0), (True, 1)]
+    # the draws are torch.randint's for the learner's generator, one call per update, in order
+    gen = torch.Generator(device=DEV)
+    gen.manual_seed(v.generator.initial_seed())
+    assert [cap for _, cap in seen] == [512] * 3 + [1024] * 3
+    for got, cap in seen:
+        want = torch.randint(cap, (256,), device=DEV, generator=gen)
+        torch.empty(256, 4, device=DEV).normal_(generator=gen)
+        assert torch.equal(got, want)
+
+
 def test_lagged_loss_readback_is_the_previous_mean():
     """Default (cfg.sync_loss off): update() returns the loss mean as of the previous update() without
     waiting for the GPU; weights are unaffected."""
