@@ -134,7 +134,9 @@ mlp_bwd_kernel(const __grid_constant__ BwdDev P) {
     tcgen05_fence_after();
     int stage = 0; uint32_t phase = 0;
     // ---- dz2 = dz3 . W3: A from shared memory, two 128-column halves of the accumulator
-#pragma unroll
+    // (tile loops not unrolled: 160 unrolled MMAs were 25 KB of straight-line code that a CTA walks once and that is
+    // never in the instruction cache during a training step)
+#pragma unroll 1
     for (int t = 0; t < 8; ++t) {
       const int kb = t >> 1, hf = t & 1;
       mbar_wait(smem_u32(&full_bar[stage]), phase);
@@ -153,12 +155,12 @@ mlp_bwd_kernel(const __grid_constant__ BwdDev P) {
     if (elect_one()) umma_commit(smem_u32(&t2_full));
     __syncwarp();
     // ---- dz1 quarter q = dz2 . W2[:, 128 q .. 128 q + 128): A from tensor memory
-#pragma unroll
+#pragma unroll 1
     for (int q = 0; q < 4; ++q) {
       const int b = q & 1;
       const uint32_t tQ = tmem + 256u + (uint32_t)(b * 128);
       if (q >= 2) { mbar_wait(smem_u32(&q_free[b]), 0); tcgen05_fence_after(); }   // epilogue of quarter q - 2 has drained Q[b]
-#pragma unroll
+#pragma unroll 1
       for (int kb = 0; kb < 8; ++kb) {
         if (q == 0 && (kb & 3) == 0) { mbar_wait(smem_u32(&t2_conv[kb >> 2]), 0); tcgen05_fence_after(); }
         mbar_wait(smem_u32(&full_bar[stage]), phase);

@@ -35,7 +35,11 @@ __device__ __forceinline__ void mlp_fwd_h_body(const MlpHDev& P, const MlpHGroup
   __shared__ __align__(8) uint64_t p_full[2], p_conv[2], y_full, y_conv[2], z_full, z_conv, a_full;
   __shared__ uint32_t tmem_slot;
   __shared__ float s_q[4][128];
-  constexpr int NP = T == 3 ? 2 : 1;            // weight tiles per (rows, k) block: hi [, lo]
+  // T = 0: the number of terms is a run-time property of the group (ONE copy of the code for policy and critic tiles:
+  // the kernel is far larger than the instruction cache, and a policy tile then runs code the critics' tiles have
+  // just pulled in instead of its own cold instantiation); T = 1 / 3: compile-time specialisations
+  const bool t3 = T == 3 || (T == 0 && G.terms == 3);
+  const int NP = t3 ? 2 : 1;                    // weight tiles per (rows, k) block: hi [, lo]
 
   const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
   const int m0 = blockIdx.x * 128;
@@ -205,7 +209,7 @@ __device__ __forceinline__ void mlp_fwd_h_body(const MlpHDev& P, const MlpHGroup
                   const uint64_t a_hi = (desc0 | (uint64_t)(((xs + (k16 >> 1) * 16384) >> 4) & 0x3FFF)) + 2u * (uint32_t)(k16 & 1);
                   if (part == 0) {
                     umma_f16(tP, a_hi, bdesc + 2u * s, idesc, (uint32_t)(k16 != 0));
-                    if (T == 3) umma_f16(tP, a_hi + 4u, bdesc + 2u * s, idesc, 1u);
+                    if (t3) umma_f16(tP, a_hi + 4u, bdesc + 2u * s, idesc, 1u);
                   } else {
                     umma_f16(tP, a_hi, bdesc + 2u * s, idesc, 1u);
                   }
@@ -239,7 +243,7 @@ __device__ __forceinline__ void mlp_fwd_h_body(const MlpHDev& P, const MlpHGroup
                 const uint32_t a_hi = tP + (uint32_t)((t >> 1) * 32 + s * 8);
                 if (part == 0) {
                   umma_f16_ts(d, a_hi, bdesc + 2u * s, idesc, (uint32_t)((c | (t >> 1) | s) != 0));
-                  if (T == 3) umma_f16_ts(d, a_hi + 64u, bdesc + 2u * s, idesc, 1u);
+                  if (t3) umma_f16_ts(d, a_hi + 64u, bdesc + 2u * s, idesc, 1u);
                 } else {
                   umma_f16_ts(d, a_hi, bdesc + 2u * s, idesc, 1u);
                 }
@@ -264,7 +268,7 @@ __device__ __forceinline__ void mlp_fwd_h_body(const MlpHDev& P, const MlpHGroup
                 const uint32_t a_hi = tY + (uint32_t)((t >> 1) * 128 + (t & 1) * 32 + s * 8);
                 if (part == 0) {
                   umma_f16_ts(tZ, a_hi, bdesc + 2u * s, idesc, (uint32_t)((t | s) != 0));
-                  if (T == 3) umma_f16_ts(tZ, a_hi + 64u, bdesc + 2u * s, idesc, 1u);
+                  if (t3) umma_f16_ts(tZ, a_hi + 64u, bdesc + 2u * s, idesc, 1u);
                 } else {
                   umma_f16_ts(tZ, a_hi, bdesc + 2u * s, idesc, 1u);
                 }
@@ -297,7 +301,7 @@ __device__ __forceinline__ void mlp_fwd_h_body(const MlpHDev& P, const MlpHGroup
               const uint32_t a_hi = tZ + (uint32_t)(kb * 32 + s * 8);
               if (part == 0) {
                 umma_f16_ts(tmem + 128u, a_hi, bdesc + 2u * s, idesc_head, (uint32_t)((kb | s) != 0));
-                if (T == 3) umma_f16_ts(tmem + 128u, a_hi + 64u, bdesc + 2u * s, idesc_head, 1u);
+                if (t3) umma_f16_ts(tmem + 128u, a_hi + 64u, bdesc + 2u * s, idesc_head, 1u);
               } else {
                 umma_f16_ts(tmem + 128u, a_hi, bdesc + 2u * s, idesc_head, 1u);
               }
@@ -347,7 +351,11 @@ __device__ __forceinline__ void mlp_fwd_h_body(const MlpHDev& P, const MlpHGroup
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
           hp[j] = pack_hi(f[2 * j], f[2 * j + 1]);
-          lp[j] = T == 3 ? pack_lo(f[2 * j], f[2 * j + 1], hp[j]) : 0u;
+          lp[j] = 0u;
+        }
+        if (t3) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) lp[j] = pack_lo(f[2 * j], f[2 * j + 1], hp[j]);
         }
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
@@ -385,13 +393,14 @@ __device__ __forceinline__ void mlp_fwd_h_body(const MlpHDev& P, const MlpHGroup
 #pragma unroll
       for (int j = 0; j < 32; ++j) v[j] = elu_fast(fmaf(v[j], kWInv, bias[n_base + col + j]));
 #pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        hp[j] = pack_hi_pos(v[2 * j], v[2 * j + 1]);
-        if (T == 3) lp[j] = pack_lo(v[2 * j], v[2 * j + 1], hp[j]);
+      for (int j = 0; j < 16; ++j) hp[j] = pack_hi_pos(v[2 * j], v[2 * j + 1]);
+      if (t3) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) lp[j] = pack_lo(v[2 * j], v[2 * j + 1], hp[j]);
       }
       named_bar_sync(1 + quarter, 128);
       tmem_st16(region + lane_sel + (uint32_t)(chunk * 16), hp);
-      if (T == 3) tmem_st16(region + lane_sel + (uint32_t)(64 + chunk * 16), lp);
+      if (t3) tmem_st16(region + lane_sel + (uint32_t)(64 + chunk * 16), lp);
       tmem_wait_st();
       tcgen05_fence_before();
       __syncwarp();
@@ -437,13 +446,14 @@ __device__ __forceinline__ void mlp_fwd_h_body(const MlpHDev& P, const MlpHGroup
       if (G.head_rows > 0) {                     // h3 back into Z as packed halves: the A operand of the head contraction
         uint32_t hp[16], lp[16];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          hp[j] = pack_hi_pos(v[2 * j], v[2 * j + 1]);
-          if (T == 3) lp[j] = pack_lo(v[2 * j], v[2 * j + 1], hp[j]);
+        for (int j = 0; j < 16; ++j) hp[j] = pack_hi_pos(v[2 * j], v[2 * j + 1]);
+        if (t3) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) lp[j] = pack_lo(v[2 * j], v[2 * j + 1], hp[j]);
         }
         named_bar_sync(1 + quarter, 128);
         tmem_st16(tZ + lane_sel + (uint32_t)(chunk * 16), hp);
-        if (T == 3) tmem_st16(tZ + lane_sel + (uint32_t)(64 + chunk * 16), lp);
+        if (t3) tmem_st16(tZ + lane_sel + (uint32_t)(64 + chunk * 16), lp);
         tmem_wait_st();
         tcgen05_fence_before();
         __syncwarp();
@@ -456,7 +466,19 @@ __device__ __forceinline__ void mlp_fwd_h_body(const MlpHDev& P, const MlpHGroup
         store_chunk(r, &G.tmH3, col);
       }
       if (G.act_n > 0 && chunk == 0) {
-        // one warp per lane quarter finishes the head: * 2^-8 + bias, tanh, (+ clipped noise, clamp)
+        // one warp per lane quarter finishes the head: * 2^-8 + bias, tanh, (+ clipped noise, clamp).  Bias and noise
+        // are fetched BEFORE the wait for the head contraction (cold global loads at the very end of a tile otherwise)
+        float hb[16], nz[16];
+#pragma unroll
+        for (int j = 0; j < 16; j += 4) {
+          float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f), n4 = b4;
+          if (j < G.act_n) {
+            b4 = *reinterpret_cast<const float4*>(G.act_b + j);            // arena biases are 128-byte aligned and padded
+            if (G.act_noise && row < P.M) n4 = *reinterpret_cast<const float4*>(G.act_noise + (long long)row * G.act_ldnoise + j);
+          }
+          hb[j] = b4.x; hb[j + 1] = b4.y; hb[j + 2] = b4.z; hb[j + 3] = b4.w;
+          nz[j] = n4.x; nz[j + 1] = n4.y; nz[j + 2] = n4.z; nz[j + 3] = n4.w;
+        }
         mbar_wait(smem_u32(&a_full), 0);
         tcgen05_fence_after();
         float a[16];
@@ -467,10 +489,10 @@ __device__ __forceinline__ void mlp_fwd_h_body(const MlpHDev& P, const MlpHGroup
           for (int j = 0; j < 16; ++j) {
             float t = 0.f, r = 0.f;
             if (j < G.act_n) {
-              t = tanhf(fmaf(a[j], kWInv, G.act_b[j]));
+              t = tanh_fast(fmaf(a[j], kWInv, hb[j]));
               r = t;
               if (G.act_noise) {                   // noise.py:19-27 on N(0,1) draws scaled by std
-                const float z = fminf(fmaxf(G.act_noise[(long long)row * G.act_ldnoise + j] * G.noise_std, -G.noise_bound), G.noise_bound);
+                const float z = fminf(fmaxf(nz[j] * G.noise_std, -G.noise_bound), G.noise_bound);
                 r = fminf(fmaxf(t + z, -1.f), 1.f);
               }
               t = r;                               // act_out2: the value itself; act_out: its TF32 operand rounding
@@ -567,8 +589,7 @@ __global__ void __launch_bounds__(kHThreads, 1)
 mlp_fwd_h_kernel(const __grid_constant__ MlpHDev P) {
   extern __shared__ uint8_t smem_raw[];
   const MlpHGroupDev& G = P.g[blockIdx.y];
-  if (G.terms == 3) mlp_fwd_h_body<3>(P, G, smem_raw);
-  else mlp_fwd_h_body<1>(P, G, smem_raw);
+  mlp_fwd_h_body<0>(P, G, smem_raw);
 }
 
 // hi[i] = fp16(scale * src[i]), lo[i] = fp16(scale * src[i] - hi[i]) (lo optional): the fp16 operand
@@ -682,7 +703,8 @@ extern "C" int pqlb_mlp_forward_h(const pqlb_mlp_h_desc* d, pqlb_stream_t stream
       // policy head: act_n a multiple of 4 up to 16, 16-byte aligned output rows
       PQLB_CHECK_ARG(!s.q && s.act_b && (s.act_out || s.act_out2) && s.act_n > 0 && (s.terms == 1 || s.act_wl));
       if (s.act_n > 16 || s.act_n % 4 || (s.act_out && (s.act_ldo % 4 || !aligned16(s.act_out))) ||
-          (s.act_out2 && (s.act_ldo2 % 4 || !aligned16(s.act_out2)))) return PQLB_E_UNSUPPORTED;
+          (s.act_out2 && (s.act_ldo2 % 4 || !aligned16(s.act_out2))) || !aligned16(s.act_b) ||
+          (s.act_noise && (s.act_ldnoise % 4 || !aligned16(s.act_noise)))) return PQLB_E_UNSUPPORTED;
       for (int p = 0; p < 2; ++p) {
         const bool have = p == 0 || s.terms == 3;
         if ((rc = make_half_map(&G.tmW4[p], have ? w4[p] : w4[0], kHH3, s.act_n, kHH3, 16)) != PQLB_OK) return rc;

@@ -211,6 +211,16 @@ __device__ __forceinline__ float elu_fast(float v) {
 }
 
 
+// tanh for the fused policy head: (1 - e) / (1 + e) with e = exp(-2|x|) from ex2.approx - eight instructions instead of
+// tanhf's ~45 (sixteen inlined copies of it were 1.2 K instructions that four warps walk once, at the very end of a
+// tile, out of a cold instruction cache).  Absolute error < 2e-7 (ex2.approx is good to 2^-22 of a result <= 1); the
+// head's output is an action in [-1, 1] that is judged, and consumed, absolutely.
+__device__ __forceinline__ float tanh_fast(float x) {
+  float e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(fabsf(x) * -2.8853900817779268f));
+  return copysignf(__fdividef(1.f - e, 1.f + e), x);
+}
+
 // tcgen05.mma with the A operand in tensor memory (lane = row, one 32-bit column per k):
 // D[tmem] (+)= A[tmem] . B[smem]   (cute SM100_MMA_TF32_TS; the trailing vector is the
 // disable-output-lane mask, all zero).
