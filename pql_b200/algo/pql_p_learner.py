@@ -58,7 +58,7 @@ class PQLPLearner:
         # cfg.dp_fused: no NCCL on the path - the optimiser kernel all-reduces over symmetric memory
         self.dp_fused = bool(getattr(cfg, "dp_fused", False)) and self.world_size > 1
         self._sync_loss = bool(getattr(cfg, "sync_loss", False))
-        self._ls = LearnerStream(cfg, self.device)
+        self._ls = LearnerStream(cfg, self.device, priority=int(os.environ.get("PQLB_P_PRIORITY", getattr(cfg, "p_stream_priority", 0))))
         self._ls.tag(self.actor)
         self.generator, self.fused_rng = make_generator(cfg, self.device, salt=1)
         if self.world_size > 1:          # rank 0's initial actor becomes everyone's (see PQLVLearner)
