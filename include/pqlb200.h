@@ -515,6 +515,9 @@ typedef struct {
    * slice reduction then runs inside the NVSwitch (multimem.ld_reduce / multimem.st), one NVLink round trip. */
   const float* grad_mc; float* red_mc;
 } pqlb_dp_desc;
+/* How long (wall-clock seconds, default 120) a rank's exchange kernel waits for a peer's flag before it traps: the
+ * ranks of a fused exchange must reach each update within this bound of one another (current device; not stream-ordered). */
+int pqlb_dp_spin_limit(double seconds);
 int pqlb_adamw_polyak_dp(float* param, float* m, float* v, float* target, float* param_tf32,
                          float* target_tf32, void* param_h, void* target_h, int64_t n,
                          const pqlb_dp_desc* dp, float max_norm,

@@ -165,6 +165,7 @@ _PROTOS = {
                                        _flt, _flt, _flt, _flt, _flt, _flt, _f, _st]),
     "pqlb_adamw_polyak_pre": (_int, [_f, _f, _f, _f, _f, _f, _f, _f, _f, _i64, _f, _int, _flt, _flt, _f, _f, _f, _st]),
     "pqlb_adamw_polyak_dp": (_int, [_f, _f, _f, _f, _f, _f, _f, _f, _i64, C.POINTER(DpDesc), _flt, _f, _f, _f, _st]),
+    "pqlb_dp_spin_limit": (_int, [C.c_double]),
     "pqlb_grad_exchange_dp": (_int, [_i64, C.POINTER(DpDesc), _st]),
     "pqlb_sum_partials": (_int, [_f, _int, _flt, _f, _f, _f, _int, _st]),
 }

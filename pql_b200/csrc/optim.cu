@@ -221,11 +221,16 @@ __device__ __forceinline__ void st_sys_f4(float* p, float4 v) {
 __device__ __forceinline__ float ld_sys_f(const float* p) { float v; asm volatile("ld.relaxed.sys.global.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory"); return v; }
 __device__ __forceinline__ void st_sys_f(float* p, float v) { asm volatile("st.relaxed.sys.global.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory"); }
 __device__ __forceinline__ unsigned long long globaltimer_ns() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
-// bounded spin: a protocol bug or a dead peer must surface as a launch failure, not as a hung GPU
+// bounded spin: a protocol bug or a dead peer must surface as a launch failure, not as a hung GPU.  The bound is
+// wall time (globaltimer, independent of the SM clock) and settable (pqlb_dp_spin_limit): a peer that is merely
+// late - checkpointing, logging, a slow env step while the other hosts run ahead - must not take every rank down.
+__device__ long long g_dp_spin_ns = 120LL * 1000000000LL;
 __device__ __forceinline__ void wait_flag(const unsigned* p, unsigned epoch) {
-  const long long t0 = clock64();
+  if ((int)(ld_acquire_sys(p) - epoch) >= 0) return;
+  const unsigned long long t0 = globaltimer_ns();
+  const unsigned long long limit = (unsigned long long)g_dp_spin_ns;
   while ((int)(ld_acquire_sys(p) - epoch) < 0) {
-    if (clock64() - t0 > 20000000000LL) __trap();
+    if (globaltimer_ns() - t0 > limit) __trap();
   }
 }
 
@@ -595,6 +600,13 @@ extern "C" int pqlb_adamw_polyak_dp(float* param, float* m, float* v, float* tar
       n, a, max_norm, reinterpret_cast<const AdamScalars*>(scalars),
       reinterpret_cast<long long*>(counter), grad_norm_out, 0);
   PQLB_LAUNCH_RET();
+}
+
+extern "C" int pqlb_dp_spin_limit(double seconds) {
+  PQLB_CHECK_ARG(seconds > 0.0 && seconds < 1e6);
+  const long long ns = (long long)(seconds * 1e9);
+  cudaError_t e = cudaMemcpyToSymbol(g_dp_spin_ns, &ns, sizeof(ns));
+  return e == cudaSuccess ? PQLB_OK : (int)e;
 }
 
 extern "C" int pqlb_grad_exchange_dp(int64_t n, const pqlb_dp_desc* dp, pqlb_stream_t stream) {
