@@ -602,8 +602,8 @@ def main():
         gc.collect(); torch.cuda.empty_cache()
         from tools.bench_loop import measure_loop
         subs = {}
-        for name, kw in (("configs[2]_c51_b16384", dict(envs=E, obs=O, act=A, memory=CAP, batch=16384, distl=True, iters=30, warmup=8)),
-                         ("configs[3]_shadowhand_loop", dict(envs=16384, obs=211, act=20, memory=5_000_000, batch=8192, iters=30, warmup=8)),
+        for name, kw in (("configs[2]_c51_b16384", dict(envs=E, obs=O, act=A, memory=CAP, batch=16384, distl=True, iters=30, warmup=8, profile=True)),
+                         ("configs[3]_shadowhand_loop", dict(envs=16384, obs=211, act=20, memory=5_000_000, batch=8192, iters=30, warmup=8, profile=True)),
                          ("configs[1]_allegro_loop", dict(envs=E, obs=O, act=A, memory=CAP, batch=B, iters=30, warmup=8))):
             try:
                 subs[name] = measure_loop(**kw)

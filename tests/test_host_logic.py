@@ -61,3 +61,40 @@ def test_bench_flop_model_matches_survey():
     assert 2 * (actor_fwd + 2 * critic_fwd + 2 * critic_dgrad_all + actor_bwd) == bench.FLOP_P
     assert bench.BYTES_INSERT == 4 * (2 * O + A + 2) + 4 * (2 * O + A + 1) + 1
     assert bench.BYTES_SAMPLE == 8 + (4 * (2 * O + A + 1) + 1) + 4 * (2 * O + A + 2)
+
+
+@pytest.mark.parametrize("shapes,B", [([(128, 256), (256, 512), (512, 104)] * 2, 8192),          # twin-Q critic, AllegroHand
+                                      ([(16, 128), (128, 256), (256, 512), (512, 88)], 8192),     # actor
+                                      ([(51, 128), (128, 256), (256, 512), (512, 104)] * 2, 16384),   # C51 critic
+                                      ([(128, 256), (256, 512), (512, 231)] * 2, 8192),           # ShadowHand critic
+                                      ([(128, 256), (256, 512), (512, 104)] * 2, 96)])            # tiny batch: few k-blocks
+def test_wgrad_plan_fills_one_wave_with_balanced_ctas(shapes, B):
+    """pqlb_wgrad_multi's split plan: at most one CTA per SM, every split owns >= 2 k-blocks, and the CTAs stream
+    about the same number of operand bytes (these GEMMs are bound by L2 -> SM ingest)."""
+    plan = K.wgrad_plan(shapes, B, target_ctas=148)
+    kb = (B + 31) // 32
+    assert len(plan) == len(shapes)
+    ctas, per_cta = 0, []
+    for (M, N), (tile_n, splits) in zip(shapes, plan):
+        assert tile_n == K.wgrad_tile_n(N) and tile_n in (32, 64, 128, 256)
+        assert 1 <= splits <= max(1, kb // 2)
+        tiles = -(-M // 128) * -(-N // tile_n)
+        ctas += tiles * splits
+        per_cta.append(4096.0 * (-(-min(M, 128) // 32) + -(-min(N, tile_n) // 32)) * kb / splits)
+    assert ctas <= 148
+    if kb >= 64:                     # enough k-blocks to balance: no CTA streams more than 1.6x the lightest full-size one
+        assert ctas >= 0.9 * 148
+        full = [c for c, (M, N) in zip(per_cta, shapes) if M >= 128]
+        assert max(full) <= 1.6 * min(full)
+
+
+def test_forward_mode_selection():
+    """Which shapes take the split-fp16 fused forward: inputs up to 128 wide with 16-byte
+    aligned half rows and a policy head of at most 16 actions; everything else runs the TF32 kernels."""
+    from pql_b200.algo._engine import forward_mode
+    assert forward_mode(None, 88, 16) == "f16x3"
+    assert forward_mode("tf32", 88, 16) == "tf32"
+    assert forward_mode(None, 211, 20) == "tf32"          # ShadowHand: 231 input columns
+    assert forward_mode(None, 24, 4) in ("f16x3", "tf32")
+    with pytest.raises(ValueError):
+        forward_mode("bf16", 88, 16)
