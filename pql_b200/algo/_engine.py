@@ -520,34 +520,54 @@ class CriticUpdate(_UpdateBase):
 
     def _capture_prefetching(self, fresh, si, allreduce):
         torch.cuda.synchronize(self.device)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self.emit_prefetching(fresh, si, allreduce)
+        return g
+
+    def emit_prefetching(self, fresh, si, allreduce=None):
+        """The launches of one update on the prefetching path, on torch's current stream, which must be capturing
+        (the side branch is a fork / join of that capture).  Also used by the lock-step driver to capture the updates
+        of a whole env step into ONE graph (pql_b200/train.py)."""
         if self._side is None:
             self._side = torch.cuda.Stream(self.device)
-        g = torch.cuda.CUDAGraph()
         main_s, side_s = self._pf_samples[si][0], self._pf_samples[1 - si][1]
-        with torch.cuda.graph(g):
-            cur = torch.cuda.current_stream(self.device)
-            if fresh:
-                self._prek_init()                     # pre_k = completed updates + 1: the side branch draws the NEXT batch
-                main_s()
-                for c in self.policy_calls[si]:
-                    c()
-            for j, c in enumerate(self.main_calls[si]):
-                if j == PF_FORK:
-                    # the side branch: batch k + 1 and its target action, concurrent with the rest of update k
-                    self._side.wait_stream(cur)
-                    with torch.cuda.stream(self._side):
-                        side_s()
-                        for c2 in self.policy_calls[1 - si]:
-                            c2()
-                        self._prek_bump()
+        cur = torch.cuda.current_stream(self.device)
+        if fresh:
+            self._prek_init()                     # pre_k = completed updates + 1: the side branch draws the NEXT batch
+            main_s()
+            for c in self.policy_calls[si]:
                 c()
-            self.reduce_call()
-            if allreduce is not None:
-                allreduce(self.opt.grad)
-                self.sumsq_call()
-            self._segment_b()
-            cur.wait_stream(self._side)
-        return g
+        for j, c in enumerate(self.main_calls[si]):
+            if j == PF_FORK:
+                # the side branch: batch k + 1 and its target action, concurrent with the rest of update k
+                self._side.wait_stream(cur)
+                with torch.cuda.stream(self._side):
+                    side_s()
+                    for c2 in self.policy_calls[1 - si]:
+                        c2()
+                    self._prek_bump()
+            c()
+        self.reduce_call()
+        if allreduce is not None:
+            allreduce(self.opt.grad)
+            self.sumsq_call()
+        self._segment_b()
+        cur.wait_stream(self._side)
+
+    def block_ready(self):
+        """Can the lock-step driver capture this learner's updates into its per-step graph?  (prefetching sampler bound,
+        next update on input set 0, no NCCL call between the launches)"""
+        return self._pf_samples is not None and self.cur_set == 0 and (self.world_size == 1 or self.dp is not None)
+
+    def block_done(self, n_updates):
+        """Host-side bookkeeping after the driver replayed a graph holding ``n_updates`` updates of this plan (the first
+        drew its own batch, the others were fed by the look-ahead)."""
+        n_pol = len(self.policy_calls[0])
+        self.graph_launches += n_updates * (2 + n_pol + len(self.main_calls[0]) + 2) + 2 + n_pol
+        last = (n_updates - 1) % 2
+        self._bind_set(last)
+        self.cur_set, self._pf_valid = 1 - last, True
 
     def _segment_a(self, sample):
         if sample is not None:

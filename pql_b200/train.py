@@ -12,11 +12,13 @@ CUDA-graph replay on its learner's stream.  Weights move between the workers as 
 copies of flat arenas (no pickling), and the host never waits for the step it has just enqueued: the
 loss read-back inside ``update()`` returns the previous step's value (DeviceTracker.mean_lagged).
 """
+import os
 import time
 
 import torch
 
 from .algo import PQLActor, PQLPLearner, PQLVLearner
+from .algo.pql_v_learner import wait_readers
 
 
 class LockStepTrainer:
@@ -35,6 +37,7 @@ class LockStepTrainer:
         self.sim_count = 0
         self._t0 = None
         self.observer = None          # optional callable(kind) after every learn() ("v" / "p"): tests read the plans' draws
+        self._block, self._block_streams, self._block_key = None, None, None     # the per-step graph of all updates (_learn_block)
 
     def _rms(self, device):
         rms = self.actor_worker.obs_rms
@@ -66,18 +69,89 @@ class LockStepTrainer:
         self.global_steps += steps
         self.sim_count += 1
         self._exchange(p_data, v_data)
-        for j in range(self.v_per_step):
-            self.v_learner.learn()
-            if self.observer is not None:
-                self.observer("v")
-            if (j + 1) % self.p_every == 0:
-                self.p_learner.learn()
+        if not self._learn_block():
+            for j in range(self.v_per_step):
+                self.v_learner.learn()
                 if self.observer is not None:
-                    self.observer("p")
+                    self.observer("v")
+                if (j + 1) % self.p_every == 0:
+                    self.p_learner.learn()
+                    if self.observer is not None:
+                        self.observer("p")
         self.actor_worker.update_noise()
         return {"train/critic_loss": self.critic_loss, "train/actor_loss": self.actor_loss,
                 "train/critic_update_times": self.critic_updates, "train/actor_update_times": self.actor_updates,
                 "train/global_steps": self.global_steps}
+
+    # ---- all updates of an env step as ONE CUDA graph ------------------------------------------------------------
+    def _learn_block(self):
+        """The ``critic_sample_ratio`` critic and ``critic_sample_ratio / critic_actor_ratio`` actor updates of this env
+        step as ONE graph launch: two branches (the learners are independent between exchanges; the V branch carries
+        the look-ahead sampler's side branches), captured once - every pointer of both launch lists is fixed and the
+        update indices, fill levels and RNG offsets live on the device.  Returns False (the caller then issues the
+        ``learn()`` calls one by one: twelve graph launches) when a test observes individual updates, the learners sit on
+        different devices or run without graphs / the fused sampler RNG, or an NCCL all-reduce sits between the launches."""
+        v, p = self.v_learner, self.p_learner
+        want = os.environ.get("PQLB_STEP_GRAPH")
+        want = bool(getattr(self.cfg, "step_graph", False)) if want is None else want != "0"
+        if self.observer is not None or not want:
+            return False
+        n_v, n_p = self.v_per_step, self.v_per_step // self.p_every
+        if v.actor is None or p.critic is None or v.device != p.device or not (v.use_cuda_graph and p.use_cuda_graph):
+            return False
+        vp, pp = v._plan, p._plan
+        if vp is None or pp is None or n_v % 2 or n_p < 1 or self.v_per_step % self.p_every:
+            return False
+        if not vp.block_ready() or pp.rng_state is None or not (pp.world_size == 1 or pp.dp is not None):
+            return False
+        if v.memory.cur_capacity <= 0 or p.cur_capacity <= 0:
+            return False
+        dev = v.device
+        with torch.cuda.device(dev):
+            if self._block is None or self._block_key != (id(vp), id(pp)):      # first step, or a learner rebuilt its plan
+                self._block = self._capture_block(vp, pp, v._sample, p._sample, n_v, n_p, dev)
+                self._block_key = (id(vp), id(pp))
+            own = v.stream is not None and p.stream is not None
+            # with per-learner streams the graph runs on a stream of its own, downstream of both (update() ran there) and
+            # upstream of both (their next update() follows it): the caller's stream - the actor worker's env step - is
+            # never ordered behind the updates, exactly as with individual learn() calls
+            bs = self._block_streams[2] if own else torch.cuda.current_stream(dev)
+            if own:
+                bs.wait_stream(v.stream)
+                bs.wait_stream(p.stream)
+            wait_readers(v.critic, bs)
+            wait_readers(p.actor, bs)
+            with torch.cuda.stream(bs):
+                self._block.replay()
+            if own:
+                v.stream.wait_stream(bs)
+                p.stream.wait_stream(bs)
+        vp.block_done(n_v)
+        pp.graph_launches += n_p * (len(pp.calls) + 1 + 2)
+        v.update_count += n_v
+        p.update_count += n_p
+        return True
+
+    def _capture_block(self, vp, pp, v_sample, p_sample, n_v, n_p, dev):
+        torch.cuda.synchronize(dev)
+        if self._block_streams is None:
+            self._block_streams = (torch.cuda.Stream(dev), torch.cuda.Stream(dev), torch.cuda.Stream(dev))
+        sv, sp = self._block_streams[:2]
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            cur = torch.cuda.current_stream(dev)
+            sv.wait_stream(cur)
+            sp.wait_stream(cur)
+            with torch.cuda.stream(sv):
+                for j in range(n_v):
+                    vp.emit_prefetching(j == 0, j % 2)
+            with torch.cuda.stream(sp):
+                for _ in range(n_p):
+                    pp._segment_a(p_sample)
+                    pp._segment_b()
+            cur.wait_stream(sv)
+            cur.wait_stream(sp)
+        return g
 
     def run(self, max_env_steps=None, max_time=None, log_every=0, log=print):
         """Run until ``max_env_steps`` transitions or ``max_time`` seconds (train_pql.py:174: max_step /

@@ -155,3 +155,37 @@ def test_lockstep_loop_matches_oracle_loop():
     # measured on B200: 8.3e-5 (critic) / 7.8e-5 (actor) over the three iterations
     assert worst["v_first"] <= 5e-4 and worst["p_first"] <= 5e-4, worst
     assert worst["v"] <= 1e-3 and worst["p"] <= 1e-3, worst
+
+
+@pytest.mark.parametrize("distl", [False, True])
+def test_step_graph_equals_individual_updates(distl):
+    """LockStepTrainer replays all updates of an env step as ONE CUDA graph (two branches + the look-ahead sampler's
+    side branches, train.py:_learn_block).  Same seeds, same schedule issued as twelve learn() calls (cfg.step_graph
+    off): weights, Polyak target, loss windows, update counts and the rings must be bit-identical."""
+    from pql_b200.train import LockStepTrainer
+    from pql_b200.utils import default_pql_cfg
+    E, O, A = 512, 24, 4
+
+    def run(step_graph):
+        torch.manual_seed(11)
+        cfg = default_pql_cfg(num_envs=E, sim_device=DEV, batch_size=1024, memory_size=50_000, warm_up=4,
+                              reward_scale=0.02 if distl else 1.0, distl=distl, v_min=-1.5, v_max=0.25)
+        cfg.step_graph = step_graph
+        cfg.learner_streams = True
+        tr = LockStepTrainer(ReachEnv(E, O, A, seed=5), cfg)
+        infos = [tr.step() for _ in range(5)]
+        torch.cuda.synchronize()
+        used = tr._block is not None
+        v, p = tr.v_learner, tr.p_learner
+        m, n = v.memory, v.memory.cur_capacity         # the ring is torch.empty storage: compare the filled rows' columns only
+        ring = torch.cat([m.buf_obs[:n], m.buf_next_obs[:n], m.buf_action[:n], m.buf_reward[:n], m.buf_done[:n].float()], 1)
+        return (v.critic.arena.flat.clone(), v._plan.t_flat.clone(), p.actor.arena.flat.clone(), v.loss_tracker.window.clone(),
+                p.loss_tracker.window.clone(), ring, v.update_count, p.update_count,
+                [(i["train/critic_loss"], i["train/actor_loss"]) for i in infos], used, int(v._plan.opt.step), int(p._plan.opt.step))
+
+    a, b = run(True), run(False)
+    assert a[9] and not b[9], "the per-step graph was not the path that ran"
+    for x, y in zip(a[:6], b[:6]):
+        assert torch.equal(x, y)
+    assert a[6:9] == b[6:9] and a[10:] == b[10:]
+    assert a[6] == 5 * 8 and a[7] == 5 * 4 and a[10] == a[6] and a[11] == a[7]
