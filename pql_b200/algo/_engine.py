@@ -557,8 +557,9 @@ class CriticUpdate(_UpdateBase):
 
     def block_ready(self):
         """Can the lock-step driver capture this learner's updates into its per-step graph?  (prefetching sampler bound,
-        next update on input set 0, no NCCL call between the launches)"""
-        return self._pf_samples is not None and self.cur_set == 0 and (self.world_size == 1 or self.dp is not None)
+        next update on input set 0; single GPU only - the data-parallel exchange inside a two-branch graph has not been
+        run on a multi-GPU box, so it is not offered)"""
+        return self._pf_samples is not None and self.cur_set == 0 and self.world_size == 1
 
     def block_done(self, n_updates):
         """Host-side bookkeeping after the driver replayed a graph holding ``n_updates`` updates of this plan (the first

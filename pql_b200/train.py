@@ -90,7 +90,7 @@ class LockStepTrainer:
         the look-ahead sampler's side branches), captured once - every pointer of both launch lists is fixed and the
         update indices, fill levels and RNG offsets live on the device.  Returns False (the caller then issues the
         ``learn()`` calls one by one: twelve graph launches) when a test observes individual updates, the learners sit on
-        different devices or run without graphs / the fused sampler RNG, or an NCCL all-reduce sits between the launches."""
+        different devices or run without graphs / the fused sampler RNG, or the learners are data parallel."""
         v, p = self.v_learner, self.p_learner
         want = os.environ.get("PQLB_STEP_GRAPH")
         want = bool(getattr(self.cfg, "step_graph", False)) if want is None else want != "0"
@@ -102,7 +102,7 @@ class LockStepTrainer:
         vp, pp = v._plan, p._plan
         if vp is None or pp is None or n_v % 2 or n_p < 1 or self.v_per_step % self.p_every:
             return False
-        if not vp.block_ready() or pp.rng_state is None or not (pp.world_size == 1 or pp.dp is not None):
+        if not vp.block_ready() or pp.rng_state is None or pp.world_size != 1:
             return False
         if v.memory.cur_capacity <= 0 or p.cur_capacity <= 0:
             return False
