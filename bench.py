@@ -609,7 +609,11 @@ def main():
                 subs[name] = measure_loop(**kw)
             except Exception as e:      # a sub-record must never take the headline down
                 subs[name] = {"error": f"{type(e).__name__}: {e}"}
-            gc.collect(); torch.cuda.empty_cache()
+            try:
+                gc.collect(); torch.cuda.empty_cache()
+            except Exception as e:      # a sticky CUDA error from a sub-record: keep what was measured, stop here
+                subs[name + "_cleanup"] = {"error": f"{type(e).__name__}: {e}"}
+                break
         line["sub_records"] = subs
         try:
             line["cuda_eager_baseline"] = cuda_eager_rate(dev)

@@ -301,7 +301,10 @@ void pqlb_mlp_forward_cluster(int cluster);
  * in desc.tile_sync once its action rows are written, and a LATER group with `wait` loads its input
  * tile only after that mark (target policy -> target critics in ONE launch: the SMs the 64 policy tiles
  * leave idle start on the critics).  tile_sync: 2 + ceil(M / 128) uint32, zero-initialised once by the
- * caller; the kernel maintains it across launches (no reset needed). */
+ * caller; the kernel maintains it across launches (no reset needed).
+ * Input width: k_in <= 128 per group, or - if any group is wider - k_in <= 256 for the whole launch (the
+ * wide-input kernel: eight 32-column input blocks resident in shared memory, a shorter weight ring;
+ * ShadowHand's critics, obs 211 + act 20, pql/models/mlp.py:186-203); wider: PQLB_E_UNSUPPORTED. */
 #define PQLB_MAX_FWD_GROUPS 5
 typedef struct {
   const float* x; int64_t ldx;

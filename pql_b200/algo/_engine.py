@@ -15,7 +15,7 @@ import torch
 
 from .. import _kernels as K
 from .. import _lib
-from ..models.mlp import (FUSED_MAX_IN, HIDDEN, NetAddrs, NetLayout, _ru, forward_calls, forward_calls_h, fwd_tile,
+from ..models.mlp import (FUSED_H_MAX_IN, FUSED_MAX_IN, HIDDEN, NetAddrs, NetLayout, _ru, forward_calls, forward_calls_h, fwd_tile,
                           half_arena)
 
 H1, H2, H3 = HIDDEN
@@ -32,15 +32,19 @@ def forward_mode(requested, obs_dim, action_dim):
     """Number format of the fused forward launches: 'f16x3' (default) - critics with split-fp16
     operands and three MMAs per product, policy nets with one fp16 MMA (pqlb_mlp_forward_h; keeps every
     gradient tensor within 1e-3 of the fp32 reference) - or 'tf32' (the round-1
-    kernels: one TF32 MMA per product everywhere).  Shapes the split-fp16 kernel does not take (inputs
-    wider than 128, weight rows that are not 16-byte aligned as halves, action widths the fused policy
-    head does not take) run as 'tf32'."""
+    kernels: one TF32 MMA per product everywhere).  Shapes 'f16x3' takes: inputs up to 128 wide whose weight
+    rows are 16-byte aligned as halves and a policy head the kernel fuses (A <= 16, multiples of 4); and
+    critics 129..256 wide (the wide-input kernel: ShadowHand's 231 columns) - there a policy net the kernel
+    does not take (models.mlp.split_f16_ok: ShadowHand's 211 observations give 8-byte-aligned half rows, 20
+    actions) runs through the TF32 launches on its own, which is the accuracy class of its one-term fp16
+    forward anyway.  Everything else runs as 'tf32'."""
     mode = _os.environ.get("PQLB_FWD_MODE") or requested or "f16x3"
     if mode not in ("f16x3", "tf32"):
         raise ValueError(f"forward mode {mode!r}: expected 'f16x3' or 'tf32'")
     O, A = int(obs_dim), int(action_dim)
-    ok = O + A <= FUSED_MAX_IN and _ru(O + A, 4) % 8 == 0 and _ru(O, 4) % 8 == 0 and O % 4 == 0 and A % 4 == 0 and A <= 16
-    return mode if ok else "tf32"
+    narrow = O + A <= FUSED_MAX_IN and _ru(O + A, 4) % 8 == 0 and _ru(O, 4) % 8 == 0 and O % 4 == 0 and A % 4 == 0 and A <= 16
+    wide = FUSED_MAX_IN < O + A <= FUSED_H_MAX_IN and _ru(O + A, 4) % 8 == 0
+    return mode if narrow or wide else "tf32"
 
 
 class _Optim:
@@ -319,7 +323,7 @@ class CriticUpdate(_UpdateBase):
         actor = NetAddrs(self.La, 0, self.a_tf, self.a_flat, self.a_h)
         cnet = [NetAddrs(self.Lc, i, self.c_tf, self.c_flat, self.c_h) for i in range(2)]
         tnet = [NetAddrs(self.Lc, i, self.t_tf, self.t_flat, self.t_h) for i in range(2)]
-        wg = [(H3, H2, H2), (H2, H1, H1), (H1, O + A, x_ld)] + ([(N, H3, H3)] if distl else [])
+        wg = [(H3, H2, H2), (H2, H1, H1), (H1, O + A, self.Lc.ldw[0])] + ([(N, H3, H3)] if distl else [])
         self._ws_init(wg, 2, [d for d in HIDDEN] * 2 + ([N, N] if distl else []),
                       extra=2 * _ru(self.nblk_head * (H3 + 1), 32) + 2 * _ru(self.nblk_head * H3, 32))
         # the launch list once per input set: identical launches, every buffer but the inputs shared
@@ -687,7 +691,8 @@ class ActorUpdate(_UpdateBase):
         dz2, dz1 = ([self.dzc[i][l] for i in range(2)] for l in (1, 0))
         calls += self._dgrad_chain(cnet, dz3, dz2, dz1, [h_c[i][0] for i in range(2)], [h_c[i][1] for i in range(2)])
         # -- d loss / d action: both critics' layer-1 dgrad summed in one contraction, tanh' fused
-        g = dict(a=K.addr(dz1[0]), lda=H1, a2=K.addr(dz1[1]), lda2=H1, ldb=x_ld, ldb2=x_ld, out=K.addr(self.dz_act),
+        ldw1 = self.Lc.ldw[0]               # row stride of the critics' first-layer weights (= x_ld for every shape so far)
+        g = dict(a=K.addr(dz1[0]), lda=H1, a2=K.addr(dz1[1]), lda2=H1, ldb=ldw1, ldb2=ldw1, out=K.addr(self.dz_act),
                  ldo=a_ld)
         if O % 4 == 0:
             g.update(b=cnet[0].W[0] + 4 * O, b2=cnet[1].W[0] + 4 * O, aux=act_addr, ldaux=act_ld)

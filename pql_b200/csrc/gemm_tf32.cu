@@ -471,13 +471,13 @@ int make_map(CUtensorMap* map, const float* base, uint64_t dim0, uint64_t dim1, 
 // Output / epilogue-operand map: [splits][rows][cols] fp32, 32x32 boxes, 128-byte swizzle (matches
 // the staging chunks the epilogue warps write / read).  Returns false when TMA cannot address it.
 bool make_tile_map(CUtensorMap* map, const float* base, uint64_t cols, uint64_t rows, int64_t ld_words,
-                          uint64_t splits, int64_t split_stride_words) {
+                          uint64_t splits, int64_t split_stride_words, uint32_t box_rows) {
   PFN_cuTensorMapEncodeTiled enc = get_encode_fn();
   if (!enc || !base || !aligned16(base) || (ld_words % 4) != 0 || ld_words < (int64_t)cols) return false;
   if (splits > 1 && ((split_stride_words % 4) != 0 || split_stride_words <= 0)) return false;
   cuuint64_t gdim[3] = {cols, rows, splits};
   cuuint64_t gstr[2] = {(cuuint64_t)ld_words * 4, (cuuint64_t)(splits > 1 ? split_stride_words : ld_words * (int64_t)rows) * 4};
-  cuuint32_t box[3] = {32, 32, 1};
+  cuuint32_t box[3] = {32, box_rows, 1};
   cuuint32_t estr[3] = {1, 1, 1};
   return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), gdim, gstr, box, estr,
              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,

@@ -29,9 +29,13 @@
 
 namespace pqlb {
 
-template <int T>
+template <int T, bool WIDE>
 __device__ __forceinline__ void mlp_fwd_h_body(const MlpHDev& P, const MlpHGroupDev& G, uint8_t* smem_raw) {
-  __shared__ __align__(8) uint64_t x_full, x_conv, full_bar[kHStages], empty_bar[kHStages];
+  // WIDE: inputs of 129..256 columns (eight 32-float blocks resident), a shorter ring, short staging chunks (mlp_fwd_h.cuh)
+  constexpr int kStages = WIDE ? kHStagesWide : kHStages;
+  constexpr int kXBytes = (WIDE ? kHXKbWide : kHXKb) * 128 * 128;
+  constexpr int kChunk = WIDE ? kHChunkWide : kHChunk;
+  __shared__ __align__(8) uint64_t x_full, x_conv, full_bar[kStages], empty_bar[kStages];
   __shared__ __align__(8) uint64_t p_full[2], p_conv[2], y_full, y_conv[2], z_full, z_conv, a_full;
   __shared__ uint32_t tmem_slot;
   __shared__ float s_q[4][128];
@@ -46,14 +50,14 @@ __device__ __forceinline__ void mlp_fwd_h_body(const MlpHDev& P, const MlpHGroup
 
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t xs = base;
-  const uint32_t ring = xs + kHXBytes;
-  const uint32_t stage_buf = ring + kHStages * kHTileBytes;
-  float* s_vec = reinterpret_cast<float*>(smem_raw + (base - smem_u32(smem_raw)) + kHXBytes + kHStages * kHTileBytes + kHEpiWarps * kHChunk);
+  const uint32_t ring = xs + kXBytes;
+  const uint32_t stage_buf = ring + kStages * kHTileBytes;
+  float* s_vec = reinterpret_cast<float*>(smem_raw + (base - smem_u32(smem_raw)) + kXBytes + kStages * kHTileBytes + kHEpiWarps * kChunk);
   float* s_b1 = s_vec; float* s_b2 = s_b1 + kHH1; float* s_b3 = s_b2 + kHH2; float* s_w4 = s_b3 + kHH3;
 
   if (threadIdx.x == 0) {
     mbar_init(smem_u32(&x_full), 1); mbar_init(smem_u32(&x_conv), kHEpiWarps);
-    for (int s = 0; s < kHStages; ++s) { mbar_init(smem_u32(&full_bar[s]), 1); mbar_init(smem_u32(&empty_bar[s]), 1); }
+    for (int s = 0; s < kStages; ++s) { mbar_init(smem_u32(&full_bar[s]), 1); mbar_init(smem_u32(&empty_bar[s]), 1); }
     for (int b = 0; b < 2; ++b) { mbar_init(smem_u32(&p_full[b]), 1); mbar_init(smem_u32(&p_conv[b]), kHEpiWarps); mbar_init(smem_u32(&y_conv[b]), kHEpiWarps); }
     mbar_init(smem_u32(&y_full), 1); mbar_init(smem_u32(&z_full), 1);
     mbar_init(smem_u32(&z_conv), kHEpiWarps); mbar_init(smem_u32(&a_full), 1);
@@ -136,7 +140,7 @@ __device__ __forceinline__ void mlp_fwd_h_body(const MlpHDev& P, const MlpHGroup
         tma_load_2d(ring + stage * kHTileBytes, map, c0, c1, smem_u32(&full_bar[stage]));
       }
       __syncwarp();
-      if (++stage == kHStages) { stage = 0; phase ^= 1u; }
+      if (++stage == kStages) { stage = 0; phase ^= 1u; }
     };
 #pragma unroll
     for (int ph = 0; ph < 9; ++ph) {
@@ -171,7 +175,7 @@ __device__ __forceinline__ void mlp_fwd_h_body(const MlpHDev& P, const MlpHGroup
           for (int kb = 0; kb < 2; ++kb) tma_load_2d(dst + kb * box_bytes, &G.tmW4[part], kb * 32, 0, bar);
         }
         __syncwarp();
-        if (++stage == kHStages) { stage = 0; phase ^= 1u; }
+        if (++stage == kStages) { stage = 0; phase ^= 1u; }
       }
     }
   } else if (warp == 1) {
@@ -189,7 +193,7 @@ __device__ __forceinline__ void mlp_fwd_h_body(const MlpHDev& P, const MlpHGroup
     auto release_tile = [&]() {                 // called by the elected lane after its MMAs
       umma_commit(smem_u32(&empty_bar[stage]));
     };
-    auto next_stage = [&]() { __syncwarp(); if (++stage == kHStages) { stage = 0; phase ^= 1u; } };
+    auto next_stage = [&]() { __syncwarp(); if (++stage == kStages) { stage = 0; phase ^= 1u; } };
 #pragma unroll
     for (int ph = 0; ph < 9; ++ph) {
       const int kind = (int)((kKinds >> (4 * ph)) & 15), arg = (int)((kArgs >> (4 * ph)) & 15);
@@ -325,9 +329,9 @@ __device__ __forceinline__ void mlp_fwd_h_body(const MlpHDev& P, const MlpHGroup
     const int row0 = m0 + quarter * 32;
     const int row = row0 + lane;
     const uint32_t lane_sel = (uint32_t)(quarter * 32) << 16;
-    const uint32_t my_stage = stage_buf + e * kHChunk;
+    const uint32_t my_stage = stage_buf + e * kChunk;
     const uint32_t swz = (uint32_t)(lane & 7) << 4;
-    const uint32_t row_off = (uint32_t)lane * 128u;
+    const uint32_t row_off = (uint32_t)(WIDE ? (lane & (kHRowsWide - 1)) : lane) * 128u;
     bool pending = false;
 
     // ---- input tile: fp32 -> [hi | lo] fp16, in place (thread = one 128-byte row of one 32-float block)
@@ -337,8 +341,10 @@ __device__ __forceinline__ void mlp_fwd_h_body(const MlpHDev& P, const MlpHGroup
     PQLB_HSTAMP(32);
     {
       const int t = (int)threadIdx.x - 64;
-      const int r = t & 127, kb = t >> 7;
-      if (kb < G.kb1) {
+      const int r = t & 127;
+      // 512 threads = four blocks of 128 rows per pass; a wide tile (up to eight blocks) takes two passes
+#pragma unroll 1
+      for (int kb = t >> 7; kb < G.kb1; kb += (WIDE ? 4 : 64)) {
         const uint32_t rowaddr = xs + (uint32_t)kb * 16384u + (uint32_t)r * 128u;
         const uint32_t sw = (uint32_t)(r & 7) << 4;
         float f[32];
@@ -373,14 +379,32 @@ __device__ __forceinline__ void mlp_fwd_h_body(const MlpHDev& P, const MlpHGroup
 
     // hands this warp's 32x32 chunk (already TF32-rounded) to a TMA store through its staging buffer
     auto store_chunk = [&](const float* v, const CUtensorMap* omap, int n_col) {
-      if (pending) { if (elect_one()) bulk_wait_read<0>(); __syncwarp(); }
+      if constexpr (WIDE) {
+        // short staging chunk: the warp's 32 rows leave in pieces of kHRowsWide rows (tile maps with 32 x kHRowsWide boxes)
+#pragma unroll 1
+        for (int half = 0; half < 32 / kHRowsWide; ++half) {
+          if (pending) { if (elect_one()) bulk_wait_read<0>(); __syncwarp(); }
+          if (lane / kHRowsWide == half) {
 #pragma unroll
-      for (int j4 = 0; j4 < 8; ++j4)
-        sts128(my_stage + row_off + (((uint32_t)j4 << 4) ^ swz), v[4 * j4], v[4 * j4 + 1], v[4 * j4 + 2], v[4 * j4 + 3]);
-      fence_proxy_async();
-      __syncwarp();
-      if (elect_one()) { tma_store_3d(omap, my_stage, n_col, row0, 0); bulk_commit(); }
-      pending = true;
+            for (int j4 = 0; j4 < 8; ++j4)
+              sts128(my_stage + row_off + (((uint32_t)j4 << 4) ^ swz), v[4 * j4], v[4 * j4 + 1], v[4 * j4 + 2], v[4 * j4 + 3]);
+          }
+          fence_proxy_async();
+          __syncwarp();
+          if (elect_one()) { tma_store_3d(omap, my_stage, n_col, row0 + kHRowsWide * half, 0); bulk_commit(); }
+          __syncwarp();
+          pending = true;
+        }
+      } else {
+        if (pending) { if (elect_one()) bulk_wait_read<0>(); __syncwarp(); }
+#pragma unroll
+        for (int j4 = 0; j4 < 8; ++j4)
+          sts128(my_stage + row_off + (((uint32_t)j4 << 4) ^ swz), v[4 * j4], v[4 * j4 + 1], v[4 * j4 + 2], v[4 * j4 + 3]);
+        fence_proxy_async();
+        __syncwarp();
+        if (elect_one()) { tma_store_3d(omap, my_stage, n_col, row0, 0); bulk_commit(); }
+        pending = true;
+      }
     };
     // Converts this warp's chunk of a 128-column accumulator region: v * 2^-8 + bias, ELU, split; the
     // region becomes [64 columns of packed hi | 64 columns of packed lo].  The four warps of a lane
@@ -589,7 +613,15 @@ __global__ void __launch_bounds__(kHThreads, 1)
 mlp_fwd_h_kernel(const __grid_constant__ MlpHDev P) {
   extern __shared__ uint8_t smem_raw[];
   const MlpHGroupDev& G = P.g[blockIdx.y];
-  mlp_fwd_h_body<0>(P, G, smem_raw);
+  mlp_fwd_h_body<0, false>(P, G, smem_raw);
+}
+
+// the same tile program for inputs of 129..256 columns (ShadowHand critics: obs 211 + act 20 = 231)
+__global__ void __launch_bounds__(kHThreads, 1)
+mlp_fwd_hw_kernel(const __grid_constant__ MlpHDev P) {
+  extern __shared__ uint8_t smem_raw[];
+  const MlpHGroupDev& G = P.g[blockIdx.y];
+  mlp_fwd_h_body<0, true>(P, G, smem_raw);
 }
 
 // hi[i] = fp16(scale * src[i]), lo[i] = fp16(scale * src[i] - hi[i]) (lo optional): the fp16 operand
@@ -625,6 +657,7 @@ extern "C" void pqlb_mlp_forward_h_mode(int mode) { g_fwd_h_mode = (mode == 1 ||
 
 extern "C" int pqlb_mlp_forward_h_init(void) {
   cudaError_t e = cudaFuncSetAttribute(mlp_fwd_h_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kHSmem);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(mlp_fwd_hw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kHSmemWide);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(mlp_fwd_hp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kHPSmem);
   return e == cudaSuccess ? PQLB_OK : (int)e;
 }
@@ -648,7 +681,7 @@ static int make_half_map(CUtensorMap* map, const void* base, int k, int rows, in
 
 extern "C" int pqlb_mlp_forward_h(const pqlb_mlp_h_desc* d, pqlb_stream_t stream) {
   PQLB_CHECK_ARG(d && d->M > 0 && d->k_in > 0 && d->n_groups >= 1 && d->n_groups <= PQLB_MAX_FWD_GROUPS);
-  if (d->k_in > kHXKb * 32) return PQLB_E_UNSUPPORTED;      // wider inputs take the per-layer path
+  if (d->k_in > kHXKbWide * 32) return PQLB_E_UNSUPPORTED;      // wider inputs take the per-layer path
   { int rc = pqlb_init(); if (rc != PQLB_OK) return rc; }
   static MlpHDev P;
   P.M = d->M;
@@ -656,12 +689,16 @@ extern "C" int pqlb_mlp_forward_h(const pqlb_mlp_h_desc* d, pqlb_stream_t stream
   P.tiles_m = (d->M + 127) / 128; P.n_groups = d->n_groups;
   P.dbg = g_fwd_h_debug;
   const int tiles_m = (d->M + 127) / 128;
+  // any group wider than 128 columns: the whole launch runs the wide-input kernel (its tile maps have short boxes)
+  bool wide = false;
+  for (int i = 0; i < d->n_groups; ++i) wide = wide || (d->g[i].k_in > 0 ? d->g[i].k_in : d->k_in) > kHXKb * 32;
+  const uint32_t box_rows = wide ? (uint32_t)kHRowsWide : 32u;
   for (int i = 0; i < d->n_groups; ++i) {
     const pqlb_mlp_h_group& s = d->g[i];
     MlpHGroupDev& G = P.g[i];
     PQLB_CHECK_ARG(s.terms == 1 || s.terms == 3);
     const int k_in = s.k_in > 0 ? s.k_in : d->k_in;          // groups of one launch may differ in input width
-    if (k_in > kHXKb * 32) return PQLB_E_UNSUPPORTED;
+    if (k_in > kHXKbWide * 32) return PQLB_E_UNSUPPORTED;
     G.kb1 = (k_in + 31) / 32; G.kw1 = (k_in + 63) / 64; G.ksteps1 = (k_in + 15) / 16;
     PQLB_CHECK_ARG(s.x && s.w1h && s.w2h && s.w3h && s.b1 && s.b2 && s.b3);
     PQLB_CHECK_ARG(s.terms == 1 || (s.w1l && s.w2l && s.w3l));
@@ -677,9 +714,9 @@ extern "C" int pqlb_mlp_forward_h(const pqlb_mlp_h_desc* d, pqlb_stream_t stream
       if ((rc = make_half_map(&G.tmW3[p], have ? w3[p] : w3[0], kHH2, kHH3, kHH2, 128)) != PQLB_OK) return rc;
     }
     G.st1 = s.h1 != nullptr; G.st2 = s.h2 != nullptr; G.st3 = s.h3 != nullptr;
-    if (G.st1 && !make_tile_map(&G.tmH1, s.h1, kHH1, (uint64_t)d->M, kHH1, 1, 0)) return PQLB_E_ALIGN;
-    if (G.st2 && !make_tile_map(&G.tmH2, s.h2, kHH2, (uint64_t)d->M, kHH2, 1, 0)) return PQLB_E_ALIGN;
-    if (G.st3 && !make_tile_map(&G.tmH3, s.h3, kHH3, (uint64_t)d->M, kHH3, 1, 0)) return PQLB_E_ALIGN;
+    if (G.st1 && !make_tile_map(&G.tmH1, s.h1, kHH1, (uint64_t)d->M, kHH1, 1, 0, box_rows)) return PQLB_E_ALIGN;
+    if (G.st2 && !make_tile_map(&G.tmH2, s.h2, kHH2, (uint64_t)d->M, kHH2, 1, 0, box_rows)) return PQLB_E_ALIGN;
+    if (G.st3 && !make_tile_map(&G.tmH3, s.h3, kHH3, (uint64_t)d->M, kHH3, 1, 0, box_rows)) return PQLB_E_ALIGN;
     if (!G.st1) G.tmH1 = G.tmX;
     if (!G.st2) G.tmH2 = G.tmX;
     if (!G.st3) G.tmH3 = G.tmX;
@@ -720,14 +757,16 @@ extern "C" int pqlb_mlp_forward_h(const pqlb_mlp_h_desc* d, pqlb_stream_t stream
     PQLB_CHECK_ARG(!s.wait || (i > 0 && d->tile_sync));
     G.publish = s.publish != 0; G.wait = s.wait != 0;
   }
-  const bool persistent = g_fwd_h_mode == 2;
+  const bool persistent = g_fwd_h_mode == 2 && !wide;      // the persistent schedule keeps the narrow geometry
   const int n_items = tiles_m * d->n_groups;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = persistent ? dim3((unsigned)(n_items < kNumSMs ? n_items : kNumSMs), 1, 1) : dim3((unsigned)tiles_m, (unsigned)d->n_groups, 1);
   cfg.blockDim = dim3(kHThreads, 1, 1);
-  cfg.dynamicSmemBytes = persistent ? kHPSmem : kHSmem;
+  cfg.dynamicSmemBytes = persistent ? kHPSmem : (wide ? kHSmemWide : kHSmem);
   cfg.stream = (cudaStream_t)stream;
-  cudaError_t le = persistent ? cudaLaunchKernelEx(&cfg, mlp_fwd_hp_kernel, P) : cudaLaunchKernelEx(&cfg, mlp_fwd_h_kernel, P);
+  cudaError_t le = persistent ? cudaLaunchKernelEx(&cfg, mlp_fwd_hp_kernel, P)
+                   : wide     ? cudaLaunchKernelEx(&cfg, mlp_fwd_hw_kernel, P)
+                              : cudaLaunchKernelEx(&cfg, mlp_fwd_h_kernel, P);
   PQLB_COUNT_LAUNCH(1);
   return le == cudaSuccess ? PQLB_OK : (int)le;
 }

@@ -17,6 +17,23 @@ constexpr int kHXBytes = kHXKb * 128 * 128;
 constexpr int kHChunk = 32 * 128;
 constexpr int kHPrefetchCtas = 2;             // row tiles per group that issue the L2 prefetch of the group's weights
 constexpr int kHSmem = 1024 + kHXBytes + kHStages * kHTileBytes + kHEpiWarps * kHChunk + (kHH1 + kHH2 + 2 * kHH3) * 4;
+// Wide inputs (129..256 columns: the ShadowHand critics, obs 211 + act 20): the input tile is eight 32-float
+// blocks = 128 KB, paid for with a four-stage weight ring and 8-row staging chunks (a warp's 32 x 32 chunk leaves in
+// four TMA stores).  Measured on the ShadowHand loop: 4 stages / 8 rows 92 us per four-critic launch, 3 stages /
+// 16 rows 97 us (the ring depth is what the L2 -> SM weight stream needs to stay in flight).
+#ifndef PQLB_WIDE_STAGES
+#define PQLB_WIDE_STAGES 4
+#endif
+#ifndef PQLB_WIDE_ROWS
+#define PQLB_WIDE_ROWS 8
+#endif
+constexpr int kHXKbWide = 8;
+constexpr int kHStagesWide = PQLB_WIDE_STAGES;
+constexpr int kHRowsWide = PQLB_WIDE_ROWS;         // rows of a staging chunk: a warp's 32 rows leave in 32 / kHRowsWide TMA stores
+constexpr int kHChunkWide = kHRowsWide * 128;
+static_assert(kHRowsWide == 8 || kHRowsWide == 16 || kHRowsWide == 32, "staging chunks are whole 8-row swizzle groups");
+constexpr int kHSmemWide = 1024 + kHXKbWide * 128 * 128 + kHStagesWide * kHTileBytes + kHEpiWarps * kHChunkWide + (kHH1 + kHH2 + 2 * kHH3) * 4;
+static_assert(kHSmemWide <= 227 * 1024, "wide-input tile does not fit shared memory");
 
 struct alignas(64) MlpHGroupDev {
   CUtensorMap tmX, tmW1[2], tmW2[2], tmW3[2], tmW4[2], tmH1, tmH2, tmH3;      // [0] hi, [1] lo

@@ -254,8 +254,8 @@ PFN_cuTensorMapEncodeTiled get_encode_fn();
 // 2-D fp32 tensor map; dim0 is the contiguous dimension.
 int make_map(CUtensorMap* map, const float* base, uint64_t dim0, uint64_t dim1, int64_t ld_words,
              uint32_t box0, uint32_t box1, CUtensorMapSwizzle swizzle);
-// [splits][rows][cols] fp32, 32x32 boxes, 128-byte swizzle (epilogue staging chunks).
+// [splits][rows][cols] fp32, 32 x box_rows boxes, 128-byte swizzle (epilogue staging chunks).
 bool make_tile_map(CUtensorMap* map, const float* base, uint64_t cols, uint64_t rows, int64_t ld_words,
-                   uint64_t splits, int64_t split_stride_words);
+                   uint64_t splits, int64_t split_stride_words, uint32_t box_rows = 32);
 
 }  // namespace pqlb

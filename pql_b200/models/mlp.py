@@ -35,7 +35,9 @@ class NetLayout:
         self.in_dim, self.out_dim, self.n_nets = int(in_dim), int(out_dim), int(n_nets)
         self.dims = [self.in_dim, *HIDDEN, self.out_dim]
         self.n_layers = len(self.dims) - 1
-        self.ldw = [_ru(d, 4) for d in self.dims[:-1]]
+        # row strides: 16-byte rows as fp32; first layers wider than 128 inputs also as fp16 (multiples of 8), which is
+        # what the TMA maps of the wide-input split-fp16 forward need (ShadowHand policy: 211 -> 216, critics: 231 -> 232)
+        self.ldw = [_ru(d, 8) if d > 128 else _ru(d, 4) for d in self.dims[:-1]]
         off = 0
         self.w_off, self.b_off = [], []
         for _ in range(self.n_nets):
@@ -137,33 +139,41 @@ def trunk_calls(B, insts, n_hidden_out=3):
 
 
 FUSED_MAX_IN = 128        # pqlb_mlp_forward keeps a 128-row input tile of at most 128 columns in shared memory
+FUSED_H_MAX_IN = 256      # pqlb_mlp_forward_h: up to 128 columns, or 129..256 with its wide-input kernel (ShadowHand critics: 231)
 
 
 def split_f16_ok(inst):
-    """Can this instance run on the split-fp16 fused forward (pqlb_mlp_forward_h)?  Needs fp16 weight
-    copies, an input at most 128 wide whose weight rows are 16-byte aligned as halves, and - for a
-    policy net - a head the kernel fuses (A <= 16, A % 4 == 0, aligned output rows)."""
+    """Can this instance's trunk run on the split-fp16 fused forward (pqlb_mlp_forward_h)?  Needs fp16 weight
+    copies and an input at most 256 wide whose weight rows are 16-byte aligned as halves."""
     n = inst["net"]
-    if n.Wh is None or inst["k_in"] > FUSED_MAX_IN or n.ldw[0] % 8:
-        return False
-    act = inst.get("act")
-    if act is not None:
-        A = n.dims[4]
-        if A > 16 or A % 4 or act.get("ldo", 0) % 4 or act.get("ldo2", 0) % 4:
-            return False
-    return True
+    return n.Wh is not None and inst["k_in"] <= FUSED_H_MAX_IN and n.ldw[0] % 8 == 0
+
+
+def fused_head_ok(inst):
+    """Does the policy head of this instance ride in the fused launch (A <= 16, A % 4 == 0, 16-byte aligned
+    output rows)?  Otherwise the trunk stores h3 and the head is its own small launch (policy_head_call)."""
+    act = inst["act"]
+    A = inst["net"].dims[4]
+    return not (A > 16 or A % 4 or act.get("ldo", 0) % 4 or act.get("ldo2", 0) % 4 or act.get("out", 0) % 16
+                or act.get("out2", 0) % 16 or act.get("ldnoise", 0) % 4 or act.get("noise", 0) % 16)
 
 
 def forward_calls_h(B, insts, scalar_head, tile_sync=None):
     """ONE split-fp16 fused launch for up to five network instances (input widths may differ).  inst as
     in ``forward_calls`` plus ``terms`` (3 = hi/lo split of both operands, 1 = hi only), ``xf`` (the
     un-rounded input rows; falls back to ``x``) and optional ``wait_flag`` / ``done_flag`` / ``epoch``."""
-    k_in = insts[0]["k_in"]
-    groups = []
+    groups, heads_left = [], []
     for it in insts:
         n = it["net"]
         st = it.get("store", (True, True, True))
         terms = int(it.get("terms", 3))
+        act = it.get("act")
+        if act is not None and not fused_head_ok(it):
+            # a head the kernel does not fuse (ShadowHand: 20 actions): the trunk leaves h3, the head is its own launch
+            if it.get("publish") or it.get("wait"):
+                raise ValueError("tile dependencies need the fused policy head")
+            st, act = (st[0], st[1], True), None
+            heads_left.append(it)
         g = dict(x=it.get("xf") or it["x"], ldx=it["x_ld"], w1h=n.Wh[0], ldw1=n.ldw[0], w2h=n.Wh[1], w3h=n.Wh[2],
                  b1=n.b[0], b2=n.b[1], b3=n.b[2], terms=terms, k_in=it["k_in"],
                  h1=it["h"][0] if st[0] else 0, h2=it["h"][1] if st[1] else 0, h3=it["h"][2] if st[2] else 0)
@@ -171,7 +181,6 @@ def forward_calls_h(B, insts, scalar_head, tile_sync=None):
             g.update(w1l=n.Wl[0], w2l=n.Wl[1], w3l=n.Wl[2])
         if scalar_head and it.get("q"):
             g.update(head_w=n.Wf[3], head_b=n.b[3], q=it["q"])
-        act = it.get("act")
         if act is not None:
             g.update(act_wh=n.Wh[3], act_b=n.b[3], act_n=n.dims[4], act_out=act.get("out", 0), act_ldo=act.get("ldo", 0),
                      act_out2=act.get("out2", 0), act_ldo2=act.get("ldo2", 0), act_noise=act.get("noise", 0),
@@ -188,17 +197,18 @@ def forward_calls_h(B, insts, scalar_head, tile_sync=None):
             if it.get(k):
                 g[k] = 1
         groups.append(g)
-    return [K.MlpForwardH(B, max(it["k_in"] for it in insts), groups, tile_sync=tile_sync)]
+    return [K.MlpForwardH(B, max(it["k_in"] for it in insts), groups, tile_sync=tile_sync)] + [policy_head_call(B, it) for it in heads_left]
 
 
 def forward_calls(B, insts, scalar_head):
     """Prepared launches of the trunk (three Linear+ELU layers) for up to four network instances.
     inst = dict(net, x, x_ld, k_in, h=[h1, h2, h3 addresses], store=(s1, s2, s3), q=addr or 0,
     act=dict(out, ldo, [out2, ldo2], [noise, ldnoise, noise_std, noise_bound]) for a policy net).
-    Inputs up to 128 wide take ONE layer-fused launch (activations stay in tensor memory, only the
-    flagged ones are written; the scalar twin-Q head or the tanh policy head ride in the same
-    launch) - the split-fp16 kernel when the instances carry fp16 weight copies, the TF32 kernel
-    otherwise; wider inputs (ShadowHand) run layer by layer."""
+    ONE layer-fused launch (activations stay in tensor memory, only the flagged ones are written; the
+    scalar twin-Q head or the tanh policy head ride in the same launch) where the shapes allow it: the
+    split-fp16 kernel when every instance carries fp16 weight copies and passes ``split_f16_ok`` (inputs up
+    to 256 wide: the ShadowHand critics included), else the TF32 kernel for inputs up to 128 wide; what is
+    left (the ShadowHand policy net: 211 inputs with 8-byte-aligned half rows, 20 actions) runs layer by layer."""
     k_in = insts[0]["k_in"]
     calls = []
     if all(split_f16_ok(it) for it in insts):

@@ -78,8 +78,13 @@ def test_split_copies_reconstruct_the_weights():
 
 
 @pytest.mark.parametrize("M,k_in,n_groups,terms", [(128, 104, 1, 3), (200, 88, 1, 1), (8192, 104, 4, 3), (300, 104, 2, 3),
-                                                   (8192, 104, 5, 3), (1000, 16, 1, 3), (8192, 88, 2, 1), (40000, 104, 2, 3)])
+                                                   (8192, 104, 5, 3), (1000, 16, 1, 3), (8192, 88, 2, 1), (40000, 104, 2, 3),
+                                                   # wide inputs (129..256 columns: mlp_fwd_hw_kernel; ShadowHand critics = 231)
+                                                   (128, 231, 1, 3), (8192, 231, 4, 3), (300, 232, 2, 3), (1000, 231, 1, 1),
+                                                   (700, 160, 2, 3), (450, 256, 2, 3)])
 def test_split_f16_trunk_and_q_head(K, mode, M, k_in, n_groups, terms):
+    if k_in > 128 and mode == 2:
+        pytest.skip("wide inputs always take the CTA-per-tile kernel")
     g = torch.Generator(device=DEV).manual_seed(11 * M + k_in + terms)
     ld = (k_in + 3) // 4 * 4
     groups, keep = [], []
@@ -129,12 +134,15 @@ def test_split_f16_trunk_and_q_head(K, mode, M, k_in, n_groups, terms):
             assert all(float(t.abs().max()) == 0.0 for t in h), "activations written although not requested"
 
 
-@pytest.mark.parametrize("M,A,noisy,terms", [(8192, 16, True, 1), (300, 16, False, 3), (1000, 8, True, 1), (128, 4, False, 1)])
-def test_split_f16_policy_head(K, mode, M, A, noisy, terms):
+@pytest.mark.parametrize("M,A,noisy,terms,k_in", [(8192, 16, True, 1, 88), (300, 16, False, 3, 88), (1000, 8, True, 1, 88),
+                                                  (128, 4, False, 1, 88), (1000, 16, True, 1, 208), (300, 12, False, 3, 200)])
+def test_split_f16_policy_head(K, mode, M, A, noisy, terms, k_in):
     """tanh(Linear(128, A)) (+ clipped N(0, std^2) noise, clamp) fused behind the trunk: act_out2 holds the
-    value, act_out its TF32 rounding (mlp.py:177-179, noise.py:19-27)."""
+    value, act_out its TF32 rounding (mlp.py:177-179, noise.py:19-27).  k_in > 128: the wide-input kernel."""
+    if k_in > 128 and mode == 2:
+        pytest.skip("wide inputs always take the CTA-per-tile kernel")
     g = torch.Generator(device=DEV).manual_seed(M + A)
-    k_in, ld = 88, 88
+    ld = k_in
     x = torch.randn(M, ld, device=DEV, generator=g)
     ws, bs, hs, ls = make_net(k_in, A, g)
     out = torch.full((M, 104), 7.0, device=DEV)

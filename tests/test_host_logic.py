@@ -90,11 +90,33 @@ def test_wgrad_plan_fills_one_wave_with_balanced_ctas(shapes, B):
 
 def test_forward_mode_selection():
     """Which shapes take the split-fp16 fused forward: inputs up to 128 wide with 16-byte
-    aligned half rows and a policy head of at most 16 actions; everything else runs the TF32 kernels."""
+    aligned half rows and a policy head of at most 16 actions; critics of 129..256 columns (the wide-input kernel),
+    whose policy net then decides for itself (split_f16_ok); everything else runs the TF32 kernels."""
     from pql_b200.algo._engine import forward_mode
+    from pql_b200.models.mlp import NetLayout, split_f16_ok
     assert forward_mode(None, 88, 16) == "f16x3"
     assert forward_mode("tf32", 88, 16) == "tf32"
-    assert forward_mode(None, 211, 20) == "tf32"          # ShadowHand: 231 input columns
+    assert forward_mode(None, 211, 20) == "f16x3"         # ShadowHand: 231 input columns, critics on the wide-input kernel
+    assert forward_mode("tf32", 211, 20) == "tf32"
+    assert forward_mode(None, 300, 20) == "tf32"          # more than 256 columns: per-layer TF32 launches
     assert forward_mode(None, 24, 4) in ("f16x3", "tf32")
     with pytest.raises(ValueError):
         forward_mode("bf16", 88, 16)
+
+    class Net:                                             # what split_f16_ok / fused_head_ok read of a NetAddrs
+        def __init__(self, in_dim, out_dim):
+            L = NetLayout(in_dim, out_dim)
+            self.dims, self.ldw, self.Wh = L.dims, L.ldw, [1]
+    from pql_b200.models.mlp import fused_head_ok
+    # ShadowHand: critics (231 -> rows of 232 halves) and policy trunk (211 -> 216) take the fused kernel; the 20-action
+    # head does not ride along (A > 16): the trunk stores h3 and the head is its own launch
+    assert NetLayout(231, 1).ldw[0] == 232 and NetLayout(211, 20).ldw[0] == 216 and NetLayout(88, 16).ldw[0] == 88
+    assert NetLayout(12, 4).ldw[0] == 12                   # narrow first layers keep 16-byte fp32 rows
+    assert split_f16_ok(dict(net=Net(231, 1), k_in=231))
+    shadow_policy = dict(net=Net(211, 20), k_in=211, act=dict(out=211 * 4, ldo=232, out2=211 * 4, ldo2=232))
+    assert split_f16_ok(shadow_policy) and not fused_head_ok(shadow_policy)
+    wide16 = dict(net=Net(208, 16), k_in=208, act=dict(out=208 * 4, ldo=224, out2=208 * 4, ldo2=224))
+    assert split_f16_ok(wide16) and fused_head_ok(wide16)
+    assert not fused_head_ok(dict(net=Net(88, 16), k_in=88, act=dict(out=88 * 4 + 4, ldo=104)))  # unaligned action rows
+    assert not split_f16_ok(dict(net=Net(260, 1), k_in=260))
+    assert not split_f16_ok(dict(net=Net(12, 4), k_in=12))  # 12 halves = 24-byte rows

@@ -43,7 +43,7 @@ class StubEnv:
 
 
 def measure_loop(envs=16384, obs=211, act=20, memory=5_000_000, batch=8192, iters=50, warmup=10, distl=False,
-                 profile=False, device="cuda:0"):
+                 profile=False, device="cuda:0", forward_mode=None):
     """Time ``iters`` iterations of LockStepTrainer.step() on the stub env; returns the result dict."""
     from pql_b200.train import LockStepTrainer
     from pql_b200.utils import default_pql_cfg
@@ -52,6 +52,8 @@ def measure_loop(envs=16384, obs=211, act=20, memory=5_000_000, batch=8192, iter
     cfg = default_pql_cfg(num_envs=envs, sim_device=str(dev), batch_size=batch, memory_size=memory, distl=distl,
                           v_learner_gpu=dev.index or 0, p_learner_gpu=dev.index or 0)
     cfg.learner_streams = True
+    if forward_mode is not None:
+        cfg.forward_mode = forward_mode          # "tf32": one TF32 MMA per product everywhere (the round-1 number format)
     tr = LockStepTrainer(StubEnv(envs, obs, act, dev), cfg)
     tr.warm_up()
     for _ in range(warmup):
@@ -87,6 +89,7 @@ def measure_loop(envs=16384, obs=211, act=20, memory=5_000_000, batch=8192, iter
             "critic_updates_per_s": tr.v_per_step / (ms * 1e-3),
             "actor_updates_per_s": tr.v_per_step / tr.p_every / (ms * 1e-3),
             "replay_gb": tr.v_learner.memory.ring.numel() * 4 / 1e9,
+            "forward_mode": tr.v_learner._plan.fwd_mode,
             "losses": {"critic": info["train/critic_loss"], "actor": info["train/actor_loss"]},
             "kernel_ms_and_launches_per_iteration": per_kernel}
 
@@ -102,9 +105,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--distl", action="store_true")
     ap.add_argument("--profile", action="store_true", help="per-kernel device time (CUDA events around every launch, graphs off)")
+    ap.add_argument("--fwd-mode", default=None, choices=["f16x3", "tf32"], help="cfg.forward_mode (default: the library's choice)")
     args = ap.parse_args()
     print(json.dumps(measure_loop(args.envs, args.obs, args.act, args.memory, args.batch, args.iters, args.warmup,
-                                  args.distl, args.profile)))
+                                  args.distl, args.profile, forward_mode=args.fwd_mode)))
 
 
 if __name__ == "__main__":
