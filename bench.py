@@ -604,6 +604,8 @@ def main():
         subs = {}
         for name, kw in (("configs[2]_c51_b16384", dict(envs=E, obs=O, act=A, memory=CAP, batch=16384, distl=True, iters=30, warmup=8, profile=True)),
                          ("configs[3]_shadowhand_loop", dict(envs=16384, obs=211, act=20, memory=5_000_000, batch=8192, iters=30, warmup=8, profile=True)),
+                         # the same loop with one TF32 MMA per product everywhere (cfg.forward_mode = "tf32": the round-1 number format)
+                         ("configs[3]_shadowhand_loop_tf32_mode", dict(envs=16384, obs=211, act=20, memory=5_000_000, batch=8192, iters=30, warmup=8, forward_mode="tf32")),
                          ("configs[1]_allegro_loop", dict(envs=E, obs=O, act=A, memory=CAP, batch=B, iters=30, warmup=8))):
             try:
                 subs[name] = measure_loop(**kw)

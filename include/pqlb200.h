@@ -304,7 +304,8 @@ void pqlb_mlp_forward_cluster(int cluster);
  * caller; the kernel maintains it across launches (no reset needed).
  * Input width: k_in <= 128 per group, or - if any group is wider - k_in <= 256 for the whole launch (the
  * wide-input kernel: eight 32-column input blocks resident in shared memory, a shorter weight ring;
- * ShadowHand's critics, obs 211 + act 20, pql/models/mlp.py:186-203); wider: PQLB_E_UNSUPPORTED. */
+ * ShadowHand's critics, obs 211 + act 20, pql/models/mlp.py:186-203); wider: PQLB_E_UNSUPPORTED.
+ * In a wide launch the policy head takes act_n <= 32 (a multiple of 4) and output rows of any alignment. */
 #define PQLB_MAX_FWD_GROUPS 5
 typedef struct {
   const float* x; int64_t ldx;

@@ -34,10 +34,10 @@ def forward_mode(requested, obs_dim, action_dim):
     gradient tensor within 1e-3 of the fp32 reference) - or 'tf32' (the round-1
     kernels: one TF32 MMA per product everywhere).  Shapes 'f16x3' takes: inputs up to 128 wide whose weight
     rows are 16-byte aligned as halves and a policy head the kernel fuses (A <= 16, multiples of 4); and
-    critics 129..256 wide (the wide-input kernel: ShadowHand's 231 columns) - there a policy net the kernel
-    does not take (models.mlp.split_f16_ok: ShadowHand's 211 observations give 8-byte-aligned half rows, 20
-    actions) runs through the TF32 launches on its own, which is the accuracy class of its one-term fp16
-    forward anyway.  Everything else runs as 'tf32'."""
+    critics 129..256 wide (the wide-input kernel: ShadowHand's 231 columns) - there the policy net decides
+    for itself (models.mlp.split_f16_ok / fused_head_ok: ShadowHand's 211 observations and 20 actions ride in
+    the wide-input kernel too; a policy net it does not take would run through the TF32 launches, which is the
+    accuracy class of its one-term fp16 forward anyway).  Everything else runs as 'tf32'."""
     mode = _os.environ.get("PQLB_FWD_MODE") or requested or "f16x3"
     if mode not in ("f16x3", "tf32"):
         raise ValueError(f"forward mode {mode!r}: expected 'f16x3' or 'tf32'")

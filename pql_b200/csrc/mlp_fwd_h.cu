@@ -291,7 +291,7 @@ __device__ __forceinline__ void mlp_fwd_h_body(const MlpHDev& P, const MlpHGroup
       // head: h3 (split in place in Z) . W4^T into head_rows columns of P1 (policy N = 16, softmax N = 64)
       mbar_wait(smem_u32(&z_conv), 0);
       tcgen05_fence_after();
-      const uint32_t idesc_head = G.head_rows == 16 ? idesc_f16(16) : idesc_f16(64);
+      const uint32_t idesc_head = G.head_rows == 16 ? idesc_f16(16) : (WIDE && G.head_rows == 32 ? idesc_f16(32) : idesc_f16(64));
       const uint32_t box_bytes = (uint32_t)G.head_rows * 128u;
 #pragma unroll
       for (int part = 0; part < NP; ++part) {
@@ -491,50 +491,69 @@ __device__ __forceinline__ void mlp_fwd_h_body(const MlpHDev& P, const MlpHGroup
       }
       if (G.act_n > 0 && chunk == 0) {
         // one warp per lane quarter finishes the head: * 2^-8 + bias, tanh, (+ clipped noise, clamp).  Bias and noise
-        // are fetched BEFORE the wait for the head contraction (cold global loads at the very end of a tile otherwise)
-        float hb[16], nz[16];
+        // are fetched BEFORE the wait for the head contraction (cold global loads at the very end of a tile otherwise).
+        // The wide-input kernel also takes heads of 17..32 actions (a second pass over columns 16..31) and output rows
+        // that are not 16-byte aligned (scalar stores): ShadowHand's 20 actions behind 211 observations.
+        const int n_pass = WIDE ? (G.act_n + 15) >> 4 : 1;
+#pragma unroll 1
+        for (int pass = 0; pass < n_pass; ++pass) {
+          const int c0 = pass * 16;
+          float hb[16], nz[16];
 #pragma unroll
-        for (int j = 0; j < 16; j += 4) {
-          float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f), n4 = b4;
-          if (j < G.act_n) {
-            b4 = *reinterpret_cast<const float4*>(G.act_b + j);            // arena biases are 128-byte aligned and padded
-            if (G.act_noise && row < P.M) n4 = *reinterpret_cast<const float4*>(G.act_noise + (long long)row * G.act_ldnoise + j);
-          }
-          hb[j] = b4.x; hb[j + 1] = b4.y; hb[j + 2] = b4.z; hb[j + 3] = b4.w;
-          nz[j] = n4.x; nz[j + 1] = n4.y; nz[j + 2] = n4.z; nz[j + 3] = n4.w;
-        }
-        mbar_wait(smem_u32(&a_full), 0);
-        tcgen05_fence_after();
-        float a[16];
-        tmem_ld16(tmem + 128u + lane_sel, a);
-        if (row < P.M) {
-          float o[16], o2[16];
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            float t = 0.f, r = 0.f;
-            if (j < G.act_n) {
-              t = tanh_fast(fmaf(a[j], kWInv, hb[j]));
-              r = t;
-              if (G.act_noise) {                   // noise.py:19-27 on N(0,1) draws scaled by std
-                const float z = fminf(fmaxf(nz[j] * G.noise_std, -G.noise_bound), G.noise_bound);
-                r = fminf(fmaxf(t + z, -1.f), 1.f);
-              }
-              t = r;                               // act_out2: the value itself; act_out: its TF32 operand rounding
-              r = rn_tf32(r);
+          for (int j = 0; j < 16; j += 4) {
+            float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f), n4 = b4;
+            if (c0 + j < G.act_n) {
+              b4 = *reinterpret_cast<const float4*>(G.act_b + c0 + j);            // arena biases are 128-byte aligned and padded
+              if (G.act_noise && row < P.M) n4 = *reinterpret_cast<const float4*>(G.act_noise + (long long)row * G.act_ldnoise + c0 + j);
             }
-            o[j] = r; o2[j] = t;
+            hb[j] = b4.x; hb[j + 1] = b4.y; hb[j + 2] = b4.z; hb[j + 3] = b4.w;
+            nz[j] = n4.x; nz[j + 1] = n4.y; nz[j + 2] = n4.z; nz[j + 3] = n4.w;
           }
-          if (G.act_out) {
-            float* dst = G.act_out + (long long)row * G.act_ldo;
+          mbar_wait(smem_u32(&a_full), 0);
+          tcgen05_fence_after();
+          float a[16];
+          tmem_ld16(tmem + 128u + (uint32_t)c0 + lane_sel, a);
+          if (row < P.M) {
+            float o[16], o2[16];
 #pragma unroll
-            for (int j = 0; j < 16; j += 4)
-              if (j < G.act_n) *reinterpret_cast<float4*>(dst + j) = make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]);
-          }
-          if (G.act_out2) {
-            float* dst2 = G.act_out2 + (long long)row * G.act_ldo2;
+            for (int j = 0; j < 16; ++j) {
+              float t = 0.f, r = 0.f;
+              if (c0 + j < G.act_n) {
+                t = tanh_fast(fmaf(a[j], kWInv, hb[j]));
+                r = t;
+                if (G.act_noise) {                   // noise.py:19-27 on N(0,1) draws scaled by std
+                  const float z = fminf(fmaxf(nz[j] * G.noise_std, -G.noise_bound), G.noise_bound);
+                  r = fminf(fmaxf(t + z, -1.f), 1.f);
+                }
+                t = r;                               // act_out2: the value itself; act_out: its TF32 operand rounding
+                r = rn_tf32(r);
+              }
+              o[j] = r; o2[j] = t;
+            }
+            if (G.act_out) {
+              float* dst = G.act_out + (long long)row * G.act_ldo + c0;
+              if (!WIDE || G.act_vec) {
 #pragma unroll
-            for (int j = 0; j < 16; j += 4)
-              if (j < G.act_n) *reinterpret_cast<float4*>(dst2 + j) = make_float4(o2[j], o2[j + 1], o2[j + 2], o2[j + 3]);
+                for (int j = 0; j < 16; j += 4)
+                  if (c0 + j < G.act_n) *reinterpret_cast<float4*>(dst + j) = make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]);
+              } else {
+#pragma unroll
+                for (int j = 0; j < 16; ++j)
+                  if (c0 + j < G.act_n) dst[j] = o[j];
+              }
+            }
+            if (G.act_out2) {
+              float* dst2 = G.act_out2 + (long long)row * G.act_ldo2 + c0;
+              if (!WIDE || G.act_vec) {
+#pragma unroll
+                for (int j = 0; j < 16; j += 4)
+                  if (c0 + j < G.act_n) *reinterpret_cast<float4*>(dst2 + j) = make_float4(o2[j], o2[j + 1], o2[j + 2], o2[j + 3]);
+              } else {
+#pragma unroll
+                for (int j = 0; j < 16; ++j)
+                  if (c0 + j < G.act_n) dst2[j] = o2[j];
+              }
+            }
           }
         }
         if (G.publish) {
@@ -722,7 +741,7 @@ extern "C" int pqlb_mlp_forward_h(const pqlb_mlp_h_desc* d, pqlb_stream_t stream
     if (!G.st3) G.tmH3 = G.tmX;
     G.b1 = s.b1; G.b2 = s.b2; G.b3 = s.b3; G.head_w = s.head_w; G.head_b = s.head_b; G.q = s.q;
     G.terms = s.terms;
-    G.act_n = 0; G.tmW4[0] = G.tmW4[1] = G.tmX;
+    G.act_n = 0; G.act_vec = 1; G.tmW4[0] = G.tmW4[1] = G.tmX;
     G.act_b = nullptr; G.act_noise = nullptr; G.act_out = nullptr; G.act_out2 = nullptr;
     G.sm_n = 0; G.sm_b = nullptr; G.sm_out = nullptr; G.sm_ldp = 0; G.head_rows = 0;
     if (s.sm_wh) {
@@ -737,16 +756,18 @@ extern "C" int pqlb_mlp_forward_h(const pqlb_mlp_h_desc* d, pqlb_stream_t stream
       G.sm_n = s.sm_n; G.sm_b = s.sm_b; G.sm_out = s.sm_out; G.sm_ldp = s.sm_ldp; G.head_rows = 64;
     }
     if (s.act_wh) {
-      // policy head: act_n a multiple of 4 up to 16, 16-byte aligned output rows
+      // policy head: act_n a multiple of 4 up to 16, 16-byte aligned output rows; the wide-input kernel also takes
+      // up to 32 actions and output rows of any alignment (scalar stores)
       PQLB_CHECK_ARG(!s.q && s.act_b && (s.act_out || s.act_out2) && s.act_n > 0 && (s.terms == 1 || s.act_wl));
-      if (s.act_n > 16 || s.act_n % 4 || (s.act_out && (s.act_ldo % 4 || !aligned16(s.act_out))) ||
-          (s.act_out2 && (s.act_ldo2 % 4 || !aligned16(s.act_out2))) || !aligned16(s.act_b) ||
+      const bool vec = !(s.act_out && (s.act_ldo % 4 || !aligned16(s.act_out))) && !(s.act_out2 && (s.act_ldo2 % 4 || !aligned16(s.act_out2)));
+      if (s.act_n > (wide ? 32 : 16) || s.act_n % 4 || (!vec && !wide) || !aligned16(s.act_b) ||
           (s.act_noise && (s.act_ldnoise % 4 || !aligned16(s.act_noise)))) return PQLB_E_UNSUPPORTED;
+      const uint32_t head_rows = s.act_n > 16 ? 32u : 16u;
       for (int p = 0; p < 2; ++p) {
         const bool have = p == 0 || s.terms == 3;
-        if ((rc = make_half_map(&G.tmW4[p], have ? w4[p] : w4[0], kHH3, s.act_n, kHH3, 16)) != PQLB_OK) return rc;
+        if ((rc = make_half_map(&G.tmW4[p], have ? w4[p] : w4[0], kHH3, s.act_n, kHH3, head_rows)) != PQLB_OK) return rc;
       }
-      G.head_rows = 16;
+      G.head_rows = (int)head_rows; G.act_vec = vec ? 1 : 0;
       G.act_n = s.act_n; G.act_b = s.act_b; G.act_noise = s.act_noise; G.act_out = s.act_out; G.act_out2 = s.act_out2;
       G.act_ldo = s.act_ldo; G.act_ldo2 = s.act_ldo2; G.act_ldnoise = s.act_ldnoise;
       G.noise_std = s.noise_std; G.noise_bound = s.noise_bound;

@@ -44,7 +44,8 @@ struct alignas(64) MlpHGroupDev {
   float noise_std, noise_bound;
   int act_n;
   const float* sm_b; float* sm_out; long long sm_ldp; int sm_n;      // fused softmax head (C51): sm_n atoms <= 64
-  int head_rows;                    // rows of the head weight tile / N of the head MMA: 16 (policy) or 64 (softmax), 0 = no head
+  int head_rows;                    // rows of the head weight tile / N of the head MMA: 16 or 32 (policy), 64 (softmax), 0 = no head
+  int act_vec;                      // policy head output rows are 16-byte aligned (float4 stores); 0: scalar stores (wide-input kernel only)
   int st1, st2, st3;
   int terms;
   int kb1, kw1, ksteps1;            // this group's input width in 32-float blocks / 64-half weight blocks / 16-wide k steps

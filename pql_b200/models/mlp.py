@@ -149,13 +149,21 @@ def split_f16_ok(inst):
     return n.Wh is not None and inst["k_in"] <= FUSED_H_MAX_IN and n.ldw[0] % 8 == 0
 
 
+_WIDE_HEAD = _os.environ.get("PQLB_WIDE_HEAD", "1") != "0"      # "0": behind a wide input the policy head is always its own launch
+
+
 def fused_head_ok(inst):
-    """Does the policy head of this instance ride in the fused launch (A <= 16, A % 4 == 0, 16-byte aligned
-    output rows)?  Otherwise the trunk stores h3 and the head is its own small launch (policy_head_call)."""
+    """Does the policy head of this instance ride in the fused launch?  A <= 16, A % 4 == 0 and 16-byte aligned
+    output rows; behind an input wider than 128 (the wide-input kernel) A <= 32 and output rows of any alignment
+    (ShadowHand: 20 actions written behind 211 observations).  Otherwise the trunk stores h3 and the head is its own
+    small launch (policy_head_call)."""
     act = inst["act"]
     A = inst["net"].dims[4]
-    return not (A > 16 or A % 4 or act.get("ldo", 0) % 4 or act.get("ldo2", 0) % 4 or act.get("out", 0) % 16
-                or act.get("out2", 0) % 16 or act.get("ldnoise", 0) % 4 or act.get("noise", 0) % 16)
+    if A % 4 or act.get("ldnoise", 0) % 4 or act.get("noise", 0) % 16:
+        return False
+    if inst["k_in"] > FUSED_MAX_IN:
+        return A <= 32 and _WIDE_HEAD
+    return not (A > 16 or act.get("ldo", 0) % 4 or act.get("ldo2", 0) % 4 or act.get("out", 0) % 16 or act.get("out2", 0) % 16)
 
 
 def forward_calls_h(B, insts, scalar_head, tile_sync=None):
@@ -207,8 +215,9 @@ def forward_calls(B, insts, scalar_head):
     ONE layer-fused launch (activations stay in tensor memory, only the flagged ones are written; the
     scalar twin-Q head or the tanh policy head ride in the same launch) where the shapes allow it: the
     split-fp16 kernel when every instance carries fp16 weight copies and passes ``split_f16_ok`` (inputs up
-    to 256 wide: the ShadowHand critics included), else the TF32 kernel for inputs up to 128 wide; what is
-    left (the ShadowHand policy net: 211 inputs with 8-byte-aligned half rows, 20 actions) runs layer by layer."""
+    to 256 wide: ShadowHand's critics and policy net included), else the TF32 kernel for inputs up to 128
+    wide; what is left (wide inputs without fp16 copies: the modules' own forward, the actor-side inference
+    plan) runs layer by layer."""
     k_in = insts[0]["k_in"]
     calls = []
     if all(split_f16_ok(it) for it in insts):

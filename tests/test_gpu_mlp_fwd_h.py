@@ -135,23 +135,28 @@ def test_split_f16_trunk_and_q_head(K, mode, M, k_in, n_groups, terms):
 
 
 @pytest.mark.parametrize("M,A,noisy,terms,k_in", [(8192, 16, True, 1, 88), (300, 16, False, 3, 88), (1000, 8, True, 1, 88),
-                                                  (128, 4, False, 1, 88), (1000, 16, True, 1, 208), (300, 12, False, 3, 200)])
+                                                  (128, 4, False, 1, 88), (1000, 16, True, 1, 208), (300, 12, False, 3, 200),
+                                                  # wide-input kernel: up to 32 actions, output rows of any alignment
+                                                  (8192, 20, True, 1, 211), (300, 32, False, 3, 232), (1000, 20, False, 1, 160)])
 def test_split_f16_policy_head(K, mode, M, A, noisy, terms, k_in):
     """tanh(Linear(128, A)) (+ clipped N(0, std^2) noise, clamp) fused behind the trunk: act_out2 holds the
     value, act_out its TF32 rounding (mlp.py:177-179, noise.py:19-27).  k_in > 128: the wide-input kernel."""
     if k_in > 128 and mode == 2:
         pytest.skip("wide inputs always take the CTA-per-tile kernel")
     g = torch.Generator(device=DEV).manual_seed(M + A)
-    ld = k_in
-    x = torch.randn(M, ld, device=DEV, generator=g)
-    ws, bs, hs, ls = make_net(k_in, A, g)
-    out = torch.full((M, 104), 7.0, device=DEV)
-    out2 = torch.full((M, 104), 7.0, device=DEV)
+    ld = (k_in + 7) // 8 * 8
+    x = torch.zeros(M, ld, device=DEV)
+    x[:, :k_in] = torch.randn(M, k_in, device=DEV, generator=g)
+    ws, bs, hs, ls = make_net(k_in, A, g, ld)
+    # the action columns sit at `off` of rows of W floats; 20 actions behind a wide input: off = 87 (rows not 16-byte aligned)
+    W, off = 124, 87 if (k_in > 128 and A == 20) else 88
+    out = torch.full((M, W), 7.0, device=DEV)
+    out2 = torch.full((M, W), 7.0, device=DEV)
     noise = torch.randn(M, A, device=DEV, generator=g)
     grp = dict(x=K.addr(x), ldx=ld, w1h=hs[0].data_ptr(), ldw1=ld, w2h=hs[1].data_ptr(), w3h=hs[2].data_ptr(),
                b1=K.addr(bs[0]), b2=K.addr(bs[1]), b3=K.addr(bs[2]), terms=terms,
-               act_wh=hs[3].data_ptr(), act_b=K.addr(bs[3]), act_n=A, act_out=K.addr(out, 88), act_ldo=104,
-               act_out2=K.addr(out2, 88), act_ldo2=104)
+               act_wh=hs[3].data_ptr(), act_b=K.addr(bs[3]), act_n=A, act_out=K.addr(out, off), act_ldo=W,
+               act_out2=K.addr(out2, off), act_ldo2=W)
     if terms == 3:
         grp.update(w1l=ls[0].data_ptr(), w2l=ls[1].data_ptr(), w3l=ls[2].data_ptr(), act_wl=ls[3].data_ptr())
     if noisy:
@@ -162,12 +167,12 @@ def test_split_f16_policy_head(K, mode, M, A, noisy, terms, k_in):
     a = torch.tanh(h3 @ ws[3][:, :128].double().t() + bs[3].double())
     if noisy:
         a = torch.clamp(a + torch.clamp(noise.double() * 0.8, -0.2, 0.2), -1.0, 1.0)
-    got2, got = out2[:, 88:88 + A], out[:, 88:88 + A]
+    got2, got = out2[:, off:off + A], out[:, off:off + A]
     tol = 1e-5 if terms == 3 else 1.2e-3
     assert rel(got2, a) <= tol, f"{rel(got2, a):.2e}"
     assert torch.equal(got, rn_tf32(got2))
-    assert float((out[:, :88] - 7.0).abs().max()) == 0.0
-    assert 88 + A == 104 or float((out[:, 88 + A:] - 7.0).abs().max()) == 0.0
+    for o in (out, out2):       # nothing but the action columns is written
+        assert float((o[:, :off] - 7.0).abs().max()) == 0.0 and float((o[:, off + A:] - 7.0).abs().max()) == 0.0
 
 
 @pytest.mark.parametrize("M", [8192, 1000])

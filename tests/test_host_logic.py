@@ -108,13 +108,15 @@ def test_forward_mode_selection():
             L = NetLayout(in_dim, out_dim)
             self.dims, self.ldw, self.Wh = L.dims, L.ldw, [1]
     from pql_b200.models.mlp import fused_head_ok
-    # ShadowHand: critics (231 -> rows of 232 halves) and policy trunk (211 -> 216) take the fused kernel; the 20-action
-    # head does not ride along (A > 16): the trunk stores h3 and the head is its own launch
+    # ShadowHand: critics (231 -> rows of 232 halves) and the policy net (211 -> 216) take the fused kernel; behind a wide
+    # input the head takes up to 32 actions and unaligned output rows (211 * 4 bytes), behind a narrow one 16 / aligned
     assert NetLayout(231, 1).ldw[0] == 232 and NetLayout(211, 20).ldw[0] == 216 and NetLayout(88, 16).ldw[0] == 88
     assert NetLayout(12, 4).ldw[0] == 12                   # narrow first layers keep 16-byte fp32 rows
     assert split_f16_ok(dict(net=Net(231, 1), k_in=231))
     shadow_policy = dict(net=Net(211, 20), k_in=211, act=dict(out=211 * 4, ldo=232, out2=211 * 4, ldo2=232))
-    assert split_f16_ok(shadow_policy) and not fused_head_ok(shadow_policy)
+    assert split_f16_ok(shadow_policy) and fused_head_ok(shadow_policy)
+    assert not fused_head_ok(dict(net=Net(211, 36), k_in=211, act=dict(out=211 * 4, ldo=248)))     # more than 32 actions
+    assert not fused_head_ok(dict(net=Net(88, 20), k_in=88, act=dict(out=88 * 4, ldo=108)))        # 20 actions, narrow input
     wide16 = dict(net=Net(208, 16), k_in=208, act=dict(out=208 * 4, ldo=224, out2=208 * 4, ldo2=224))
     assert split_f16_ok(wide16) and fused_head_ok(wide16)
     assert not fused_head_ok(dict(net=Net(88, 16), k_in=88, act=dict(out=88 * 4 + 4, ldo=104)))  # unaligned action rows
