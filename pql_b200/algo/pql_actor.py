@@ -19,11 +19,12 @@ import torch
 
 from .. import _kernels as K
 from .. import _lib
-from ..models.mlp import HIDDEN, NetAddrs, NetLayout, _ru, forward_calls
+from ..models.mlp import FUSED_H_MAX_IN, FUSED_MAX_IN, HIDDEN, NetAddrs, NetLayout, _ru, forward_calls, half_arena
 from ..replay.nstep_replay import NStepReplay
 from ..utils.common import DeviceTracker
 from ..utils.schedule_util import ExponentialSchedule, LinearSchedule
 from ..utils.torch_util import RunningMeanStd
+from ._engine import _operand_copies
 from .pql_v_learner import _PRODUCER_STREAM, module_flat, note_read
 
 
@@ -115,14 +116,19 @@ class PQLActor:
         p.a_flat, p.a_tf = z(La.total), z(La.total)
         p.x, p.noise, p.act_tf = z(E, p.x_ld), z(E, A), z(E, p.a_ld)
         p.h = [z(E, d) for d in HIDDEN]
-        net = NetAddrs(La, 0, p.a_tf, p.a_flat)
+        # observations wider than 128 (ShadowHand: 211): the layer-fused TF32 kernel does not take them, the wide-input
+        # split-fp16 kernel does (one fp16 MMA per product = the accuracy of the TF32 launches it replaces); it reads
+        # fp16 copies of the weights, refreshed with the TF32 twin whenever the driver hands over a new actor
+        wide = FUSED_MAX_IN < O <= FUSED_H_MAX_IN and La.ldw[0] % 8 == 0 and A % 4 == 0 and A <= 32
+        p.a_h = half_arena(La, dev) if wide else None
+        net = NetAddrs(La, 0, p.a_tf, p.a_flat, p.a_h)
 
         def make(noisy):
             act = dict(out=K.addr(p.act_tf), ldo=p.a_ld, out2=K.addr(p.act_tf), ldo2=p.a_ld)
             if noisy:       # the draw is pre-scaled by its std (pqlb_actor_inputs): std 1, no noise clamp
                 act.update(noise=K.addr(p.noise), ldnoise=A, noise_std=1.0, noise_bound=3.0e38)
             inst = dict(net=net, x=K.addr(p.x), x_ld=p.x_ld, k_in=O, h=[K.addr(t) for t in p.h],
-                        store=(False, False, False), act=act)
+                        store=(False, False, False), act=act, terms=1)
             return forward_calls(E, [inst], False)
         p.calls = {True: make(True), False: make(False)}
         self._plan = p
@@ -130,7 +136,7 @@ class PQLActor:
     def _head_desc(self, calls):
         """(descriptor group, field prefix) of the launch that writes the action."""
         last = calls[-1]
-        if isinstance(last, K.MlpForward):
+        if isinstance(last, (K.MlpForward, K.MlpForwardH)):
             return last.desc.g[0], "act_"
         return last.desc.g[0], ""
 
@@ -146,7 +152,7 @@ class PQLActor:
                 torch.cuda.current_stream(self.sim_device).wait_stream(src)
             p.a_flat.copy_(module_flat(self._actor, p.La.total, self.sim_device), non_blocking=True)
             note_read(self._actor)           # the P-learner's next in-place update waits for this copy
-            _lib.call("pqlb_round_tf32", _lib.ptr(p.a_flat), _lib.ptr(p.a_tf), p.a_flat.numel())
+            _operand_copies(p.a_flat, p.a_tf, p.a_h)
             self._weights_stale = False
 
     # ---- reference API -------------------------------------------------------------------------
