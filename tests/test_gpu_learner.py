@@ -41,6 +41,13 @@ def test_full_batch_allegro_doubleq():
     print(res)
 
 
+def test_full_batch_shadowhand_doubleq():
+    """BASELINE config 4's shapes (obs 211, act 20) at the benchmark's batch size: critics, policy net and heads on the
+    wide-input split-fp16 kernel (csrc/mlp_fwd_h.cu, mlp_fwd_hw_kernel); same flat 1e-3 as every other case."""
+    res = parity.run_learner_parity(seed=21, B=8192, obs_dim=211, act_dim=20, distl=False, steps=1, device=DEV)
+    print(res)
+
+
 def test_free_running_trace_vs_reference_fixture(golden_dir):
     """Three unsynchronised updates from the reference's initial weights: losses recorded from
     the reference run itself (tests/golden/learner_doubleq.npz).  TF32 rounding compounds
