@@ -216,8 +216,8 @@ def forward_calls(B, insts, scalar_head):
     scalar twin-Q head or the tanh policy head ride in the same launch) where the shapes allow it: the
     split-fp16 kernel when every instance carries fp16 weight copies and passes ``split_f16_ok`` (inputs up
     to 256 wide: ShadowHand's critics and policy net included), else the TF32 kernel for inputs up to 128
-    wide; what is left (wide inputs without fp16 copies: the modules' own forward, the actor-side inference
-    plan) runs layer by layer."""
+    wide; what is left (inputs wider than 256, wide inputs without fp16 copies: the modules' own forward)
+    runs layer by layer."""
     k_in = insts[0]["k_in"]
     calls = []
     if all(split_f16_ok(it) for it in insts):
