@@ -17,7 +17,6 @@ import argparse
 import gc
 import json
 import os
-import subprocess
 import sys
 import threading
 import time

@@ -15,8 +15,7 @@ import torch
 
 from .. import _kernels as K
 from .. import _lib
-from ..models.mlp import (FUSED_H_MAX_IN, FUSED_MAX_IN, HIDDEN, NetAddrs, NetLayout, _ru, forward_calls, forward_calls_h, fwd_tile,
-                          half_arena)
+from ..models.mlp import FUSED_H_MAX_IN, FUSED_MAX_IN, HIDDEN, NetAddrs, NetLayout, _ru, forward_calls, fwd_tile, half_arena
 
 H1, H2, H3 = HIDDEN
 import os as _os

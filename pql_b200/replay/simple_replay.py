@@ -5,8 +5,6 @@ include/pqlb200.h) instead of the reference's five column tensors: a uniformly s
 transition is then one contiguous, sector-aligned 800-byte read (AllegroHand) instead of
 five scattered ones.  ``buf_obs`` ... ``buf_done`` remain available as views.
 """
-import ctypes as C
-
 import torch
 
 from .. import _lib
