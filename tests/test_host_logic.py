@@ -122,3 +122,54 @@ def test_forward_mode_selection():
     assert not fused_head_ok(dict(net=Net(88, 16), k_in=88, act=dict(out=88 * 4 + 4, ldo=104)))  # unaligned action rows
     assert not split_f16_ok(dict(net=Net(260, 1), k_in=260))
     assert not split_f16_ok(dict(net=Net(12, 4), k_in=12))  # 12 halves = 24-byte rows
+
+
+def test_forward_launch_plans():
+    """Which launches a forward becomes (models/mlp.py: forward_calls), built on fake addresses - no GPU needed:
+    ShadowHand's critics, policy net and 20-action head are ONE fused split-fp16 launch each (no per-layer GEMM);
+    a head the kernel does not fuse becomes one extra launch behind a trunk that stores h3; nets without fp16
+    copies and inputs wider than 128 run layer by layer."""
+    import torch
+    from pql_b200 import _kernels as K
+    from pql_b200.models.mlp import NetAddrs, NetLayout, forward_calls
+    B, base = 8192, 1 << 20
+
+    def net(in_dim, out_dim, halves=True):
+        L = NetLayout(in_dim, out_dim)
+        half = torch.zeros(2 * L.total, dtype=torch.float16) if halves else None
+        return NetAddrs(L, 0, base, base + 4 * L.total, half), half
+
+    def inst(n, k_in, x_ld, **kw):
+        return dict(net=n, x=base, xf=base + 64, x_ld=x_ld, k_in=k_in, h=[base, base, base], **kw)
+
+    keep = []
+    # ShadowHand critics: four networks, scalar heads, one launch on the wide-input kernel
+    crit = []
+    for i in range(4):
+        n, h = net(231, 1); keep.append(h)
+        crit.append(inst(n, 231, 232, q=base + 128, terms=3, store=(i < 2,) * 3))
+    calls = forward_calls(B, crit, True)
+    assert len(calls) == 1 and isinstance(calls[0], K.MlpForwardH)
+    d = calls[0].desc
+    assert (d.M, d.k_in, d.n_groups) == (B, 231, 4) and d.g[0].ldw1 == 232 and d.g[0].terms == 3
+    assert bool(d.g[0].h1) and not bool(d.g[2].h1) and bool(d.g[3].q)
+    # ShadowHand policy: 211 observations (rows of 216 halves), 20 actions written at column 211 of the critics' rows
+    n, h = net(211, 20); keep.append(h)
+    act = dict(out=base + 4 * 211, ldo=232, out2=base + 64 + 4 * 211, ldo2=232, noise=base + 256, ldnoise=20, noise_std=0.8, noise_bound=0.2)
+    calls = forward_calls(B, [inst(n, 211, 232, act=act, terms=1, store=(False,) * 3)], False)
+    assert len(calls) == 1 and isinstance(calls[0], K.MlpForwardH)
+    g = calls[0].desc.g[0]
+    assert g.act_n == 20 and g.ldw1 == 216 and g.terms == 1 and not bool(g.h3) and g.act_ldo == 232
+    # 36 actions: the trunk is still one fused launch (it stores h3), the head is its own GEMM
+    n, h = net(211, 36); keep.append(h)
+    calls = forward_calls(B, [inst(n, 211, 248, act=dict(out=base + 4 * 211, ldo=248), terms=1, store=(False,) * 3)], False)
+    assert [type(c) for c in calls] == [K.MlpForwardH, K.Gemm]
+    assert bool(calls[0].desc.g[0].h3) and calls[0].desc.g[0].act_n == 0
+    # no fp16 copies (a module's own forward): 211 inputs run layer by layer - three trunk GEMMs + the head
+    n, _ = net(211, 20, halves=False)
+    calls = forward_calls(B, [inst(n, 211, 216, act=dict(out=base, ldo=20))], False)
+    assert [type(c) for c in calls] == [K.Gemm] * 4
+    # AllegroHand policy without fp16 copies: the TF32 layer-fused kernel
+    n, _ = net(88, 16, halves=False)
+    calls = forward_calls(B, [inst(n, 88, 88, act=dict(out=base, ldo=16))], False)
+    assert len(calls) == 1 and isinstance(calls[0], K.MlpForward)
